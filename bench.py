@@ -1,0 +1,339 @@
+#!/usr/bin/env python
+"""bench.py -- BASELINE.json's metric: Msymbols/s of bit-exact ANS encode+decode on B200(s).
+
+Workload (BASELINE.json configs[1]): 1e8 i.i.d. int32 symbols ~ QuantizedGaussian(-50,50,3.2,9.6),
+dealt round-robin to K lane-streams (one independent reference coder per GPU lane), CDF tables in
+shared memory.  A "step" is one pass of the hot path over the batch: ANS encode of all streams
+(coder kernel + compaction into the dense container), [N>1: NCCL all-gather of the compressed
+containers], ANS decode of all streams.  `value` is measured with inputs resident in HBM; `e2e` is
+the same step through the host-buffer C ABI (pinned host buffers, H2D/D2H copies inside the timed
+region).  Weak scaling: every GPU gets its own 1e8-symbol shard.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+`--impl reference` times the reference's CPU algorithm (the oracle's C restatement; the Rust crate
+cannot be built in this image) on the host cores for the same config.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+MODEL = (-50, 50, 3.2, 9.6)
+METRIC = "Msymbols/s ANS encode+decode (bit-exact)"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--symbols", type=int, default=100_000_000, help="symbols per GPU")
+    ap.add_argument("--streams", type=int, default=148 * 1024, help="independent coders (lanes) per GPU")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--cpu-sample", type=int, default=50_000_000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def measured_peak_gbs():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def synth_symbols_numpy(n, seed):
+    rng = np.random.default_rng(seed)
+    return np.clip(np.rint(rng.normal(MODEL[2], MODEL[3], size=n)), MODEL[0], MODEL[1]).astype(np.int32)
+
+
+# ----------------------------------------------------------------------------------------------------
+# clocks sampling (B200_PROFILING.md recipe)
+# ----------------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.samples = []
+        self._stop = threading.Event()
+        self._thread = None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.FIELDS}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [p.strip() for p in out.strip().split(",")]
+                if len(parts) >= 7:
+                    self.samples.append(parts)
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self._thread = threading.Thread(target=self._run, daemon=True)
+        self._thread.start()
+        return self
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        self._thread.join(timeout=10)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm = sorted(float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit())
+        mx = [float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[3 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.samples)}
+
+
+# ----------------------------------------------------------------------------------------------------
+# CPU legs (oracle; test infrastructure used only as the reported baseline / reference arm)
+# ----------------------------------------------------------------------------------------------------
+def cpu_round_trip(oracle, syms, k, cdf, threads):
+    """K independent reference coders over contiguous chunks (the cache-friendly way to split a message
+    on a CPU; same number of coders and symbols as the GPU batch)."""
+    chunks = (np.arange(k + 1, dtype=np.uint64) * np.uint64(syms.size)) // np.uint64(k)
+    t0 = time.perf_counter()
+    words, off = oracle.multi_ans_encode(syms, k, cdf, MODEL[0], sym_offsets=chunks, threads=threads)
+    t1 = time.perf_counter()
+    out = oracle.multi_ans_decode(words, off, syms.size, k, cdf, MODEL[0], sym_offsets=chunks, threads=threads)
+    t2 = time.perf_counter()
+    assert np.array_equal(out, syms)
+    return t1 - t0, t2 - t1
+
+
+def cpu_baseline(n_sample, k, threads):
+    from oracle import refapi as O
+    cdf = O.qgauss_cdf(*MODEL)
+    syms = synth_symbols_numpy(n_sample, 2)
+    cpu_round_trip(O, syms[: n_sample // 10], k, cdf, threads)  # warm the threads / caches
+    te, td = min((cpu_round_trip(O, syms, k, cdf, threads) for _ in range(2)), key=sum)
+    return {"value": n_sample / (te + td) / 1e6, "unit": "Msymbols/s", "cores": threads, "kind": "port",
+            "sample": f"{n_sample} symbols of the same workload in {k} streams, tabulated model, C restatement "
+                      f"(oracle/) of stack.rs encode/decode, {threads} threads; encode {te:.3f}s decode {td:.3f}s"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import refapi as O
+    threads = os.cpu_count() or 1
+    cdf = O.qgauss_cdf(*MODEL)
+    n_sample = min(args.symbols, args.cpu_sample)
+    k = args.streams
+    syms = synth_symbols_numpy(n_sample, 2)
+    for _ in range(args.warmup):
+        cpu_round_trip(O, syms, k, cdf, threads)
+    times = []
+    for _ in range(args.steps):
+        te, td = cpu_round_trip(O, syms, k, cdf, threads)
+        times.append(te + td)
+    t = sum(times) / len(times)
+    value = n_sample / t / 1e6
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "Msymbols/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": {"workload": "configs[1]: 1e8 i.i.d. symbols, QuantizedGaussian(-50,50,3.2,9.6), ANS encode+decode",
+                   "symbols_per_step": n_sample, "streams": k,
+                   "note": "reference = CPU restatement of constriction's stack.rs loops (Rust toolchain absent); "
+                           "each step is a bounded sample of the workload"},
+        "cpu_baseline": {"value": value, "unit": "Msymbols/s", "cores": threads, "kind": "port",
+                         "sample": f"{n_sample} symbols per step, {k} streams, tabulated model, {threads} threads"},
+        "e2e": {"value": value, "unit": "Msymbols/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from constriction_b200 import _native as N
+    from constriction_b200 import batch as B
+    from constriction_b200 import dist as D
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl ours needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    lib = N.load()
+    n, k = args.symbols, args.streams
+
+    # synthetic shard, generated on the device (seed differs per rank), resident in HBM
+    g = torch.Generator(device="cuda")
+    g.manual_seed(2 + rank)
+    syms = torch.clamp(torch.round(torch.randn(n, device="cuda", generator=g) * MODEL[3] + MODEL[2]), MODEL[0],
+                       MODEL[1]).to(torch.int32)
+    model = B.ModelTable.quantized_gaussian(MODEL[0], MODEL[1], [MODEL[2]], [MODEL[3]])
+    bc = B.BatchCoder()
+    out = torch.empty_like(syms)
+    comp = None
+
+    def step():
+        nonlocal comp
+        comp = bc.ans_encode(syms, model, n_streams=k, out=comp)
+        if world > 1:
+            gc = D.all_gather_compressed(comp.words, comp.offsets)
+            lo, hi = gc.stream_base[rank], gc.stream_base[rank] + k
+            mine = B.Compressed(gc.words, gc.offsets[lo:hi + 1].contiguous(), k, n, "ans")
+            bc.ans_decode(mine, model, out=out)
+        else:
+            bc.ans_decode(comp, model, out=out)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    bc.check()
+    assert torch.equal(out, syms), "decode(encode(x)) != x"
+    total_words = comp.total_words()
+
+    # ---- timed region: device-resident inputs --------------------------------------------------------
+    lib.ctr_profile_enable(1)
+    lib.ctr_profile_read(0, None, None)
+    lib.ctr_profile_read(1, None, None)
+    launches0 = B.kernel_launch_count()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    sync_all()
+    with ClockSampler(local_rank) as clocks:
+        ev[0].record()
+        for i in range(args.steps):
+            step()
+            ev[i + 1].record()
+        sync_all()
+    launches = B.kernel_launch_count() - launches0
+    lib.ctr_profile_enable(0)
+    total_ms = ev[0].elapsed_time(ev[-1])
+    t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    ms_per_step = total_ms / args.steps
+    value = world * n / (ms_per_step * 1e-3) / 1e6
+    bc.check()
+
+    enc_ms, dec_ms = C.c_double(), C.c_double()
+    enc_n, dec_n = C.c_uint64(), C.c_uint64()
+    lib.ctr_profile_read(0, C.byref(enc_ms), C.byref(enc_n))
+    lib.ctr_profile_read(1, C.byref(dec_ms), C.byref(dec_n))
+    enc_kernel_ms = enc_ms.value / max(enc_n.value, 1)
+    dec_kernel_ms = dec_ms.value / max(dec_n.value, 1)
+
+    # ---- roofline of the dominant kernel ---------------------------------------------------------------
+    peak, peak_src = measured_peak_gbs()
+    bytes_per_launch = 4.0 * n + 4.0 * total_words  # symbols in/out + compressed words out/in (same for both kernels)
+    dom_name, dom_ms = ("ans_encode_kernel", enc_kernel_ms) if enc_kernel_ms >= dec_kernel_ms else ("ans_decode_kernel", dec_kernel_ms)
+    achieved = bytes_per_launch / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
+    roofline = {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": bytes_per_launch,
+                "kernel_ms": {"ans_encode_kernel": enc_kernel_ms, "ans_decode_kernel": dec_kernel_ms},
+                "frac_of_step": {"ans_encode_kernel": enc_kernel_ms / ms_per_step, "ans_decode_kernel": dec_kernel_ms / ms_per_step}}
+
+    # ---- e2e: host buffers through the C ABI, copies inside the timed region ---------------------------
+    h_syms = torch.empty(n, dtype=torch.int32).pin_memory()
+    h_syms.copy_(syms)
+    L = N.Layout()
+    L.n_streams, L.n_symbols = k, n
+    cap = int(lib.ctr_ans_max_compressed_words(C.byref(L)))
+    h_words = torch.empty(cap, dtype=torch.int32).pin_memory()
+    h_off = torch.empty(k + 1, dtype=torch.int64).pin_memory()
+    h_out = torch.empty(n, dtype=torch.int32).pin_memory()
+    status, bad = C.c_int(), C.c_uint64()
+
+    def e2e_step():
+        rc = lib.ctr_ans_encode_reverse_host(model.handle, h_syms.data_ptr(), n, k, None, None, 0, h_words.data_ptr(), cap,
+                                             h_off.data_ptr(), C.byref(status), C.byref(bad))
+        assert rc == 0 and status.value == 0, (rc, status.value)
+        rc = lib.ctr_ans_decode_host(model.handle, h_words.data_ptr(), h_off.data_ptr(), n, k, None, None, 0,
+                                     h_out.data_ptr(), C.byref(status), C.byref(bad))
+        assert rc == 0 and status.value == 0, (rc, status.value)
+
+    e2e_step()
+    e2e_step()
+    assert torch.equal(h_out, h_syms)
+    sync_all()
+    t0 = time.perf_counter()
+    for _ in range(args.e2e_steps):
+        e2e_step()
+    e2e_s = (time.perf_counter() - t0) / args.e2e_steps
+    t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_s = float(t.item())
+    words_bytes = 4 * int(h_off[-1].item())
+    e2e = {"value": world * n / e2e_s / 1e6, "unit": "Msymbols/s",
+           "h2d_bytes_per_step": 4 * n + words_bytes + 8 * (k + 1),
+           "d2h_bytes_per_step": words_bytes + 8 * (k + 1) + 4 * n + 32,
+           "ms_per_step": e2e_s * 1e3, "steps": args.e2e_steps,
+           "api": "ctr_ans_encode_reverse_host + ctr_ans_decode_host (pinned host buffers)"}
+
+    if rank == 0:
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            cpu = cpu_baseline(min(n, args.cpu_sample), k, os.cpu_count() or 1)
+        line = {
+            "metric": METRIC, "value": value, "unit": "Msymbols/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "config": {"workload": "configs[1]: 1e8 i.i.d. int32 symbols per GPU, QuantizedGaussian(-50,50,3.2,9.6), "
+                                   "lane-interleaved rANS (one reference coder per lane), CDF in shared memory",
+                       "symbols_per_gpu": n, "streams_per_gpu": k, "compressed_words_per_gpu": total_words,
+                       "bits_per_symbol": 32.0 * total_words / n,
+                       "l2": "inputs (400 MB symbols) larger than the 126 MB L2; no flush between steps",
+                       "step": "ANS encode (kernel + compaction) -> [all-gather of containers if N>1] -> ANS decode"},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+            "clocks": clocks.summary(),
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,62 @@
+"""Builds libconstriction_b200.so (the C-ABI CUDA library) in-tree with nvcc for sm_100a.
+
+The library travels to the GPU box with the repo snapshot (built `.so` files are git-ignored but not
+gpurun-ignored).  Flags that matter:
+  -gencode arch=compute_100a,code=sm_100a   B200 only
+  -fmad=false / -ffp-contract=off           model tabulation must not fuse a*b+c (the reference is
+                                            Rust, which never contracts); the integer coder kernels
+                                            are unaffected
+  -lineinfo                                 so that ncu's source page maps to the .cuh files
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "libconstriction_b200.so")
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-O3", "-std=c++17", "-lineinfo", "-fmad=false",
+    "--shared", "-Xcompiler", "-fPIC,-ffp-contract=off,-fno-fast-math,-Wall",
+    "-Xptxas", "-v",
+    "-cudart", "shared",
+]
+
+
+def sources():
+    return [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cu", ".cuh"))] + [
+        os.path.join(os.path.dirname(HERE), "include", "constriction_b200.h")]
+
+
+def is_stale() -> bool:
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    return any(os.path.getmtime(f) > t for f in sources())
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    if not force and not is_stale():
+        return LIB
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        raise RuntimeError("nvcc not found: cannot build libconstriction_b200.so")
+    cmd = [nvcc] + NVCC_FLAGS + ["-o", LIB, os.path.join(CSRC, "capi.cu")]
+    proc = subprocess.run(cmd, capture_output=True, text=True)
+    if proc.returncode != 0:
+        sys.stderr.write(proc.stdout + proc.stderr)
+        raise RuntimeError("nvcc failed building libconstriction_b200.so")
+    if verbose:
+        sys.stderr.write(proc.stderr)
+    with open(os.path.join(HERE, "build_ptxas.log"), "w") as f:
+        f.write(proc.stderr)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose=True))

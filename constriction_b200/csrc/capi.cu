@@ -1,0 +1,820 @@
+// capi.cu -- the C ABI declared in include/constriction_b200.h: argument checking, workspace layout,
+// kernel launches.  No torch types, no host synchronisation on the device-pointer entry points, no
+// CPU fallback (every compute entry point needs a CUDA device).
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <atomic>
+#include <mutex>
+#include <new>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "../../include/constriction_b200.h"
+#include "ans_kernels.cuh"
+#include "compact.cuh"
+#include "model_tables.cuh"
+#include "range_kernels.cuh"
+
+using namespace ctr;
+
+namespace {
+
+thread_local std::string g_last_cuda_error;
+std::atomic<uint64_t> g_launches{0};
+
+// ---- optional kernel timing (ctr_profile_*) ---------------------------------------------------------
+struct ProfileSlot {
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending;  // recorded, not yet read
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> free_list;
+};
+std::atomic<int> g_profile_on{0};
+std::mutex g_profile_mutex;
+ProfileSlot g_profile[4];
+
+struct ProfileScope {  // records start now, stop at destruction
+    int which;
+    cudaStream_t s;
+    std::pair<cudaEvent_t, cudaEvent_t> ev{nullptr, nullptr};
+    ProfileScope(int which_, cudaStream_t s_) : which(which_), s(s_) {
+        if (!g_profile_on.load(std::memory_order_relaxed)) return;
+        std::lock_guard<std::mutex> lock(g_profile_mutex);
+        ProfileSlot &slot = g_profile[which];
+        if (!slot.free_list.empty()) {
+            ev = slot.free_list.back();
+            slot.free_list.pop_back();
+        } else {
+            cudaEventCreate(&ev.first);
+            cudaEventCreate(&ev.second);
+        }
+        cudaEventRecord(ev.first, s);
+    }
+    ~ProfileScope() {
+        if (!ev.first) return;
+        cudaEventRecord(ev.second, s);
+        std::lock_guard<std::mutex> lock(g_profile_mutex);
+        g_profile[which].pending.push_back(ev);
+    }
+};
+
+int cuda_fail(cudaError_t e, const char *what) {
+    g_last_cuda_error = std::string(what) + ": " + cudaGetErrorString(e);
+    return CTR_ERR_CUDA;
+}
+
+#define CUDA_TRY(expr)                                       \
+    do {                                                     \
+        cudaError_t e__ = (expr);                            \
+        if (e__ != cudaSuccess) return cuda_fail(e__, #expr); \
+    } while (0)
+
+#define LAUNCH_CHECK(name)                                    \
+    do {                                                      \
+        g_launches.fetch_add(1, std::memory_order_relaxed);   \
+        cudaError_t e__ = cudaGetLastError();                 \
+        if (e__ != cudaSuccess) return cuda_fail(e__, name);  \
+    } while (0)
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+inline unsigned grid_for(uint64_t n, unsigned block) { return (unsigned)((n + block - 1) / block); }
+
+}  // namespace
+
+struct ctr_model_s {
+    uint32_t n_models = 0, alphabet = 0;
+    int32_t min_symbol = 0;
+    uint32_t *d_cdf = nullptr;  // [n_models][alphabet+1]
+    uint4 *d_enc = nullptr;     // [n_models][alphabet], built on first encode
+    uint32_t *d_dec = nullptr;  // model 0: pairs + bucket index, built on first decode
+    uint32_t dec_pairs_bytes = 0;
+    bool shared_ok = false;  // small enough for the shared-memory table kernels
+};
+
+namespace {
+
+// ---- model construction ---------------------------------------------------------------------------
+
+int model_alloc(uint32_t n_models, uint32_t alphabet, int32_t min_symbol, ctr_model_s **out) {
+    if (n_models == 0 || alphabet < 2 || alphabet > kTotal) return CTR_ERR_BAD_MODEL;
+    ctr_model_s *m = new (std::nothrow) ctr_model_s();
+    if (!m) return CTR_ERR_BAD_ARGUMENT;
+    m->n_models = n_models;
+    m->alphabet = alphabet;
+    m->min_symbol = min_symbol;
+    m->dec_pairs_bytes = (uint32_t)align_up((size_t)alphabet * 8, 16);
+    m->shared_ok = alphabet <= kMaxSharedAlphabet;
+    cudaError_t e = cudaMalloc(&m->d_cdf, (size_t)n_models * ((size_t)alphabet + 1) * 4);
+    if (e != cudaSuccess) {
+        delete m;
+        return cuda_fail(e, "cudaMalloc(cdf)");
+    }
+    *out = m;
+    return CTR_OK;
+}
+
+int ensure_enc_table(ctr_model_s *m, cudaStream_t s) {
+    if (m->d_enc) return CTR_OK;
+    const uint64_t entries = (uint64_t)m->n_models * m->alphabet;
+    CUDA_TRY(cudaMalloc(&m->d_enc, entries * 16));
+    build_enc_table_kernel<<<grid_for(entries, 256), 256, 0, s>>>(m->d_cdf, m->n_models, m->alphabet, m->d_enc);
+    LAUNCH_CHECK("build_enc_table_kernel");
+    return CTR_OK;
+}
+
+int ensure_dec_table(ctr_model_s *m, cudaStream_t s) {
+    if (m->d_dec || !m->shared_ok) return CTR_OK;
+    CUDA_TRY(cudaMalloc(&m->d_dec, m->dec_pairs_bytes + kLutSize * 4));
+    const uint32_t threads = m->alphabet + 2 > (uint32_t)kLutSize ? m->alphabet + 2 : (uint32_t)kLutSize;
+    build_dec_table_kernel<<<grid_for(threads, 256), 256, 0, s>>>(m->d_cdf, m->alphabet, m->dec_pairs_bytes, m->d_dec);
+    LAUNCH_CHECK("build_dec_table_kernel");
+    return CTR_OK;
+}
+
+// runs the validation kernel, builds the derived tables (the encoder table only when it is small;
+// huge model pools get it on first encode) and turns device error bits into a status.
+// Synchronises `s`: model construction is not on the hot path.
+int model_finish(ctr_model_s *m, uint32_t *d_err, int strict, cudaStream_t s) {
+    const uint64_t entries = (uint64_t)m->n_models * ((uint64_t)m->alphabet + 1);
+    validate_cdf_kernel<<<grid_for(entries, 256), 256, 0, s>>>(m->d_cdf, m->n_models, m->alphabet, strict, d_err);
+    LAUNCH_CHECK("validate_cdf_kernel");
+    int rc = ensure_dec_table(m, s);
+    if (rc) return rc;
+    if (entries <= (8ull << 20) && (rc = ensure_enc_table(m, s))) return rc;
+    uint32_t h_err = 0;
+    CUDA_TRY(cudaMemcpyAsync(&h_err, d_err, 4, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    return h_err ? CTR_ERR_BAD_MODEL : CTR_OK;
+}
+
+struct ErrWord {
+    uint32_t *d = nullptr;
+    int init(cudaStream_t s) {
+        CUDA_TRY(cudaMalloc(&d, 4));
+        CUDA_TRY(cudaMemsetAsync(d, 0, 4, s));
+        return CTR_OK;
+    }
+    ~ErrWord() {
+        if (d) cudaFree(d);
+    }
+};
+
+ModelView model_view(const ctr_model_s *m) {
+    ModelView v;
+    v.cdf = m->d_cdf;
+    v.enc = m->d_enc;
+    v.dec = m->d_dec;
+    v.n_models = m->n_models;
+    v.alphabet = m->alphabet;
+    v.min_symbol = m->min_symbol;
+    v.dec_pairs_bytes = m->dec_pairs_bytes;
+    return v;
+}
+
+// ---- layout checks / workspace -----------------------------------------------------------------------
+
+int check_layout(const ctr_layout *L) {
+    if (!L) return CTR_ERR_BAD_ARGUMENT;
+    if (L->model_index_mode < 0 || L->model_index_mode > 2) return CTR_ERR_BAD_ARGUMENT;
+    if (L->model_index_mode != CTR_INDEX_NONE && !L->model_index_dev) return CTR_ERR_BAD_ARGUMENT;
+    if (L->n_streams == 0 && L->n_symbols != 0) return CTR_ERR_BAD_ARGUMENT;
+    return CTR_OK;
+}
+
+struct EncodeWorkspace {
+    uint64_t scratch_words;
+    size_t lengths_off, tiles_off, total;
+    uint64_t n_tiles;
+};
+
+EncodeWorkspace encode_workspace(const ctr_layout *L) {
+    EncodeWorkspace w;
+    w.scratch_words = scratch_start(L->n_symbols, L->n_streams) + 32;
+    w.lengths_off = align_up((size_t)w.scratch_words * 4, 256);
+    w.n_tiles = (L->n_streams + kScanTile - 1) / kScanTile;
+    w.tiles_off = align_up(w.lengths_off + (size_t)L->n_streams * 4, 256);
+    w.total = w.tiles_off + (size_t)(w.n_tiles + 1) * 8;
+    return w;
+}
+
+// prefix sum of per-stream lengths + gather into the dense container
+int compact_streams(const ctr_layout *L, const EncodeWorkspace &w, char *ws, uint32_t *words_out, uint64_t capacity,
+                    uint64_t *offsets_out, uint32_t *status, cudaStream_t s) {
+    const uint32_t *scratch = reinterpret_cast<const uint32_t *>(ws);
+    const uint32_t *lengths = reinterpret_cast<const uint32_t *>(ws + w.lengths_off);
+    uint64_t *tiles = reinterpret_cast<uint64_t *>(ws + w.tiles_off);
+    const uint64_t K = L->n_streams;
+    scan_tile_sums_kernel<<<(unsigned)w.n_tiles, kScanBlock, 0, s>>>(lengths, K, tiles);
+    LAUNCH_CHECK("scan_tile_sums_kernel");
+    scan_top_kernel<<<1, kScanBlock, 0, s>>>(tiles, w.n_tiles, offsets_out, K);
+    LAUNCH_CHECK("scan_top_kernel");
+    scan_apply_kernel<<<(unsigned)w.n_tiles, kScanBlock, 0, s>>>(lengths, K, tiles, offsets_out);
+    LAUNCH_CHECK("scan_apply_kernel");
+    compact_copy_kernel<<<grid_for(K * 32, 256), 256, 0, s>>>(scratch, lengths, offsets_out, K, L->n_symbols,
+                                                               L->sym_offsets_dev, words_out, capacity, status);
+    LAUNCH_CHECK("compact_copy_kernel");
+    return CTR_OK;
+}
+
+template <typename Kernel>
+int set_smem(Kernel kernel, size_t bytes) {
+    if (bytes > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    return CTR_OK;
+}
+
+}  // namespace
+
+// =====================================================================================================
+// library
+// =====================================================================================================
+extern "C" int ctr_abi_version(void) { return CTR_ABI_VERSION; }
+
+extern "C" const char *ctr_status_string(int code) {
+    switch (code) {
+        case CTR_OK: return "ok";
+        case CTR_ERR_IMPOSSIBLE_SYMBOL: return "Tried to encode symbol that has zero probability under the used entropy model.";
+        case CTR_ERR_INVALID_DATA: return "Tried to decode invalid compressed data.";
+        case CTR_ERR_TRAILING_ZERO: return "Invalid compressed data: ANS compressed data never ends in a zero word.";
+        case CTR_ERR_NOT_SEALED: return "Cannot unseal compressed data because it doesn't fit into integer number of words.";
+        case CTR_ERR_BAD_MODEL: return "Probability distribution not normalizable or invalid model parameter.";
+        case CTR_ERR_SEEK: return "Invalid coder state or tried to seek past end of stream.";
+        case CTR_ERR_OUT_OF_SPACE: return "Output buffer too small for the compressed data.";
+        case CTR_ERR_BAD_ARGUMENT: return "Bad argument.";
+        case CTR_ERR_CUDA: return "CUDA error (see ctr_last_cuda_error).";
+        default: return "unknown status";
+    }
+}
+
+extern "C" const char *ctr_last_cuda_error(void) { return g_last_cuda_error.c_str(); }
+
+extern "C" int ctr_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+extern "C" uint64_t ctr_kernel_launch_count(void) { return g_launches.load(); }
+
+extern "C" void ctr_profile_enable(int on) { g_profile_on.store(on ? 1 : 0); }
+
+extern "C" int ctr_profile_read(int which, double *total_ms, uint64_t *launches) {
+    if (which < 0 || which > 3) return CTR_ERR_BAD_ARGUMENT;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> evs;
+    {
+        std::lock_guard<std::mutex> lock(g_profile_mutex);
+        evs.swap(g_profile[which].pending);
+    }
+    double total = 0.0;
+    for (auto &ev : evs) {
+        CUDA_TRY(cudaEventSynchronize(ev.second));
+        float ms = 0.f;
+        CUDA_TRY(cudaEventElapsedTime(&ms, ev.first, ev.second));
+        total += ms;
+    }
+    if (total_ms) *total_ms = total;
+    if (launches) *launches = evs.size();
+    std::lock_guard<std::mutex> lock(g_profile_mutex);
+    for (auto &ev : evs) g_profile[which].free_list.push_back(ev);
+    return CTR_OK;
+}
+
+// =====================================================================================================
+// models
+// =====================================================================================================
+extern "C" int ctr_model_quantized_gaussian(int32_t min_symbol, int32_t max_symbol, const double *means_host,
+                                            const double *stds_host, uint32_t n_models, void *stream,
+                                            ctr_model_t *out) {
+    if (!out || !means_host || !stds_host || n_models == 0) return CTR_ERR_BAD_ARGUMENT;
+    if (!(max_symbol > min_symbol)) return CTR_ERR_BAD_MODEL;
+    const uint64_t support = (uint64_t)((int64_t)max_symbol - (int64_t)min_symbol) + 1;
+    if (support > kTotal) return CTR_ERR_BAD_MODEL;
+    for (uint32_t i = 0; i < n_models; ++i)
+        if (!(stds_host[i] > 0.0) || !(means_host[i] == means_host[i])) return CTR_ERR_BAD_MODEL;
+    cudaStream_t s = (cudaStream_t)stream;
+    ctr_model_s *m = nullptr;
+    int rc = model_alloc(n_models, (uint32_t)support, min_symbol, &m);
+    if (rc) return rc;
+    double *d_params = nullptr;
+    ErrWord err;
+    auto cleanup = [&](int code) {
+        if (d_params) cudaFree(d_params);
+        if (code) ctr_model_destroy(m);
+        return code;
+    };
+    if ((rc = err.init(s))) return cleanup(rc);
+    if (cudaMalloc(&d_params, (size_t)n_models * 16) != cudaSuccess) return cleanup(cuda_fail(cudaGetLastError(), "cudaMalloc(params)"));
+    if (cudaMemcpyAsync(d_params, means_host, (size_t)n_models * 8, cudaMemcpyHostToDevice, s) != cudaSuccess ||
+        cudaMemcpyAsync(d_params + n_models, stds_host, (size_t)n_models * 8, cudaMemcpyHostToDevice, s) != cudaSuccess)
+        return cleanup(cuda_fail(cudaGetLastError(), "cudaMemcpyAsync(params)"));
+    const uint64_t entries = (uint64_t)n_models * (support + 1);
+    qgauss_cdf_kernel<<<grid_for(entries, 128), 128, 0, s>>>(min_symbol, max_symbol, d_params, d_params + n_models,
+                                                             n_models, (uint32_t)support, m->d_cdf, err.d);
+    g_launches.fetch_add(1);
+    if (cudaGetLastError() != cudaSuccess) return cleanup(cuda_fail(cudaGetLastError(), "qgauss_cdf_kernel"));
+    rc = model_finish(m, err.d, /*strict=*/1, s);
+    if (rc) return cleanup(rc);
+    *out = m;
+    return cleanup(CTR_OK);
+}
+
+namespace {
+template <typename F>
+int model_categorical(const F *pmf, int is_device, uint32_t n_models, uint32_t alphabet, void *stream,
+                      ctr_model_t *out) {
+    if (!out || !pmf || n_models == 0) return CTR_ERR_BAD_ARGUMENT;
+    if (alphabet < 2 || alphabet >= kTotal - 1) return CTR_ERR_BAD_MODEL;  // categorical.rs:30-34
+    cudaStream_t s = (cudaStream_t)stream;
+    ctr_model_s *m = nullptr;
+    int rc = model_alloc(n_models, alphabet, 0, &m);
+    if (rc) return rc;
+    F *d_pmf = nullptr;
+    ErrWord err;
+    auto cleanup = [&](int code) {
+        if (d_pmf) cudaFree(d_pmf);
+        if (code) ctr_model_destroy(m);
+        return code;
+    };
+    if ((rc = err.init(s))) return cleanup(rc);
+    const F *src = pmf;
+    if (!is_device) {
+        const size_t bytes = (size_t)n_models * alphabet * sizeof(F);
+        if (cudaMalloc(&d_pmf, bytes) != cudaSuccess) return cleanup(cuda_fail(cudaGetLastError(), "cudaMalloc(pmf)"));
+        if (cudaMemcpyAsync(d_pmf, pmf, bytes, cudaMemcpyHostToDevice, s) != cudaSuccess)
+            return cleanup(cuda_fail(cudaGetLastError(), "cudaMemcpyAsync(pmf)"));
+        src = d_pmf;
+    }
+    categorical_cdf_kernel<F><<<grid_for(n_models, 64), 64, 0, s>>>(src, n_models, alphabet, m->d_cdf, err.d);
+    g_launches.fetch_add(1);
+    if (cudaGetLastError() != cudaSuccess) return cleanup(cuda_fail(cudaGetLastError(), "categorical_cdf_kernel"));
+    rc = model_finish(m, err.d, /*strict=*/0, s);
+    if (rc) return cleanup(rc);
+    *out = m;
+    return cleanup(CTR_OK);
+}
+}  // namespace
+
+extern "C" int ctr_model_categorical_f32(const float *pmf, int is_device, uint32_t n_models, uint32_t alphabet,
+                                         void *stream, ctr_model_t *out) {
+    return model_categorical<float>(pmf, is_device, n_models, alphabet, stream, out);
+}
+extern "C" int ctr_model_categorical_f64(const double *pmf, int is_device, uint32_t n_models, uint32_t alphabet,
+                                         void *stream, ctr_model_t *out) {
+    return model_categorical<double>(pmf, is_device, n_models, alphabet, stream, out);
+}
+
+extern "C" int ctr_model_from_cdf(const uint32_t *cdf, int is_device, uint32_t n_models, uint32_t alphabet,
+                                  int32_t min_symbol, void *stream, ctr_model_t *out) {
+    if (!out || !cdf || n_models == 0) return CTR_ERR_BAD_ARGUMENT;
+    cudaStream_t s = (cudaStream_t)stream;
+    ctr_model_s *m = nullptr;
+    int rc = model_alloc(n_models, alphabet, min_symbol, &m);
+    if (rc) return rc;
+    ErrWord err;
+    if ((rc = err.init(s))) {
+        ctr_model_destroy(m);
+        return rc;
+    }
+    const size_t bytes = (size_t)n_models * ((size_t)alphabet + 1) * 4;
+    if (cudaMemcpyAsync(m->d_cdf, cdf, bytes, is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s) !=
+        cudaSuccess) {
+        ctr_model_destroy(m);
+        return cuda_fail(cudaGetLastError(), "cudaMemcpyAsync(cdf)");
+    }
+    rc = model_finish(m, err.d, /*strict=*/0, s);
+    if (rc) {
+        ctr_model_destroy(m);
+        return rc;
+    }
+    *out = m;
+    return CTR_OK;
+}
+
+extern "C" int ctr_model_uniform(uint32_t size, void *stream, ctr_model_t *out) {
+    if (!out) return CTR_ERR_BAD_ARGUMENT;
+    if (size < 2 || size > kTotal) return CTR_ERR_BAD_MODEL;  // uniform.rs:44-77
+    cudaStream_t s = (cudaStream_t)stream;
+    ctr_model_s *m = nullptr;
+    int rc = model_alloc(1, size, 0, &m);
+    if (rc) return rc;
+    uniform_cdf_kernel<<<grid_for((uint64_t)size + 1, 256), 256, 0, s>>>(size, m->d_cdf);
+    g_launches.fetch_add(1);
+    if (cudaGetLastError() != cudaSuccess) {
+        ctr_model_destroy(m);
+        return cuda_fail(cudaGetLastError(), "uniform_cdf_kernel");
+    }
+    ErrWord err;
+    if ((rc = err.init(s)) || (rc = model_finish(m, err.d, /*strict=*/1, s))) {
+        ctr_model_destroy(m);
+        return rc;
+    }
+    *out = m;
+    return CTR_OK;
+}
+
+extern "C" int ctr_model_destroy(ctr_model_t m) {
+    if (!m) return CTR_OK;
+    if (m->d_cdf) cudaFree(m->d_cdf);
+    if (m->d_enc) cudaFree(m->d_enc);
+    if (m->d_dec) cudaFree(m->d_dec);
+    delete m;
+    return CTR_OK;
+}
+
+extern "C" int ctr_model_info(ctr_model_t m, uint32_t *n_models, uint32_t *alphabet, int32_t *min_symbol) {
+    if (!m) return CTR_ERR_BAD_ARGUMENT;
+    if (n_models) *n_models = m->n_models;
+    if (alphabet) *alphabet = m->alphabet;
+    if (min_symbol) *min_symbol = m->min_symbol;
+    return CTR_OK;
+}
+
+extern "C" const uint32_t *ctr_model_cdf_dev(ctr_model_t m) { return m ? m->d_cdf : nullptr; }
+
+extern "C" int ctr_model_copy_cdf_host(ctr_model_t m, uint32_t *cdf_host, void *stream) {
+    if (!m || !cdf_host) return CTR_ERR_BAD_ARGUMENT;
+    cudaStream_t s = (cudaStream_t)stream;
+    CUDA_TRY(cudaMemcpyAsync(cdf_host, m->d_cdf, (size_t)m->n_models * ((size_t)m->alphabet + 1) * 4,
+                             cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    return CTR_OK;
+}
+
+// =====================================================================================================
+// ANS
+// =====================================================================================================
+extern "C" size_t ctr_ans_encode_workspace_bytes(const ctr_layout *L) {
+    if (check_layout(L)) return 0;
+    return encode_workspace(L).total;
+}
+
+extern "C" uint64_t ctr_ans_max_compressed_words(const ctr_layout *L) {
+    if (check_layout(L)) return 0;
+    // <= 24 bits per symbol plus two state words per stream
+    return scratch_words_for(L->n_symbols) + 4 * L->n_streams + 32;
+}
+
+namespace {
+
+bool use_shared_tables(const ctr_model_s *m, const ctr_layout *L) {
+    return L->model_index_mode == CTR_INDEX_NONE && m->shared_ok;
+}
+
+size_t coder_smem_bytes(size_t table_bytes, const ctr_layout *L, int warps) {
+    const bool contig = L->sym_offsets_dev != nullptr;
+    int tiles = 1;  // word rows
+    if (contig) tiles += 1 + (L->model_index_mode == CTR_INDEX_PER_SYMBOL ? 1 : 0);
+    return table_bytes + (size_t)tiles * warps * kTileWords * 4;
+}
+
+template <template <bool, bool> class Launcher>
+int dispatch(bool shared, bool contig, const AnsParams &p, size_t smem, unsigned grid, cudaStream_t s) {
+    if (shared)
+        return contig ? Launcher<true, true>::run(p, smem, grid, s) : Launcher<true, false>::run(p, smem, grid, s);
+    return contig ? Launcher<false, true>::run(p, smem, grid, s) : Launcher<false, false>::run(p, smem, grid, s);
+}
+
+template <bool SHARED, bool CONTIG>
+struct AnsEncodeLauncher {
+    static int run(const AnsParams &p, size_t smem, unsigned grid, cudaStream_t s) {
+        int rc = set_smem(ans_encode_kernel<SHARED, CONTIG>, smem);
+        if (rc) return rc;
+        ProfileScope prof(0, s);
+        ans_encode_kernel<SHARED, CONTIG><<<grid, kAnsBlock, smem, s>>>(p);
+        LAUNCH_CHECK("ans_encode_kernel");
+        return CTR_OK;
+    }
+};
+template <bool SHARED, bool CONTIG>
+struct AnsDecodeLauncher {
+    static int run(const AnsParams &p, size_t smem, unsigned grid, cudaStream_t s) {
+        int rc = set_smem(ans_decode_kernel<SHARED, CONTIG>, smem);
+        if (rc) return rc;
+        ProfileScope prof(1, s);
+        ans_decode_kernel<SHARED, CONTIG><<<grid, kAnsBlock, smem, s>>>(p);
+        LAUNCH_CHECK("ans_decode_kernel");
+        return CTR_OK;
+    }
+};
+template <bool SHARED, bool CONTIG>
+struct RangeEncodeLauncher {
+    static int run(const AnsParams &p, size_t smem, unsigned grid, cudaStream_t s) {
+        int rc = set_smem(range_encode_kernel<SHARED, CONTIG>, smem);
+        if (rc) return rc;
+        ProfileScope prof(2, s);
+        range_encode_kernel<SHARED, CONTIG><<<grid, kAnsBlock, smem, s>>>(p);
+        LAUNCH_CHECK("range_encode_kernel");
+        return CTR_OK;
+    }
+};
+template <bool SHARED, bool CONTIG>
+struct RangeDecodeLauncher {
+    static int run(const AnsParams &p, size_t smem, unsigned grid, cudaStream_t s) {
+        int rc = set_smem(range_decode_kernel<SHARED, CONTIG>, smem);
+        if (rc) return rc;
+        ProfileScope prof(3, s);
+        range_decode_kernel<SHARED, CONTIG><<<grid, kAnsBlock, smem, s>>>(p);
+        LAUNCH_CHECK("range_decode_kernel");
+        return CTR_OK;
+    }
+};
+
+AnsParams base_params(const ctr_model_s *m, const ctr_layout *L) {
+    AnsParams p;
+    memset(&p, 0, sizeof p);
+    p.model = model_view(m);
+    p.K = L->n_streams;
+    p.N = L->n_symbols;
+    p.sym_off = L->sym_offsets_dev;
+    p.model_index = L->model_index_dev;
+    p.index_mode = L->model_index_mode;
+    p.flags = L->flags;
+    return p;
+}
+
+// writes offsets[0..K] = 0 for an empty batch
+int empty_offsets(uint64_t *offsets, uint64_t K, cudaStream_t s) {
+    CUDA_TRY(cudaMemsetAsync(offsets, 0, (size_t)(K + 1) * 8, s));
+    return CTR_OK;
+}
+
+template <template <bool, bool> class EncLauncher>
+int encode_common(ctr_model_t model, const int32_t *symbols_dev, const ctr_layout *L, const uint64_t *states_in,
+                  void *workspace, size_t workspace_bytes, uint32_t *words_out, uint64_t capacity,
+                  uint64_t *offsets_out, uint64_t *states_out, uint32_t *status, void *stream) {
+    int rc = check_layout(L);
+    if (rc) return rc;
+    if (!model || !offsets_out || (!symbols_dev && L->n_symbols)) return CTR_ERR_BAD_ARGUMENT;
+    if (ctr_device_count() == 0) return cuda_fail(cudaErrorNoDevice, "no CUDA device");
+    cudaStream_t s = (cudaStream_t)stream;
+    if (L->n_streams == 0) return empty_offsets(offsets_out, 0, s);
+    const EncodeWorkspace w = encode_workspace(L);
+    if (!workspace || workspace_bytes < w.total || !words_out) return CTR_ERR_BAD_ARGUMENT;
+    if ((rc = ensure_enc_table(model, s))) return rc;
+
+    AnsParams p = base_params(model, L);
+    p.symbols_in = symbols_dev;
+    p.states_in = states_in;
+    p.states_out = states_out;
+    p.status = status;
+    char *ws = static_cast<char *>(workspace);
+    p.scratch = reinterpret_cast<uint32_t *>(ws);
+    p.lengths = reinterpret_cast<uint32_t *>(ws + w.lengths_off);
+
+    const bool shared = use_shared_tables(model, L);
+    const bool contig = L->sym_offsets_dev != nullptr;
+    const size_t smem = coder_smem_bytes(shared ? (size_t)model->alphabet * 16 : 0, L, kAnsBlock / 32);
+    rc = dispatch<EncLauncher>(shared, contig, p, smem, grid_for(L->n_streams, kAnsBlock), s);
+    if (rc) return rc;
+    return compact_streams(L, w, ws, words_out, capacity, offsets_out, status, s);
+}
+
+template <template <bool, bool> class DecLauncher>
+int decode_common(ctr_model_t model, const uint32_t *words, const uint64_t *offsets, const ctr_layout *L,
+                  const uint64_t *states_in, int32_t *symbols_out, uint64_t *states_out, uint64_t *words_left,
+                  uint32_t *status, void *stream) {
+    int rc = check_layout(L);
+    if (rc) return rc;
+    if (!model || !offsets || (!symbols_out && L->n_symbols)) return CTR_ERR_BAD_ARGUMENT;
+    if ((L->flags & CTR_FLAG_RAW) && !states_in) return CTR_ERR_BAD_ARGUMENT;
+    if (ctr_device_count() == 0) return cuda_fail(cudaErrorNoDevice, "no CUDA device");
+    cudaStream_t s = (cudaStream_t)stream;
+    if (L->n_streams == 0) return CTR_OK;
+    if ((rc = ensure_dec_table(model, s))) return rc;
+
+    AnsParams p = base_params(model, L);
+    p.symbols_out = symbols_out;
+    p.states_in = states_in;
+    p.states_out = states_out;
+    p.status = status;
+    p.words = words;
+    p.offsets = offsets;
+    p.words_left = words_left;
+
+    const bool shared = use_shared_tables(model, L);
+    const bool contig = L->sym_offsets_dev != nullptr;
+    const size_t smem = coder_smem_bytes(shared ? (size_t)model->dec_pairs_bytes + kLutSize * 4 : 0, L, kAnsBlock / 32);
+    return dispatch<DecLauncher>(shared, contig, p, smem, grid_for(L->n_streams, kAnsBlock), s);
+}
+
+}  // namespace
+
+extern "C" int ctr_ans_encode_reverse(ctr_model_t model, const int32_t *symbols_dev, const ctr_layout *layout,
+                                      const uint64_t *states_in_dev, void *workspace_dev, size_t workspace_bytes,
+                                      uint32_t *words_out_dev, uint64_t words_capacity, uint64_t *offsets_out_dev,
+                                      uint64_t *states_out_dev, uint32_t *status_dev, void *stream) {
+    return encode_common<AnsEncodeLauncher>(model, symbols_dev, layout, states_in_dev, workspace_dev, workspace_bytes,
+                                            words_out_dev, words_capacity, offsets_out_dev, states_out_dev, status_dev,
+                                            stream);
+}
+
+extern "C" int ctr_ans_decode(ctr_model_t model, const uint32_t *words_dev, const uint64_t *offsets_dev,
+                              const ctr_layout *layout, const uint64_t *states_in_dev, int32_t *symbols_out_dev,
+                              uint64_t *states_out_dev, uint64_t *words_left_dev, uint32_t *status_dev, void *stream) {
+    return decode_common<AnsDecodeLauncher>(model, words_dev, offsets_dev, layout, states_in_dev, symbols_out_dev,
+                                            states_out_dev, words_left_dev, status_dev, stream);
+}
+
+// =====================================================================================================
+// Range coder
+// =====================================================================================================
+extern "C" size_t ctr_range_encode_workspace_bytes(const ctr_layout *L) { return ctr_ans_encode_workspace_bytes(L); }
+extern "C" uint64_t ctr_range_max_compressed_words(const ctr_layout *L) { return ctr_ans_max_compressed_words(L); }
+
+extern "C" int ctr_range_encode(ctr_model_t model, const int32_t *symbols_dev, const ctr_layout *layout,
+                                const uint64_t *states_in_dev, void *workspace_dev, size_t workspace_bytes,
+                                uint32_t *words_out_dev, uint64_t words_capacity, uint64_t *offsets_out_dev,
+                                uint64_t *states_out_dev, uint32_t *status_dev, void *stream) {
+    return encode_common<RangeEncodeLauncher>(model, symbols_dev, layout, states_in_dev, workspace_dev,
+                                              workspace_bytes, words_out_dev, words_capacity, offsets_out_dev,
+                                              states_out_dev, status_dev, stream);
+}
+
+extern "C" int ctr_range_decode(ctr_model_t model, const uint32_t *words_dev, const uint64_t *offsets_dev,
+                                const ctr_layout *layout, const uint64_t *states_in_dev, int32_t *symbols_out_dev,
+                                uint64_t *states_out_dev, uint64_t *words_read_dev, uint32_t *status_dev,
+                                void *stream) {
+    return decode_common<RangeDecodeLauncher>(model, words_dev, offsets_dev, layout, states_in_dev, symbols_out_dev,
+                                              states_out_dev, words_read_dev, status_dev, stream);
+}
+
+// =====================================================================================================
+// host-buffer convenience
+// =====================================================================================================
+namespace {
+
+struct DeviceBuf {
+    void *p = nullptr;
+    cudaStream_t s = nullptr;
+    int alloc(size_t bytes, cudaStream_t stream) {
+        s = stream;
+        CUDA_TRY(cudaMallocAsync(&p, bytes ? bytes : 16, stream));
+        return CTR_OK;
+    }
+    template <typename T>
+    T *as() {
+        return static_cast<T *>(p);
+    }
+    ~DeviceBuf() {
+        if (p) cudaFreeAsync(p, s);
+    }
+};
+
+cudaStream_t host_stream() {
+    static thread_local cudaStream_t s = nullptr;
+    if (!s) {
+        cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking);
+        // keep freed blocks in the pool instead of returning them to the driver at every sync
+        int dev = 0;
+        cudaMemPool_t pool;
+        if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+            uint64_t threshold = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold);
+        }
+    }
+    return s;
+}
+
+uint64_t index_count(int mode, uint64_t N, uint64_t K) { return mode == 1 ? N : (mode == 2 ? K : 0); }
+
+int read_status(uint32_t *d_status, cudaStream_t s, int *data_status, uint64_t *failing_stream) {
+    uint32_t h[4];
+    CUDA_TRY(cudaMemcpyAsync(h, d_status, 16, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    if (data_status) *data_status = (int)h[0];
+    if (failing_stream) *failing_stream = ((uint64_t)h[3] << 32) | h[2];
+    return CTR_OK;
+}
+
+template <bool RANGE>
+int encode_host(ctr_model_t model, const int32_t *symbols, uint64_t N, uint64_t K, const uint64_t *sym_off,
+                const uint32_t *model_index, int32_t index_mode, uint32_t *words_out, uint64_t words_capacity,
+                uint64_t *offsets_out, int *data_status, uint64_t *failing_stream) {
+    if (!model || !words_out || !offsets_out || (!symbols && N)) return CTR_ERR_BAD_ARGUMENT;
+    if (ctr_device_count() == 0) return cuda_fail(cudaErrorNoDevice, "no CUDA device");
+    cudaStream_t s = host_stream();
+    DeviceBuf d_sym, d_off, d_idx, d_ws, d_words, d_offsets, d_status;
+    int rc;
+    ctr_layout L;
+    memset(&L, 0, sizeof L);
+    L.n_streams = K;
+    L.n_symbols = N;
+    L.model_index_mode = index_mode;
+    if ((rc = d_sym.alloc(N * 4, s))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(d_sym.p, symbols, N * 4, cudaMemcpyHostToDevice, s));
+    if (sym_off) {
+        if ((rc = d_off.alloc((K + 1) * 8, s))) return rc;
+        CUDA_TRY(cudaMemcpyAsync(d_off.p, sym_off, (K + 1) * 8, cudaMemcpyHostToDevice, s));
+        L.sym_offsets_dev = d_off.as<uint64_t>();
+    }
+    const uint64_t n_idx = index_count(index_mode, N, K);
+    if (n_idx) {
+        if (!model_index) return CTR_ERR_BAD_ARGUMENT;
+        if ((rc = d_idx.alloc(n_idx * 4, s))) return rc;
+        CUDA_TRY(cudaMemcpyAsync(d_idx.p, model_index, n_idx * 4, cudaMemcpyHostToDevice, s));
+        L.model_index_dev = d_idx.as<uint32_t>();
+    }
+    const size_t ws_bytes = ctr_ans_encode_workspace_bytes(&L);
+    const uint64_t cap = ctr_ans_max_compressed_words(&L);
+    if ((rc = d_ws.alloc(ws_bytes, s))) return rc;
+    if ((rc = d_words.alloc(cap * 4, s))) return rc;
+    if ((rc = d_offsets.alloc((K + 1) * 8, s))) return rc;
+    if ((rc = d_status.alloc(16, s))) return rc;
+    CUDA_TRY(cudaMemsetAsync(d_status.p, 0, 16, s));
+    if (RANGE)
+        rc = ctr_range_encode(model, d_sym.as<int32_t>(), &L, nullptr, d_ws.p, ws_bytes, d_words.as<uint32_t>(), cap,
+                              d_offsets.as<uint64_t>(), nullptr, d_status.as<uint32_t>(), s);
+    else
+        rc = ctr_ans_encode_reverse(model, d_sym.as<int32_t>(), &L, nullptr, d_ws.p, ws_bytes, d_words.as<uint32_t>(),
+                                    cap, d_offsets.as<uint64_t>(), nullptr, d_status.as<uint32_t>(), s);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(offsets_out, d_offsets.p, (K + 1) * 8, cudaMemcpyDeviceToHost, s));
+    if ((rc = read_status(d_status.as<uint32_t>(), s, data_status, failing_stream))) return rc;
+    const uint64_t total = offsets_out[K];
+    if (total > words_capacity) return CTR_ERR_OUT_OF_SPACE;
+    if (total) CUDA_TRY(cudaMemcpyAsync(words_out, d_words.p, total * 4, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    return CTR_OK;
+}
+
+template <bool RANGE>
+int decode_host(ctr_model_t model, const uint32_t *words, const uint64_t *offsets, uint64_t N, uint64_t K,
+                const uint64_t *sym_off, const uint32_t *model_index, int32_t index_mode, int32_t *symbols_out,
+                int *data_status, uint64_t *failing_stream) {
+    if (!model || !offsets || (!symbols_out && N)) return CTR_ERR_BAD_ARGUMENT;
+    if (ctr_device_count() == 0) return cuda_fail(cudaErrorNoDevice, "no CUDA device");
+    cudaStream_t s = host_stream();
+    DeviceBuf d_sym, d_off, d_idx, d_words, d_offsets, d_status;
+    int rc;
+    ctr_layout L;
+    memset(&L, 0, sizeof L);
+    L.n_streams = K;
+    L.n_symbols = N;
+    L.model_index_mode = index_mode;
+    const uint64_t total = offsets[K];
+    if ((rc = d_words.alloc(total * 4, s))) return rc;
+    if (total) CUDA_TRY(cudaMemcpyAsync(d_words.p, words, total * 4, cudaMemcpyHostToDevice, s));
+    if ((rc = d_offsets.alloc((K + 1) * 8, s))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(d_offsets.p, offsets, (K + 1) * 8, cudaMemcpyHostToDevice, s));
+    if (sym_off) {
+        if ((rc = d_off.alloc((K + 1) * 8, s))) return rc;
+        CUDA_TRY(cudaMemcpyAsync(d_off.p, sym_off, (K + 1) * 8, cudaMemcpyHostToDevice, s));
+        L.sym_offsets_dev = d_off.as<uint64_t>();
+    }
+    const uint64_t n_idx = index_count(index_mode, N, K);
+    if (n_idx) {
+        if (!model_index) return CTR_ERR_BAD_ARGUMENT;
+        if ((rc = d_idx.alloc(n_idx * 4, s))) return rc;
+        CUDA_TRY(cudaMemcpyAsync(d_idx.p, model_index, n_idx * 4, cudaMemcpyHostToDevice, s));
+        L.model_index_dev = d_idx.as<uint32_t>();
+    }
+    if ((rc = d_sym.alloc(N * 4, s))) return rc;
+    if ((rc = d_status.alloc(16, s))) return rc;
+    CUDA_TRY(cudaMemsetAsync(d_status.p, 0, 16, s));
+    if (RANGE)
+        rc = ctr_range_decode(model, d_words.as<uint32_t>(), d_offsets.as<uint64_t>(), &L, nullptr,
+                              d_sym.as<int32_t>(), nullptr, nullptr, d_status.as<uint32_t>(), s);
+    else
+        rc = ctr_ans_decode(model, d_words.as<uint32_t>(), d_offsets.as<uint64_t>(), &L, nullptr, d_sym.as<int32_t>(),
+                            nullptr, nullptr, d_status.as<uint32_t>(), s);
+    if (rc) return rc;
+    if (N) CUDA_TRY(cudaMemcpyAsync(symbols_out, d_sym.p, N * 4, cudaMemcpyDeviceToHost, s));
+    return read_status(d_status.as<uint32_t>(), s, data_status, failing_stream);
+}
+
+}  // namespace
+
+extern "C" int ctr_ans_encode_reverse_host(ctr_model_t model, const int32_t *symbols_host, uint64_t n_symbols,
+    uint64_t n_streams, const uint64_t *sym_offsets_host, const uint32_t *model_index_host, int32_t model_index_mode,
+    uint32_t *words_out_host, uint64_t words_capacity, uint64_t *offsets_out_host, int *data_status,
+    uint64_t *failing_stream) {
+    return encode_host<false>(model, symbols_host, n_symbols, n_streams, sym_offsets_host, model_index_host,
+                              model_index_mode, words_out_host, words_capacity, offsets_out_host, data_status,
+                              failing_stream);
+}
+extern "C" int ctr_range_encode_host(ctr_model_t model, const int32_t *symbols_host, uint64_t n_symbols,
+    uint64_t n_streams, const uint64_t *sym_offsets_host, const uint32_t *model_index_host, int32_t model_index_mode,
+    uint32_t *words_out_host, uint64_t words_capacity, uint64_t *offsets_out_host, int *data_status,
+    uint64_t *failing_stream) {
+    return encode_host<true>(model, symbols_host, n_symbols, n_streams, sym_offsets_host, model_index_host,
+                              model_index_mode, words_out_host, words_capacity, offsets_out_host, data_status,
+                              failing_stream);
+}
+extern "C" int ctr_ans_decode_host(ctr_model_t model, const uint32_t *words_host, const uint64_t *offsets_host,
+                                   uint64_t n_symbols, uint64_t n_streams, const uint64_t *sym_offsets_host,
+                                   const uint32_t *model_index_host, int32_t model_index_mode,
+                                   int32_t *symbols_out_host, int *data_status, uint64_t *failing_stream) {
+    return decode_host<false>(model, words_host, offsets_host, n_symbols, n_streams, sym_offsets_host,
+                              model_index_host, model_index_mode, symbols_out_host, data_status, failing_stream);
+}
+extern "C" int ctr_range_decode_host(ctr_model_t model, const uint32_t *words_host, const uint64_t *offsets_host,
+                                     uint64_t n_symbols, uint64_t n_streams, const uint64_t *sym_offsets_host,
+                                     const uint32_t *model_index_host, int32_t model_index_mode,
+                                     int32_t *symbols_out_host, int *data_status, uint64_t *failing_stream) {
+    return decode_host<true>(model, words_host, offsets_host, n_symbols, n_streams, sym_offsets_host,
+                             model_index_host, model_index_mode, symbols_out_host, data_status, failing_stream);
+}

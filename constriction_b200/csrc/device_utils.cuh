@@ -1,0 +1,136 @@
+// device_utils.cuh -- warp/CTA plumbing shared by the coder kernels (sm_100a).
+//
+//   * 1-D bulk async copy (TMA engine, `cp.async.bulk`, SASS UBLKCP) of a model's tables from HBM
+//     into shared memory, completion tracked by an mbarrier;
+//   * per-lane shared-memory "rows" that turn each lane's private, variable-rate word stream into
+//     128-byte coalesced global transactions (one warp-wide store/load per 32 words of one lane);
+//   * 32x32 tile transposition for contiguous (one-stream-per-lane) symbol arrays;
+//   * per-batch status reporting.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "coder_math.cuh"
+
+namespace ctr {
+
+constexpr int kWarp = 32;
+constexpr unsigned kFullMask = 0xffffffffu;
+// rows/tiles are [32 lanes][32 words], padded to a stride of 33 words so that both the "every lane
+// touches its own row" and the "whole warp touches one row" access patterns are bank-conflict free.
+constexpr int kRowWords = 32;
+constexpr int kRowStride = 33;
+constexpr int kTileWords = kWarp * kRowStride;  // 1056 words = 4224 B per warp
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// ---- mbarrier + bulk copy ---------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// global -> shared, `bytes` a multiple of 16, both addresses 16-byte aligned.
+__device__ __forceinline__ void bulk_copy_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// Stage `bytes` (multiple of 16) of table data into shared memory; all threads of the CTA call it
+// and may read the data when it returns.  One elected thread drives the TMA engine.
+__device__ __forceinline__ void stage_table(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        mbar_expect_tx(bar, bytes);
+        // the bulk-copy size field is limited; split big tables into 32 KiB pieces
+        uint32_t done = 0;
+        while (done < bytes) {
+            uint32_t piece = bytes - done < 32768u ? bytes - done : 32768u;
+            bulk_copy_g2s((char *)dst_smem + done, (const char *)src_gmem + done, piece, bar);
+            done += piece;
+        }
+    }
+    mbar_wait(bar, 0);
+}
+
+// ---- streaming global accesses -----------------------------------------------------------------
+__device__ __forceinline__ uint32_t ld_stream_u32(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ int32_t ld_stream_s32(const int32_t *p) {
+    int32_t v;
+    asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void st_stream_u32(uint32_t *p, uint32_t v) {
+    asm volatile("st.global.L1::no_allocate.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void st_stream_s32(int32_t *p, int32_t v) {
+    asm volatile("st.global.L1::no_allocate.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+__device__ __forceinline__ uint64_t shfl_u64(uint64_t v, int src) {
+    uint32_t lo = __shfl_sync(kFullMask, (uint32_t)v, src);
+    uint32_t hi = __shfl_sync(kFullMask, (uint32_t)(v >> 32), src);
+    return ((uint64_t)hi << 32) | lo;
+}
+
+// ---- status --------------------------------------------------------------------------------------
+// status[0] = max error code, status[2..3] = index of one stream that raised it.
+__device__ __forceinline__ void report_error(uint32_t *status, uint32_t code, uint64_t stream) {
+    if (status == nullptr) return;
+    if (atomicMax(&status[0], code) < code) {
+        status[2] = (uint32_t)stream;
+        status[3] = (uint32_t)(stream >> 32);
+    }
+}
+
+// ---- geometry ------------------------------------------------------------------------------------
+// interleaved deal: stream k owns symbols k, k+K, ...; its length and the offset of its first symbol
+// in "stream-major" counting (used only to place scratch regions).
+__device__ __host__ __forceinline__ uint64_t interleaved_len(uint64_t N, uint64_t K, uint64_t k) {
+    return k < N ? (N - k + K - 1) / K : 0;
+}
+__device__ __host__ __forceinline__ uint64_t interleaved_start(uint64_t N, uint64_t K, uint64_t k) {
+    const uint64_t T = K ? (N + K - 1) / K : 0;            // symbols of the longest stream
+    const uint64_t full = T ? N - (T - 1) * K : 0;         // streams that have T symbols (1..K)
+    return T ? k * (T - 1) + (k < full ? k : full) : 0;
+}
+// Scratch region of stream k whose symbols start at stream-major offset `o`: 32-word aligned and
+// guaranteed to hold 25n/32 + 32 words.  A stream of n symbols needs at most 24 bits per symbol
+// (ANS), or 24 + log2(1/(1-2^-8)) < 24.006 bits per symbol (range coder, truncation of range>>24),
+// plus at most a handful of state / seal words, i.e. < 0.7502 n + 4 words; 25/32 = 0.78125.
+__device__ __host__ __forceinline__ uint64_t scratch_words_for(uint64_t o) {
+    return (o / 32) * 25 + ((o % 32) * 25) / 32;
+}
+__device__ __host__ __forceinline__ uint64_t scratch_start(uint64_t o, uint64_t k) {
+    return 32ull * (scratch_words_for(o) / 32 + 2 * k);
+}
+
+}  // namespace ctr

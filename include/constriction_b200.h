@@ -1,0 +1,217 @@
+/*
+ * constriction_b200.h -- C ABI of the B200-native entropy-coding engine.
+ *
+ * This is the drop-in boundary for the ONE hot path of bamler-lab/constriction (v0.5.0) that this
+ * project replaces: the per-symbol ANS / range-coder state-update loop, its entropy-model lookup
+ * and its word I/O, for the "Default" preset the reference's Python API exposes
+ * (Word=u32, State=u64, Probability=u32, PRECISION=24, Symbol=i32;
+ *  reference: src/pybindings/stream/model/internals.rs:21-39).
+ *
+ * The reference has no C ABI on this path (its only FFI is the pyo3 module,
+ * src/pybindings/mod.rs:178-184).  Every entry point below therefore cites the reference
+ * *functions* a binding would route to it; INTEGRATION.md shows the Rust `extern "C"` block and the
+ * pyo3 / ctypes stubs.  One call processes a *batch* of K independent coders ("streams"): stream k
+ * of a batch is bit-identical to one reference coder object fed the same symbols and models.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / CUDA types in signatures (`stream` is a
+ *     cudaStream_t passed as void*, NULL = legacy default stream);
+ *   - `*_dev` pointers are device memory owned by the caller; all work is enqueued on `stream`
+ *     without host synchronisation, unless the function name ends in `_host` (those take host
+ *     buffers, copy in/out and synchronise before returning);
+ *   - every function returns CTR_OK or a CTR_ERR_* code for *call-level* errors; *data-level*
+ *     errors (impossible symbol, invalid compressed data, ...) are reported per batch through four
+ *     device words `status_dev[4]` = {max error code, 0, index of one failing stream (lo, hi)},
+ *     which the caller zeroes before the first call that uses them;
+ *   - there is no CPU fallback: without a CUDA device every compute entry point returns
+ *     CTR_ERR_CUDA.
+ *
+ * Symbol layouts of a batch (ctr_layout):
+ *   - interleaved (sym_offsets_dev == NULL): stream k owns symbols k, k+K, k+2K, ... of the flat
+ *     array ("lane-interleaved rANS": lane = coder, warp reads 128 contiguous bytes per step);
+ *   - contiguous: stream k owns symbols[sym_offsets[k] .. sym_offsets[k+1]).
+ * Compressed container of a batch: `words` (u32) + `offsets` (u64[K+1]); words[offsets[k] ..
+ * offsets[k+1]) is exactly what the reference's `into_compressed()` / `get_compressed()` returns
+ * for coder k, so any single stream can be handed to stock constriction.
+ */
+#ifndef CONSTRICTION_B200_H
+#define CONSTRICTION_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CTR_ABI_VERSION 1
+
+/* call-level and data-level status codes */
+#define CTR_OK 0
+#define CTR_ERR_IMPOSSIBLE_SYMBOL 1 /* lib.rs:376 DefaultEncoderFrontendError::ImpossibleSymbol (py: KeyError)  */
+#define CTR_ERR_INVALID_DATA 2      /* queue.rs:1401 DecoderFrontendError::InvalidData     (py: AssertionError) */
+#define CTR_ERR_TRAILING_ZERO 3     /* stack.rs:1555 CompressedDataEndsWithZeroWord         (py: ValueError)     */
+#define CTR_ERR_NOT_SEALED 4        /* stack.rs:944-955 into_binary on a non-sealed state                        */
+#define CTR_ERR_BAD_MODEL 5         /* not normalisable / std <= 0 / support too large / malformed CDF          */
+#define CTR_ERR_SEEK 6              /* seek past the end / invalid state                                         */
+#define CTR_ERR_OUT_OF_SPACE 7      /* backends.rs:1512 BoundedWriteError::OutOfSpace (output capacity)          */
+#define CTR_ERR_BAD_ARGUMENT 8
+#define CTR_ERR_CUDA 9 /* CUDA runtime error or no device; see ctr_last_cuda_error() */
+
+/* model_index_mode */
+#define CTR_INDEX_NONE 0       /* every symbol uses model 0 of the table set (i.i.d.)          */
+#define CTR_INDEX_PER_SYMBOL 1 /* model_index[i] belongs to symbols[i] (same layout as symbols) */
+#define CTR_INDEX_PER_STREAM 2 /* model_index[k] belongs to stream k                            */
+
+/* flags */
+#define CTR_FLAG_RAW 1u /* states are exchanged through states_in/states_out instead of being      \
+                           appended to / parsed from the words (Pos/Seek, stack.rs:1107-1139,      \
+                           queue.rs:182-196,911-928; from_raw_parts / into_raw_parts)              */
+
+typedef struct ctr_model_s *ctr_model_t; /* opaque: device-resident 24-bit CDF tables of M models */
+
+typedef struct {
+    uint64_t n_streams;              /* K                                                    */
+    uint64_t n_symbols;              /* N, total over all streams                            */
+    const uint64_t *sym_offsets_dev; /* u64[K+1] or NULL (interleaved deal)                   */
+    const uint32_t *model_index_dev; /* u32[N] / u32[K] / NULL according to model_index_mode  */
+    int32_t model_index_mode;        /* CTR_INDEX_*                                           */
+    uint32_t flags;                  /* CTR_FLAG_*                                            */
+} ctr_layout;
+
+/* ---- library ------------------------------------------------------------------------------ */
+int ctr_abi_version(void);
+const char *ctr_status_string(int code);
+const char *ctr_last_cuda_error(void); /* text of the last CUDA failure on this thread, or "" */
+int ctr_device_count(void);            /* 0 without a usable CUDA device */
+
+/* ---- entropy models (K5: tabulation) --------------------------------------------------------
+ * A model set is M models over one alphabet {min_symbol .. min_symbol+alphabet-1}; model m is a
+ * CDF row u32[alphabet+1] with cdf[0]=0, cdf[alphabet]=2^24, non-decreasing.
+ * Replaces, evaluated once per model instead of once per symbol:
+ *   EncoderModel::left_cumulative_and_probability   src/stream/model.rs:333-336
+ *   DecoderModel::quantile_function                 src/stream/model.rs:457-464          */
+
+/* QuantizedGaussian: LeakyQuantizer<f64,i32,u32,24>::quantize(Gaussian) for M (mean,std) pairs.
+ * Reference: src/stream/model/quantize.rs:284-308,525-568; pybindings/stream/model.rs:645-708.
+ * means/stds are HOST arrays of length n_models.  Returns CTR_ERR_BAD_MODEL if a std is not > 0. */
+int ctr_model_quantized_gaussian(int32_t min_symbol, int32_t max_symbol, const double *means_host,
+                                 const double *stds_host, uint32_t n_models, void *stream, ctr_model_t *out);
+
+/* Categorical, `fast_quantized_cdf` rounding in the caller's float type (what Python
+ * `Categorical(probs, perfect=False)` produces).  pmf is a HOST or DEVICE (is_device != 0)
+ * row-major array [n_models][alphabet]; symbols are 0..alphabet-1.
+ * Reference: src/stream/model/categorical.rs:16-54; categorical/contiguous.rs:203,499-512;
+ * categorical/lazy_contiguous.rs:131-167,228-257. */
+int ctr_model_categorical_f32(const float *pmf, int is_device, uint32_t n_models, uint32_t alphabet, void *stream,
+                              ctr_model_t *out);
+int ctr_model_categorical_f64(const double *pmf, int is_device, uint32_t n_models, uint32_t alphabet, void *stream,
+                              ctr_model_t *out);
+
+/* From ready-made fixed-point CDF rows u32[n_models][alphabet+1] (HOST or DEVICE memory; copied).
+ * Reference: categorical/contiguous.rs:471-520 from_nonzero_fixed_point_probabilities /
+ * from_fixed_point_cdf; lookup_contiguous.rs:297-333. */
+int ctr_model_from_cdf(const uint32_t *cdf, int is_device, uint32_t n_models, uint32_t alphabet, int32_t min_symbol,
+                       void *stream, ctr_model_t *out);
+
+/* Uniform model over {0..size-1}: src/stream/model/uniform.rs:44-146. */
+int ctr_model_uniform(uint32_t size, void *stream, ctr_model_t *out);
+
+int ctr_model_destroy(ctr_model_t model);
+int ctr_model_info(ctr_model_t model, uint32_t *n_models, uint32_t *alphabet, int32_t *min_symbol);
+/* device pointer to the CDF rows, u32[n_models][alphabet+1] (owned by the model) */
+const uint32_t *ctr_model_cdf_dev(ctr_model_t model);
+/* copies the CDF rows to HOST memory (synchronises `stream`) */
+int ctr_model_copy_cdf_host(ctr_model_t model, uint32_t *cdf_host, void *stream);
+
+/* ---- ANS coder, stack semantics (K1/K2) -----------------------------------------------------
+ * Replaces AnsCoder::encode_symbol (src/stream/stack.rs:1014-1048) under the driver loops
+ * encode_symbols_reverse / encode_iid_symbols_reverse (stack.rs:784-849, stream/mod.rs:592-607,
+ * 671-684), decode_symbol (stack.rs:1070-1100) under decode_symbols / decode_iid_symbols
+ * (stream/mod.rs:893-910,1016-1031,1274-1297), into_compressed / get_compressed
+ * (stack.rs:537-547,891-895,1148-1196; lib.rs:719-730) and from_compressed
+ * (stack.rs:299-318,440-462), with Vec<u32> push/pop word I/O (src/backends.rs:470-557). */
+
+/* bytes of device workspace ctr_ans_encode_reverse needs for this layout */
+size_t ctr_ans_encode_workspace_bytes(const ctr_layout *layout);
+/* upper bound on the total number of compressed words of a batch (capacity for words_out_dev) */
+uint64_t ctr_ans_max_compressed_words(const ctr_layout *layout);
+
+/* Every stream k encodes its symbols in REVERSE order onto coder k.
+ *   states_in_dev   u64[K] or NULL (= fresh coders, state 0)
+ *   words_out_dev   compact output, capacity words_capacity
+ *   offsets_out_dev u64[K+1]; offsets[K] = total words
+ *   states_out_dev  u64[K] or NULL; final coder states
+ * Without CTR_FLAG_RAW stream k's words are bulk ++ state words (= get_compressed());
+ * with it they are only the words pushed by this call (append them to the coder's bulk).   */
+int ctr_ans_encode_reverse(ctr_model_t model, const int32_t *symbols_dev, const ctr_layout *layout,
+                           const uint64_t *states_in_dev, void *workspace_dev, size_t workspace_bytes,
+                           uint32_t *words_out_dev, uint64_t words_capacity, uint64_t *offsets_out_dev,
+                           uint64_t *states_out_dev, uint32_t *status_dev, void *stream);
+
+/* Every stream k decodes its symbols (forward order) from words[offsets[k]..offsets[k+1]).
+ *   states_in_dev    u64[K]; required with CTR_FLAG_RAW (all words are bulk), else NULL
+ *   states_out_dev   u64[K] or NULL
+ *   words_left_dev   u64[K] or NULL; bulk words not consumed (Pos::pos().0, stack.rs:1107-1115)
+ * Decoding past the end of a stream is allowed and deterministic (stack.rs:1062-1065).       */
+int ctr_ans_decode(ctr_model_t model, const uint32_t *words_dev, const uint64_t *offsets_dev,
+                   const ctr_layout *layout, const uint64_t *states_in_dev, int32_t *symbols_out_dev,
+                   uint64_t *states_out_dev, uint64_t *words_left_dev, uint32_t *status_dev, void *stream);
+
+/* ---- Range coder, queue semantics (K3/K4) ---------------------------------------------------
+ * Replaces RangeEncoder::encode_symbol (src/stream/queue.rs:612-705), seal / get_compressed
+ * (queue.rs:349-376,458-523), RangeDecoder::from_compressed / read_point (queue.rs:755-773,847-868)
+ * and decode_symbol (queue.rs:968-1035).
+ * Range state on the wire (states_*): 4 x u64 per stream = {lower, range, num_inverted,
+ * first_inverted_word} for encoders, {lower, range, point, unused} for decoders.               */
+size_t ctr_range_encode_workspace_bytes(const ctr_layout *layout);
+uint64_t ctr_range_max_compressed_words(const ctr_layout *layout);
+
+int ctr_range_encode(ctr_model_t model, const int32_t *symbols_dev, const ctr_layout *layout,
+                     const uint64_t *states_in_dev, void *workspace_dev, size_t workspace_bytes,
+                     uint32_t *words_out_dev, uint64_t words_capacity, uint64_t *offsets_out_dev,
+                     uint64_t *states_out_dev, uint32_t *status_dev, void *stream);
+
+int ctr_range_decode(ctr_model_t model, const uint32_t *words_dev, const uint64_t *offsets_dev,
+                     const ctr_layout *layout, const uint64_t *states_in_dev, int32_t *symbols_out_dev,
+                     uint64_t *states_out_dev, uint64_t *words_read_dev, uint32_t *status_dev, void *stream);
+
+/* ---- host-buffer entry points (the reference-facing call: host in, host out) ------------------
+ * Same semantics with HOST buffers (pinned memory makes the copies asynchronous DMA): device memory
+ * comes from the stream-ordered CUDA memory pool, inputs are copied in, the kernels run, results are
+ * copied back and the call synchronises before returning.  The caller owns all buffers:
+ * `words_out_host` needs room for `words_capacity` words (ctr_ans_max_compressed_words gives a safe
+ * bound; CTR_ERR_OUT_OF_SPACE if the batch needs more).  `*data_status` / `*failing_stream` receive
+ * the data-level status.  These are what a pyo3 / Rust binding for
+ * `AnsCoder::encode_iid_symbols_reverse` / `decode_iid_symbols` over many coders would call;
+ * bench.py's `e2e` number times them. */
+int ctr_ans_encode_reverse_host(ctr_model_t model, const int32_t *symbols_host, uint64_t n_symbols,
+                                uint64_t n_streams, const uint64_t *sym_offsets_host,
+                                const uint32_t *model_index_host, int32_t model_index_mode,
+                                uint32_t *words_out_host, uint64_t words_capacity, uint64_t *offsets_out_host,
+                                int *data_status, uint64_t *failing_stream);
+int ctr_ans_decode_host(ctr_model_t model, const uint32_t *words_host, const uint64_t *offsets_host,
+                        uint64_t n_symbols, uint64_t n_streams, const uint64_t *sym_offsets_host,
+                        const uint32_t *model_index_host, int32_t model_index_mode, int32_t *symbols_out_host,
+                        int *data_status, uint64_t *failing_stream);
+int ctr_range_encode_host(ctr_model_t model, const int32_t *symbols_host, uint64_t n_symbols, uint64_t n_streams,
+                          const uint64_t *sym_offsets_host, const uint32_t *model_index_host,
+                          int32_t model_index_mode, uint32_t *words_out_host, uint64_t words_capacity,
+                          uint64_t *offsets_out_host, int *data_status, uint64_t *failing_stream);
+int ctr_range_decode_host(ctr_model_t model, const uint32_t *words_host, const uint64_t *offsets_host,
+                          uint64_t n_symbols, uint64_t n_streams, const uint64_t *sym_offsets_host,
+                          const uint32_t *model_index_host, int32_t model_index_mode, int32_t *symbols_out_host,
+                          int *data_status, uint64_t *failing_stream);
+
+/* ---- launch accounting and kernel timing (bench.py's `gpu_launches` and `roofline`) ----------
+ * With profiling enabled the library brackets every main coder kernel (not the compaction helpers)
+ * with CUDA events on the launching stream.  ctr_profile_read synchronises those events and returns
+ * the summed durations since the last read: which = 0 ANS encode, 1 ANS decode, 2 range encode,
+ * 3 range decode. */
+uint64_t ctr_kernel_launch_count(void); /* kernels this library has launched in this process */
+void ctr_profile_enable(int on);
+int ctr_profile_read(int which, double *total_ms, uint64_t *launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CONSTRICTION_B200_H */

@@ -1,0 +1,143 @@
+// Host build of the product's `__host__ __device__` coder / model arithmetic
+// (constriction_b200/csrc/coder_math.cuh, model_math.cuh) so that it can be fuzzed against the oracle
+// on a machine without a GPU.  Test infrastructure only; compiled by tests/host_harness.py with
+//   g++ -O2 -ffp-contract=off -shared -fPIC
+#include <stdint.h>
+#include <stdlib.h>
+
+#include <vector>
+
+#include "../constriction_b200/csrc/coder_math.cuh"
+#include "../constriction_b200/csrc/model_math.cuh"
+
+using namespace ctr;
+
+extern "C" {
+
+void h_divmod(uint64_t n, uint32_t d, uint64_t *q, uint32_t *r) {
+    divmod_by_reciprocal(n, d, reciprocal_u64(d), *q, *r);
+}
+
+// returns number of mismatches vs native / and % over `count` (n, d) pairs
+uint64_t h_divmod_check(const uint64_t *n, const uint32_t *d, uint64_t count) {
+    uint64_t bad = 0;
+    for (uint64_t i = 0; i < count; ++i) {
+        uint64_t q;
+        uint32_t r;
+        divmod_by_reciprocal(n[i], d[i], reciprocal_u64(d[i]), q, r);
+        if (q != n[i] / d[i] || r != (uint32_t)(n[i] % d[i])) ++bad;
+    }
+    return bad;
+}
+
+// One ANS coder: encode symbols (reverse) with cdf; returns words (bulk ++ state).  out must hold n+2.
+uint64_t h_ans_encode(const int32_t *symbols, uint64_t n, const uint32_t *cdf, int32_t min_symbol,
+                      uint64_t init_state, uint32_t *out, uint64_t *state_out) {
+    uint64_t state = init_state, len = 0;
+    for (uint64_t i = n; i-- > 0;) {
+        const uint32_t idx = (uint32_t)symbols[i] - (uint32_t)min_symbol;
+        const uint32_t left = cdf[idx], prob = cdf[idx + 1] - cdf[idx];
+        if (ans_encode_needs_flush(state, prob)) {
+            out[len++] = (uint32_t)state;
+            state >>= 32;
+        }
+        state = ans_encode_update(state, left, prob, reciprocal_u64(prob));
+    }
+    *state_out = state;
+    const uint32_t ns = ans_state_words(state);
+    if (ns >= 1) out[len++] = (uint32_t)state;
+    if (ns == 2) out[len++] = (uint32_t)(state >> 32);
+    return len;
+}
+
+void h_ans_decode(const uint32_t *words, uint64_t n_words, int32_t *symbols, uint64_t n, const uint32_t *cdf,
+                  uint32_t alphabet, int32_t min_symbol) {
+    uint64_t len = n_words, state = 0;
+    if (len) {
+        state = words[--len];
+        if (len) state = (state << 32) | words[--len];
+    }
+    for (uint64_t i = 0; i < n; ++i) {
+        const uint32_t q = ans_peek_quantile(state);
+        uint32_t lo = 0, hi = alphabet - 1;
+        while (lo < hi) {
+            const uint32_t mid = (lo + hi + 1) >> 1;
+            if (cdf[mid] <= q) lo = mid; else hi = mid - 1;
+        }
+        state = ans_decode_update(state, q, cdf[lo], cdf[lo + 1] - cdf[lo]);
+        if ((state >> 32) == 0 && len) state = (state << 32) | words[--len];
+        symbols[i] = (int32_t)((uint32_t)min_symbol + lo);
+    }
+}
+
+// One range encoder incl. seal.  out must hold n + 8 words.
+uint64_t h_range_encode(const int32_t *symbols, uint64_t n, const uint32_t *cdf, int32_t min_symbol, uint32_t *out) {
+    RangeEncState st = range_enc_init();
+    uint64_t len = 0;
+    for (uint64_t i = 0; i < n; ++i) {
+        const uint32_t idx = (uint32_t)symbols[i] - (uint32_t)min_symbol;
+        RangeEmit em;
+        if (!range_encode_step(st, cdf[idx], cdf[idx + 1] - cdf[idx], em)) return ~0ull;
+        for (uint32_t j = 0; j < em.n_burst; ++j) out[len++] = j == 0 ? em.burst_first : em.burst_fill;
+        if (em.emit) out[len++] = em.word;
+    }
+    const uint32_t ns = range_num_seal_words(st);
+    for (uint32_t j = 0; j < ns; ++j) out[len++] = range_seal_word(st, j);
+    return len;
+}
+
+int h_range_decode(const uint32_t *words, uint64_t n_words, int32_t *symbols, uint64_t n, const uint32_t *cdf,
+                   uint32_t alphabet, int32_t min_symbol) {
+    RangeDecState st;
+    st.lower = 0;
+    st.range = ~0ull;
+    st.point = 0;
+    uint64_t pos = 0;
+    if (n_words >= 1) st.point = (uint64_t)words[pos++] << 32;
+    if (n_words >= 2) st.point |= words[pos++];
+    for (uint64_t i = 0; i < n; ++i) {
+        uint32_t q;
+        if (!range_peek_quantile(st, q)) return 2;
+        uint32_t lo = 0, hi = alphabet - 1;
+        while (lo < hi) {
+            const uint32_t mid = (lo + hi + 1) >> 1;
+            if (cdf[mid] <= q) lo = mid; else hi = mid - 1;
+        }
+        if (range_decode_update(st, cdf[lo], cdf[lo + 1] - cdf[lo])) {
+            if (pos < n_words) st.point |= words[pos++];
+        }
+        symbols[i] = (int32_t)((uint32_t)min_symbol + lo);
+    }
+    return 0;
+}
+
+// returns mismatches of range_peek_quantile against native u64 division
+uint64_t h_range_quantile_check(const uint64_t *diff, const uint64_t *range, uint64_t count) {
+    uint64_t bad = 0;
+    for (uint64_t i = 0; i < count; ++i) {
+        RangeDecState st;
+        st.lower = 0;
+        st.range = range[i];
+        st.point = diff[i];
+        const uint64_t scale = range[i] >> 24;
+        const uint64_t q_true = diff[i] / scale;
+        uint32_t q;
+        const bool ok = range_peek_quantile(st, q);
+        if (ok != (q_true < (1ull << 24))) ++bad;
+        else if (ok && q != (uint32_t)q_true) ++bad;
+    }
+    return bad;
+}
+
+double h_erf(double x) { return mm::erf_msun(x); }
+double h_exp(double x) { return mm::exp_msun(x); }
+
+int h_qgauss_cdf(int32_t min_symbol, int32_t max_symbol, double mean, double std, uint32_t *cdf) {
+    double fw;
+    if (!mm::leaky_free_weight(min_symbol, max_symbol, fw)) return 5;
+    const uint32_t n = (uint32_t)((int64_t)max_symbol - (int64_t)min_symbol) + 1;
+    for (uint32_t i = 0; i < n; ++i) cdf[i] = mm::leaky_gaussian_left(fw, min_symbol, mean, std, i);
+    cdf[n] = kTotal;
+    return 0;
+}
+}
