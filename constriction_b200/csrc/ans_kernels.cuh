@@ -5,13 +5,22 @@
 // loop-carried dependency of the reference's per-symbol loop (stream/mod.rs:592-607,1274-1297) is
 // private to a lane and 32 such chains advance per warp instruction.  Everything that touches HBM is
 // warp-cooperative and coalesced:
-//   - symbols: interleaved layout -> one 128-byte row per warp step; contiguous layout -> 32x32 tiles
-//     transposed through shared memory;
-//   - compressed words: each lane appends to / pops from a private 32-word shared-memory row; a full
-//     (empty) row is written (refilled) by the whole warp as one 128-byte transaction;
+//   - symbols: interleaved layout -> one 128-byte row per warp step (pointer bumped by K per step);
+//     contiguous layout -> 32x32 tiles transposed through shared memory;
+//   - compressed words: each lane appends to / pops from a private shared-memory row; rows are moved
+//     to / from HBM 32 words (128 bytes) at a time by the whole warp;
 //   - the model: for a single shared model the encoder table (left, prob, 64-bit reciprocal) or the
 //     decoder table (CDF pairs + 4096-bucket quantile index) is staged into shared memory by the TMA
 //     engine (cp.async.bulk); model sets too big for that are read through L1/L2 (`ld.global.nc`).
+//
+// The kernels are issue-bound (integer pipe), so the per-symbol instruction count is what matters:
+//   - hot loops have uniform trip counts (the ragged last row of the interleaved deal is peeled off);
+//   - lanes that own no stream run the same instructions on clamped addresses (their pushes are
+//     disabled through a shift amount, their stores predicated off);
+//   - data errors never branch: an out-of-range symbol is clamped to a sentinel table entry with
+//     probability 0 and detected at the end from a running minimum;
+//   - shared memory is addressed with 32-bit shared addresses (no generic-pointer arithmetic);
+//   - word rows are inspected once per kCheckEvery symbols, and the flush / refill is a cold path.
 //
 // Per-stream results equal the reference's `AnsCoder` (src/stream/stack.rs:1014-1100) word for word.
 #pragma once
@@ -19,15 +28,16 @@
 
 namespace ctr {
 
-constexpr int kAnsBlock = 128;  // threads per CTA (4 warps)
+constexpr int kAnsBlock = 256;  // threads per CTA (8 warps)
 constexpr int kLutBits = 12;
 constexpr int kLutSize = 1 << kLutBits;            // quantile buckets of the decoder index
 constexpr int kLutShift = kPrecision - kLutBits;   // q >> 12
-constexpr uint32_t kMaxSharedAlphabet = 4096;      // bigger alphabets use the global-table path
+constexpr uint32_t kMaxSharedAlphabet = 4095;      // bigger alphabets use the global-table path
 
 struct ModelView {
     const uint32_t *cdf;   // [n_models][alphabet + 1]
-    const uint4 *enc;      // [n_models][alphabet]   {left, prob, rcp_lo, rcp_hi}
+    const uint4 *enc;      // [n_models][alphabet + 1] {left, prob, reciprocal lo, hi}; entry [alphabet] is
+                           // the all-zero sentinel that out-of-range symbols are clamped to
     const uint32_t *dec;   // model 0 only: pairs uint2[alphabet_padded] ++ lut u32[kLutSize]
     uint32_t n_models;
     uint32_t alphabet;
@@ -56,11 +66,11 @@ struct AnsParams {
     uint64_t *words_left;
 };
 
-// ---- warp-cooperative row I/O ---------------------------------------------------------------------
+// ---- warp-cooperative tile I/O for the contiguous layout and the range kernels (generic pointers) ----
 
-// Write row i (its first count_i words) of the warp's row buffer to dst_i, for every lane i in `mask`.
-__device__ __forceinline__ void warp_flush_rows(unsigned mask, const uint32_t *rows, uint32_t *dst, uint32_t count,
-                                                int lane) {
+// Write the first count_i words of row i to dst_i, for every lane i in `mask` (rows of kRowStride words).
+__device__ __noinline__ void warp_flush_rows(unsigned mask, const uint32_t *rows, uint32_t *dst, uint32_t count,
+                                             int lane) {
     __syncwarp();
     while (mask) {
         const int i = __ffs(mask) - 1;
@@ -73,36 +83,148 @@ __device__ __forceinline__ void warp_flush_rows(unsigned mask, const uint32_t *r
 }
 
 // Fill row i with the `count_i` words at src_i, for every lane i in `mask`.
-template <typename T>
-__device__ __forceinline__ void warp_fill_rows(unsigned mask, T *rows, const T *src, uint32_t count, int lane) {
+__device__ __noinline__ void warp_fill_rows(unsigned mask, uint32_t *rows, const uint32_t *src, uint32_t count,
+                                            int lane) {
     __syncwarp();
     while (mask) {
         const int i = __ffs(mask) - 1;
         mask &= mask - 1;
-        const T *s = (const T *)shfl_u64((uint64_t)src, i);
+        const uint32_t *s = (const uint32_t *)shfl_u64((uint64_t)src, i);
         const uint32_t c = __shfl_sync(kFullMask, count, i);
-        if ((uint32_t)lane < c) rows[i * kRowStride + lane] = (T)ld_stream_u32((const uint32_t *)(s + lane));
+        if ((uint32_t)lane < c) rows[i * kRowStride + lane] = ld_stream_u32(s + lane);
     }
     __syncwarp();
 }
 
+// ---- word rows of the ANS kernels (32-bit shared addresses, rows of kWordRowStride words) -------------
+
+// Results of the cold paths are returned by value: by-reference parameters of a non-inlined function
+// would force the hot loop's cursors into local memory.
+struct RowUpdate {
+    uint32_t ptr;    // new shared-memory cursor of my row
+    uint32_t moved;  // words moved to / from HBM for my row (0 or up to 32)
+    uint32_t failed; // 1 if my row did not fit into its scratch region
+};
+
+// Encoder, cold: every lane in `mask` has >= 32 words in its row.  The warp writes the first 32 words of
+// each such row to that lane's scratch cursor (one 128-byte store), the lane keeps what is left over.
+__device__ __noinline__ RowUpdate ans_flush_rows_cold(unsigned mask, uint32_t rows_addr, uint32_t row_addr, uint32_t wptr,
+                                                      uint32_t *gptr, uint32_t *gend, int lane) {
+    const bool mine = (mask >> lane) & 1u;
+    const bool fits = gptr + kRowWords <= gend;
+    unsigned todo = __ballot_sync(kFullMask, mine && fits);
+    __syncwarp();
+    while (todo) {
+        const int i = __ffs(todo) - 1;
+        todo &= todo - 1;
+        uint32_t *d = (uint32_t *)shfl_u64((uint64_t)gptr, i);
+        st_stream_u32(d + lane, lds_u32(rows_addr + (uint32_t)(i * kWordRowStride + lane) * 4u));
+    }
+    __syncwarp();
+    RowUpdate u;
+    u.ptr = wptr;
+    u.moved = 0;
+    u.failed = 0;
+    if (mine) {
+        const uint32_t left = (wptr - row_addr) / 4u - kRowWords;  // 0 .. kCheckEvery-1
+        for (uint32_t j = 0; j < left; ++j) sts_u32(row_addr + j * 4u, lds_u32(row_addr + (kRowWords + j) * 4u));
+        u.ptr = row_addr + left * 4u;
+        u.moved = fits ? kRowWords : 0u;
+        u.failed = fits ? 0u : 1u;
+    }
+    __syncwarp();
+    return u;
+}
+
+// Encoder, end of stream: write the remaining cnt_i (< 32) words of every row.
+__device__ __noinline__ void ans_flush_tail_cold(uint32_t rows_addr, uint32_t cnt, uint32_t *gptr, bool ok, int lane) {
+    unsigned todo = __ballot_sync(kFullMask, cnt > 0 && ok);
+    __syncwarp();
+    while (todo) {
+        const int i = __ffs(todo) - 1;
+        todo &= todo - 1;
+        uint32_t *d = (uint32_t *)shfl_u64((uint64_t)gptr, i);
+        const uint32_t c = __shfl_sync(kFullMask, cnt, i);
+        if ((uint32_t)lane < c) st_stream_u32(d + lane, lds_u32(rows_addr + (uint32_t)(i * kWordRowStride + lane) * 4u));
+    }
+    __syncwarp();
+}
+
+// Decoder, cold: every lane in `mask` is down to < kCheckEvery staged words and has more in HBM.  The warp
+// loads the next (up to) 32 words below each such lane's cursor; chunks end on 128-byte boundaries of the
+// global address space, so every refill after a stream's first is one aligned line.
+__device__ __noinline__ RowUpdate ans_refill_rows_cold(unsigned mask, uint32_t rows_addr, uint32_t row_addr, uint32_t rptr,
+                                                       const uint32_t *gtop, const uint32_t *gbase, int lane) {
+    const bool mine = (mask >> lane) & 1u;
+    // keep my unread words (they are older than the chunk that is about to arrive, so they go on top)
+    const uint32_t left = mine ? (rptr - row_addr) / 4u : 0u;  // 0 .. kCheckEvery-1
+    uint32_t keep[kCheckEvery - 1];
+#pragma unroll
+    for (int j = 0; j < kCheckEvery - 1; ++j) keep[j] = (uint32_t)j < left ? lds_u32(row_addr + j * 4u) : 0u;
+    const uint32_t *lo = (const uint32_t *)(((uint64_t)(gtop - 1)) & ~(uint64_t)127);
+    if (lo < gbase) lo = gbase;
+    const uint32_t c = mine ? (uint32_t)(gtop - lo) : 0u;
+    unsigned todo = mask;
+    __syncwarp();
+    while (todo) {
+        const int i = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const uint32_t *s = (const uint32_t *)shfl_u64((uint64_t)lo, i);
+        const uint32_t ci = __shfl_sync(kFullMask, c, i);
+        if ((uint32_t)lane < ci) sts_u32(rows_addr + (uint32_t)(i * kWordRowStride + lane) * 4u, ld_stream_u32(s + lane));
+    }
+    __syncwarp();
+    RowUpdate u;
+    u.ptr = rptr;
+    u.moved = c;
+    u.failed = 0;
+    if (mine) {
+#pragma unroll
+        for (int j = 0; j < kCheckEvery - 1; ++j)
+            if ((uint32_t)j < left) sts_u32(row_addr + (c + j) * 4u, keep[j]);
+        u.ptr = row_addr + (c + left) * 4u;
+    }
+    __syncwarp();
+    return u;
+}
+
 // ---- model lookups ----------------------------------------------------------------------------------
 
-// decoder: quantile -> (symbol index, left, right) in a shared-memory table with bucket index
+// bucket index entry: low 16 bits = symbol containing the bucket's first quantile, high 16 bits = how many
+// further symbols the bucket reaches into (0 for almost every bucket)
+__device__ __forceinline__ uint32_t lut_pack(uint32_t lo, uint32_t hi) { return lo | ((hi - lo) << 16); }
+
+// decoder, generic-pointer version (range kernels): quantile -> (symbol index, left, right)
 __device__ __forceinline__ uint32_t lookup_shared(const uint2 *pairs, const uint32_t *lut, uint32_t q, uint32_t &left,
                                                   uint32_t &right) {
-    const uint32_t lh = lut[q >> kLutShift];
-    uint32_t lo = lh & 0xffffu, hi = lh >> 16;
-    while (lo < hi) {  // almost always zero iterations: the bucket lies inside one symbol's interval
-        const uint32_t mid = (lo + hi + 1) >> 1;
-        if (pairs[mid].x <= q)
-            lo = mid;
-        else
-            hi = mid - 1;
+    uint32_t lo = lut[q >> kLutShift];
+    if (lo > 0xffffu) {  // rare: the bucket straddles a symbol boundary
+        uint32_t h = (lo & 0xffffu) + (lo >> 16);
+        lo &= 0xffffu;
+        while (lo < h) {
+            const uint32_t mid = (lo + h + 1) >> 1;
+            if (pairs[mid].x <= q)
+                lo = mid;
+            else
+                h = mid - 1;
+        }
     }
     const uint2 pr = pairs[lo];
     left = pr.x;
     right = pr.y;
+    return lo;
+}
+
+// decoder, cold part of the shared-address version: binary search inside a straddling bucket
+__device__ __noinline__ uint32_t lookup_straddle_cold(uint32_t pairs_addr, uint32_t packed, uint32_t q) {
+    uint32_t lo = packed & 0xffffu, h = lo + (packed >> 16);
+    while (lo < h) {
+        const uint32_t mid = (lo + h + 1) >> 1;
+        if (lds_table_u32(pairs_addr + mid * 8u) <= q)
+            lo = mid;
+        else
+            h = mid - 1;
+    }
     return lo;
 }
 
@@ -123,12 +245,35 @@ __device__ __forceinline__ uint32_t lookup_global(const uint32_t *row, uint32_t 
     return lo;
 }
 
+// Geometry of the interleaved deal shared by all kernels.
+struct Interleave {
+    uint64_t T;     // rows (symbols of the longest stream)
+    uint64_t last;  // streams that own a symbol in row T-1 (1..K), 0 if N == 0
+};
+__device__ __forceinline__ Interleave interleave_of(uint64_t N, uint64_t K) {
+    Interleave g;
+    g.T = (N + K - 1) / K;
+    g.last = g.T ? N - (g.T - 1) * K : 0;
+    return g;
+}
+
+__device__ __forceinline__ uint64_t warp_max_u64(uint64_t v, int lane) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        const uint64_t o = shfl_u64(v, lane ^ d);
+        v = o > v ? o : v;
+    }
+    return v;
+}
+
 // =====================================================================================================
 // encode
 // =====================================================================================================
 //   SHARED : model 0's encoder table lives in shared memory (index_mode == NONE, small alphabet)
 //   CONTIG : stream k owns symbols[sym_off[k] .. sym_off[k+1]) (else interleaved deal)
-template <bool SHARED, bool CONTIG>
+//   PERSYM : a model index per symbol (else one model per stream / model 0)
+//   F64DIV : the table holds double-precision reciprocals and the quotient estimate uses the FP64 pipe
+template <bool SHARED, bool CONTIG, bool PERSYM, bool F64DIV>
 __global__ void __launch_bounds__(kAnsBlock) ans_encode_kernel(const AnsParams p) {
     extern __shared__ __align__(16) uint32_t smem[];
     __shared__ uint64_t bar;
@@ -138,17 +283,19 @@ __global__ void __launch_bounds__(kAnsBlock) ans_encode_kernel(const AnsParams p
     constexpr int kWarpsPerCta = kAnsBlock / 32;
 
     // shared memory carve-up: [table][word rows][symbol tiles][index tiles]
-    const uint32_t table_words = SHARED ? p.model.alphabet * 4 : 0;
-    const uint4 *s_enc = reinterpret_cast<const uint4 *>(smem);
-    uint32_t *rows = smem + table_words + warp_in_cta * kTileWords;
-    int32_t *sym_tile = reinterpret_cast<int32_t *>(smem + table_words + kWarpsPerCta * kTileWords) + warp_in_cta * kTileWords;
-    uint32_t *idx_tile = smem + table_words + 2 * kWarpsPerCta * kTileWords + warp_in_cta * kTileWords;
+    const uint32_t alphabet = p.model.alphabet;
+    const uint32_t table_words = SHARED ? (alphabet + 1) * 4 : 0;
+    const uint32_t table_addr = smem_u32_pinned(smem);
+    const uint32_t rows_addr = smem_u32_pinned(smem + table_words + warp_in_cta * kWordRowsWords);
+    uint32_t *sym_tile = smem + table_words + kWarpsPerCta * kWordRowsWords + warp_in_cta * kTileWords;
+    uint32_t *idx_tile = sym_tile + kWarpsPerCta * kTileWords;
 
-    if (SHARED) stage_table(smem, p.model.enc, p.model.alphabet * 16u, &bar);
+    if (SHARED) stage_table(smem, p.model.enc, (alphabet + 1) * 16u, &bar);
 
-    const uint64_t k = (uint64_t)blockIdx.x * kAnsBlock + threadIdx.x;
-    const bool valid = k < p.K;
     const uint64_t K = p.K, N = p.N;
+    const uint64_t k = (uint64_t)blockIdx.x * kAnsBlock + threadIdx.x;
+    const bool valid = k < K;
+    const uint64_t kc = valid ? k : K - 1;  // lanes without a stream shadow the last one (loads only)
 
     // stream geometry
     uint64_t n_k = 0, o_k = 0;
@@ -161,163 +308,166 @@ __global__ void __launch_bounds__(kAnsBlock) ans_encode_kernel(const AnsParams p
             o_k = interleaved_start(N, K, k);
         }
     }
-    uint32_t *const region = p.scratch + scratch_start(o_k, k);
-    const uint64_t capacity = valid ? scratch_start(o_k + n_k, k + 1) - scratch_start(o_k, k) : 0;
+    uint32_t *gptr = p.scratch + scratch_start(o_k, k);                                  // next word of my region
+    uint32_t *const gbegin = gptr;
+    uint32_t *const gend = valid ? p.scratch + scratch_start(o_k + n_k, k + 1) : gptr;  // capacity limit
 
     uint64_t state = (valid && p.states_in) ? p.states_in[k] : 0;
-    uint32_t cnt = 0;        // words in my row
-    uint64_t flushed = 0;    // words already written to my scratch region
-    bool alive = valid;
-    const uint32_t stream_model = (p.index_mode == 2 && valid) ? p.model_index[k] : 0u;
-    const uint32_t alphabet = p.model.alphabet;
-    const int32_t min_symbol = p.model.min_symbol;
-
-    auto fail = [&](uint32_t code) {
-        report_error(p.status, code, k);
-        alive = false;
-    };
+    const uint32_t row_addr = rows_addr + (uint32_t)lane * (kWordRowStride * 4u);
+    uint32_t wptr = row_addr;           // shared address of the next free slot of my row
+    uint32_t min_prob = 0xffffffffu;    // running minimum of the probabilities used (0 <=> impossible symbol)
+    bool overflow = false;              // scratch region too small (cannot happen with the sizing above)
+    const uint32_t push_shift = valid ? 8u : 32u;  // (state >> 32) >> 32 == 0: lanes without a stream never push
+    const uint32_t stream_model = (p.index_mode == 2) ? p.model_index[kc] : 0u;
+    const uint32_t n_models = p.model.n_models;
+    const uint32_t min_symbol = (uint32_t)p.model.min_symbol;
 
     // one reference encode_symbol (stack.rs:1014-1048)
     auto encode_one = [&](int32_t sym, uint32_t m) {
-        const uint32_t idx = (uint32_t)sym - (uint32_t)min_symbol;
-        if (idx >= alphabet || (!SHARED && m >= p.model.n_models)) {
-            fail(kErrImpossibleSymbol);
-            return;
+        uint32_t idx = min((uint32_t)sym - min_symbol, alphabet);  // out of range -> sentinel entry
+        uint4 e;
+        if (SHARED) {
+            e = lds_table_v4(table_addr + idx * 16u);
+        } else {
+            const bool ok = m < n_models;
+            idx = ok ? idx : alphabet;
+            m = ok ? m : 0u;
+            e = __ldg(p.model.enc + (uint64_t)m * (alphabet + 1) + idx);
         }
-        const uint4 e = SHARED ? s_enc[idx] : __ldg(p.model.enc + (uint64_t)m * alphabet + idx);
-        if (e.y == 0) {
-            fail(kErrImpossibleSymbol);
-            return;
+        min_prob = min(min_prob, e.y);
+        uint32_t lo = (uint32_t)state, hi = (uint32_t)(state >> 32);
+        if (shr_clamp(hi, push_shift) >= e.y) {  // stack.rs:1035-1040
+            sts_u32(wptr, lo);
+            wptr += 4u;
+            lo = hi;
+            hi = 0u;
         }
-        if (ans_encode_needs_flush(state, e.y)) {
-            rows[lane * kRowStride + cnt] = (uint32_t)state;
-            cnt += 1;
-            state >>= 32;
+        const uint64_t n = ((uint64_t)hi << 32) | lo;
+        uint64_t q;
+        if (F64DIV) {
+            q = __double2ull_rz(__ull2double_rz(n) * __hiloint2double((int)e.w, (int)e.z));
+        } else {
+            q = __umul64hi(n, ((uint64_t)e.w << 32) | e.z);
         }
-        state = ans_encode_update(state, e.x, e.y, ((uint64_t)e.w << 32) | e.z);
+        uint32_t r = lo - (uint32_t)q * e.y;  // remainder of the estimate, in [0, 2 prob)
+        const bool fix = r >= e.y;
+        r -= fix ? e.y : 0u;
+        q += fix ? 1u : 0u;
+        state = (q << kPrecision) + (uint64_t)(e.x + r);  // stack.rs:1042-1045 (left + r < 2^24)
     };
 
-    // after each step: write out the rows that filled up
-    auto flush_full = [&]() {
-        const bool full = cnt == kRowWords;
-        const unsigned mask = __ballot_sync(kFullMask, full);
+    // every kCheckEvery symbols: move rows that reached 32 words to HBM (cold)
+    auto check_rows = [&]() {
+        const unsigned mask = __ballot_sync(kFullMask, wptr >= row_addr + kRowWords * 4u);
         if (mask) {
-            bool ok = true;
-            if (full && flushed + kRowWords > capacity) ok = false;
-            const unsigned okmask = __ballot_sync(kFullMask, full && ok);
-            warp_flush_rows(okmask, rows, region + flushed, cnt, lane);
-            if (full) {
-                if (ok)
-                    flushed += kRowWords;
-                else
-                    fail(kErrOutOfSpace);
-                cnt = 0;
-            }
+            const RowUpdate u = ans_flush_rows_cold(mask, rows_addr, row_addr, wptr, gptr, gend, lane);
+            wptr = u.ptr;
+            gptr += u.moved;
+            overflow |= u.failed != 0u;
         }
     };
 
     if (!CONTIG) {
-        // ---- interleaved deal: step t touches symbols[t*K + k]; one coalesced row per warp --------
-        const uint64_t T = K ? (N + K - 1) / K : 0;
-        constexpr int U = 4;  // symbols prefetched per lane
-        int32_t buf[U];
-        uint32_t mbuf[U];
-        auto load_batch = [&](uint64_t t_hi) {  // loads steps t_hi-1 .. t_hi-U (those >= 0)
+        // ---- interleaved deal: row t holds symbols[t*K .. t*K+K); coded from the last row backwards ---
+        const Interleave g = interleave_of(N, K);
+        if (g.T > 0) {  // ragged last row
+            if (valid && k < g.last) {
+                const uint64_t i = (g.T - 1) * K + k;
+                encode_one(ld_stream_s32(p.symbols_in + i), PERSYM ? ld_stream_u32(p.model_index + i) : stream_model);
+            }
+        }
+        if (g.T > 1) {
+            uint64_t rows_left = g.T - 1;  // full rows T-2 .. 0
+            const int32_t *ps = p.symbols_in + (g.T - 2) * K + kc;
+            const uint32_t *pm = PERSYM ? p.model_index + (g.T - 2) * K + kc : nullptr;
+            while (rows_left >= (uint64_t)kCheckEvery) {
+                int32_t buf[kCheckEvery];
+                uint32_t mbuf[kCheckEvery];
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-                buf[u] = 0;
-                mbuf[u] = stream_model;
-                if (t_hi >= (uint64_t)(u + 1)) {
-                    const uint64_t i = (t_hi - 1 - u) * K + k;
-                    if (valid && i < N) {
-                        buf[u] = ld_stream_s32(p.symbols_in + i);
-                        if (p.index_mode == 1) mbuf[u] = ld_stream_u32(p.model_index + i);
+                for (int u = 0; u < kCheckEvery; ++u) {
+                    buf[u] = ld_stream_s32(ps);
+                    ps -= K;
+                    if (PERSYM) {
+                        mbuf[u] = ld_stream_u32(pm);
+                        pm -= K;
+                    } else {
+                        mbuf[u] = stream_model;
                     }
                 }
-            }
-        };
-        uint64_t t_hi = T;
-        while (t_hi > 0) {
-            load_batch(t_hi);
+                check_rows();  // room for kCheckEvery more words in every row
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-                if (t_hi >= (uint64_t)(u + 1)) {
-                    const uint64_t i = (t_hi - 1 - u) * K + k;
-                    if (alive && i < N) encode_one(buf[u], mbuf[u]);
-                    flush_full();
-                }
+                for (int u = 0; u < kCheckEvery; ++u) encode_one(buf[u], mbuf[u]);
+                rows_left -= kCheckEvery;
             }
-            t_hi = t_hi > U ? t_hi - U : 0;
+            check_rows();
+            while (rows_left > 0) {  // at most kCheckEvery-1 more symbols
+                const int32_t sym = ld_stream_s32(ps);
+                ps -= K;
+                uint32_t m = stream_model;
+                if (PERSYM) {
+                    m = ld_stream_u32(pm);
+                    pm -= K;
+                }
+                encode_one(sym, m);
+                rows_left -= 1;
+            }
         }
     } else {
         // ---- contiguous: 32x32 tiles, transposed through shared memory ---------------------------
         uint64_t remaining = n_k;  // symbols of my stream not yet loaded (I consume from the end)
-        uint64_t max_n = n_k;
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) {
-            const uint64_t o = shfl_u64(max_n, lane ^ d);
-            max_n = o > max_n ? o : max_n;
-        }
-        const uint64_t rounds = (max_n + 31) / 32;
+        const uint64_t rounds = (warp_max_u64(n_k, lane) + 31) / 32;
         for (uint64_t r = 0; r < rounds; ++r) {
             const uint32_t c = remaining < 32 ? (uint32_t)remaining : 32u;
             remaining -= c;
-            const int32_t *src = p.symbols_in + o_k + remaining;
             const unsigned have = __ballot_sync(kFullMask, c > 0);
-            warp_fill_rows<int32_t>(have, sym_tile, src, c, lane);
-            if (p.index_mode == 1) warp_fill_rows<uint32_t>(have, idx_tile, p.model_index + o_k + remaining, c, lane);
-            for (uint32_t s = 0; s < 32; ++s) {
-                if (alive && s < c) {
-                    const int32_t sym = sym_tile[lane * kRowStride + (c - 1 - s)];
-                    const uint32_t m = p.index_mode == 1 ? idx_tile[lane * kRowStride + (c - 1 - s)] : stream_model;
+            warp_fill_rows(have, sym_tile, reinterpret_cast<const uint32_t *>(p.symbols_in + o_k + remaining), c, lane);
+            if (PERSYM) warp_fill_rows(have, idx_tile, p.model_index + o_k + remaining, c, lane);
+            const uint32_t cmax = __reduce_max_sync(kFullMask, c);
+            for (uint32_t s = 0; s < cmax; ++s) {
+                if ((s & (kCheckEvery - 1)) == 0) check_rows();
+                if (s < c) {
+                    const int32_t sym = (int32_t)sym_tile[lane * kRowStride + (c - 1 - s)];
+                    const uint32_t m = PERSYM ? idx_tile[lane * kRowStride + (c - 1 - s)] : stream_model;
                     encode_one(sym, m);
                 }
-                flush_full();
             }
         }
     }
 
     // ---- finalize: state words (lib.rs:719-730, low word first), remaining partial rows --------------
+    check_rows();
     const bool raw = (p.flags & 1u) != 0;
-    uint32_t n_state = (valid && !raw) ? ans_state_words(state) : 0u;
-    {
-        // make room for the state words
-        const bool tight = cnt + n_state > kRowWords;
-        bool ok = !(tight && flushed + cnt > capacity);
-        const unsigned mask = __ballot_sync(kFullMask, tight && ok);
-        warp_flush_rows(mask, rows, region + flushed, cnt, lane);
-        if (tight) {
-            if (ok) {
-                flushed += cnt;
-                cnt = 0;
-            } else {
-                fail(kErrOutOfSpace);
-                cnt = 0;
-                n_state = 0;
-            }
-        }
+    const uint32_t n_state = (valid && !raw) ? ans_state_words(state) : 0u;
+    if (n_state >= 1) {
+        sts_u32(wptr, (uint32_t)state);
+        wptr += 4u;
     }
-    if (n_state >= 1) rows[lane * kRowStride + cnt++] = (uint32_t)state;
-    if (n_state == 2) rows[lane * kRowStride + cnt++] = (uint32_t)(state >> 32);
+    if (n_state == 2) {
+        sts_u32(wptr, (uint32_t)(state >> 32));
+        wptr += 4u;
+    }
+    check_rows();
+    uint32_t cnt = (wptr - row_addr) / 4u;  // < 32
     {
-        bool ok = flushed + cnt <= capacity;
-        const unsigned mask = __ballot_sync(kFullMask, cnt > 0 && ok);
-        warp_flush_rows(mask, rows, region + flushed, cnt, lane);
+        const bool ok = gptr + cnt <= gend;
+        ans_flush_tail_cold(rows_addr, cnt, gptr, ok, lane);
         if (cnt > 0 && !ok) {
-            report_error(p.status, kErrOutOfSpace, k);
+            overflow = true;
             cnt = 0;
         }
     }
     if (valid) {
-        p.lengths[k] = (uint32_t)(flushed + cnt);
+        p.lengths[k] = (uint32_t)(gptr - gbegin) + cnt;
         if (p.states_out) p.states_out[k] = state;
+        if (min_prob == 0u) report_error(p.status, kErrImpossibleSymbol, k);
+        if (overflow) report_error(p.status, kErrOutOfSpace, k);
     }
 }
 
 // =====================================================================================================
 // decode
 // =====================================================================================================
-template <bool SHARED, bool CONTIG>
+template <bool SHARED, bool CONTIG, bool PERSYM>
 __global__ void __launch_bounds__(kAnsBlock) ans_decode_kernel(const AnsParams p) {
     extern __shared__ __align__(16) uint32_t smem[];
     __shared__ uint64_t bar;
@@ -326,135 +476,163 @@ __global__ void __launch_bounds__(kAnsBlock) ans_decode_kernel(const AnsParams p
     const int warp_in_cta = threadIdx.x >> 5;
     constexpr int kWarpsPerCta = kAnsBlock / 32;
 
+    const uint32_t alphabet = p.model.alphabet;
     const uint32_t table_words = SHARED ? (p.model.dec_pairs_bytes / 4 + kLutSize) : 0;
-    const uint2 *s_pairs = reinterpret_cast<const uint2 *>(smem);
-    const uint32_t *s_lut = smem + (SHARED ? p.model.dec_pairs_bytes / 4 : 0);
-    uint32_t *rows = smem + table_words + warp_in_cta * kTileWords;
-    int32_t *sym_tile = reinterpret_cast<int32_t *>(smem + table_words + kWarpsPerCta * kTileWords) + warp_in_cta * kTileWords;
-    uint32_t *idx_tile = smem + table_words + 2 * kWarpsPerCta * kTileWords + warp_in_cta * kTileWords;
+    const uint32_t pairs_addr = smem_u32_pinned(smem);
+    uint32_t lut_addr = pairs_addr + (SHARED ? p.model.dec_pairs_bytes : 0);
+    asm volatile("" : "+r"(lut_addr));
+    const uint32_t rows_addr = smem_u32_pinned(smem + table_words + warp_in_cta * kWordRowsWords);
+    uint32_t *sym_tile = smem + table_words + kWarpsPerCta * kWordRowsWords + warp_in_cta * kTileWords;
+    uint32_t *idx_tile = sym_tile + kWarpsPerCta * kTileWords;
 
     if (SHARED) stage_table(smem, p.model.dec, p.model.dec_pairs_bytes + kLutSize * 4u, &bar);
 
-    const uint64_t k = (uint64_t)blockIdx.x * kAnsBlock + threadIdx.x;
-    const bool valid = k < p.K;
     const uint64_t K = p.K, N = p.N;
+    const uint64_t k = (uint64_t)blockIdx.x * kAnsBlock + threadIdx.x;
+    const bool valid = k < K;
+    const uint64_t kc = valid ? k : K - 1;
     const bool raw = (p.flags & 1u) != 0;
 
     uint64_t n_k = 0, o_k = 0;
-    const uint32_t *base = p.words;
-    uint64_t rem = 0;  // words of my stream not yet staged into my row
+    const uint32_t *gbase = p.words;  // first word of my stream
+    const uint32_t *gtop = p.words;   // one past the highest word that is not yet staged in my row
     if (valid) {
         if (CONTIG) {
             o_k = p.sym_off[k];
             n_k = p.sym_off[k + 1] - o_k;
-        } else {
-            n_k = interleaved_len(N, K, k);
         }
-        const uint64_t b = p.offsets[k];
-        base = p.words + b;
-        rem = p.offsets[k + 1] - b;
+        gbase = p.words + p.offsets[k];
+        gtop = p.words + p.offsets[k + 1];
     }
-    uint32_t cnt = 0;
-    const uint32_t alphabet = p.model.alphabet;
-    const int32_t min_symbol = p.model.min_symbol;
-    const uint32_t stream_model = (p.index_mode == 2 && valid) ? p.model_index[k] : 0u;
+    const uint32_t row_addr = rows_addr + (uint32_t)lane * (kWordRowStride * 4u);
+    uint32_t rptr = row_addr;  // my row holds the unread words [row_addr, rptr)
+    const uint32_t n_models = p.model.n_models;
+    const uint32_t min_symbol = (uint32_t)p.model.min_symbol;
+    const uint32_t stream_model = (p.index_mode == 2) ? p.model_index[kc] : 0u;
 
-    // stage the next (up to) 32 words below my cursor; chunks end on 128-byte boundaries of the
-    // global address space so that every refill after the first is one aligned line
-    auto refill = [&]() {
-        const bool need = cnt == 0 && rem > 0;
-        const unsigned mask = __ballot_sync(kFullMask, need);
-        if (mask) {
-            const uint32_t *top = base + rem;  // one past the highest unstaged word
-            uint64_t lo_addr = ((uint64_t)(top - 1)) & ~(uint64_t)127;
-            const uint32_t *lo = (const uint32_t *)lo_addr;
-            if (lo < base) lo = base;
-            const uint32_t c = need ? (uint32_t)(top - lo) : 0u;
-            warp_fill_rows<uint32_t>(mask, rows, lo, c, lane);
-            if (need) {
-                cnt = c;
-                rem -= c;
-            }
+    // every kCheckEvery symbols: rows that are down to < kCheckEvery words get the next 32 (cold).  The first
+    // chunk of a stream only reaches down to the next 128-byte boundary and may be shorter than
+    // kCheckEvery words, hence the loop (it runs twice at most).
+    auto check_rows = [&]() {
+        unsigned mask = __ballot_sync(kFullMask, rptr < row_addr + kCheckEvery * 4u && gtop != gbase);
+        while (mask) {
+            const RowUpdate u = ans_refill_rows_cold(mask, rows_addr, row_addr, rptr, gtop, gbase, lane);
+            rptr = u.ptr;
+            gtop -= u.moved;
+            mask = __ballot_sync(kFullMask, rptr < row_addr + kCheckEvery * 4u && gtop != gbase);
         }
     };
-    auto pop = [&]() -> uint32_t { return rows[lane * kRowStride + (--cnt)]; };
 
     // ---- initial state: stack.rs:299-318, 440-462 (from_compressed) or the caller's raw state ------
-    uint64_t state = 0;
-    bool alive = valid;
+    uint32_t lo = 0, hi = 0;  // the coder state
+    bool trailing_zero = false;
+    check_rows();
     if (raw) {
-        if (valid && p.states_in) state = p.states_in[k];
-        refill();
-    } else {
-        refill();
-        if (valid && cnt > 0) {
-            const uint32_t w = pop();
-            if (w == 0) {
-                report_error(p.status, kErrTrailingZero, k);
-                alive = false;
-            }
-            state = w;
+        if (valid && p.states_in) {
+            const uint64_t s = p.states_in[k];
+            lo = (uint32_t)s;
+            hi = (uint32_t)(s >> 32);
         }
-        refill();
-        if (valid && alive && cnt > 0 && state != 0) state = (state << 32) | pop();
-        refill();
+    } else {
+        if (rptr != row_addr) {
+            rptr -= 4u;
+            lo = lds_u32(rptr);
+            trailing_zero = lo == 0u;
+            if (rptr != row_addr && lo != 0u) {
+                hi = lo;
+                rptr -= 4u;
+                lo = lds_u32(rptr);
+            }
+        }
+        check_rows();
     }
 
     // one reference decode_symbol (stack.rs:1070-1100)
     auto decode_one = [&](uint32_t m) -> int32_t {
-        const uint32_t q = ans_peek_quantile(state);
+        const uint32_t q = lo & kQuantileMask;
         uint32_t left, right, s;
         if (SHARED) {
-            s = lookup_shared(s_pairs, s_lut, q, left, right);
+            s = lds_table_u32(lut_addr + ((lo >> (kLutShift - 2)) & ((kLutSize - 1) << 2)));
+            if (s > 0xffffu) s = lookup_straddle_cold(pairs_addr, s, q);
+            const uint2 pr = lds_table_v2(pairs_addr + s * 8u);
+            left = pr.x;
+            right = pr.y;
         } else {
-            if (m >= p.model.n_models) m = p.model.n_models - 1;  // cannot report through Infallible
+            m = m < n_models ? m : n_models - 1;  // decoding cannot fail (stack.rs:1062-1065)
             s = lookup_global(p.model.cdf + (uint64_t)m * (alphabet + 1), alphabet, q, left, right);
         }
-        state = ans_decode_update(state, q, left, right - left);
-        if ((state >> 32) == 0 && cnt > 0) state = (state << 32) | pop();
-        return (int32_t)((uint32_t)min_symbol + s);
+        const uint64_t st = (((uint64_t)hi << 32 | lo) >> kPrecision) * (uint64_t)(right - left) + (uint64_t)(q - left);
+        lo = (uint32_t)st;
+        hi = (uint32_t)(st >> 32);
+        if (hi == 0u && rptr != row_addr) {  // stack.rs:1091-1097
+            hi = lo;
+            rptr -= 4u;
+            lo = lds_u32(rptr);
+        }
+        return (int32_t)(min_symbol + s);
     };
 
     if (!CONTIG) {
-        const uint64_t T = K ? (N + K - 1) / K : 0;
-        for (uint64_t t = 0; t < T; ++t) {
-            const uint64_t i = t * K + k;
-            const bool act = alive && i < N;
-            uint32_t m = stream_model;
-            if (act && p.index_mode == 1) m = ld_stream_u32(p.model_index + i);
-            if (act) st_stream_s32(p.symbols_out + i, decode_one(m));
-            refill();
+        const Interleave g = interleave_of(N, K);
+        if (g.T > 1) {
+            int32_t *po = p.symbols_out + kc;
+            const uint32_t *pm = PERSYM ? p.model_index + kc : nullptr;
+            uint64_t rows_left = g.T - 1;  // full rows 0 .. T-2
+            while (rows_left >= (uint64_t)kCheckEvery) {
+                uint32_t mbuf[kCheckEvery];
+#pragma unroll
+                for (int u = 0; u < kCheckEvery; ++u) mbuf[u] = PERSYM ? ld_stream_u32(pm + (uint64_t)u * K) : stream_model;
+                if (PERSYM) pm += (uint64_t)kCheckEvery * K;
+#pragma unroll
+                for (int u = 0; u < kCheckEvery; ++u) {
+                    const int32_t sym = decode_one(mbuf[u]);
+                    if (valid) st_stream_s32(po, sym);
+                    po += K;
+                }
+                check_rows();
+                rows_left -= kCheckEvery;
+            }
+            while (rows_left > 0) {  // at most kCheckEvery-1 more symbols
+                const int32_t sym = decode_one(PERSYM ? ld_stream_u32(pm) : stream_model);
+                if (PERSYM) pm += K;
+                if (valid) st_stream_s32(po, sym);
+                po += K;
+                rows_left -= 1;
+            }
+            check_rows();
+        }
+        if (g.T > 0) {  // ragged last row
+            if (valid && k < g.last) {
+                const uint64_t i = (g.T - 1) * K + k;
+                const int32_t sym = decode_one(PERSYM ? ld_stream_u32(p.model_index + i) : stream_model);
+                st_stream_s32(p.symbols_out + i, sym);
+            }
         }
     } else {
         uint64_t done = 0;  // symbols of my stream already produced
-        uint64_t max_n = n_k;
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) {
-            const uint64_t o = shfl_u64(max_n, lane ^ d);
-            max_n = o > max_n ? o : max_n;
-        }
-        const uint64_t rounds = (max_n + 31) / 32;
+        const uint64_t rounds = (warp_max_u64(n_k, lane) + 31) / 32;
         for (uint64_t r = 0; r < rounds; ++r) {
             const uint64_t left_n = n_k - done;
             const uint32_t c = left_n < 32 ? (uint32_t)left_n : 32u;
             const unsigned have = __ballot_sync(kFullMask, c > 0);
-            if (p.index_mode == 1) warp_fill_rows<uint32_t>(have, idx_tile, p.model_index + o_k + done, c, lane);
-            for (uint32_t s = 0; s < 32; ++s) {
-                if (alive && s < c) {
-                    const uint32_t m = p.index_mode == 1 ? idx_tile[lane * kRowStride + s] : stream_model;
-                    sym_tile[lane * kRowStride + s] = decode_one(m);
+            if (PERSYM) warp_fill_rows(have, idx_tile, p.model_index + o_k + done, c, lane);
+            const uint32_t cmax = __reduce_max_sync(kFullMask, c);
+            for (uint32_t s = 0; s < cmax; ++s) {
+                if ((s & (kCheckEvery - 1)) == 0) check_rows();
+                if (s < c) {
+                    const uint32_t m = PERSYM ? idx_tile[lane * kRowStride + s] : stream_model;
+                    sym_tile[lane * kRowStride + s] = (uint32_t)decode_one(m);
                 }
-                refill();
             }
-            warp_flush_rows(have, reinterpret_cast<const uint32_t *>(sym_tile),
-                            reinterpret_cast<uint32_t *>(p.symbols_out + o_k + done), alive ? c : 0u, lane);
+            warp_flush_rows(have, sym_tile, reinterpret_cast<uint32_t *>(p.symbols_out + o_k + done), c, lane);
             done += c;
         }
     }
 
     if (valid) {
-        if (p.states_out) p.states_out[k] = state;
-        if (p.words_left) p.words_left[k] = rem + cnt;
+        if (p.states_out) p.states_out[k] = ((uint64_t)hi << 32) | lo;
+        if (p.words_left) p.words_left[k] = (uint64_t)(gtop - gbase) + (uint64_t)((rptr - row_addr) / 4u);
+        if (trailing_zero) report_error(p.status, kErrTrailingZero, k);
     }
 }
 

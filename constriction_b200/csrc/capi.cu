@@ -91,6 +91,7 @@ struct ctr_model_s {
     uint32_t *d_dec = nullptr;  // model 0: pairs + bucket index, built on first decode
     uint32_t dec_pairs_bytes = 0;
     bool shared_ok = false;  // small enough for the shared-memory table kernels
+    bool enc_f64 = false;    // d_enc holds double-precision reciprocals (CTR_DIV=f64)
 };
 
 namespace {
@@ -115,11 +116,22 @@ int model_alloc(uint32_t n_models, uint32_t alphabet, int32_t min_symbol, ctr_mo
     return CTR_OK;
 }
 
+// CTR_DIV=f64 selects the FP64-pipe quotient estimate in the ANS encoder (A/B switch; default: integer)
+bool use_f64_division() {
+    static const bool on = [] {
+        const char *e = getenv("CTR_DIV");
+        return e && strcmp(e, "f64") == 0;
+    }();
+    return on;
+}
+
 int ensure_enc_table(ctr_model_s *m, cudaStream_t s) {
     if (m->d_enc) return CTR_OK;
-    const uint64_t entries = (uint64_t)m->n_models * m->alphabet;
+    const uint64_t entries = (uint64_t)m->n_models * ((uint64_t)m->alphabet + 1);
     CUDA_TRY(cudaMalloc(&m->d_enc, entries * 16));
-    build_enc_table_kernel<<<grid_for(entries, 256), 256, 0, s>>>(m->d_cdf, m->n_models, m->alphabet, m->d_enc);
+    m->enc_f64 = use_f64_division();
+    build_enc_table_kernel<<<grid_for(entries, 256), 256, 0, s>>>(m->d_cdf, m->n_models, m->alphabet,
+                                                                  m->enc_f64 ? 1 : 0, m->d_enc);
     LAUNCH_CHECK("build_enc_table_kernel");
     return CTR_OK;
 }
@@ -466,60 +478,52 @@ bool use_shared_tables(const ctr_model_s *m, const ctr_layout *L) {
 
 size_t coder_smem_bytes(size_t table_bytes, const ctr_layout *L, int warps) {
     const bool contig = L->sym_offsets_dev != nullptr;
-    int tiles = 1;  // word rows
+    int tiles = 0;  // 32x32 transposition tiles
     if (contig) tiles += 1 + (L->model_index_mode == CTR_INDEX_PER_SYMBOL ? 1 : 0);
-    return table_bytes + (size_t)tiles * warps * kTileWords * 4;
+    // word rows are sized for the ANS kernels (35-word rows); the range kernels use 33 of each 35
+    return table_bytes + (size_t)warps * kWordRowsWords * 4 + (size_t)tiles * warps * kTileWords * 4;
 }
 
-template <template <bool, bool> class Launcher>
-int dispatch(bool shared, bool contig, const AnsParams &p, size_t smem, unsigned grid, cudaStream_t s) {
-    if (shared)
-        return contig ? Launcher<true, true>::run(p, smem, grid, s) : Launcher<true, false>::run(p, smem, grid, s);
-    return contig ? Launcher<false, true>::run(p, smem, grid, s) : Launcher<false, false>::run(p, smem, grid, s);
-}
+// SHARED implies one model for the whole batch, hence no per-symbol index.
+#define CTR_DISPATCH(KERNEL, SLOT, ...)                                                                    \
+    do {                                                                                                   \
+        auto launch = [&](auto kernel) -> int {                                                            \
+            int rc__ = set_smem(kernel, smem);                                                             \
+            if (rc__) return rc__;                                                                         \
+            ProfileScope prof(SLOT, s);                                                                    \
+            kernel<<<grid, kAnsBlock, smem, s>>>(p);                                                       \
+            LAUNCH_CHECK(#KERNEL);                                                                         \
+            return CTR_OK;                                                                                 \
+        };                                                                                                 \
+        if (shared) return contig ? launch(KERNEL<true, true, false __VA_ARGS__>) : launch(KERNEL<true, false, false __VA_ARGS__>); \
+        if (persym) return contig ? launch(KERNEL<false, true, true __VA_ARGS__>) : launch(KERNEL<false, false, true __VA_ARGS__>); \
+        return contig ? launch(KERNEL<false, true, false __VA_ARGS__>) : launch(KERNEL<false, false, false __VA_ARGS__>);          \
+    } while (0)
 
-template <bool SHARED, bool CONTIG>
 struct AnsEncodeLauncher {
-    static int run(const AnsParams &p, size_t smem, unsigned grid, cudaStream_t s) {
-        int rc = set_smem(ans_encode_kernel<SHARED, CONTIG>, smem);
-        if (rc) return rc;
-        ProfileScope prof(0, s);
-        ans_encode_kernel<SHARED, CONTIG><<<grid, kAnsBlock, smem, s>>>(p);
-        LAUNCH_CHECK("ans_encode_kernel");
-        return CTR_OK;
+    static int run(bool shared, bool contig, bool persym, bool f64, const AnsParams &p, size_t smem, unsigned grid,
+                   cudaStream_t s) {
+#define CTR_COMMA ,
+        if (f64) CTR_DISPATCH(ans_encode_kernel, 0, CTR_COMMA true);
+        CTR_DISPATCH(ans_encode_kernel, 0, CTR_COMMA false);
     }
 };
-template <bool SHARED, bool CONTIG>
 struct AnsDecodeLauncher {
-    static int run(const AnsParams &p, size_t smem, unsigned grid, cudaStream_t s) {
-        int rc = set_smem(ans_decode_kernel<SHARED, CONTIG>, smem);
-        if (rc) return rc;
-        ProfileScope prof(1, s);
-        ans_decode_kernel<SHARED, CONTIG><<<grid, kAnsBlock, smem, s>>>(p);
-        LAUNCH_CHECK("ans_decode_kernel");
-        return CTR_OK;
+    static int run(bool shared, bool contig, bool persym, bool, const AnsParams &p, size_t smem, unsigned grid,
+                   cudaStream_t s) {
+        CTR_DISPATCH(ans_decode_kernel, 1);
     }
 };
-template <bool SHARED, bool CONTIG>
 struct RangeEncodeLauncher {
-    static int run(const AnsParams &p, size_t smem, unsigned grid, cudaStream_t s) {
-        int rc = set_smem(range_encode_kernel<SHARED, CONTIG>, smem);
-        if (rc) return rc;
-        ProfileScope prof(2, s);
-        range_encode_kernel<SHARED, CONTIG><<<grid, kAnsBlock, smem, s>>>(p);
-        LAUNCH_CHECK("range_encode_kernel");
-        return CTR_OK;
+    static int run(bool shared, bool contig, bool persym, bool, const AnsParams &p, size_t smem, unsigned grid,
+                   cudaStream_t s) {
+        CTR_DISPATCH(range_encode_kernel, 2);
     }
 };
-template <bool SHARED, bool CONTIG>
 struct RangeDecodeLauncher {
-    static int run(const AnsParams &p, size_t smem, unsigned grid, cudaStream_t s) {
-        int rc = set_smem(range_decode_kernel<SHARED, CONTIG>, smem);
-        if (rc) return rc;
-        ProfileScope prof(3, s);
-        range_decode_kernel<SHARED, CONTIG><<<grid, kAnsBlock, smem, s>>>(p);
-        LAUNCH_CHECK("range_decode_kernel");
-        return CTR_OK;
+    static int run(bool shared, bool contig, bool persym, bool, const AnsParams &p, size_t smem, unsigned grid,
+                   cudaStream_t s) {
+        CTR_DISPATCH(range_decode_kernel, 3);
     }
 };
 
@@ -542,7 +546,7 @@ int empty_offsets(uint64_t *offsets, uint64_t K, cudaStream_t s) {
     return CTR_OK;
 }
 
-template <template <bool, bool> class EncLauncher>
+template <class EncLauncher>
 int encode_common(ctr_model_t model, const int32_t *symbols_dev, const ctr_layout *L, const uint64_t *states_in,
                   void *workspace, size_t workspace_bytes, uint32_t *words_out, uint64_t capacity,
                   uint64_t *offsets_out, uint64_t *states_out, uint32_t *status, void *stream) {
@@ -567,13 +571,14 @@ int encode_common(ctr_model_t model, const int32_t *symbols_dev, const ctr_layou
 
     const bool shared = use_shared_tables(model, L);
     const bool contig = L->sym_offsets_dev != nullptr;
-    const size_t smem = coder_smem_bytes(shared ? (size_t)model->alphabet * 16 : 0, L, kAnsBlock / 32);
-    rc = dispatch<EncLauncher>(shared, contig, p, smem, grid_for(L->n_streams, kAnsBlock), s);
+    const size_t smem = coder_smem_bytes(shared ? ((size_t)model->alphabet + 1) * 16 : 0, L, kAnsBlock / 32);
+    rc = EncLauncher::run(shared, contig, L->model_index_mode == CTR_INDEX_PER_SYMBOL, model->enc_f64, p, smem,
+                          grid_for(L->n_streams, kAnsBlock), s);
     if (rc) return rc;
     return compact_streams(L, w, ws, words_out, capacity, offsets_out, status, s);
 }
 
-template <template <bool, bool> class DecLauncher>
+template <class DecLauncher>
 int decode_common(ctr_model_t model, const uint32_t *words, const uint64_t *offsets, const ctr_layout *L,
                   const uint64_t *states_in, int32_t *symbols_out, uint64_t *states_out, uint64_t *words_left,
                   uint32_t *status, void *stream) {
@@ -598,7 +603,8 @@ int decode_common(ctr_model_t model, const uint32_t *words, const uint64_t *offs
     const bool shared = use_shared_tables(model, L);
     const bool contig = L->sym_offsets_dev != nullptr;
     const size_t smem = coder_smem_bytes(shared ? (size_t)model->dec_pairs_bytes + kLutSize * 4 : 0, L, kAnsBlock / 32);
-    return dispatch<DecLauncher>(shared, contig, p, smem, grid_for(L->n_streams, kAnsBlock), s);
+    return DecLauncher::run(shared, contig, L->model_index_mode == CTR_INDEX_PER_SYMBOL, false, p, smem,
+                            grid_for(L->n_streams, kAnsBlock), s);
 }
 
 }  // namespace

@@ -21,8 +21,54 @@ constexpr unsigned kFullMask = 0xffffffffu;
 constexpr int kRowWords = 32;
 constexpr int kRowStride = 33;
 constexpr int kTileWords = kWarp * kRowStride;  // 1056 words = 4224 B per warp
+// The coder kernels' word rows are longer: a row is flushed (refilled) in units of 32 words, but it is
+// only inspected every kCheckEvery symbols, during which a lane can push (pop) up to kCheckEvery words.
+// Stride 35 is odd, so lane-private and warp-wide accesses stay conflict free.
+constexpr int kCheckEvery = 4;
+constexpr int kWordRowStride = kRowWords + kCheckEvery - 1;  // 35 words
+constexpr int kWordRowsWords = kWarp * kWordRowStride;       // 1120 words = 4480 B per warp
+
+// ---- explicit shared-memory accesses by 32-bit shared address ------------------------------------------
+// (generic pointers into shared memory cost 64-bit address arithmetic in the hot loops)
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) {
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+// logical right shift whose amount may be >= 32 (PTX clamps: the result is then 0; in C++ it would be UB)
+__device__ __forceinline__ uint32_t shr_clamp(uint32_t v, uint32_t amount) {
+    uint32_t r;
+    asm("shr.u32 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(amount));
+    return r;
+}
+// table reads: the tables are immutable once staged, so these may be scheduled freely
+__device__ __forceinline__ uint32_t lds_table_u32(uint32_t addr) {
+    uint32_t v;
+    asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint2 lds_table_v2(uint32_t addr) {
+    uint2 v;
+    asm("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint4 lds_table_v4(uint32_t addr) {
+    uint4 v;
+    asm("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+// Same, but opaque to the optimiser: the value stays in a register instead of being rematerialised from the
+// CTA's shared-window base (several uniform-datapath instructions) at every use in a hot loop.
+__device__ __forceinline__ uint32_t smem_u32_pinned(const void *p) {
+    uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+    asm volatile("" : "+r"(a));
+    return a;
+}
 
 // ---- mbarrier + bulk copy ---------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {

@@ -96,20 +96,35 @@ __global__ void validate_cdf_kernel(const uint32_t *cdf, uint32_t n_models, uint
     if (strict && next == v) atomicOr(err, kTabZeroProb);
 }
 
-// encoder entries {left, prob, reciprocal}: thread per (model, symbol)
-__global__ void build_enc_table_kernel(const uint32_t *cdf, uint32_t n_models, uint32_t alphabet, uint4 *enc) {
+// encoder entries {left, prob, reciprocal}: thread per (model, entry); entry [alphabet] of every model is the
+// all-zero sentinel that the kernels clamp out-of-range symbols to (probability 0 = impossible symbol).
+// The reciprocal is floor((2^64-1)/prob) for the integer estimate, or, with `f64`, the double
+// (1/prob)*(1-2^-50), which keeps trunc(double(n) * rcp) in {floor(n/prob)-1, floor(n/prob)} for all
+// n < prob * 2^40 (every rounding error involved is below 2^-52 relative, the bias is 2^-50).
+__global__ void build_enc_table_kernel(const uint32_t *cdf, uint32_t n_models, uint32_t alphabet, int f64, uint4 *enc) {
     const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (tid >= (uint64_t)alphabet * n_models) return;
-    const uint64_t m = tid / alphabet;
-    const uint32_t s = (uint32_t)(tid % alphabet);
-    const uint32_t *row = cdf + m * ((uint64_t)alphabet + 1);
+    const uint64_t per = (uint64_t)alphabet + 1;
+    if (tid >= per * n_models) return;
+    const uint64_t m = tid / per;
+    const uint32_t s = (uint32_t)(tid % per);
+    if (s == alphabet) {
+        enc[tid] = make_uint4(0u, 0u, 0u, 0u);
+        return;
+    }
+    const uint32_t *row = cdf + m * per;
     const uint32_t left = row[s], prob = row[s + 1] - row[s];
-    const uint64_t rcp = reciprocal_u64(prob);
+    uint64_t rcp;
+    if (f64) {
+        const double r = (1.0 / (double)prob) * (1.0 - 8.8817841970012523e-16);  // 2^-50
+        rcp = prob ? (uint64_t)__double_as_longlong(r) : 0ull;
+    } else {
+        rcp = reciprocal_u64(prob);
+    }
     enc[tid] = make_uint4(left, prob, (uint32_t)rcp, (uint32_t)(rcp >> 32));
 }
 
 // decoder table of model 0: pairs (left, right) per symbol, then the bucket index:
-// lut[b] = lo | hi << 16 where lo / hi are the symbols containing the first / last quantile of bucket b.
+// lut[b] = lo | (hi - lo) << 16 where lo / hi are the symbols containing the first / last quantile of bucket b.
 __global__ void build_dec_table_kernel(const uint32_t *cdf, uint32_t alphabet, uint32_t pairs_bytes, uint32_t *dec) {
     const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
     uint2 *pairs = reinterpret_cast<uint2 *>(dec);
@@ -129,7 +144,8 @@ __global__ void build_dec_table_kernel(const uint32_t *cdf, uint32_t alphabet, u
             return lo;
         };
         const uint32_t q0 = tid << 12;
-        lut[tid] = last_le(q0) | (last_le(q0 + 4095u) << 16);
+        const uint32_t lo = last_le(q0), hi = last_le(q0 + 4095u);
+        lut[tid] = lo | ((hi - lo) << 16);
     }
 }
 
