@@ -24,6 +24,7 @@
 //
 // Per-stream results equal the reference's `AnsCoder` (src/stream/stack.rs:1014-1100) word for word.
 #pragma once
+#include "compact.cuh"
 #include "device_utils.cuh"
 
 namespace ctr {
@@ -38,11 +39,11 @@ struct ModelView {
     const uint32_t *cdf;   // [n_models][alphabet + 1]
     const uint4 *enc;      // [n_models][alphabet + 1] {left, prob, reciprocal lo, hi}; entry [alphabet] is
                            // the all-zero sentinel that out-of-range symbols are clamped to
-    const uint32_t *dec;   // model 0 only: pairs uint2[alphabet_padded] ++ lut u32[kLutSize]
+    const uint32_t *dec;   // model 0 only: uint4[alphabet] {cdf[s], cdf[s+1], cdf[s+2], 0} ++ lut u16[kLutSize]
     uint32_t n_models;
     uint32_t alphabet;
     int32_t min_symbol;
-    uint32_t dec_pairs_bytes;  // alphabet * 8 rounded up to 16
+    uint32_t dec_pairs_bytes;  // alphabet * 16: size of the uint4 part of `dec`
 };
 
 struct AnsParams {
@@ -58,8 +59,8 @@ struct AnsParams {
     uint64_t *states_out;
     uint32_t *status;
     // encode
-    uint32_t *scratch;   // strided per-stream regions
-    uint32_t *lengths;   // u32[K] words written per stream
+    uint32_t *scratch;      // strided per-stream regions
+    CompactParams compact;  // fused compaction into the dense container
     // decode
     const uint32_t *words;
     const uint64_t *offsets;
@@ -164,6 +165,7 @@ __device__ __noinline__ RowUpdate ans_refill_rows_cold(unsigned mask, uint32_t r
     const uint32_t *lo = (const uint32_t *)(((uint64_t)(gtop - 1)) & ~(uint64_t)127);
     if (lo < gbase) lo = gbase;
     const uint32_t c = mine ? (uint32_t)(gtop - lo) : 0u;
+    if (mine && lo > gbase) prefetch_l2(lo - 1);  // the line below: it is needed ~200 symbols from now
     unsigned todo = mask;
     __syncwarp();
     while (todo) {
@@ -190,42 +192,40 @@ __device__ __noinline__ RowUpdate ans_refill_rows_cold(unsigned mask, uint32_t r
 
 // ---- model lookups ----------------------------------------------------------------------------------
 
-// bucket index entry: low 16 bits = symbol containing the bucket's first quantile, high 16 bits = how many
-// further symbols the bucket reaches into (0 for almost every bucket)
-__device__ __forceinline__ uint32_t lut_pack(uint32_t lo, uint32_t hi) { return lo | ((hi - lo) << 16); }
-
-// decoder, generic-pointer version (range kernels): quantile -> (symbol index, left, right)
-__device__ __forceinline__ uint32_t lookup_shared(const uint2 *pairs, const uint32_t *lut, uint32_t q, uint32_t &left,
-                                                  uint32_t &right) {
-    uint32_t lo = lut[q >> kLutShift];
-    if (lo > 0xffffu) {  // rare: the bucket straddles a symbol boundary
-        uint32_t h = (lo & 0xffffu) + (lo >> 16);
-        lo &= 0xffffu;
-        while (lo < h) {
-            const uint32_t mid = (lo + h + 1) >> 1;
-            if (pairs[mid].x <= q)
-                lo = mid;
-            else
-                h = mid - 1;
-        }
+// Decoder table of a shared model (built by build_dec_table_kernel):
+//   trip[s] = {cdf[s], cdf[s+1], cdf[s+2], 0}   one 16-byte load yields the interval of s and of s+1
+//   lut[b]  = the symbol that contains quantile b << 12 (u16)
+// A 4096-wide bucket almost never reaches beyond the symbol after lut[b], so the lookup is branch-free:
+// probe s = lut[b], step to s+1 with selects if the quantile lies beyond cdf[s+1]; only when it also
+// lies beyond cdf[s+2] (several tiny-probability symbols inside one bucket) a cold search runs.
+__device__ __noinline__ uint32_t lookup_far_cold(uint32_t trip_addr, uint32_t alphabet, uint32_t s, uint32_t q) {
+    uint32_t lo = s + 1, hi = alphabet - 1;  // cdf[s + 1] <= q is known
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi + 1) >> 1;
+        if (lds_table_u32(trip_addr + mid * 16u) <= q)
+            lo = mid;
+        else
+            hi = mid - 1;
     }
-    const uint2 pr = pairs[lo];
-    left = pr.x;
-    right = pr.y;
     return lo;
 }
 
-// decoder, cold part of the shared-address version: binary search inside a straddling bucket
-__device__ __noinline__ uint32_t lookup_straddle_cold(uint32_t pairs_addr, uint32_t packed, uint32_t q) {
-    uint32_t lo = packed & 0xffffu, h = lo + (packed >> 16);
-    while (lo < h) {
-        const uint32_t mid = (lo + h + 1) >> 1;
-        if (lds_table_u32(pairs_addr + mid * 8u) <= q)
-            lo = mid;
-        else
-            h = mid - 1;
+// `word` is any value whose low 24 bits are the quantile q
+__device__ __forceinline__ uint32_t lookup_shared(uint32_t trip_addr, uint32_t lut_addr, uint32_t alphabet, uint32_t word,
+                                                  uint32_t q, uint32_t &left, uint32_t &right) {
+    uint32_t s = lds_table_u16(lut_addr + ((word >> (kLutShift - 1)) & ((kLutSize - 1) << 1)));
+    uint4 t = lds_table_v4(trip_addr + s * 16u);
+    const bool adv = q >= t.y;
+    left = adv ? t.y : t.x;
+    right = adv ? t.z : t.y;
+    s += adv ? 1u : 0u;
+    if (q >= right) {
+        s = lookup_far_cold(trip_addr, alphabet, s, q);
+        t = lds_table_v4(trip_addr + s * 16u);
+        left = t.x;
+        right = t.y;
     }
-    return lo;
+    return s;
 }
 
 // decoder: binary search of a CDF row in global memory (through L1/L2):
@@ -293,7 +293,8 @@ __global__ void __launch_bounds__(kAnsBlock) ans_encode_kernel(const AnsParams p
     if (SHARED) stage_table(smem, p.model.enc, (alphabet + 1) * 16u, &bar);
 
     const uint64_t K = p.K, N = p.N;
-    const uint64_t k = (uint64_t)blockIdx.x * kAnsBlock + threadIdx.x;
+    const uint32_t tile = take_tile_ticket(p.compact.ticket);  // which 256 streams this CTA codes
+    const uint64_t k = (uint64_t)tile * kAnsBlock + threadIdx.x;
     const bool valid = k < K;
     const uint64_t kc = valid ? k : K - 1;  // lanes without a stream shadow the last one (loads only)
 
@@ -380,24 +381,45 @@ __global__ void __launch_bounds__(kAnsBlock) ans_encode_kernel(const AnsParams p
             uint64_t rows_left = g.T - 1;  // full rows T-2 .. 0
             const int32_t *ps = p.symbols_in + (g.T - 2) * K + kc;
             const uint32_t *pm = PERSYM ? p.model_index + (g.T - 2) * K + kc : nullptr;
-            while (rows_left >= (uint64_t)kCheckEvery) {
-                int32_t buf[kCheckEvery];
-                uint32_t mbuf[kCheckEvery];
+            // batches of kCheckEvery symbols; the loads of the next batch are in flight while this one is coded
+            int32_t buf[2][kCheckEvery];
+            uint32_t mbuf[2][kCheckEvery];
+            auto load_batch = [&](int which) {
 #pragma unroll
                 for (int u = 0; u < kCheckEvery; ++u) {
-                    buf[u] = ld_stream_s32(ps);
+                    buf[which][u] = ld_stream_s32(ps);
                     ps -= K;
                     if (PERSYM) {
-                        mbuf[u] = ld_stream_u32(pm);
+                        mbuf[which][u] = ld_stream_u32(pm);
                         pm -= K;
                     } else {
-                        mbuf[u] = stream_model;
+                        mbuf[which][u] = stream_model;
                     }
                 }
+            };
+            auto code_batch = [&](int which) {
                 check_rows();  // room for kCheckEvery more words in every row
 #pragma unroll
-                for (int u = 0; u < kCheckEvery; ++u) encode_one(buf[u], mbuf[u]);
-                rows_left -= kCheckEvery;
+                for (int u = 0; u < kCheckEvery; ++u) encode_one(buf[which][u], mbuf[which][u]);
+            };
+            uint64_t batches = rows_left / kCheckEvery;
+            rows_left -= batches * kCheckEvery;
+            if (batches > 0) {
+                load_batch(0);
+                while (batches > 2) {
+                    load_batch(1);
+                    code_batch(0);
+                    load_batch(0);
+                    code_batch(1);
+                    batches -= 2;
+                }
+                if (batches == 2) {
+                    load_batch(1);
+                    code_batch(0);
+                    code_batch(1);
+                } else {
+                    code_batch(0);
+                }
             }
             check_rows();
             while (rows_left > 0) {  // at most kCheckEvery-1 more symbols
@@ -457,11 +479,12 @@ __global__ void __launch_bounds__(kAnsBlock) ans_encode_kernel(const AnsParams p
         }
     }
     if (valid) {
-        p.lengths[k] = (uint32_t)(gptr - gbegin) + cnt;
         if (p.states_out) p.states_out[k] = state;
         if (min_prob == 0u) report_error(p.status, kErrImpossibleSymbol, k);
         if (overflow) report_error(p.status, kErrOutOfSpace, k);
     }
+    // ---- K6: place my stream in the dense container ---------------------------------------------------
+    compact_tail<kAnsBlock>(p.compact, tile, k, K, valid, gbegin, valid ? (uint32_t)(gptr - gbegin) + cnt : 0u, p.status);
 }
 
 // =====================================================================================================
@@ -477,7 +500,7 @@ __global__ void __launch_bounds__(kAnsBlock) ans_decode_kernel(const AnsParams p
     constexpr int kWarpsPerCta = kAnsBlock / 32;
 
     const uint32_t alphabet = p.model.alphabet;
-    const uint32_t table_words = SHARED ? (p.model.dec_pairs_bytes / 4 + kLutSize) : 0;
+    const uint32_t table_words = SHARED ? (p.model.dec_pairs_bytes / 4 + kLutSize / 2) : 0;
     const uint32_t pairs_addr = smem_u32_pinned(smem);
     uint32_t lut_addr = pairs_addr + (SHARED ? p.model.dec_pairs_bytes : 0);
     asm volatile("" : "+r"(lut_addr));
@@ -485,7 +508,7 @@ __global__ void __launch_bounds__(kAnsBlock) ans_decode_kernel(const AnsParams p
     uint32_t *sym_tile = smem + table_words + kWarpsPerCta * kWordRowsWords + warp_in_cta * kTileWords;
     uint32_t *idx_tile = sym_tile + kWarpsPerCta * kTileWords;
 
-    if (SHARED) stage_table(smem, p.model.dec, p.model.dec_pairs_bytes + kLutSize * 4u, &bar);
+    if (SHARED) stage_table(smem, p.model.dec, p.model.dec_pairs_bytes + kLutSize * 2u, &bar);
 
     const uint64_t K = p.K, N = p.N;
     const uint64_t k = (uint64_t)blockIdx.x * kAnsBlock + threadIdx.x;
@@ -552,11 +575,7 @@ __global__ void __launch_bounds__(kAnsBlock) ans_decode_kernel(const AnsParams p
         const uint32_t q = lo & kQuantileMask;
         uint32_t left, right, s;
         if (SHARED) {
-            s = lds_table_u32(lut_addr + ((lo >> (kLutShift - 2)) & ((kLutSize - 1) << 2)));
-            if (s > 0xffffu) s = lookup_straddle_cold(pairs_addr, s, q);
-            const uint2 pr = lds_table_v2(pairs_addr + s * 8u);
-            left = pr.x;
-            right = pr.y;
+            s = lookup_shared(pairs_addr, lut_addr, alphabet, lo, q, left, right);
         } else {
             m = m < n_models ? m : n_models - 1;  // decoding cannot fail (stack.rs:1062-1065)
             s = lookup_global(p.model.cdf + (uint64_t)m * (alphabet + 1), alphabet, q, left, right);

@@ -105,7 +105,7 @@ int model_alloc(uint32_t n_models, uint32_t alphabet, int32_t min_symbol, ctr_mo
     m->n_models = n_models;
     m->alphabet = alphabet;
     m->min_symbol = min_symbol;
-    m->dec_pairs_bytes = (uint32_t)align_up((size_t)alphabet * 8, 16);
+    m->dec_pairs_bytes = alphabet <= kMaxSharedAlphabet ? alphabet * 16u : 0u;
     m->shared_ok = alphabet <= kMaxSharedAlphabet;
     cudaError_t e = cudaMalloc(&m->d_cdf, (size_t)n_models * ((size_t)alphabet + 1) * 4);
     if (e != cudaSuccess) {
@@ -138,7 +138,7 @@ int ensure_enc_table(ctr_model_s *m, cudaStream_t s) {
 
 int ensure_dec_table(ctr_model_s *m, cudaStream_t s) {
     if (m->d_dec || !m->shared_ok) return CTR_OK;
-    CUDA_TRY(cudaMalloc(&m->d_dec, m->dec_pairs_bytes + kLutSize * 4));
+    CUDA_TRY(cudaMalloc(&m->d_dec, m->dec_pairs_bytes + kLutSize * 2));
     const uint32_t threads = m->alphabet + 2 > (uint32_t)kLutSize ? m->alphabet + 2 : (uint32_t)kLutSize;
     build_dec_table_kernel<<<grid_for(threads, 256), 256, 0, s>>>(m->d_cdf, m->alphabet, m->dec_pairs_bytes, m->d_dec);
     LAUNCH_CHECK("build_dec_table_kernel");
@@ -197,37 +197,19 @@ int check_layout(const ctr_layout *L) {
 
 struct EncodeWorkspace {
     uint64_t scratch_words;
-    size_t lengths_off, tiles_off, total;
+    size_t status_off, ticket_off, total;
     uint64_t n_tiles;
 };
 
+// [scratch regions][tile status u64[n_tiles]][ticket u32]
 EncodeWorkspace encode_workspace(const ctr_layout *L) {
     EncodeWorkspace w;
     w.scratch_words = scratch_start(L->n_symbols, L->n_streams) + 32;
-    w.lengths_off = align_up((size_t)w.scratch_words * 4, 256);
-    w.n_tiles = (L->n_streams + kScanTile - 1) / kScanTile;
-    w.tiles_off = align_up(w.lengths_off + (size_t)L->n_streams * 4, 256);
-    w.total = w.tiles_off + (size_t)(w.n_tiles + 1) * 8;
+    w.n_tiles = (L->n_streams + kAnsBlock - 1) / kAnsBlock;
+    w.status_off = align_up((size_t)w.scratch_words * 4, 256);
+    w.ticket_off = w.status_off + (size_t)w.n_tiles * 8;
+    w.total = align_up(w.ticket_off + 8, 256);
     return w;
-}
-
-// prefix sum of per-stream lengths + gather into the dense container
-int compact_streams(const ctr_layout *L, const EncodeWorkspace &w, char *ws, uint32_t *words_out, uint64_t capacity,
-                    uint64_t *offsets_out, uint32_t *status, cudaStream_t s) {
-    const uint32_t *scratch = reinterpret_cast<const uint32_t *>(ws);
-    const uint32_t *lengths = reinterpret_cast<const uint32_t *>(ws + w.lengths_off);
-    uint64_t *tiles = reinterpret_cast<uint64_t *>(ws + w.tiles_off);
-    const uint64_t K = L->n_streams;
-    scan_tile_sums_kernel<<<(unsigned)w.n_tiles, kScanBlock, 0, s>>>(lengths, K, tiles);
-    LAUNCH_CHECK("scan_tile_sums_kernel");
-    scan_top_kernel<<<1, kScanBlock, 0, s>>>(tiles, w.n_tiles, offsets_out, K);
-    LAUNCH_CHECK("scan_top_kernel");
-    scan_apply_kernel<<<(unsigned)w.n_tiles, kScanBlock, 0, s>>>(lengths, K, tiles, offsets_out);
-    LAUNCH_CHECK("scan_apply_kernel");
-    compact_copy_kernel<<<grid_for(K * 32, 256), 256, 0, s>>>(scratch, lengths, offsets_out, K, L->n_symbols,
-                                                               L->sym_offsets_dev, words_out, capacity, status);
-    LAUNCH_CHECK("compact_copy_kernel");
-    return CTR_OK;
 }
 
 template <typename Kernel>
@@ -567,15 +549,18 @@ int encode_common(ctr_model_t model, const int32_t *symbols_dev, const ctr_layou
     p.status = status;
     char *ws = static_cast<char *>(workspace);
     p.scratch = reinterpret_cast<uint32_t *>(ws);
-    p.lengths = reinterpret_cast<uint32_t *>(ws + w.lengths_off);
+    p.compact.tile_status = reinterpret_cast<uint64_t *>(ws + w.status_off);
+    p.compact.ticket = reinterpret_cast<unsigned int *>(ws + w.ticket_off);
+    p.compact.words_out = words_out;
+    p.compact.words_capacity = capacity;
+    p.compact.offsets_out = offsets_out;
+    CUDA_TRY(cudaMemsetAsync(ws + w.status_off, 0, w.total - w.status_off, s));
 
     const bool shared = use_shared_tables(model, L);
     const bool contig = L->sym_offsets_dev != nullptr;
     const size_t smem = coder_smem_bytes(shared ? ((size_t)model->alphabet + 1) * 16 : 0, L, kAnsBlock / 32);
-    rc = EncLauncher::run(shared, contig, L->model_index_mode == CTR_INDEX_PER_SYMBOL, model->enc_f64, p, smem,
-                          grid_for(L->n_streams, kAnsBlock), s);
-    if (rc) return rc;
-    return compact_streams(L, w, ws, words_out, capacity, offsets_out, status, s);
+    return EncLauncher::run(shared, contig, L->model_index_mode == CTR_INDEX_PER_SYMBOL, model->enc_f64, p, smem,
+                            grid_for(L->n_streams, kAnsBlock), s);
 }
 
 template <class DecLauncher>
@@ -602,7 +587,7 @@ int decode_common(ctr_model_t model, const uint32_t *words, const uint64_t *offs
 
     const bool shared = use_shared_tables(model, L);
     const bool contig = L->sym_offsets_dev != nullptr;
-    const size_t smem = coder_smem_bytes(shared ? (size_t)model->dec_pairs_bytes + kLutSize * 4 : 0, L, kAnsBlock / 32);
+    const size_t smem = coder_smem_bytes(shared ? (size_t)model->dec_pairs_bytes + kLutSize * 2 : 0, L, kAnsBlock / 32);
     return DecLauncher::run(shared, contig, L->model_index_mode == CTR_INDEX_PER_SYMBOL, false, p, smem,
                             grid_for(L->n_streams, kAnsBlock), s);
 }

@@ -1,18 +1,60 @@
-// compact.cuh -- K6: variable-length compaction.  The encode kernels leave stream k's words in a
-// worst-case-sized scratch region; here the per-stream lengths are prefix-summed into the container's
-// `offsets` (u64[K+1]) and the words are gathered into one dense buffer, so that
-// words[offsets[k] .. offsets[k+1]) is stream k's `get_compressed()` (stack.rs:537-547,
-// queue.rs:349-355).
+// compact.cuh -- K6: variable-length compaction, fused into the tail of the encode kernels.
+//
+// While a stream is being encoded its final length is unknown, so its words first go to a
+// worst-case-sized scratch region.  When a CTA has finished its 256 streams it
+//   1. prefix-sums their lengths inside the CTA,
+//   2. obtains the total length of all preceding streams with a single-pass "decoupled look-back"
+//      over per-CTA status words (aggregate published first, inclusive prefix as soon as it is known),
+//   3. writes the container's `offsets` (u64[K+1]) and gathers its streams' words from scratch (still
+//      L2-resident: this CTA wrote them microseconds ago) into the dense `words` buffer, so that
+//      words[offsets[k] .. offsets[k+1]) is stream k's `get_compressed()` (stack.rs:537-547,
+//      queue.rs:349-355).
+// There is no separate scan / gather launch and no second pass over HBM-cold data.
+//
+// CTAs take their tile (block of 256 consecutive streams) from an atomic ticket at kernel start, so a
+// CTA only ever waits for tiles whose CTAs started earlier and are therefore resident and running:
+// the look-back cannot deadlock whatever the grid size or dispatch order.
 #pragma once
 #include "device_utils.cuh"
 
 namespace ctr {
 
-constexpr int kScanBlock = 256;
-constexpr int kScanItems = 16;
-constexpr int kScanTile = kScanBlock * kScanItems;  // lengths per CTA
+constexpr uint64_t kTileInvalid = 0ull;          // status not yet published
+constexpr uint64_t kTileAggregate = 1ull << 62;  // value = total of this tile only
+constexpr uint64_t kTilePrefix = 2ull << 62;     // value = total of this tile and all before it
+constexpr uint64_t kTileValueMask = (1ull << 62) - 1;
 
-__device__ __forceinline__ uint64_t warp_inclusive_scan(uint64_t v, int lane) {
+struct CompactParams {
+    uint64_t *tile_status;    // u64[n_tiles], zeroed before the launch
+    unsigned int *ticket;     // zeroed before the launch
+    uint32_t *words_out;      // dense container
+    uint64_t words_capacity;  // capacity of words_out in words
+    uint64_t *offsets_out;    // u64[K+1]
+};
+
+__device__ __forceinline__ uint64_t ld_volatile_u64(const uint64_t *p) {
+    uint64_t v;
+    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_volatile_u64(uint64_t *p, uint64_t v) {
+    asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_cg_u32(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// The tile this CTA works on (all threads get the same value).
+__device__ __forceinline__ uint32_t take_tile_ticket(unsigned int *ticket) {
+    __shared__ uint32_t s_tile;
+    if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
+    __syncthreads();
+    return s_tile;
+}
+
+__device__ __forceinline__ uint64_t warp_inclusive_scan_u64(uint64_t v, int lane) {
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
         const uint64_t o = shfl_u64(v, lane >= d ? lane - d : lane);
@@ -21,96 +63,94 @@ __device__ __forceinline__ uint64_t warp_inclusive_scan(uint64_t v, int lane) {
     return v;
 }
 
-// exclusive scan of one value per thread across a CTA of kScanBlock threads; returns the CTA total
-__device__ __forceinline__ uint64_t block_exclusive_scan(uint64_t v, uint64_t &total) {
-    __shared__ uint64_t warp_sums[kScanBlock / 32];
+__device__ __forceinline__ uint64_t warp_sum_u64(uint64_t v, int lane) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += shfl_u64(v, lane ^ d);
+    return v;
+}
+
+// Called by every thread of the CTA once its stream is complete in scratch.
+//   tile    : this CTA's tile index (stream k = tile * blockDim.x + threadIdx.x)
+//   src/len : my stream's words in scratch (len = 0 for threads without a stream)
+template <int BLOCK>
+__device__ __forceinline__ void compact_tail(const CompactParams &c, uint32_t tile, uint64_t k, uint64_t K, bool valid,
+                                             const uint32_t *src, uint32_t len, uint32_t *status) {
+    constexpr int kWarps = BLOCK / 32;
+    __shared__ uint64_t s_warp_totals[kWarps];
+    __shared__ uint64_t s_tile_base;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint64_t inc = warp_inclusive_scan(v, lane);
-    if (lane == 31) warp_sums[warp] = inc;
+
+    // 1. offsets inside the CTA
+    const uint64_t inc = warp_inclusive_scan_u64(len, lane);
+    if (lane == 31) s_warp_totals[warp] = inc;
     __syncthreads();
-    uint64_t base = 0, tot = 0;
+    uint64_t before = 0, tile_total = 0;
 #pragma unroll
-    for (int w = 0; w < kScanBlock / 32; ++w) {
-        const uint64_t s = warp_sums[w];
-        if (w < warp) base += s;
-        tot += s;
+    for (int w = 0; w < kWarps; ++w) {
+        const uint64_t t = s_warp_totals[w];
+        if (w < warp) before += t;
+        tile_total += t;
+    }
+
+    // 2. decoupled look-back by warp 0: lane j inspects tile (tile - 1 - j - 32 * round)
+    if (warp == 0) {
+        if (lane == 0) st_volatile_u64(c.tile_status + tile, (tile == 0 ? kTilePrefix : kTileAggregate) | tile_total);
+        uint64_t exclusive = 0;
+        int64_t idx = (int64_t)tile - 1 - lane;
+        bool done = tile == 0;
+        while (!done) {
+            uint64_t v = kTilePrefix;  // tiles before the first one contribute a prefix of 0
+            if (idx >= 0) {
+                do {
+                    v = ld_volatile_u64(c.tile_status + idx);
+                } while ((v >> 62) == 0);
+            }
+            const unsigned has_prefix = __ballot_sync(kFullMask, (v >> 62) == 2);
+            // nearest predecessor with a full prefix ends the walk; nearer ones contribute their aggregates
+            const int stop = has_prefix ? __ffs(has_prefix) - 1 : 31;
+            exclusive += warp_sum_u64(lane <= stop ? (v & kTileValueMask) : 0ull, lane);
+            done = has_prefix != 0;
+            idx -= 32;
+        }
+        if (lane == 0) {
+            if (tile != 0) st_volatile_u64(c.tile_status + tile, kTilePrefix | (exclusive + tile_total));
+            s_tile_base = exclusive;
+        }
     }
     __syncthreads();
-    total = tot;
-    return base + inc - v;
-}
+    const uint64_t my_off = s_tile_base + before + inc - len;
 
-// pass 1: sum of each tile of lengths
-__global__ void __launch_bounds__(kScanBlock) scan_tile_sums_kernel(const uint32_t *lengths, uint64_t K,
-                                                                    uint64_t *tile_sums) {
-    const uint64_t first = (uint64_t)blockIdx.x * kScanTile;
-    uint64_t v = 0;
+    // 3. offsets + gather
+    if (valid) {
+        c.offsets_out[k] = my_off;
+        if (k + 1 == K) c.offsets_out[K] = my_off + len;
+    }
+    const bool fits = my_off + len <= c.words_capacity;
+    if (valid && !fits) report_error(status, kErrOutOfSpace, k);
+    const uint32_t n = (valid && fits) ? len : 0u;
+    const uint32_t n_max = __reduce_max_sync(kFullMask, n);
+    if (n_max == 0) return;
+    uint32_t *dst = c.words_out + my_off;
+    __syncwarp();
+    for (int i = 0; i < 32; ++i) {
+        const uint32_t ni = __shfl_sync(kFullMask, n, i);
+        if (ni == 0) continue;
+        const uint32_t *s = (const uint32_t *)shfl_u64((uint64_t)src, i);
+        uint32_t *d = (uint32_t *)shfl_u64((uint64_t)dst, i);
+        for (uint32_t j0 = 0; j0 < ni; j0 += 128) {  // four independent loads in flight per lane
+            uint32_t v[4];
 #pragma unroll
-    for (int j = 0; j < kScanItems; ++j) {
-        const uint64_t i = first + (uint64_t)j * kScanBlock + threadIdx.x;
-        if (i < K) v += lengths[i];
-    }
-    uint64_t total;
-    block_exclusive_scan(v, total);
-    if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
-}
-
-// pass 2 (one CTA): exclusive scan of the tile sums in place; total -> offsets[K]
-__global__ void __launch_bounds__(kScanBlock) scan_top_kernel(uint64_t *tile_sums, uint64_t n_tiles, uint64_t *offsets,
-                                                              uint64_t K) {
-    uint64_t carry = 0;
-    for (uint64_t first = 0; first < n_tiles; first += kScanBlock) {
-        const uint64_t i = first + threadIdx.x;
-        const uint64_t v = i < n_tiles ? tile_sums[i] : 0;
-        uint64_t total;
-        const uint64_t ex = block_exclusive_scan(v, total);
-        if (i < n_tiles) tile_sums[i] = carry + ex;
-        carry += total;
-    }
-    if (threadIdx.x == 0) offsets[K] = carry;
-}
-
-// pass 3: offsets[k] for every stream.  Thread t of a tile owns the kScanItems consecutive lengths
-// starting at first + t*kScanItems.
-__global__ void __launch_bounds__(kScanBlock) scan_apply_kernel(const uint32_t *lengths, uint64_t K,
-                                                                const uint64_t *tile_offsets, uint64_t *offsets) {
-    const uint64_t first = (uint64_t)blockIdx.x * kScanTile + (uint64_t)threadIdx.x * kScanItems;
-    uint32_t local[kScanItems];
-    uint64_t v = 0;
+            for (int u = 0; u < 4; ++u) {
+                const uint32_t j = j0 + u * 32 + lane;
+                if (j < ni) v[u] = ld_cg_u32(s + j);
+            }
 #pragma unroll
-    for (int j = 0; j < kScanItems; ++j) {
-        const uint64_t i = first + j;
-        local[j] = i < K ? lengths[i] : 0u;
-        v += local[j];
+            for (int u = 0; u < 4; ++u) {
+                const uint32_t j = j0 + u * 32 + lane;
+                if (j < ni) d[j] = v[u];
+            }
+        }
     }
-    uint64_t total;
-    uint64_t run = tile_offsets[blockIdx.x] + block_exclusive_scan(v, total);
-#pragma unroll
-    for (int j = 0; j < kScanItems; ++j) {
-        const uint64_t i = first + j;
-        if (i < K) offsets[i] = run;
-        run += local[j];
-    }
-}
-
-// gather: one warp per stream copies scratch region -> dense words
-__global__ void __launch_bounds__(256) compact_copy_kernel(const uint32_t *scratch, const uint32_t *lengths,
-                                                           const uint64_t *offsets, uint64_t K, uint64_t N,
-                                                           const uint64_t *sym_off, uint32_t *words,
-                                                           uint64_t capacity, uint32_t *status) {
-    const uint64_t k = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (k >= K) return;
-    const uint64_t o_k = sym_off ? sym_off[k] : interleaved_start(N, K, k);
-    const uint32_t *src = scratch + scratch_start(o_k, k);
-    const uint64_t dst0 = offsets[k];
-    const uint32_t len = lengths[k];
-    if (dst0 + len > capacity) {
-        if (lane == 0) report_error(status, kErrOutOfSpace, k);
-        return;
-    }
-    uint32_t *dst = words + dst0;
-    for (uint32_t i = lane; i < len; i += 32) dst[i] = src[i];
 }
 
 }  // namespace ctr

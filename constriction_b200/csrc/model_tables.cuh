@@ -123,29 +123,25 @@ __global__ void build_enc_table_kernel(const uint32_t *cdf, uint32_t n_models, u
     enc[tid] = make_uint4(left, prob, (uint32_t)rcp, (uint32_t)(rcp >> 32));
 }
 
-// decoder table of model 0: pairs (left, right) per symbol, then the bucket index:
-// lut[b] = lo | (hi - lo) << 16 where lo / hi are the symbols containing the first / last quantile of bucket b.
-__global__ void build_dec_table_kernel(const uint32_t *cdf, uint32_t alphabet, uint32_t pairs_bytes, uint32_t *dec) {
+// decoder table of model 0 (see lookup_shared in ans_kernels.cuh):
+//   trip[s] = {cdf[s], cdf[s+1], cdf[s+2] (2^24 past the end), 0}, then lut[b] (u16) = the last symbol whose
+//   left cumulative is <= b << 12, i.e. the symbol containing the first quantile of bucket b.
+__global__ void build_dec_table_kernel(const uint32_t *cdf, uint32_t alphabet, uint32_t trip_bytes, uint32_t *dec) {
     const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
-    uint2 *pairs = reinterpret_cast<uint2 *>(dec);
-    uint32_t *lut = dec + pairs_bytes / 4;
-    if (tid < alphabet) pairs[tid] = make_uint2(cdf[tid], cdf[tid + 1]);
-    if (tid >= alphabet && tid < pairs_bytes / 8) pairs[tid] = make_uint2(kTotal, kTotal);
+    uint4 *trip = reinterpret_cast<uint4 *>(dec);
+    uint16_t *lut = reinterpret_cast<uint16_t *>(dec + trip_bytes / 4);
+    if (tid < alphabet) trip[tid] = make_uint4(cdf[tid], cdf[tid + 1], tid + 2 <= alphabet ? cdf[tid + 2] : kTotal, 0u);
     if (tid < (uint32_t)(1u << 12)) {
-        auto last_le = [&](uint32_t q) {
-            uint32_t lo = 0, hi = alphabet - 1;
-            while (lo < hi) {
-                const uint32_t mid = (lo + hi + 1) >> 1;
-                if (cdf[mid] <= q)
-                    lo = mid;
-                else
-                    hi = mid - 1;
-            }
-            return lo;
-        };
-        const uint32_t q0 = tid << 12;
-        const uint32_t lo = last_le(q0), hi = last_le(q0 + 4095u);
-        lut[tid] = lo | ((hi - lo) << 16);
+        const uint32_t q = tid << 12;
+        uint32_t lo = 0, hi = alphabet - 1;
+        while (lo < hi) {
+            const uint32_t mid = (lo + hi + 1) >> 1;
+            if (cdf[mid] <= q)
+                lo = mid;
+            else
+                hi = mid - 1;
+        }
+        lut[tid] = (uint16_t)lo;
     }
 }
 

@@ -37,7 +37,8 @@ __global__ void __launch_bounds__(kAnsBlock) range_encode_kernel(const AnsParams
     if (SHARED) stage_table(smem, p.model.enc, (p.model.alphabet + 1) * 16u, &bar);
 
     const uint64_t K = p.K, N = p.N;
-    const uint64_t k = (uint64_t)blockIdx.x * kAnsBlock + threadIdx.x;
+    const uint32_t tile = take_tile_ticket(p.compact.ticket);  // which 256 streams this CTA codes
+    const uint64_t k = (uint64_t)tile * kAnsBlock + threadIdx.x;
     const bool valid = k < K;
     const uint64_t kc = valid ? k : K - 1;
 
@@ -209,7 +210,6 @@ __global__ void __launch_bounds__(kAnsBlock) range_encode_kernel(const AnsParams
         }
     }
     if (valid) {
-        p.lengths[k] = (uint32_t)(gptr - gbegin) + cnt;
         if (p.states_out) {
             p.states_out[4 * k] = st.lower;
             p.states_out[4 * k + 1] = st.range;
@@ -219,6 +219,8 @@ __global__ void __launch_bounds__(kAnsBlock) range_encode_kernel(const AnsParams
         if (bad) report_error(p.status, kErrImpossibleSymbol, k);
         if (overflow) report_error(p.status, kErrOutOfSpace, k);
     }
+    // ---- K6: place my stream in the dense container ---------------------------------------------------
+    compact_tail<kAnsBlock>(p.compact, tile, k, K, valid, gbegin, valid ? (uint32_t)(gptr - gbegin) + cnt : 0u, p.status);
 }
 
 template <bool SHARED, bool CONTIG, bool PERSYM>
@@ -230,14 +232,14 @@ __global__ void __launch_bounds__(kAnsBlock) range_decode_kernel(const AnsParams
     const int warp_in_cta = threadIdx.x >> 5;
     constexpr int kWarpsPerCta = kAnsBlock / 32;
 
-    const uint32_t table_words = SHARED ? (p.model.dec_pairs_bytes / 4 + kLutSize) : 0;
-    const uint2 *s_pairs = reinterpret_cast<const uint2 *>(smem);
-    const uint32_t *s_lut = smem + (SHARED ? p.model.dec_pairs_bytes / 4 : 0);
+    const uint32_t table_words = SHARED ? (p.model.dec_pairs_bytes / 4 + kLutSize / 2) : 0;
+    const uint32_t trip_addr = smem_u32_pinned(smem);
+    const uint32_t lut_addr = trip_addr + (SHARED ? p.model.dec_pairs_bytes : 0);
     uint32_t *rows = smem + table_words + warp_in_cta * kTileWords;
     uint32_t *sym_tile = smem + table_words + (kWarpsPerCta + warp_in_cta) * kTileWords;
     uint32_t *idx_tile = smem + table_words + (2 * kWarpsPerCta + warp_in_cta) * kTileWords;
 
-    if (SHARED) stage_table(smem, p.model.dec, p.model.dec_pairs_bytes + kLutSize * 4u, &bar);
+    if (SHARED) stage_table(smem, p.model.dec, p.model.dec_pairs_bytes + kLutSize * 2u, &bar);
 
     const uint64_t K = p.K, N = p.N;
     const uint64_t k = (uint64_t)blockIdx.x * kAnsBlock + threadIdx.x;
@@ -316,7 +318,7 @@ __global__ void __launch_bounds__(kAnsBlock) range_decode_kernel(const AnsParams
         invalid_data |= !range_peek_quantile(st, q);
         uint32_t left, right, s;
         if (SHARED) {
-            s = lookup_shared(s_pairs, s_lut, q, left, right);
+            s = lookup_shared(trip_addr, lut_addr, alphabet, q, q, left, right);
         } else {
             m = m < n_models ? m : n_models - 1;
             s = lookup_global(p.model.cdf + (uint64_t)m * (alphabet + 1), alphabet, q, left, right);
