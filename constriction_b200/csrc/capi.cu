@@ -116,11 +116,13 @@ int model_alloc(uint32_t n_models, uint32_t alphabet, int32_t min_symbol, ctr_mo
     return CTR_OK;
 }
 
-// CTR_DIV=f64 selects the FP64-pipe quotient estimate in the ANS encoder (A/B switch; default: integer)
+// The ANS encoder's quotient estimate runs on the FP64 pipe by default (3 instructions instead of a
+// 7-instruction 64x64 high multiply; measured ~8 % faster on B200).  CTR_DIV=int selects the integer
+// estimate; both are followed by the same exact integer correction and give identical words.
 bool use_f64_division() {
     static const bool on = [] {
         const char *e = getenv("CTR_DIV");
-        return e && strcmp(e, "f64") == 0;
+        return !(e && strcmp(e, "int") == 0);
     }();
     return on;
 }

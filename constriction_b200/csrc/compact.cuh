@@ -132,23 +132,38 @@ __device__ __forceinline__ void compact_tail(const CompactParams &c, uint32_t ti
     if (n_max == 0) return;
     uint32_t *dst = c.words_out + my_off;
     __syncwarp();
-    for (int i = 0; i < 32; ++i) {
-        const uint32_t ni = __shfl_sync(kFullMask, n, i);
-        if (ni == 0) continue;
-        const uint32_t *s = (const uint32_t *)shfl_u64((uint64_t)src, i);
-        uint32_t *d = (uint32_t *)shfl_u64((uint64_t)dst, i);
-        for (uint32_t j0 = 0; j0 < ni; j0 += 128) {  // four independent loads in flight per lane
-            uint32_t v[4];
+    // The copy is latency-bound (one L2 round trip per batch of loads), so the loads of kGroup streams are
+    // put in flight together: lane l moves words l, l+32, ... of each stream; kSlots chunks per stream cover
+    // streams of up to 32*kSlots words in one pass (longer ones loop).
+    constexpr int kGroup = 4, kSlots = 4;
+    for (int i0 = 0; i0 < 32; i0 += kGroup) {
+        uint32_t ni[kGroup];
+        const uint32_t *si[kGroup];
+        uint32_t *di[kGroup];
+        uint32_t group_max = 0;
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const uint32_t j = j0 + u * 32 + lane;
-                if (j < ni) v[u] = ld_cg_u32(s + j);
-            }
+        for (int g = 0; g < kGroup; ++g) {
+            ni[g] = __shfl_sync(kFullMask, n, i0 + g);
+            si[g] = (const uint32_t *)shfl_u64((uint64_t)src, i0 + g);
+            di[g] = (uint32_t *)shfl_u64((uint64_t)dst, i0 + g);
+            group_max = max(group_max, ni[g]);
+        }
+        for (uint32_t j0 = 0; j0 < group_max; j0 += 32 * kSlots) {
+            uint32_t v[kGroup][kSlots];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const uint32_t j = j0 + u * 32 + lane;
-                if (j < ni) d[j] = v[u];
-            }
+            for (int g = 0; g < kGroup; ++g)
+#pragma unroll
+                for (int u = 0; u < kSlots; ++u) {
+                    const uint32_t j = j0 + u * 32 + lane;
+                    if (j < ni[g]) v[g][u] = ld_cg_u32(si[g] + j);
+                }
+#pragma unroll
+            for (int g = 0; g < kGroup; ++g)
+#pragma unroll
+                for (int u = 0; u < kSlots; ++u) {
+                    const uint32_t j = j0 + u * 32 + lane;
+                    if (j < ni[g]) di[g][j] = v[g][u];
+                }
         }
     }
 }
