@@ -30,9 +30,6 @@
 namespace ctr {
 
 constexpr int kAnsBlock = 256;  // threads per CTA (8 warps)
-constexpr int kLutBits = 12;
-constexpr int kLutSize = 1 << kLutBits;            // quantile buckets of the decoder index
-constexpr int kLutShift = kPrecision - kLutBits;   // q >> 12
 constexpr uint32_t kMaxSharedAlphabet = 4095;      // bigger alphabets use the global-table path
 
 struct ModelView {
@@ -44,6 +41,7 @@ struct ModelView {
     uint32_t alphabet;
     int32_t min_symbol;
     uint32_t dec_pairs_bytes;  // alphabet * 16: size of the uint4 part of `dec`
+    uint32_t lut_bytes;        // kLutSize (u8 entries, alphabet <= 256) or 2 * kLutSize (u16 entries)
 };
 
 struct AnsParams {
@@ -99,54 +97,76 @@ __device__ __noinline__ void warp_fill_rows(unsigned mask, uint32_t *rows, const
 
 // ---- word rows of the ANS kernels (32-bit shared addresses, rows of kWordRowStride words) -------------
 
-// Results of the cold paths are returned by value: by-reference parameters of a non-inlined function
-// would force the hot loop's cursors into local memory.
-struct RowUpdate {
-    uint32_t ptr;    // new shared-memory cursor of my row
-    uint32_t moved;  // words moved to / from HBM for my row (0 or up to 32)
-    uint32_t failed; // 1 if my row did not fit into its scratch region
-};
+// Per-thread "cold slot" (16 bytes of shared memory per lane): everything a lane needs only when one of its
+// rows is moved to / from HBM lives here, not in registers, so that the hot loops fit 5 CTAs per SM.
+//   encoder: {scratch cursor lo, hi, words of scratch capacity left, words flushed so far | overflow bit}
+//   decoder: {cursor lo, hi (one past the highest word not yet staged), words not yet staged, unused}
+constexpr uint32_t kColdSlotBytes = 16;
+constexpr uint32_t kColdOverflowBit = 0x80000000u;
+
+__device__ __forceinline__ void cold_store(uint32_t slot, const void *ptr, uint32_t a, uint32_t b) {
+    const uint64_t v = (uint64_t)ptr;
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(slot), "r"((uint32_t)v), "r"((uint32_t)(v >> 32)), "r"(a),
+                 "r"(b)
+                 : "memory");
+}
+__device__ __forceinline__ uint4 cold_load(uint32_t slot) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(slot) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint32_t *cold_ptr(const uint4 &v) { return (uint32_t *)(((uint64_t)v.y << 32) | v.x); }
 
 // Encoder, cold: every lane in `mask` has >= 32 words in its row.  The warp writes the first 32 words of
 // each such row to that lane's scratch cursor (one 128-byte store), the lane keeps what is left over.
-__device__ __noinline__ RowUpdate ans_flush_rows_cold(unsigned mask, uint32_t rows_addr, uint32_t row_addr, uint32_t wptr,
-                                                      uint32_t *gptr, uint32_t *gend, int lane) {
-    const bool mine = (mask >> lane) & 1u;
-    const bool fits = gptr + kRowWords <= gend;
-    unsigned todo = __ballot_sync(kFullMask, mine && fits);
+// Returns the lane's new row cursor.
+__device__ __noinline__ uint32_t ans_flush_rows_cold(unsigned mask, uint32_t rows_addr, uint32_t slots_addr,
+                                                     uint32_t row_addr, uint32_t wptr, int lane) {
     __syncwarp();
+    unsigned todo = mask;
     while (todo) {
         const int i = __ffs(todo) - 1;
         todo &= todo - 1;
-        uint32_t *d = (uint32_t *)shfl_u64((uint64_t)gptr, i);
-        st_stream_u32(d + lane, lds_u32(rows_addr + (uint32_t)(i * kWordRowStride + lane) * 4u));
+        const uint4 c = cold_load(slots_addr + (uint32_t)i * kColdSlotBytes);  // broadcast read of lane i's slot
+        if (c.z >= (uint32_t)kRowWords)
+            st_stream_u32(cold_ptr(c) + lane, lds_u32(rows_addr + (uint32_t)(i * kWordRowStride + lane) * 4u));
     }
     __syncwarp();
-    RowUpdate u;
-    u.ptr = wptr;
-    u.moved = 0;
-    u.failed = 0;
-    if (mine) {
+    if ((mask >> lane) & 1u) {
+        const uint32_t slot = slots_addr + (uint32_t)lane * kColdSlotBytes;
+        const uint4 c = cold_load(slot);
+        if (c.z >= (uint32_t)kRowWords)
+            cold_store(slot, cold_ptr(c) + kRowWords, c.z - kRowWords, c.w + kRowWords);
+        else
+            cold_store(slot, cold_ptr(c), c.z, c.w | kColdOverflowBit);  // words dropped, stream flagged
         const uint32_t left = (wptr - row_addr) / 4u - kRowWords;  // 0 .. kCheckEvery-1
         for (uint32_t j = 0; j < left; ++j) sts_u32(row_addr + j * 4u, lds_u32(row_addr + (kRowWords + j) * 4u));
-        u.ptr = row_addr + left * 4u;
-        u.moved = fits ? kRowWords : 0u;
-        u.failed = fits ? 0u : 1u;
+        wptr = row_addr + left * 4u;
     }
     __syncwarp();
-    return u;
+    return wptr;
 }
 
 // Encoder, end of stream: write the remaining cnt_i (< 32) words of every row.
-__device__ __noinline__ void ans_flush_tail_cold(uint32_t rows_addr, uint32_t cnt, uint32_t *gptr, bool ok, int lane) {
-    unsigned todo = __ballot_sync(kFullMask, cnt > 0 && ok);
+__device__ __noinline__ void ans_flush_tail_cold(uint32_t rows_addr, uint32_t slots_addr, uint32_t cnt, int lane) {
     __syncwarp();
+    unsigned todo = __ballot_sync(kFullMask, cnt > 0);
     while (todo) {
         const int i = __ffs(todo) - 1;
         todo &= todo - 1;
-        uint32_t *d = (uint32_t *)shfl_u64((uint64_t)gptr, i);
-        const uint32_t c = __shfl_sync(kFullMask, cnt, i);
-        if ((uint32_t)lane < c) st_stream_u32(d + lane, lds_u32(rows_addr + (uint32_t)(i * kWordRowStride + lane) * 4u));
+        const uint4 c = cold_load(slots_addr + (uint32_t)i * kColdSlotBytes);
+        const uint32_t ci = __shfl_sync(kFullMask, cnt, i);
+        if (c.z >= ci && (uint32_t)lane < ci)
+            st_stream_u32(cold_ptr(c) + lane, lds_u32(rows_addr + (uint32_t)(i * kWordRowStride + lane) * 4u));
+    }
+    __syncwarp();
+    if (cnt > 0) {
+        const uint32_t slot = slots_addr + (uint32_t)lane * kColdSlotBytes;
+        const uint4 c = cold_load(slot);
+        if (c.z >= cnt)
+            cold_store(slot, cold_ptr(c) + cnt, c.z - cnt, c.w + cnt);
+        else
+            cold_store(slot, cold_ptr(c), c.z, c.w | kColdOverflowBit);
     }
     __syncwarp();
 }
@@ -154,48 +174,59 @@ __device__ __noinline__ void ans_flush_tail_cold(uint32_t rows_addr, uint32_t cn
 // Decoder, cold: every lane in `mask` is down to < kCheckEvery staged words and has more in HBM.  The warp
 // loads the next (up to) 32 words below each such lane's cursor; chunks end on 128-byte boundaries of the
 // global address space, so every refill after a stream's first is one aligned line.
-__device__ __noinline__ RowUpdate ans_refill_rows_cold(unsigned mask, uint32_t rows_addr, uint32_t row_addr, uint32_t rptr,
-                                                       const uint32_t *gtop, const uint32_t *gbase, int lane) {
+// Returns {new row cursor, new refill mark (0 when nothing is left in HBM)}.
+struct RefillResult {
+    uint32_t rptr, mark;
+};
+__device__ __noinline__ RefillResult ans_refill_rows_cold(unsigned mask, uint32_t rows_addr, uint32_t slots_addr,
+                                                          uint32_t row_addr, uint32_t rptr, uint32_t mark, int lane) {
     const bool mine = (mask >> lane) & 1u;
     // keep my unread words (they are older than the chunk that is about to arrive, so they go on top)
     const uint32_t left = mine ? (rptr - row_addr) / 4u : 0u;  // 0 .. kCheckEvery-1
     uint32_t keep[kCheckEvery - 1];
 #pragma unroll
     for (int j = 0; j < kCheckEvery - 1; ++j) keep[j] = (uint32_t)j < left ? lds_u32(row_addr + j * 4u) : 0u;
-    const uint32_t *lo = (const uint32_t *)(((uint64_t)(gtop - 1)) & ~(uint64_t)127);
-    if (lo < gbase) lo = gbase;
-    const uint32_t c = mine ? (uint32_t)(gtop - lo) : 0u;
-    if (mine && lo > gbase) prefetch_l2(lo - 1);  // the line below: it is needed ~200 symbols from now
-    unsigned todo = mask;
     __syncwarp();
+    unsigned todo = mask;
+    uint32_t my_c = 0;
     while (todo) {
         const int i = __ffs(todo) - 1;
         todo &= todo - 1;
-        const uint32_t *s = (const uint32_t *)shfl_u64((uint64_t)lo, i);
-        const uint32_t ci = __shfl_sync(kFullMask, c, i);
-        if ((uint32_t)lane < ci) sts_u32(rows_addr + (uint32_t)(i * kWordRowStride + lane) * 4u, ld_stream_u32(s + lane));
+        const uint4 c = cold_load(slots_addr + (uint32_t)i * kColdSlotBytes);
+        const uint32_t *top = cold_ptr(c);
+        // chunk = [max(stream begin, 128-byte line of the top word), top)
+        uint32_t ci = (uint32_t)((((uint64_t)(top - 1)) & 127u) / 4u) + 1u;
+        ci = ci < c.z ? ci : c.z;
+        if ((uint32_t)lane < ci)
+            sts_u32(rows_addr + (uint32_t)(i * kWordRowStride + lane) * 4u, ld_stream_u32(top - ci + lane));
+        if (i == lane) my_c = ci;
     }
     __syncwarp();
-    RowUpdate u;
-    u.ptr = rptr;
-    u.moved = c;
-    u.failed = 0;
+    RefillResult r;
+    r.rptr = rptr;
+    r.mark = mark;
     if (mine) {
+        const uint32_t slot = slots_addr + (uint32_t)lane * kColdSlotBytes;
+        const uint4 c = cold_load(slot);
+        const uint32_t *top = cold_ptr(c) - my_c;
+        cold_store(slot, top, c.z - my_c, 0u);
+        if (c.z - my_c != 0u) prefetch_l2(top - 1);  // the line below: needed ~200 symbols from now
 #pragma unroll
         for (int j = 0; j < kCheckEvery - 1; ++j)
-            if ((uint32_t)j < left) sts_u32(row_addr + (c + j) * 4u, keep[j]);
-        u.ptr = row_addr + (c + left) * 4u;
+            if ((uint32_t)j < left) sts_u32(row_addr + (my_c + j) * 4u, keep[j]);
+        r.rptr = row_addr + (my_c + left) * 4u;
+        r.mark = (c.z - my_c != 0u) ? row_addr + kCheckEvery * 4u : 0u;
     }
     __syncwarp();
-    return u;
+    return r;
 }
 
 // ---- model lookups ----------------------------------------------------------------------------------
 
 // Decoder table of a shared model (built by build_dec_table_kernel):
 //   trip[s] = {cdf[s], cdf[s+1], cdf[s+2], 0}   one 16-byte load yields the interval of s and of s+1
-//   lut[b]  = the symbol that contains quantile b << 12 (u16)
-// A 4096-wide bucket almost never reaches beyond the symbol after lut[b], so the lookup is branch-free:
+//   lut[b]  = the symbol that contains quantile b << kLutShift (u16)
+// A bucket (2^kLutShift quantiles) almost never reaches beyond the symbol after lut[b], so the lookup is branch-free:
 // probe s = lut[b], step to s+1 with selects if the quantile lies beyond cdf[s+1]; only when it also
 // lies beyond cdf[s+2] (several tiny-probability symbols inside one bucket) a cold search runs.
 __device__ __noinline__ uint32_t lookup_far_cold(uint32_t trip_addr, uint32_t alphabet, uint32_t s, uint32_t q) {
@@ -211,9 +242,11 @@ __device__ __noinline__ uint32_t lookup_far_cold(uint32_t trip_addr, uint32_t al
 }
 
 // `word` is any value whose low 24 bits are the quantile q
+template <bool LUT8>
 __device__ __forceinline__ uint32_t lookup_shared(uint32_t trip_addr, uint32_t lut_addr, uint32_t alphabet, uint32_t word,
                                                   uint32_t q, uint32_t &left, uint32_t &right) {
-    uint32_t s = lds_table_u16(lut_addr + ((word >> (kLutShift - 1)) & ((kLutSize - 1) << 1)));
+    uint32_t s = LUT8 ? lds_table_u8(lut_addr + ((word >> kLutShift) & (kLutSize - 1)))
+                      : lds_table_u16(lut_addr + ((word >> (kLutShift - 1)) & ((kLutSize - 1) << 1)));
     uint4 t = lds_table_v4(trip_addr + s * 16u);
     const bool adv = q >= t.y;
     left = adv ? t.y : t.x;
@@ -269,12 +302,15 @@ __device__ __forceinline__ uint64_t warp_max_u64(uint64_t v, int lane) {
 // =====================================================================================================
 // encode
 // =====================================================================================================
+// per-warp staging block in shared memory: word rows, then the 32 cold slots
+constexpr int kWarpStageWords = kWordRowsWords + kWarp * (int)(kColdSlotBytes / 4);
+
 //   SHARED : model 0's encoder table lives in shared memory (index_mode == NONE, small alphabet)
 //   CONTIG : stream k owns symbols[sym_off[k] .. sym_off[k+1]) (else interleaved deal)
 //   PERSYM : a model index per symbol (else one model per stream / model 0)
 //   F64DIV : the table holds double-precision reciprocals and the quotient estimate uses the FP64 pipe
 template <bool SHARED, bool CONTIG, bool PERSYM, bool F64DIV>
-__global__ void __launch_bounds__(kAnsBlock) ans_encode_kernel(const AnsParams p) {
+__global__ void __launch_bounds__(kAnsBlock, 5) ans_encode_kernel(const AnsParams p) {
     extern __shared__ __align__(16) uint32_t smem[];
     __shared__ uint64_t bar;
 
@@ -282,12 +318,13 @@ __global__ void __launch_bounds__(kAnsBlock) ans_encode_kernel(const AnsParams p
     const int warp_in_cta = threadIdx.x >> 5;
     constexpr int kWarpsPerCta = kAnsBlock / 32;
 
-    // shared memory carve-up: [table][word rows][symbol tiles][index tiles]
+    // shared memory carve-up: [table][per warp: word rows + cold slots][symbol tiles][index tiles]
     const uint32_t alphabet = p.model.alphabet;
     const uint32_t table_words = SHARED ? (alphabet + 1) * 4 : 0;
     const uint32_t table_addr = smem_u32_pinned(smem);
-    const uint32_t rows_addr = smem_u32_pinned(smem + table_words + warp_in_cta * kWordRowsWords);
-    uint32_t *sym_tile = smem + table_words + kWarpsPerCta * kWordRowsWords + warp_in_cta * kTileWords;
+    const uint32_t rows_addr = smem_u32_pinned(smem + table_words + warp_in_cta * kWarpStageWords);
+    const uint32_t slots_addr = rows_addr + kWordRowsWords * 4u;
+    uint32_t *sym_tile = smem + table_words + kWarpsPerCta * kWarpStageWords + warp_in_cta * kTileWords;
     uint32_t *idx_tile = sym_tile + kWarpsPerCta * kTileWords;
 
     if (SHARED) stage_table(smem, p.model.enc, (alphabet + 1) * 16u, &bar);
@@ -298,7 +335,7 @@ __global__ void __launch_bounds__(kAnsBlock) ans_encode_kernel(const AnsParams p
     const bool valid = k < K;
     const uint64_t kc = valid ? k : K - 1;  // lanes without a stream shadow the last one (loads only)
 
-    // stream geometry
+    // stream geometry; the scratch cursor and capacity go to my cold slot
     uint64_t n_k = 0, o_k = 0;
     if (valid) {
         if (CONTIG) {
@@ -309,15 +346,17 @@ __global__ void __launch_bounds__(kAnsBlock) ans_encode_kernel(const AnsParams p
             o_k = interleaved_start(N, K, k);
         }
     }
-    uint32_t *gptr = p.scratch + scratch_start(o_k, k);                                  // next word of my region
-    uint32_t *const gbegin = gptr;
-    uint32_t *const gend = valid ? p.scratch + scratch_start(o_k + n_k, k + 1) : gptr;  // capacity limit
+    const uint32_t my_slot = slots_addr + (uint32_t)lane * kColdSlotBytes;
+    {
+        const uint64_t begin = scratch_start(o_k, k);
+        const uint64_t room = valid ? scratch_start(o_k + n_k, k + 1) - begin : 0;
+        cold_store(my_slot, p.scratch + begin, room > 0x7fffffffu ? 0x7fffffffu : (uint32_t)room, 0u);
+    }
 
     uint64_t state = (valid && p.states_in) ? p.states_in[k] : 0;
     const uint32_t row_addr = rows_addr + (uint32_t)lane * (kWordRowStride * 4u);
     uint32_t wptr = row_addr;           // shared address of the next free slot of my row
     uint32_t min_prob = 0xffffffffu;    // running minimum of the probabilities used (0 <=> impossible symbol)
-    bool overflow = false;              // scratch region too small (cannot happen with the sizing above)
     const uint32_t push_shift = valid ? 8u : 32u;  // (state >> 32) >> 32 == 0: lanes without a stream never push
     const uint32_t stream_model = (p.index_mode == 2) ? p.model_index[kc] : 0u;
     const uint32_t n_models = p.model.n_models;
@@ -360,12 +399,7 @@ __global__ void __launch_bounds__(kAnsBlock) ans_encode_kernel(const AnsParams p
     // every kCheckEvery symbols: move rows that reached 32 words to HBM (cold)
     auto check_rows = [&]() {
         const unsigned mask = __ballot_sync(kFullMask, wptr >= row_addr + kRowWords * 4u);
-        if (mask) {
-            const RowUpdate u = ans_flush_rows_cold(mask, rows_addr, row_addr, wptr, gptr, gend, lane);
-            wptr = u.ptr;
-            gptr += u.moved;
-            overflow |= u.failed != 0u;
-        }
+        if (mask) wptr = ans_flush_rows_cold(mask, rows_addr, slots_addr, row_addr, wptr, lane);
     };
 
     if (!CONTIG) {
@@ -378,7 +412,7 @@ __global__ void __launch_bounds__(kAnsBlock) ans_encode_kernel(const AnsParams p
             }
         }
         if (g.T > 1) {
-            uint64_t rows_left = g.T - 1;  // full rows T-2 .. 0
+            const uint64_t rows_total = g.T - 1;  // full rows T-2 .. 0
             const int32_t *ps = p.symbols_in + (g.T - 2) * K + kc;
             const uint32_t *pm = PERSYM ? p.model_index + (g.T - 2) * K + kc : nullptr;
             // batches of kCheckEvery symbols; the loads of the next batch are in flight while this one is coded
@@ -402,8 +436,9 @@ __global__ void __launch_bounds__(kAnsBlock) ans_encode_kernel(const AnsParams p
 #pragma unroll
                 for (int u = 0; u < kCheckEvery; ++u) encode_one(buf[which][u], mbuf[which][u]);
             };
-            uint64_t batches = rows_left / kCheckEvery;
-            rows_left -= batches * kCheckEvery;
+            // (a stream of >= 2^34 symbols is split by the caller; 32-bit counters keep the loop lean)
+            uint32_t batches = (uint32_t)(rows_total / kCheckEvery);
+            uint32_t rows_left = (uint32_t)(rows_total - (uint64_t)batches * kCheckEvery);
             if (batches > 0) {
                 load_batch(0);
                 while (batches > 2) {
@@ -469,29 +504,24 @@ __global__ void __launch_bounds__(kAnsBlock) ans_encode_kernel(const AnsParams p
         wptr += 4u;
     }
     check_rows();
-    uint32_t cnt = (wptr - row_addr) / 4u;  // < 32
-    {
-        const bool ok = gptr + cnt <= gend;
-        ans_flush_tail_cold(rows_addr, cnt, gptr, ok, lane);
-        if (cnt > 0 && !ok) {
-            overflow = true;
-            cnt = 0;
-        }
-    }
+    ans_flush_tail_cold(rows_addr, slots_addr, (wptr - row_addr) / 4u, lane);  // < 32 words each
+    const uint4 fin = cold_load(my_slot);
+    const uint32_t len = fin.w & ~kColdOverflowBit;
     if (valid) {
         if (p.states_out) p.states_out[k] = state;
         if (min_prob == 0u) report_error(p.status, kErrImpossibleSymbol, k);
-        if (overflow) report_error(p.status, kErrOutOfSpace, k);
+        if (fin.w & kColdOverflowBit) report_error(p.status, kErrOutOfSpace, k);
     }
     // ---- K6: place my stream in the dense container ---------------------------------------------------
-    compact_tail<kAnsBlock>(p.compact, tile, k, K, valid, gbegin, valid ? (uint32_t)(gptr - gbegin) + cnt : 0u, p.status);
+    compact_tail<kAnsBlock>(p.compact, tile, k, K, valid, cold_ptr(fin) - len, valid ? len : 0u, p.status);
 }
 
 // =====================================================================================================
 // decode
 // =====================================================================================================
-template <bool SHARED, bool CONTIG, bool PERSYM>
-__global__ void __launch_bounds__(kAnsBlock) ans_decode_kernel(const AnsParams p) {
+//   LUT8 : (SHARED only) the quantile index has u8 entries (alphabet <= 256)
+template <bool SHARED, bool CONTIG, bool PERSYM, bool LUT8>
+__global__ void __launch_bounds__(kAnsBlock, 5) ans_decode_kernel(const AnsParams p) {
     extern __shared__ __align__(16) uint32_t smem[];
     __shared__ uint64_t bar;
 
@@ -500,15 +530,16 @@ __global__ void __launch_bounds__(kAnsBlock) ans_decode_kernel(const AnsParams p
     constexpr int kWarpsPerCta = kAnsBlock / 32;
 
     const uint32_t alphabet = p.model.alphabet;
-    const uint32_t table_words = SHARED ? (p.model.dec_pairs_bytes / 4 + kLutSize / 2) : 0;
+    const uint32_t table_words = SHARED ? (p.model.dec_pairs_bytes + p.model.lut_bytes) / 4 : 0;
     const uint32_t pairs_addr = smem_u32_pinned(smem);
     uint32_t lut_addr = pairs_addr + (SHARED ? p.model.dec_pairs_bytes : 0);
     asm volatile("" : "+r"(lut_addr));
-    const uint32_t rows_addr = smem_u32_pinned(smem + table_words + warp_in_cta * kWordRowsWords);
-    uint32_t *sym_tile = smem + table_words + kWarpsPerCta * kWordRowsWords + warp_in_cta * kTileWords;
+    const uint32_t rows_addr = smem_u32_pinned(smem + table_words + warp_in_cta * kWarpStageWords);
+    const uint32_t slots_addr = rows_addr + kWordRowsWords * 4u;
+    uint32_t *sym_tile = smem + table_words + kWarpsPerCta * kWarpStageWords + warp_in_cta * kTileWords;
     uint32_t *idx_tile = sym_tile + kWarpsPerCta * kTileWords;
 
-    if (SHARED) stage_table(smem, p.model.dec, p.model.dec_pairs_bytes + kLutSize * 2u, &bar);
+    if (SHARED) stage_table(smem, p.model.dec, p.model.dec_pairs_bytes + p.model.lut_bytes, &bar);
 
     const uint64_t K = p.K, N = p.N;
     const uint64_t k = (uint64_t)blockIdx.x * kAnsBlock + threadIdx.x;
@@ -517,32 +548,40 @@ __global__ void __launch_bounds__(kAnsBlock) ans_decode_kernel(const AnsParams p
     const bool raw = (p.flags & 1u) != 0;
 
     uint64_t n_k = 0, o_k = 0;
-    const uint32_t *gbase = p.words;  // first word of my stream
-    const uint32_t *gtop = p.words;   // one past the highest word that is not yet staged in my row
-    if (valid) {
-        if (CONTIG) {
-            o_k = p.sym_off[k];
-            n_k = p.sym_off[k + 1] - o_k;
-        }
-        gbase = p.words + p.offsets[k];
-        gtop = p.words + p.offsets[k + 1];
-    }
+    const uint32_t my_slot = slots_addr + (uint32_t)lane * kColdSlotBytes;
     const uint32_t row_addr = rows_addr + (uint32_t)lane * (kWordRowStride * 4u);
     uint32_t rptr = row_addr;  // my row holds the unread words [row_addr, rptr)
+    uint32_t mark = 0;         // row_addr + 16 while words remain in HBM (refill when rptr drops below), else 0
+    {
+        uint64_t begin = 0, end = 0;
+        if (valid) {
+            if (CONTIG) {
+                o_k = p.sym_off[k];
+                n_k = p.sym_off[k + 1] - o_k;
+            }
+            begin = p.offsets[k];
+            end = p.offsets[k + 1];
+        }
+        const uint64_t len = end - begin;
+        // (a stream of >= 2^32 words does not exist: the encoder's lengths are 32-bit)
+        cold_store(my_slot, p.words + end, (uint32_t)len, 0u);
+        mark = len ? row_addr + kCheckEvery * 4u : 0u;
+    }
     const uint32_t n_models = p.model.n_models;
-    const uint32_t min_symbol = (uint32_t)p.model.min_symbol;
+    uint32_t min_symbol = (uint32_t)p.model.min_symbol;
+    asm volatile("" : "+r"(min_symbol));
     const uint32_t stream_model = (p.index_mode == 2) ? p.model_index[kc] : 0u;
 
     // every kCheckEvery symbols: rows that are down to < kCheckEvery words get the next 32 (cold).  The first
     // chunk of a stream only reaches down to the next 128-byte boundary and may be shorter than
     // kCheckEvery words, hence the loop (it runs twice at most).
     auto check_rows = [&]() {
-        unsigned mask = __ballot_sync(kFullMask, rptr < row_addr + kCheckEvery * 4u && gtop != gbase);
+        unsigned mask = __ballot_sync(kFullMask, rptr < mark);
         while (mask) {
-            const RowUpdate u = ans_refill_rows_cold(mask, rows_addr, row_addr, rptr, gtop, gbase, lane);
-            rptr = u.ptr;
-            gtop -= u.moved;
-            mask = __ballot_sync(kFullMask, rptr < row_addr + kCheckEvery * 4u && gtop != gbase);
+            const RefillResult u = ans_refill_rows_cold(mask, rows_addr, slots_addr, row_addr, rptr, mark, lane);
+            rptr = u.rptr;
+            mark = u.mark;
+            mask = __ballot_sync(kFullMask, rptr < mark);
         }
     };
 
@@ -575,7 +614,7 @@ __global__ void __launch_bounds__(kAnsBlock) ans_decode_kernel(const AnsParams p
         const uint32_t q = lo & kQuantileMask;
         uint32_t left, right, s;
         if (SHARED) {
-            s = lookup_shared(pairs_addr, lut_addr, alphabet, lo, q, left, right);
+            s = lookup_shared<LUT8>(pairs_addr, lut_addr, alphabet, lo, q, left, right);
         } else {
             m = m < n_models ? m : n_models - 1;  // decoding cannot fail (stack.rs:1062-1065)
             s = lookup_global(p.model.cdf + (uint64_t)m * (alphabet + 1), alphabet, q, left, right);
@@ -596,8 +635,10 @@ __global__ void __launch_bounds__(kAnsBlock) ans_decode_kernel(const AnsParams p
         if (g.T > 1) {
             int32_t *po = p.symbols_out + kc;
             const uint32_t *pm = PERSYM ? p.model_index + kc : nullptr;
-            uint64_t rows_left = g.T - 1;  // full rows 0 .. T-2
-            while (rows_left >= (uint64_t)kCheckEvery) {
+            const uint64_t rows_total = g.T - 1;  // full rows 0 .. T-2
+            uint32_t batches = (uint32_t)(rows_total / kCheckEvery);
+            uint32_t rows_left = (uint32_t)(rows_total - (uint64_t)batches * kCheckEvery);
+            for (; batches > 0; --batches) {
                 uint32_t mbuf[kCheckEvery];
 #pragma unroll
                 for (int u = 0; u < kCheckEvery; ++u) mbuf[u] = PERSYM ? ld_stream_u32(pm + (uint64_t)u * K) : stream_model;
@@ -609,7 +650,6 @@ __global__ void __launch_bounds__(kAnsBlock) ans_decode_kernel(const AnsParams p
                     po += K;
                 }
                 check_rows();
-                rows_left -= kCheckEvery;
             }
             while (rows_left > 0) {  // at most kCheckEvery-1 more symbols
                 const int32_t sym = decode_one(PERSYM ? ld_stream_u32(pm) : stream_model);
@@ -650,7 +690,7 @@ __global__ void __launch_bounds__(kAnsBlock) ans_decode_kernel(const AnsParams p
 
     if (valid) {
         if (p.states_out) p.states_out[k] = ((uint64_t)hi << 32) | lo;
-        if (p.words_left) p.words_left[k] = (uint64_t)(gtop - gbase) + (uint64_t)((rptr - row_addr) / 4u);
+        if (p.words_left) p.words_left[k] = (uint64_t)cold_load(my_slot).z + (uint64_t)((rptr - row_addr) / 4u);
         if (trailing_zero) report_error(p.status, kErrTrailingZero, k);
     }
 }

@@ -90,6 +90,7 @@ struct ctr_model_s {
     uint4 *d_enc = nullptr;     // [n_models][alphabet], built on first encode
     uint32_t *d_dec = nullptr;  // model 0: pairs + bucket index, built on first decode
     uint32_t dec_pairs_bytes = 0;
+    uint32_t lut_bytes = 0;  // kLutSize (u8 index) for alphabets <= 256, else 2 * kLutSize (u16)
     bool shared_ok = false;  // small enough for the shared-memory table kernels
     bool enc_f64 = false;    // d_enc holds double-precision reciprocals (CTR_DIV=f64)
 };
@@ -106,6 +107,7 @@ int model_alloc(uint32_t n_models, uint32_t alphabet, int32_t min_symbol, ctr_mo
     m->alphabet = alphabet;
     m->min_symbol = min_symbol;
     m->dec_pairs_bytes = alphabet <= kMaxSharedAlphabet ? alphabet * 16u : 0u;
+    m->lut_bytes = alphabet <= 256 ? (uint32_t)kLutSize : 2u * kLutSize;
     m->shared_ok = alphabet <= kMaxSharedAlphabet;
     cudaError_t e = cudaMalloc(&m->d_cdf, (size_t)n_models * ((size_t)alphabet + 1) * 4);
     if (e != cudaSuccess) {
@@ -140,9 +142,10 @@ int ensure_enc_table(ctr_model_s *m, cudaStream_t s) {
 
 int ensure_dec_table(ctr_model_s *m, cudaStream_t s) {
     if (m->d_dec || !m->shared_ok) return CTR_OK;
-    CUDA_TRY(cudaMalloc(&m->d_dec, m->dec_pairs_bytes + kLutSize * 2));
+    CUDA_TRY(cudaMalloc(&m->d_dec, m->dec_pairs_bytes + m->lut_bytes));
     const uint32_t threads = m->alphabet + 2 > (uint32_t)kLutSize ? m->alphabet + 2 : (uint32_t)kLutSize;
-    build_dec_table_kernel<<<grid_for(threads, 256), 256, 0, s>>>(m->d_cdf, m->alphabet, m->dec_pairs_bytes, m->d_dec);
+    build_dec_table_kernel<<<grid_for(threads, 256), 256, 0, s>>>(m->d_cdf, m->alphabet, m->dec_pairs_bytes,
+                                                                  m->lut_bytes == (uint32_t)kLutSize ? 1 : 0, m->d_dec);
     LAUNCH_CHECK("build_dec_table_kernel");
     return CTR_OK;
 }
@@ -184,6 +187,7 @@ ModelView model_view(const ctr_model_s *m) {
     v.alphabet = m->alphabet;
     v.min_symbol = m->min_symbol;
     v.dec_pairs_bytes = m->dec_pairs_bytes;
+    v.lut_bytes = m->lut_bytes;
     return v;
 }
 
@@ -464,8 +468,9 @@ size_t coder_smem_bytes(size_t table_bytes, const ctr_layout *L, int warps) {
     const bool contig = L->sym_offsets_dev != nullptr;
     int tiles = 0;  // 32x32 transposition tiles
     if (contig) tiles += 1 + (L->model_index_mode == CTR_INDEX_PER_SYMBOL ? 1 : 0);
-    // word rows are sized for the ANS kernels (35-word rows); the range kernels use 33 of each 35
-    return table_bytes + (size_t)warps * kWordRowsWords * 4 + (size_t)tiles * warps * kTileWords * 4;
+    // the per-warp staging block is sized for the ANS kernels (35-word rows + cold slots); the range
+    // kernels use a 33-word-row tile of it
+    return table_bytes + (size_t)warps * kWarpStageWords * 4 + (size_t)tiles * warps * kTileWords * 4;
 }
 
 // SHARED implies one model for the whole batch, hence no per-symbol index.
@@ -495,7 +500,8 @@ struct AnsEncodeLauncher {
 struct AnsDecodeLauncher {
     static int run(bool shared, bool contig, bool persym, bool, const AnsParams &p, size_t smem, unsigned grid,
                    cudaStream_t s) {
-        CTR_DISPATCH(ans_decode_kernel, 1);
+        if (shared && p.model.lut_bytes == (uint32_t)kLutSize) CTR_DISPATCH(ans_decode_kernel, 1, CTR_COMMA true);
+        CTR_DISPATCH(ans_decode_kernel, 1, CTR_COMMA false);
     }
 };
 struct RangeEncodeLauncher {
@@ -589,7 +595,7 @@ int decode_common(ctr_model_t model, const uint32_t *words, const uint64_t *offs
 
     const bool shared = use_shared_tables(model, L);
     const bool contig = L->sym_offsets_dev != nullptr;
-    const size_t smem = coder_smem_bytes(shared ? (size_t)model->dec_pairs_bytes + kLutSize * 2 : 0, L, kAnsBlock / 32);
+    const size_t smem = coder_smem_bytes(shared ? (size_t)model->dec_pairs_bytes + model->lut_bytes : 0, L, kAnsBlock / 32);
     return DecLauncher::run(shared, contig, L->model_index_mode == CTR_INDEX_PER_SYMBOL, false, p, smem,
                             grid_for(L->n_streams, kAnsBlock), s);
 }

@@ -55,6 +55,11 @@ __device__ __forceinline__ uint32_t lds_table_u16(uint32_t addr) {
     asm("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr));
     return (uint32_t)v;
 }
+__device__ __forceinline__ uint32_t lds_table_u8(uint32_t addr) {
+    uint16_t v;
+    asm("ld.shared.u8 %0, [%1];" : "=h"(v) : "r"(addr));
+    return (uint32_t)v;
+}
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ uint2 lds_table_v2(uint32_t addr) {
     uint2 v;
@@ -66,6 +71,12 @@ __device__ __forceinline__ uint4 lds_table_v4(uint32_t addr) {
     asm("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
     return v;
 }
+
+// decoder quantile index: 2^kLutBits buckets of 2^kLutShift quantiles each; u8 entries (2 KB) for alphabets
+// of up to 256 symbols, u16 entries (4 KB) otherwise
+constexpr int kLutBits = 11;
+constexpr int kLutSize = 1 << kLutBits;
+constexpr int kLutShift = kPrecision - kLutBits;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 // Same, but opaque to the optimiser: the value stays in a register instead of being rematerialised from the

@@ -124,15 +124,16 @@ __global__ void build_enc_table_kernel(const uint32_t *cdf, uint32_t n_models, u
 }
 
 // decoder table of model 0 (see lookup_shared in ans_kernels.cuh):
-//   trip[s] = {cdf[s], cdf[s+1], cdf[s+2] (2^24 past the end), 0}, then lut[b] (u16) = the last symbol whose
-//   left cumulative is <= b << 12, i.e. the symbol containing the first quantile of bucket b.
-__global__ void build_dec_table_kernel(const uint32_t *cdf, uint32_t alphabet, uint32_t trip_bytes, uint32_t *dec) {
+//   trip[s] = {cdf[s], cdf[s+1], cdf[s+2] (2^24 past the end), 0}, then lut[b] (u8 or u16) = the last symbol whose
+//   left cumulative is <= b << kLutShift, i.e. the symbol containing the first quantile of bucket b.
+__global__ void build_dec_table_kernel(const uint32_t *cdf, uint32_t alphabet, uint32_t trip_bytes, int lut8, uint32_t *dec) {
     const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
     uint4 *trip = reinterpret_cast<uint4 *>(dec);
-    uint16_t *lut = reinterpret_cast<uint16_t *>(dec + trip_bytes / 4);
+    uint16_t *lut16 = reinterpret_cast<uint16_t *>(dec + trip_bytes / 4);
+    uint8_t *lut8p = reinterpret_cast<uint8_t *>(dec + trip_bytes / 4);
     if (tid < alphabet) trip[tid] = make_uint4(cdf[tid], cdf[tid + 1], tid + 2 <= alphabet ? cdf[tid + 2] : kTotal, 0u);
-    if (tid < (uint32_t)(1u << 12)) {
-        const uint32_t q = tid << 12;
+    if (tid < (uint32_t)kLutSize) {
+        const uint32_t q = tid << kLutShift;
         uint32_t lo = 0, hi = alphabet - 1;
         while (lo < hi) {
             const uint32_t mid = (lo + hi + 1) >> 1;
@@ -141,7 +142,10 @@ __global__ void build_dec_table_kernel(const uint32_t *cdf, uint32_t alphabet, u
             else
                 hi = mid - 1;
         }
-        lut[tid] = (uint16_t)lo;
+        if (lut8)
+            lut8p[tid] = (uint8_t)lo;
+        else
+            lut16[tid] = (uint16_t)lo;
     }
 }
 
