@@ -24,6 +24,8 @@
 //
 // Per-stream results equal the reference's `AnsCoder` (src/stream/stack.rs:1014-1100) word for word.
 #pragma once
+#include <type_traits>
+
 #include "compact.cuh"
 #include "device_utils.cuh"
 
@@ -36,12 +38,11 @@ struct ModelView {
     const uint32_t *cdf;   // [n_models][alphabet + 1]
     const uint4 *enc;      // [n_models][alphabet + 1] {left, prob, reciprocal lo, hi}; entry [alphabet] is
                            // the all-zero sentinel that out-of-range symbols are clamped to
-    const uint32_t *dec;   // model 0 only: uint4[alphabet] {cdf[s], cdf[s+1], cdf[s+2], 0} ++ lut u16[kLutSize]
+    const uint32_t *dec;   // model 0 only: quantile index uint2[kLutSize] ++ cdf u32[alphabet + 2] (padded to 16 B)
     uint32_t n_models;
     uint32_t alphabet;
     int32_t min_symbol;
-    uint32_t dec_pairs_bytes;  // alphabet * 16: size of the uint4 part of `dec`
-    uint32_t lut_bytes;        // kLutSize (u8 entries, alphabet <= 256) or 2 * kLutSize (u16 entries)
+    uint32_t dec_cdf_bytes;    // size of the cdf part of `dec`: (alphabet + 2) * 4 rounded up to 16
 };
 
 struct AnsParams {
@@ -223,17 +224,19 @@ __device__ __noinline__ RefillResult ans_refill_rows_cold(unsigned mask, uint32_
 
 // ---- model lookups ----------------------------------------------------------------------------------
 
-// Decoder table of a shared model (built by build_dec_table_kernel):
-//   trip[s] = {cdf[s], cdf[s+1], cdf[s+2], 0}   one 16-byte load yields the interval of s and of s+1
-//   lut[b]  = the symbol that contains quantile b << kLutShift (u16)
-// A bucket (2^kLutShift quantiles) almost never reaches beyond the symbol after lut[b], so the lookup is branch-free:
-// probe s = lut[b], step to s+1 with selects if the quantile lies beyond cdf[s+1]; only when it also
-// lies beyond cdf[s+2] (several tiny-probability symbols inside one bucket) a cold search runs.
-__device__ __noinline__ uint32_t lookup_far_cold(uint32_t trip_addr, uint32_t alphabet, uint32_t s, uint32_t q) {
+// Decoder table of a shared model (built by build_dec_table_kernel), staged in shared memory:
+//   lut[b] (8 bytes) describes the symbol s that contains the first quantile of bucket b (b = q >> 12):
+//       x = cdf[s] | (s & 0xff) << 24,   y = cdf[s+1] | (s >> 8) << 25
+//     One 8-byte load resolves every quantile whose bucket does not reach beyond s.  Otherwise the
+//     quantile belongs to a later symbol; the (few) lanes concerned read cdf[s+2] and step to s+1, and
+//     only if that is not enough either (several tiny-probability symbols in one bucket) a cold binary
+//     search runs.
+//   cdf[0 .. alphabet] is the plain CDF row, cdf[alphabet + 1] = 2^24 pads the last probe.
+__device__ __noinline__ uint32_t lookup_far_cold(uint32_t cdf_addr, uint32_t alphabet, uint32_t s, uint32_t q) {
     uint32_t lo = s + 1, hi = alphabet - 1;  // cdf[s + 1] <= q is known
     while (lo < hi) {
         const uint32_t mid = (lo + hi + 1) >> 1;
-        if (lds_table_u32(trip_addr + mid * 16u) <= q)
+        if (lds_table_u32(cdf_addr + mid * 4u) <= q)
             lo = mid;
         else
             hi = mid - 1;
@@ -241,22 +244,28 @@ __device__ __noinline__ uint32_t lookup_far_cold(uint32_t trip_addr, uint32_t al
     return lo;
 }
 
-// `word` is any value whose low 24 bits are the quantile q
-template <bool LUT8>
-__device__ __forceinline__ uint32_t lookup_shared(uint32_t trip_addr, uint32_t lut_addr, uint32_t alphabet, uint32_t word,
+// `word` is any value whose low 24 bits are the quantile q; SMALL: alphabet <= 256 (s fits the top byte of x)
+template <bool SMALL>
+__device__ __forceinline__ uint32_t lookup_shared(uint32_t lut_addr, uint32_t cdf_addr, uint32_t alphabet, uint32_t word,
                                                   uint32_t q, uint32_t &left, uint32_t &right) {
-    uint32_t s = LUT8 ? lds_table_u8(lut_addr + ((word >> kLutShift) & (kLutSize - 1)))
-                      : lds_table_u16(lut_addr + ((word >> (kLutShift - 1)) & ((kLutSize - 1) << 1)));
-    uint4 t = lds_table_v4(trip_addr + s * 16u);
-    const bool adv = q >= t.y;
-    left = adv ? t.y : t.x;
-    right = adv ? t.z : t.y;
-    s += adv ? 1u : 0u;
+    const uint2 e = lds_table_v2(lut_addr + ((word >> (kLutShift - 3)) & ((kLutSize - 1) << 3)));
+    uint32_t s = e.x >> 24;
+    left = e.x & kQuantileMask;
+    right = e.y;
+    if (!SMALL) {
+        s |= (e.y >> 25) << 8;
+        right = e.y & 0x1ffffffu;
+    }
+    const bool beyond = q >= right;  // the bucket straddles the boundary and q lies past it
+    uint32_t next = right;
+    if (beyond) next = lds_table_u32(cdf_addr + (s + 2) * 4u);
+    left = beyond ? right : left;
+    right = beyond ? next : right;
+    s += beyond ? 1u : 0u;
     if (q >= right) {
-        s = lookup_far_cold(trip_addr, alphabet, s, q);
-        t = lds_table_v4(trip_addr + s * 16u);
-        left = t.x;
-        right = t.y;
+        s = lookup_far_cold(cdf_addr, alphabet, s, q);
+        left = lds_table_u32(cdf_addr + s * 4u);
+        right = lds_table_u32(cdf_addr + s * 4u + 4u);
     }
     return s;
 }
@@ -413,26 +422,32 @@ __global__ void __launch_bounds__(kAnsBlock, 5) ans_encode_kernel(const AnsParam
         }
         if (g.T > 1) {
             const uint64_t rows_total = g.T - 1;  // full rows T-2 .. 0
-            const int32_t *ps = p.symbols_in + (g.T - 2) * K + kc;
-            const uint32_t *pm = PERSYM ? p.model_index + (g.T - 2) * K + kc : nullptr;
+            const char *ps = reinterpret_cast<const char *>(p.symbols_in + (g.T - 2) * K + kc);
+            const char *pm = PERSYM ? reinterpret_cast<const char *>(p.model_index + (g.T - 2) * K + kc) : nullptr;
+            uint64_t row_bytes = K * 4u;  // distance between consecutive symbols of a stream
+            asm volatile("" : "+l"(row_bytes));
             // batches of kCheckEvery symbols; the loads of the next batch are in flight while this one is coded
             int32_t buf[2][kCheckEvery];
             uint32_t mbuf[2][kCheckEvery];
             auto load_batch = [&](int which) {
 #pragma unroll
                 for (int u = 0; u < kCheckEvery; ++u) {
-                    buf[which][u] = ld_stream_s32(ps);
-                    ps -= K;
+                    buf[which][u] = ld_stream_s32(reinterpret_cast<const int32_t *>(ps));
+                    ps -= row_bytes;
                     if (PERSYM) {
-                        mbuf[which][u] = ld_stream_u32(pm);
-                        pm -= K;
+                        mbuf[which][u] = ld_stream_u32(reinterpret_cast<const uint32_t *>(pm));
+                        pm -= row_bytes;
                     } else {
                         mbuf[which][u] = stream_model;
                     }
                 }
             };
-            auto code_batch = [&](int which) {
+            // The row check (a potential call into the cold path) comes first, then the loads of the next
+            // batch are issued, then this batch is coded: no load is in flight across the call site, so
+            // the register shuffling around it never waits for memory.
+            auto code_batch = [&](int which, bool load_next) {
                 check_rows();  // room for kCheckEvery more words in every row
+                if (load_next) load_batch(which ^ 1);
 #pragma unroll
                 for (int u = 0; u < kCheckEvery; ++u) encode_one(buf[which][u], mbuf[which][u]);
             };
@@ -442,28 +457,25 @@ __global__ void __launch_bounds__(kAnsBlock, 5) ans_encode_kernel(const AnsParam
             if (batches > 0) {
                 load_batch(0);
                 while (batches > 2) {
-                    load_batch(1);
-                    code_batch(0);
-                    load_batch(0);
-                    code_batch(1);
+                    code_batch(0, true);
+                    code_batch(1, true);
                     batches -= 2;
                 }
                 if (batches == 2) {
-                    load_batch(1);
-                    code_batch(0);
-                    code_batch(1);
+                    code_batch(0, true);
+                    code_batch(1, false);
                 } else {
-                    code_batch(0);
+                    code_batch(0, false);
                 }
             }
             check_rows();
             while (rows_left > 0) {  // at most kCheckEvery-1 more symbols
-                const int32_t sym = ld_stream_s32(ps);
-                ps -= K;
+                const int32_t sym = ld_stream_s32(reinterpret_cast<const int32_t *>(ps));
+                ps -= row_bytes;
                 uint32_t m = stream_model;
                 if (PERSYM) {
-                    m = ld_stream_u32(pm);
-                    pm -= K;
+                    m = ld_stream_u32(reinterpret_cast<const uint32_t *>(pm));
+                    pm -= row_bytes;
                 }
                 encode_one(sym, m);
                 rows_left -= 1;
@@ -519,30 +531,35 @@ __global__ void __launch_bounds__(kAnsBlock, 5) ans_encode_kernel(const AnsParam
 // =====================================================================================================
 // decode
 // =====================================================================================================
-//   LUT8 : (SHARED only) the quantile index has u8 entries (alphabet <= 256)
-template <bool SHARED, bool CONTIG, bool PERSYM, bool LUT8>
-__global__ void __launch_bounds__(kAnsBlock, 5) ans_decode_kernel(const AnsParams p) {
+//   SMALL : (SHARED only) alphabet <= 256
+// With a shared model and the interleaved layout the CTA is 1024 threads so that the 32 KB quantile index is
+// staged once per SM; otherwise (transposition tiles, or global tables: nothing to amortise) 256 threads.
+constexpr int kDecBlockShared = 1024;
+template <bool SHARED, bool CONTIG, bool PERSYM, bool SMALL>
+__global__ void __launch_bounds__((SHARED && !CONTIG) ? kDecBlockShared : kAnsBlock, (SHARED && !CONTIG) ? 1 : 2)
+    ans_decode_kernel(const AnsParams p) {
     extern __shared__ __align__(16) uint32_t smem[];
     __shared__ uint64_t bar;
 
+    constexpr int kBlock = (SHARED && !CONTIG) ? kDecBlockShared : kAnsBlock;
     const int lane = threadIdx.x & 31;
     const int warp_in_cta = threadIdx.x >> 5;
-    constexpr int kWarpsPerCta = kAnsBlock / 32;
+    constexpr int kWarpsPerCta = kBlock / 32;
 
     const uint32_t alphabet = p.model.alphabet;
-    const uint32_t table_words = SHARED ? (p.model.dec_pairs_bytes + p.model.lut_bytes) / 4 : 0;
-    const uint32_t pairs_addr = smem_u32_pinned(smem);
-    uint32_t lut_addr = pairs_addr + (SHARED ? p.model.dec_pairs_bytes : 0);
-    asm volatile("" : "+r"(lut_addr));
+    const uint32_t table_words = SHARED ? (kLutBytes + p.model.dec_cdf_bytes) / 4 : 0;
+    const uint32_t lut_addr = smem_u32_pinned(smem);
+    uint32_t cdf_addr = lut_addr + kLutBytes;
+    asm volatile("" : "+r"(cdf_addr));
     const uint32_t rows_addr = smem_u32_pinned(smem + table_words + warp_in_cta * kWarpStageWords);
     const uint32_t slots_addr = rows_addr + kWordRowsWords * 4u;
     uint32_t *sym_tile = smem + table_words + kWarpsPerCta * kWarpStageWords + warp_in_cta * kTileWords;
     uint32_t *idx_tile = sym_tile + kWarpsPerCta * kTileWords;
 
-    if (SHARED) stage_table(smem, p.model.dec, p.model.dec_pairs_bytes + p.model.lut_bytes, &bar);
+    if (SHARED) stage_table(smem, p.model.dec, kLutBytes + p.model.dec_cdf_bytes, &bar);
 
     const uint64_t K = p.K, N = p.N;
-    const uint64_t k = (uint64_t)blockIdx.x * kAnsBlock + threadIdx.x;
+    const uint64_t k = (uint64_t)blockIdx.x * kBlock + threadIdx.x;
     const bool valid = k < K;
     const uint64_t kc = valid ? k : K - 1;
     const bool raw = (p.flags & 1u) != 0;
@@ -614,14 +631,16 @@ __global__ void __launch_bounds__(kAnsBlock, 5) ans_decode_kernel(const AnsParam
         const uint32_t q = lo & kQuantileMask;
         uint32_t left, right, s;
         if (SHARED) {
-            s = lookup_shared<LUT8>(pairs_addr, lut_addr, alphabet, lo, q, left, right);
+            s = lookup_shared<SMALL>(lut_addr, cdf_addr, alphabet, lo, q, left, right);
         } else {
             m = m < n_models ? m : n_models - 1;  // decoding cannot fail (stack.rs:1062-1065)
             s = lookup_global(p.model.cdf + (uint64_t)m * (alphabet + 1), alphabet, q, left, right);
         }
-        const uint64_t st = (((uint64_t)hi << 32 | lo) >> kPrecision) * (uint64_t)(right - left) + (uint64_t)(q - left);
-        lo = (uint32_t)st;
-        hi = (uint32_t)(st >> 32);
+        // state = (state >> 24) * prob + (q - left), in 32-bit pieces (state >> 24 has 40 bits)
+        const uint32_t prob = right - left;
+        const uint64_t t = (uint64_t)__funnelshift_r(lo, hi, kPrecision) * prob + (uint64_t)(q - left);
+        hi = (uint32_t)(t >> 32) + (hi >> kPrecision) * prob;
+        lo = (uint32_t)t;
         if (hi == 0u && rptr != row_addr) {  // stack.rs:1091-1097
             hi = lo;
             rptr -= 4u;
@@ -633,32 +652,51 @@ __global__ void __launch_bounds__(kAnsBlock, 5) ans_decode_kernel(const AnsParam
     if (!CONTIG) {
         const Interleave g = interleave_of(N, K);
         if (g.T > 1) {
-            int32_t *po = p.symbols_out + kc;
-            const uint32_t *pm = PERSYM ? p.model_index + kc : nullptr;
+            char *po = reinterpret_cast<char *>(p.symbols_out + kc);
+            const char *pm = PERSYM ? reinterpret_cast<const char *>(p.model_index + kc) : nullptr;
+            uint64_t row_bytes = K * 4u;  // distance between consecutive symbols of a stream
+            asm volatile("" : "+l"(row_bytes));
             const uint64_t rows_total = g.T - 1;  // full rows 0 .. T-2
-            uint32_t batches = (uint32_t)(rows_total / kCheckEvery);
-            uint32_t rows_left = (uint32_t)(rows_total - (uint64_t)batches * kCheckEvery);
-            for (; batches > 0; --batches) {
-                uint32_t mbuf[kCheckEvery];
+            // FULL: every lane of the warp owns a stream, so nothing in the loop is predicated on `valid`
+            auto run_rows = [&](auto full_tag) {
+                constexpr bool FULL = decltype(full_tag)::value;
+                uint32_t batches = (uint32_t)(rows_total / kCheckEvery);
+                uint32_t rows_left = (uint32_t)(rows_total - (uint64_t)batches * kCheckEvery);
+                for (; batches > 0; --batches) {
+                    uint32_t mbuf[kCheckEvery];
 #pragma unroll
-                for (int u = 0; u < kCheckEvery; ++u) mbuf[u] = PERSYM ? ld_stream_u32(pm + (uint64_t)u * K) : stream_model;
-                if (PERSYM) pm += (uint64_t)kCheckEvery * K;
+                    for (int u = 0; u < kCheckEvery; ++u) {
+                        mbuf[u] = stream_model;
+                        if (PERSYM) {
+                            mbuf[u] = ld_stream_u32(reinterpret_cast<const uint32_t *>(pm));
+                            pm += row_bytes;
+                        }
+                    }
 #pragma unroll
-                for (int u = 0; u < kCheckEvery; ++u) {
-                    const int32_t sym = decode_one(mbuf[u]);
-                    if (valid) st_stream_s32(po, sym);
-                    po += K;
+                    for (int u = 0; u < kCheckEvery; ++u) {
+                        const int32_t sym = decode_one(mbuf[u]);
+                        if (FULL || valid) st_stream_s32(reinterpret_cast<int32_t *>(po), sym);
+                        po += row_bytes;
+                    }
+                    check_rows();
+                }
+                while (rows_left > 0) {  // at most kCheckEvery-1 more symbols
+                    uint32_t m = stream_model;
+                    if (PERSYM) {
+                        m = ld_stream_u32(reinterpret_cast<const uint32_t *>(pm));
+                        pm += row_bytes;
+                    }
+                    const int32_t sym = decode_one(m);
+                    if (FULL || valid) st_stream_s32(reinterpret_cast<int32_t *>(po), sym);
+                    po += row_bytes;
+                    rows_left -= 1;
                 }
                 check_rows();
-            }
-            while (rows_left > 0) {  // at most kCheckEvery-1 more symbols
-                const int32_t sym = decode_one(PERSYM ? ld_stream_u32(pm) : stream_model);
-                if (PERSYM) pm += K;
-                if (valid) st_stream_s32(po, sym);
-                po += K;
-                rows_left -= 1;
-            }
-            check_rows();
+            };
+            if (__all_sync(kFullMask, valid))
+                run_rows(std::true_type{});
+            else
+                run_rows(std::false_type{});
         }
         if (g.T > 0) {  // ragged last row
             if (valid && k < g.last) {

@@ -89,8 +89,7 @@ struct ctr_model_s {
     uint32_t *d_cdf = nullptr;  // [n_models][alphabet+1]
     uint4 *d_enc = nullptr;     // [n_models][alphabet], built on first encode
     uint32_t *d_dec = nullptr;  // model 0: pairs + bucket index, built on first decode
-    uint32_t dec_pairs_bytes = 0;
-    uint32_t lut_bytes = 0;  // kLutSize (u8 index) for alphabets <= 256, else 2 * kLutSize (u16)
+    uint32_t dec_cdf_bytes = 0;  // (alphabet + 2) * 4 rounded up to 16: the cdf part of d_dec
     bool shared_ok = false;  // small enough for the shared-memory table kernels
     bool enc_f64 = false;    // d_enc holds double-precision reciprocals (CTR_DIV=f64)
 };
@@ -106,8 +105,7 @@ int model_alloc(uint32_t n_models, uint32_t alphabet, int32_t min_symbol, ctr_mo
     m->n_models = n_models;
     m->alphabet = alphabet;
     m->min_symbol = min_symbol;
-    m->dec_pairs_bytes = alphabet <= kMaxSharedAlphabet ? alphabet * 16u : 0u;
-    m->lut_bytes = alphabet <= 256 ? (uint32_t)kLutSize : 2u * kLutSize;
+    m->dec_cdf_bytes = (uint32_t)align_up(((size_t)alphabet + 2) * 4, 16);
     m->shared_ok = alphabet <= kMaxSharedAlphabet;
     cudaError_t e = cudaMalloc(&m->d_cdf, (size_t)n_models * ((size_t)alphabet + 1) * 4);
     if (e != cudaSuccess) {
@@ -142,10 +140,9 @@ int ensure_enc_table(ctr_model_s *m, cudaStream_t s) {
 
 int ensure_dec_table(ctr_model_s *m, cudaStream_t s) {
     if (m->d_dec || !m->shared_ok) return CTR_OK;
-    CUDA_TRY(cudaMalloc(&m->d_dec, m->dec_pairs_bytes + m->lut_bytes));
+    CUDA_TRY(cudaMalloc(&m->d_dec, kLutBytes + m->dec_cdf_bytes));
     const uint32_t threads = m->alphabet + 2 > (uint32_t)kLutSize ? m->alphabet + 2 : (uint32_t)kLutSize;
-    build_dec_table_kernel<<<grid_for(threads, 256), 256, 0, s>>>(m->d_cdf, m->alphabet, m->dec_pairs_bytes,
-                                                                  m->lut_bytes == (uint32_t)kLutSize ? 1 : 0, m->d_dec);
+    build_dec_table_kernel<<<grid_for(threads, 256), 256, 0, s>>>(m->d_cdf, m->alphabet, m->d_dec);
     LAUNCH_CHECK("build_dec_table_kernel");
     return CTR_OK;
 }
@@ -186,8 +183,7 @@ ModelView model_view(const ctr_model_s *m) {
     v.n_models = m->n_models;
     v.alphabet = m->alphabet;
     v.min_symbol = m->min_symbol;
-    v.dec_pairs_bytes = m->dec_pairs_bytes;
-    v.lut_bytes = m->lut_bytes;
+    v.dec_cdf_bytes = m->dec_cdf_bytes;
     return v;
 }
 
@@ -480,7 +476,7 @@ size_t coder_smem_bytes(size_t table_bytes, const ctr_layout *L, int warps) {
             int rc__ = set_smem(kernel, smem);                                                             \
             if (rc__) return rc__;                                                                         \
             ProfileScope prof(SLOT, s);                                                                    \
-            kernel<<<grid, kAnsBlock, smem, s>>>(p);                                                       \
+            kernel<<<grid, block, smem, s>>>(p);                                                           \
             LAUNCH_CHECK(#KERNEL);                                                                         \
             return CTR_OK;                                                                                 \
         };                                                                                                 \
@@ -490,29 +486,33 @@ size_t coder_smem_bytes(size_t table_bytes, const ctr_layout *L, int warps) {
     } while (0)
 
 struct AnsEncodeLauncher {
+    static unsigned block_for(bool, bool) { return kAnsBlock; }
     static int run(bool shared, bool contig, bool persym, bool f64, const AnsParams &p, size_t smem, unsigned grid,
-                   cudaStream_t s) {
+                   unsigned block, cudaStream_t s) {
 #define CTR_COMMA ,
         if (f64) CTR_DISPATCH(ans_encode_kernel, 0, CTR_COMMA true);
         CTR_DISPATCH(ans_encode_kernel, 0, CTR_COMMA false);
     }
 };
 struct AnsDecodeLauncher {
+    static unsigned block_for(bool shared, bool contig) { return (shared && !contig) ? kDecBlockShared : kAnsBlock; }
     static int run(bool shared, bool contig, bool persym, bool, const AnsParams &p, size_t smem, unsigned grid,
-                   cudaStream_t s) {
-        if (shared && p.model.lut_bytes == (uint32_t)kLutSize) CTR_DISPATCH(ans_decode_kernel, 1, CTR_COMMA true);
+                   unsigned block, cudaStream_t s) {
+        if (shared && p.model.alphabet <= 256) CTR_DISPATCH(ans_decode_kernel, 1, CTR_COMMA true);
         CTR_DISPATCH(ans_decode_kernel, 1, CTR_COMMA false);
     }
 };
 struct RangeEncodeLauncher {
+    static unsigned block_for(bool, bool) { return kAnsBlock; }
     static int run(bool shared, bool contig, bool persym, bool, const AnsParams &p, size_t smem, unsigned grid,
-                   cudaStream_t s) {
+                   unsigned block, cudaStream_t s) {
         CTR_DISPATCH(range_encode_kernel, 2);
     }
 };
 struct RangeDecodeLauncher {
+    static unsigned block_for(bool, bool) { return kAnsBlock; }
     static int run(bool shared, bool contig, bool persym, bool, const AnsParams &p, size_t smem, unsigned grid,
-                   cudaStream_t s) {
+                   unsigned block, cudaStream_t s) {
         CTR_DISPATCH(range_decode_kernel, 3);
     }
 };
@@ -566,9 +566,10 @@ int encode_common(ctr_model_t model, const int32_t *symbols_dev, const ctr_layou
 
     const bool shared = use_shared_tables(model, L);
     const bool contig = L->sym_offsets_dev != nullptr;
-    const size_t smem = coder_smem_bytes(shared ? ((size_t)model->alphabet + 1) * 16 : 0, L, kAnsBlock / 32);
+    const unsigned block = EncLauncher::block_for(shared, contig);
+    const size_t smem = coder_smem_bytes(shared ? ((size_t)model->alphabet + 1) * 16 : 0, L, block / 32);
     return EncLauncher::run(shared, contig, L->model_index_mode == CTR_INDEX_PER_SYMBOL, model->enc_f64, p, smem,
-                            grid_for(L->n_streams, kAnsBlock), s);
+                            grid_for(L->n_streams, block), block, s);
 }
 
 template <class DecLauncher>
@@ -595,9 +596,10 @@ int decode_common(ctr_model_t model, const uint32_t *words, const uint64_t *offs
 
     const bool shared = use_shared_tables(model, L);
     const bool contig = L->sym_offsets_dev != nullptr;
-    const size_t smem = coder_smem_bytes(shared ? (size_t)model->dec_pairs_bytes + model->lut_bytes : 0, L, kAnsBlock / 32);
+    const unsigned block = DecLauncher::block_for(shared, contig);
+    const size_t smem = coder_smem_bytes(shared ? (size_t)kLutBytes + model->dec_cdf_bytes : 0, L, block / 32);
     return DecLauncher::run(shared, contig, L->model_index_mode == CTR_INDEX_PER_SYMBOL, false, p, smem,
-                            grid_for(L->n_streams, kAnsBlock), s);
+                            grid_for(L->n_streams, block), block, s);
 }
 
 }  // namespace

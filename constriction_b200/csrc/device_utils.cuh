@@ -72,11 +72,11 @@ __device__ __forceinline__ uint4 lds_table_v4(uint32_t addr) {
     return v;
 }
 
-// decoder quantile index: 2^kLutBits buckets of 2^kLutShift quantiles each; u8 entries (2 KB) for alphabets
-// of up to 256 symbols, u16 entries (4 KB) otherwise
-constexpr int kLutBits = 11;
+// decoder quantile index of a shared model: 2^kLutBits buckets of 2^kLutShift quantiles, 8 bytes each
+constexpr int kLutBits = 12;
 constexpr int kLutSize = 1 << kLutBits;
 constexpr int kLutShift = kPrecision - kLutBits;
+constexpr uint32_t kLutBytes = kLutSize * 8u;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 // Same, but opaque to the optimiser: the value stays in a register instead of being rematerialised from the

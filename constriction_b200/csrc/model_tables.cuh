@@ -123,18 +123,16 @@ __global__ void build_enc_table_kernel(const uint32_t *cdf, uint32_t n_models, u
     enc[tid] = make_uint4(left, prob, (uint32_t)rcp, (uint32_t)(rcp >> 32));
 }
 
-// decoder table of model 0 (see lookup_shared in ans_kernels.cuh):
-//   trip[s] = {cdf[s], cdf[s+1], cdf[s+2] (2^24 past the end), 0}, then lut[b] (u8 or u16) = the last symbol whose
-//   left cumulative is <= b << kLutShift, i.e. the symbol containing the first quantile of bucket b.
-__global__ void build_dec_table_kernel(const uint32_t *cdf, uint32_t alphabet, uint32_t trip_bytes, int lut8, uint32_t *dec) {
+// decoder table of model 0 (see lookup_shared in ans_kernels.cuh): quantile index uint2[kLutSize], then the
+// CDF row with one extra 2^24 entry.
+__global__ void build_dec_table_kernel(const uint32_t *cdf, uint32_t alphabet, uint32_t *dec) {
     const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
-    uint4 *trip = reinterpret_cast<uint4 *>(dec);
-    uint16_t *lut16 = reinterpret_cast<uint16_t *>(dec + trip_bytes / 4);
-    uint8_t *lut8p = reinterpret_cast<uint8_t *>(dec + trip_bytes / 4);
-    if (tid < alphabet) trip[tid] = make_uint4(cdf[tid], cdf[tid + 1], tid + 2 <= alphabet ? cdf[tid + 2] : kTotal, 0u);
+    uint2 *lut = reinterpret_cast<uint2 *>(dec);
+    uint32_t *row = dec + kLutBytes / 4;
+    if (tid <= alphabet + 1) row[tid] = tid <= alphabet ? cdf[tid] : kTotal;
     if (tid < (uint32_t)kLutSize) {
         const uint32_t q = tid << kLutShift;
-        uint32_t lo = 0, hi = alphabet - 1;
+        uint32_t lo = 0, hi = alphabet - 1;  // last symbol whose left cumulative is <= q
         while (lo < hi) {
             const uint32_t mid = (lo + hi + 1) >> 1;
             if (cdf[mid] <= q)
@@ -142,10 +140,7 @@ __global__ void build_dec_table_kernel(const uint32_t *cdf, uint32_t alphabet, u
             else
                 hi = mid - 1;
         }
-        if (lut8)
-            lut8p[tid] = (uint8_t)lo;
-        else
-            lut16[tid] = (uint16_t)lo;
+        lut[tid] = make_uint2(cdf[lo] | ((lo & 0xffu) << 24), cdf[lo + 1] | ((lo >> 8) << 25));
     }
 }
 

@@ -232,14 +232,14 @@ __global__ void __launch_bounds__(kAnsBlock) range_decode_kernel(const AnsParams
     const int warp_in_cta = threadIdx.x >> 5;
     constexpr int kWarpsPerCta = kAnsBlock / 32;
 
-    const uint32_t table_words = SHARED ? (p.model.dec_pairs_bytes + p.model.lut_bytes) / 4 : 0;
-    const uint32_t trip_addr = smem_u32_pinned(smem);
-    const uint32_t lut_addr = trip_addr + (SHARED ? p.model.dec_pairs_bytes : 0);
+    const uint32_t table_words = SHARED ? (kLutBytes + p.model.dec_cdf_bytes) / 4 : 0;
+    const uint32_t lut_addr = smem_u32_pinned(smem);
+    const uint32_t cdf_addr = lut_addr + kLutBytes;
     uint32_t *rows = smem + table_words + warp_in_cta * kTileWords;
     uint32_t *sym_tile = smem + table_words + (kWarpsPerCta + warp_in_cta) * kTileWords;
     uint32_t *idx_tile = smem + table_words + (2 * kWarpsPerCta + warp_in_cta) * kTileWords;
 
-    if (SHARED) stage_table(smem, p.model.dec, p.model.dec_pairs_bytes + p.model.lut_bytes, &bar);
+    if (SHARED) stage_table(smem, p.model.dec, kLutBytes + p.model.dec_cdf_bytes, &bar);
 
     const uint64_t K = p.K, N = p.N;
     const uint64_t k = (uint64_t)blockIdx.x * kAnsBlock + threadIdx.x;
@@ -318,8 +318,7 @@ __global__ void __launch_bounds__(kAnsBlock) range_decode_kernel(const AnsParams
         invalid_data |= !range_peek_quantile(st, q);
         uint32_t left, right, s;
         if (SHARED) {
-            s = p.model.lut_bytes == (uint32_t)kLutSize ? lookup_shared<true>(trip_addr, lut_addr, alphabet, q, q, left, right)
-                                                        : lookup_shared<false>(trip_addr, lut_addr, alphabet, q, q, left, right);
+            s = lookup_shared<false>(lut_addr, cdf_addr, alphabet, q, q, left, right);
         } else {
             m = m < n_models ? m : n_models - 1;
             s = lookup_global(p.model.cdf + (uint64_t)m * (alphabet + 1), alphabet, q, left, right);
