@@ -7,8 +7,11 @@
 // warp-cooperative and coalesced:
 //   - symbols: interleaved layout -> one 128-byte row per warp step (pointer bumped by K per step);
 //     contiguous layout -> 32x32 tiles transposed through shared memory;
-//   - compressed words: each lane appends to / pops from a private shared-memory row; rows are moved
-//     to / from HBM 32 words (128 bytes) at a time by the whole warp;
+//   - compressed words: each lane appends to / pops from a small private ring in shared memory; the ring
+//     is drained / topped up 16 bytes at a time with lane-private vector accesses (encoder: LDS.128 +
+//     STG.128 into the lane's scratch region; decoder: asynchronous LDGSTS.128 from the lane's stream),
+//     so there is no warp-cooperative phase, no shuffle and no divergence in the word path; the L2
+//     merges the two 16-byte halves of each 32-byte sector;
 //   - the model: for a single shared model the encoder table (left, prob, 64-bit reciprocal) or the
 //     decoder table (CDF pairs + 4096-bucket quantile index) is staged into shared memory by the TMA
 //     engine (cp.async.bulk); model sets too big for that are read through L1/L2 (`ld.global.nc`).
@@ -20,7 +23,7 @@
 //   - data errors never branch: an out-of-range symbol is clamped to a sentinel table entry with
 //     probability 0 and detected at the end from a running minimum;
 //   - shared memory is addressed with 32-bit shared addresses (no generic-pointer arithmetic);
-//   - word rows are inspected once per kCheckEvery symbols, and the flush / refill is a cold path.
+//   - the word rings are inspected once per kCheckEvery symbols with straight-line predicated code.
 //
 // Per-stream results equal the reference's `AnsCoder` (src/stream/stack.rs:1014-1100) word for word.
 #pragma once
@@ -94,132 +97,6 @@ __device__ __noinline__ void warp_fill_rows(unsigned mask, uint32_t *rows, const
         if ((uint32_t)lane < c) rows[i * kRowStride + lane] = ld_stream_u32(s + lane);
     }
     __syncwarp();
-}
-
-// ---- word rows of the ANS kernels (32-bit shared addresses, rows of kWordRowStride words) -------------
-
-// Per-thread "cold slot" (16 bytes of shared memory per lane): everything a lane needs only when one of its
-// rows is moved to / from HBM lives here, not in registers, so that the hot loops fit 5 CTAs per SM.
-//   encoder: {scratch cursor lo, hi, words of scratch capacity left, words flushed so far | overflow bit}
-//   decoder: {cursor lo, hi (one past the highest word not yet staged), words not yet staged, unused}
-constexpr uint32_t kColdSlotBytes = 16;
-constexpr uint32_t kColdOverflowBit = 0x80000000u;
-
-__device__ __forceinline__ void cold_store(uint32_t slot, const void *ptr, uint32_t a, uint32_t b) {
-    const uint64_t v = (uint64_t)ptr;
-    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(slot), "r"((uint32_t)v), "r"((uint32_t)(v >> 32)), "r"(a),
-                 "r"(b)
-                 : "memory");
-}
-__device__ __forceinline__ uint4 cold_load(uint32_t slot) {
-    uint4 v;
-    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(slot) : "memory");
-    return v;
-}
-__device__ __forceinline__ uint32_t *cold_ptr(const uint4 &v) { return (uint32_t *)(((uint64_t)v.y << 32) | v.x); }
-
-// Encoder, cold: every lane in `mask` has >= 32 words in its row.  The warp writes the first 32 words of
-// each such row to that lane's scratch cursor (one 128-byte store), the lane keeps what is left over.
-// Returns the lane's new row cursor.
-__device__ __noinline__ uint32_t ans_flush_rows_cold(unsigned mask, uint32_t rows_addr, uint32_t slots_addr,
-                                                     uint32_t row_addr, uint32_t wptr, int lane) {
-    __syncwarp();
-    unsigned todo = mask;
-    while (todo) {
-        const int i = __ffs(todo) - 1;
-        todo &= todo - 1;
-        const uint4 c = cold_load(slots_addr + (uint32_t)i * kColdSlotBytes);  // broadcast read of lane i's slot
-        if (c.z >= (uint32_t)kRowWords)
-            st_stream_u32(cold_ptr(c) + lane, lds_u32(rows_addr + (uint32_t)(i * kWordRowStride + lane) * 4u));
-    }
-    __syncwarp();
-    if ((mask >> lane) & 1u) {
-        const uint32_t slot = slots_addr + (uint32_t)lane * kColdSlotBytes;
-        const uint4 c = cold_load(slot);
-        if (c.z >= (uint32_t)kRowWords)
-            cold_store(slot, cold_ptr(c) + kRowWords, c.z - kRowWords, c.w + kRowWords);
-        else
-            cold_store(slot, cold_ptr(c), c.z, c.w | kColdOverflowBit);  // words dropped, stream flagged
-        const uint32_t left = (wptr - row_addr) / 4u - kRowWords;  // 0 .. kCheckEvery-1
-        for (uint32_t j = 0; j < left; ++j) sts_u32(row_addr + j * 4u, lds_u32(row_addr + (kRowWords + j) * 4u));
-        wptr = row_addr + left * 4u;
-    }
-    __syncwarp();
-    return wptr;
-}
-
-// Encoder, end of stream: write the remaining cnt_i (< 32) words of every row.
-__device__ __noinline__ void ans_flush_tail_cold(uint32_t rows_addr, uint32_t slots_addr, uint32_t cnt, int lane) {
-    __syncwarp();
-    unsigned todo = __ballot_sync(kFullMask, cnt > 0);
-    while (todo) {
-        const int i = __ffs(todo) - 1;
-        todo &= todo - 1;
-        const uint4 c = cold_load(slots_addr + (uint32_t)i * kColdSlotBytes);
-        const uint32_t ci = __shfl_sync(kFullMask, cnt, i);
-        if (c.z >= ci && (uint32_t)lane < ci)
-            st_stream_u32(cold_ptr(c) + lane, lds_u32(rows_addr + (uint32_t)(i * kWordRowStride + lane) * 4u));
-    }
-    __syncwarp();
-    if (cnt > 0) {
-        const uint32_t slot = slots_addr + (uint32_t)lane * kColdSlotBytes;
-        const uint4 c = cold_load(slot);
-        if (c.z >= cnt)
-            cold_store(slot, cold_ptr(c) + cnt, c.z - cnt, c.w + cnt);
-        else
-            cold_store(slot, cold_ptr(c), c.z, c.w | kColdOverflowBit);
-    }
-    __syncwarp();
-}
-
-// Decoder, cold: every lane in `mask` is down to < kCheckEvery staged words and has more in HBM.  The warp
-// loads the next (up to) 32 words below each such lane's cursor; chunks end on 128-byte boundaries of the
-// global address space, so every refill after a stream's first is one aligned line.
-// Returns {new row cursor, new refill mark (0 when nothing is left in HBM)}.
-struct RefillResult {
-    uint32_t rptr, mark;
-};
-__device__ __noinline__ RefillResult ans_refill_rows_cold(unsigned mask, uint32_t rows_addr, uint32_t slots_addr,
-                                                          uint32_t row_addr, uint32_t rptr, uint32_t mark, int lane) {
-    const bool mine = (mask >> lane) & 1u;
-    // keep my unread words (they are older than the chunk that is about to arrive, so they go on top)
-    const uint32_t left = mine ? (rptr - row_addr) / 4u : 0u;  // 0 .. kCheckEvery-1
-    uint32_t keep[kCheckEvery - 1];
-#pragma unroll
-    for (int j = 0; j < kCheckEvery - 1; ++j) keep[j] = (uint32_t)j < left ? lds_u32(row_addr + j * 4u) : 0u;
-    __syncwarp();
-    unsigned todo = mask;
-    uint32_t my_c = 0;
-    while (todo) {
-        const int i = __ffs(todo) - 1;
-        todo &= todo - 1;
-        const uint4 c = cold_load(slots_addr + (uint32_t)i * kColdSlotBytes);
-        const uint32_t *top = cold_ptr(c);
-        // chunk = [max(stream begin, 128-byte line of the top word), top)
-        uint32_t ci = (uint32_t)((((uint64_t)(top - 1)) & 127u) / 4u) + 1u;
-        ci = ci < c.z ? ci : c.z;
-        if ((uint32_t)lane < ci)
-            sts_u32(rows_addr + (uint32_t)(i * kWordRowStride + lane) * 4u, ld_stream_u32(top - ci + lane));
-        if (i == lane) my_c = ci;
-    }
-    __syncwarp();
-    RefillResult r;
-    r.rptr = rptr;
-    r.mark = mark;
-    if (mine) {
-        const uint32_t slot = slots_addr + (uint32_t)lane * kColdSlotBytes;
-        const uint4 c = cold_load(slot);
-        const uint32_t *top = cold_ptr(c) - my_c;
-        cold_store(slot, top, c.z - my_c, 0u);
-        if (c.z - my_c != 0u) prefetch_l2(top - 1);  // the line below: needed ~200 symbols from now
-#pragma unroll
-        for (int j = 0; j < kCheckEvery - 1; ++j)
-            if ((uint32_t)j < left) sts_u32(row_addr + (my_c + j) * 4u, keep[j]);
-        r.rptr = row_addr + (my_c + left) * 4u;
-        r.mark = (c.z - my_c != 0u) ? row_addr + kCheckEvery * 4u : 0u;
-    }
-    __syncwarp();
-    return r;
 }
 
 // ---- model lookups ----------------------------------------------------------------------------------
@@ -311,32 +188,32 @@ __device__ __forceinline__ uint64_t warp_max_u64(uint64_t v, int lane) {
 // =====================================================================================================
 // encode
 // =====================================================================================================
-// per-warp staging block in shared memory: word rows, then the 32 cold slots
-constexpr int kWarpStageWords = kWordRowsWords + kWarp * (int)(kColdSlotBytes / 4);
-
 //   SHARED : model 0's encoder table lives in shared memory (index_mode == NONE, small alphabet)
 //   CONTIG : stream k owns symbols[sym_off[k] .. sym_off[k+1]) (else interleaved deal)
 //   PERSYM : a model index per symbol (else one model per stream / model 0)
 //   F64DIV : the table holds double-precision reciprocals and the quotient estimate uses the FP64 pipe
 template <bool SHARED, bool CONTIG, bool PERSYM, bool F64DIV>
-__global__ void __launch_bounds__(kAnsBlock, 5) ans_encode_kernel(const AnsParams p) {
-    extern __shared__ __align__(16) uint32_t smem[];
+__global__ void __launch_bounds__(kAnsBlock, 4) ans_encode_kernel(const AnsParams p) {
+    extern __shared__ __align__(128) uint32_t smem[];
     __shared__ uint64_t bar;
 
     const int lane = threadIdx.x & 31;
     const int warp_in_cta = threadIdx.x >> 5;
     constexpr int kWarpsPerCta = kAnsBlock / 32;
 
-    // shared memory carve-up: [table][per warp: word rows + cold slots][symbol tiles][index tiles]
+    // shared memory carve-up: [lane rings (32 B each) + per-thread parking slots (16 B each)][table][symbol
+    // tiles][index tiles].  The parking slot keeps values that are only needed again at the very end
+    // (scratch base, capacity) out of the hot loop's registers.
     const uint32_t alphabet = p.model.alphabet;
     const uint32_t table_words = SHARED ? (alphabet + 1) * 4 : 0;
-    const uint32_t table_addr = smem_u32_pinned(smem);
-    const uint32_t rows_addr = smem_u32_pinned(smem + table_words + warp_in_cta * kWarpStageWords);
-    const uint32_t slots_addr = rows_addr + kWordRowsWords * 4u;
-    uint32_t *sym_tile = smem + table_words + kWarpsPerCta * kWarpStageWords + warp_in_cta * kTileWords;
+    constexpr uint32_t kRingsWords = kAnsBlock * (kEncRingWords + 4);
+    const uint32_t ring = smem_u32_pinned(smem) + threadIdx.x * kEncRingBytes;  // 32-byte aligned
+    const uint32_t park = smem_u32(smem) + kAnsBlock * kEncRingBytes + threadIdx.x * 16u;
+    const uint32_t table_addr = smem_u32_pinned(smem + kRingsWords);
+    uint32_t *sym_tile = smem + kRingsWords + table_words + warp_in_cta * kTileWords;
     uint32_t *idx_tile = sym_tile + kWarpsPerCta * kTileWords;
 
-    if (SHARED) stage_table(smem, p.model.enc, (alphabet + 1) * 16u, &bar);
+    if (SHARED) stage_table(smem + kRingsWords, p.model.enc, (alphabet + 1) * 16u, &bar);
 
     const uint64_t K = p.K, N = p.N;
     const uint32_t tile = take_tile_ticket(p.compact.ticket);  // which 256 streams this CTA codes
@@ -344,7 +221,7 @@ __global__ void __launch_bounds__(kAnsBlock, 5) ans_encode_kernel(const AnsParam
     const bool valid = k < K;
     const uint64_t kc = valid ? k : K - 1;  // lanes without a stream shadow the last one (loads only)
 
-    // stream geometry; the scratch cursor and capacity go to my cold slot
+    // stream geometry and my scratch region
     uint64_t n_k = 0, o_k = 0;
     if (valid) {
         if (CONTIG) {
@@ -355,17 +232,21 @@ __global__ void __launch_bounds__(kAnsBlock, 5) ans_encode_kernel(const AnsParam
             o_k = interleaved_start(N, K, k);
         }
     }
-    const uint32_t my_slot = slots_addr + (uint32_t)lane * kColdSlotBytes;
+    char *gw;        // write cursor in my scratch region (128-byte aligned start)
+    uint32_t room;   // bytes of scratch capacity left
     {
-        const uint64_t begin = scratch_start(o_k, k);
-        const uint64_t room = valid ? scratch_start(o_k + n_k, k + 1) - begin : 0;
-        cold_store(my_slot, p.scratch + begin, room > 0x7fffffffu ? 0x7fffffffu : (uint32_t)room, 0u);
+        uint32_t *const gbegin = p.scratch + scratch_start(o_k, k);
+        const uint64_t r = valid ? scratch_start(o_k + n_k, k + 1) - scratch_start(o_k, k) : 0;
+        room = r > 0x3ffffff0u ? 0xffffffc0u : (uint32_t)r * 4u;
+        gw = reinterpret_cast<char *>(gbegin);
+        const uint64_t gb = (uint64_t)gbegin;
+        asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(park), "r"((uint32_t)gb), "r"((uint32_t)(gb >> 32)) : "memory");
     }
 
     uint64_t state = (valid && p.states_in) ? p.states_in[k] : 0;
-    const uint32_t row_addr = rows_addr + (uint32_t)lane * (kWordRowStride * 4u);
-    uint32_t wptr = row_addr;           // shared address of the next free slot of my row
-    uint32_t min_prob = 0xffffffffu;    // running minimum of the probabilities used (0 <=> impossible symbol)
+    uint32_t pushed = 0;             // bytes pushed into my ring so far (ring slot = pushed & 31)
+    uint32_t pending = 0;            // bytes in my ring that are not yet written to scratch
+    uint32_t min_prob = 0xffffffffu; // running minimum of the probabilities used (0 <=> impossible symbol)
     const uint32_t push_shift = valid ? 8u : 32u;  // (state >> 32) >> 32 == 0: lanes without a stream never push
     const uint32_t stream_model = (p.index_mode == 2) ? p.model_index[kc] : 0u;
     const uint32_t n_models = p.model.n_models;
@@ -386,8 +267,9 @@ __global__ void __launch_bounds__(kAnsBlock, 5) ans_encode_kernel(const AnsParam
         min_prob = min(min_prob, e.y);
         uint32_t lo = (uint32_t)state, hi = (uint32_t)(state >> 32);
         if (shr_clamp(hi, push_shift) >= e.y) {  // stack.rs:1035-1040
-            sts_u32(wptr, lo);
-            wptr += 4u;
+            sts_u32(ring | (pushed & (kEncRingBytes - 1u)), lo);
+            pushed += 4u;
+            pending += 4u;
             lo = hi;
             hi = 0u;
         }
@@ -405,10 +287,21 @@ __global__ void __launch_bounds__(kAnsBlock, 5) ans_encode_kernel(const AnsParam
         state = (q << kPrecision) + (uint64_t)(e.x + r);  // stack.rs:1042-1045 (left + r < 2^24)
     };
 
-    // every kCheckEvery symbols: move rows that reached 32 words to HBM (cold)
-    auto check_rows = [&]() {
-        const unsigned mask = __ballot_sync(kFullMask, wptr >= row_addr + kRowWords * 4u);
-        if (mask) wptr = ans_flush_rows_cold(mask, rows_addr, slots_addr, row_addr, wptr, lane);
+    // every kCheckEvery symbols: a complete 16-byte group of my ring goes to my scratch region.  A lane
+    // pushes at most kCheckEvery words in between, so one group per check keeps up with any input.
+    auto drain_ring = [&]() {
+        if (pending >= 16u) {
+            const uint4 v = lds_v4(ring | ((pushed - pending) & (kEncRingBytes - 1u)));
+            if (room >= 16u) {
+                st_stream_v4(gw, v);
+                gw += 16;
+                room -= 16u;
+            } else {
+                room = 0u;  // words dropped: the stream is flagged at the end (room == 0 with words pending)
+                pushed |= 0x80000000u;
+            }
+            pending -= 16u;
+        }
     };
 
     if (!CONTIG) {
@@ -442,12 +335,9 @@ __global__ void __launch_bounds__(kAnsBlock, 5) ans_encode_kernel(const AnsParam
                     }
                 }
             };
-            // The row check (a potential call into the cold path) comes first, then the loads of the next
-            // batch are issued, then this batch is coded: no load is in flight across the call site, so
-            // the register shuffling around it never waits for memory.
             auto code_batch = [&](int which, bool load_next) {
-                check_rows();  // room for kCheckEvery more words in every row
                 if (load_next) load_batch(which ^ 1);
+                drain_ring();
 #pragma unroll
                 for (int u = 0; u < kCheckEvery; ++u) encode_one(buf[which][u], mbuf[which][u]);
             };
@@ -468,7 +358,7 @@ __global__ void __launch_bounds__(kAnsBlock, 5) ans_encode_kernel(const AnsParam
                     code_batch(0, false);
                 }
             }
-            check_rows();
+            drain_ring();
             while (rows_left > 0) {  // at most kCheckEvery-1 more symbols
                 const int32_t sym = ld_stream_s32(reinterpret_cast<const int32_t *>(ps));
                 ps -= row_bytes;
@@ -493,7 +383,7 @@ __global__ void __launch_bounds__(kAnsBlock, 5) ans_encode_kernel(const AnsParam
             if (PERSYM) warp_fill_rows(have, idx_tile, p.model_index + o_k + remaining, c, lane);
             const uint32_t cmax = __reduce_max_sync(kFullMask, c);
             for (uint32_t s = 0; s < cmax; ++s) {
-                if ((s & (kCheckEvery - 1)) == 0) check_rows();
+                if ((s & (kCheckEvery - 1)) == 0) drain_ring();
                 if (s < c) {
                     const int32_t sym = (int32_t)sym_tile[lane * kRowStride + (c - 1 - s)];
                     const uint32_t m = PERSYM ? idx_tile[lane * kRowStride + (c - 1 - s)] : stream_model;
@@ -503,29 +393,43 @@ __global__ void __launch_bounds__(kAnsBlock, 5) ans_encode_kernel(const AnsParam
         }
     }
 
-    // ---- finalize: state words (lib.rs:719-730, low word first), remaining partial rows --------------
-    check_rows();
+    // ---- finalize: state words (lib.rs:719-730, low word first), then the rest of my ring --------------
+    drain_ring();  // <= 3 words left in the ring
     const bool raw = (p.flags & 1u) != 0;
     const uint32_t n_state = (valid && !raw) ? ans_state_words(state) : 0u;
     if (n_state >= 1) {
-        sts_u32(wptr, (uint32_t)state);
-        wptr += 4u;
+        sts_u32(ring | (pushed & (kEncRingBytes - 1u)), (uint32_t)state);
+        pushed += 4u;
+        pending += 4u;
     }
     if (n_state == 2) {
-        sts_u32(wptr, (uint32_t)(state >> 32));
-        wptr += 4u;
+        sts_u32(ring | (pushed & (kEncRingBytes - 1u)), (uint32_t)(state >> 32));
+        pushed += 4u;
+        pending += 4u;
     }
-    check_rows();
-    ans_flush_tail_cold(rows_addr, slots_addr, (wptr - row_addr) / 4u, lane);  // < 32 words each
-    const uint4 fin = cold_load(my_slot);
-    const uint32_t len = fin.w & ~kColdOverflowBit;
+    drain_ring();
+    bool overflow = (pushed & 0x80000000u) != 0u;
+    while (pending != 0u) {  // < 4 words, one at a time
+        if (room >= 4u) {
+            *reinterpret_cast<uint32_t *>(gw) = lds_u32(ring | ((pushed - pending) & (kEncRingBytes - 1u)));
+            gw += 4;
+            room -= 4u;
+        } else {
+            overflow = true;
+        }
+        pending -= 4u;
+    }
     if (valid) {
         if (p.states_out) p.states_out[k] = state;
         if (min_prob == 0u) report_error(p.status, kErrImpossibleSymbol, k);
-        if (fin.w & kColdOverflowBit) report_error(p.status, kErrOutOfSpace, k);
+        if (overflow) report_error(p.status, kErrOutOfSpace, k);
     }
     // ---- K6: place my stream in the dense container ---------------------------------------------------
-    compact_tail<kAnsBlock>(p.compact, tile, k, K, valid, cold_ptr(fin) - len, valid ? len : 0u, p.status);
+    uint32_t gb_lo, gb_hi;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(gb_lo), "=r"(gb_hi) : "r"(park) : "memory");
+    const uint32_t *gbegin = reinterpret_cast<const uint32_t *>(((uint64_t)gb_hi << 32) | gb_lo);
+    compact_tail<kAnsBlock>(p.compact, tile, k, K, valid, gbegin,
+                            (valid && !overflow) ? (uint32_t)((reinterpret_cast<const uint32_t *>(gw)) - gbegin) : 0u, p.status);
 }
 
 // =====================================================================================================
@@ -538,7 +442,7 @@ constexpr int kDecBlockShared = 1024;
 template <bool SHARED, bool CONTIG, bool PERSYM, bool SMALL>
 __global__ void __launch_bounds__((SHARED && !CONTIG) ? kDecBlockShared : kAnsBlock, (SHARED && !CONTIG) ? 1 : 2)
     ans_decode_kernel(const AnsParams p) {
-    extern __shared__ __align__(16) uint32_t smem[];
+    extern __shared__ __align__(128) uint32_t smem[];
     __shared__ uint64_t bar;
 
     constexpr int kBlock = (SHARED && !CONTIG) ? kDecBlockShared : kAnsBlock;
@@ -546,17 +450,18 @@ __global__ void __launch_bounds__((SHARED && !CONTIG) ? kDecBlockShared : kAnsBl
     const int warp_in_cta = threadIdx.x >> 5;
     constexpr int kWarpsPerCta = kBlock / 32;
 
+    // shared memory carve-up: [lane rings (64 B each)][quantile index + cdf][symbol tiles][index tiles]
     const uint32_t alphabet = p.model.alphabet;
     const uint32_t table_words = SHARED ? (kLutBytes + p.model.dec_cdf_bytes) / 4 : 0;
-    const uint32_t lut_addr = smem_u32_pinned(smem);
+    constexpr uint32_t kRingsWords = kBlock * kDecRingWords;
+    const uint32_t ring = smem_u32_pinned(smem) + threadIdx.x * kDecRingBytes;  // 64-byte aligned
+    const uint32_t lut_addr = smem_u32_pinned(smem + kRingsWords);
     uint32_t cdf_addr = lut_addr + kLutBytes;
     asm volatile("" : "+r"(cdf_addr));
-    const uint32_t rows_addr = smem_u32_pinned(smem + table_words + warp_in_cta * kWarpStageWords);
-    const uint32_t slots_addr = rows_addr + kWordRowsWords * 4u;
-    uint32_t *sym_tile = smem + table_words + kWarpsPerCta * kWarpStageWords + warp_in_cta * kTileWords;
+    uint32_t *sym_tile = smem + kRingsWords + table_words + warp_in_cta * kTileWords;
     uint32_t *idx_tile = sym_tile + kWarpsPerCta * kTileWords;
 
-    if (SHARED) stage_table(smem, p.model.dec, kLutBytes + p.model.dec_cdf_bytes, &bar);
+    if (SHARED) stage_table(smem + kRingsWords, p.model.dec, kLutBytes + p.model.dec_cdf_bytes, &bar);
 
     const uint64_t K = p.K, N = p.N;
     const uint64_t k = (uint64_t)blockIdx.x * kBlock + threadIdx.x;
@@ -564,48 +469,67 @@ __global__ void __launch_bounds__((SHARED && !CONTIG) ? kDecBlockShared : kAnsBl
     const uint64_t kc = valid ? k : K - 1;
     const bool raw = (p.flags & 1u) != 0;
 
+    // My stream is words[begin, end); I pop from the end.  The ring slot of a word is its global address
+    // mod 64, so aligned 16-byte blocks of the stream map to aligned 16-byte groups of the ring
+    // (the words buffer is 16-byte aligned: checked by the host).
     uint64_t n_k = 0, o_k = 0;
-    const uint32_t my_slot = slots_addr + (uint32_t)lane * kColdSlotBytes;
-    const uint32_t row_addr = rows_addr + (uint32_t)lane * (kWordRowStride * 4u);
-    uint32_t rptr = row_addr;  // my row holds the unread words [row_addr, rptr)
-    uint32_t mark = 0;         // row_addr + 16 while words remain in HBM (refill when rptr drops below), else 0
-    {
-        uint64_t begin = 0, end = 0;
-        if (valid) {
-            if (CONTIG) {
-                o_k = p.sym_off[k];
-                n_k = p.sym_off[k + 1] - o_k;
-            }
-            begin = p.offsets[k];
-            end = p.offsets[k + 1];
+    uint64_t begin = 0, end = 0;
+    if (valid) {
+        if (CONTIG) {
+            o_k = p.sym_off[k];
+            n_k = p.sym_off[k + 1] - o_k;
         }
-        const uint64_t len = end - begin;
-        // (a stream of >= 2^32 words does not exist: the encoder's lengths are 32-bit)
-        cold_store(my_slot, p.words + end, (uint32_t)len, 0u);
-        mark = len ? row_addr + kCheckEvery * 4u : 0u;
+        begin = p.offsets[k];
+        end = p.offsets[k + 1];
     }
-    const uint32_t n_models = p.model.n_models;
-    uint32_t min_symbol = (uint32_t)p.model.min_symbol;
-    asm volatile("" : "+r"(min_symbol));
-    const uint32_t stream_model = (p.index_mode == 2) ? p.model_index[kc] : 0u;
+    // low 32 bits of the global byte address just past the next word to pop
+    uint32_t pop_off = (uint32_t)(uintptr_t)(p.words + end);
+    uint32_t avail = 0;                     // words in my ring that have landed and are unread
+    uint32_t pending = 0;                   // words of the 16-byte block that is in flight
+    // (a stream of >= 2^32 words does not exist: the encoder's lengths are 32-bit)
+    uint32_t unstaged = (uint32_t)(end - begin);  // words of my stream not yet requested
+    const char *gblock = reinterpret_cast<const char *>(p.words) + ((end * 4u) & ~(uint64_t)15);  // block holding word end
+    if ((end & 3u) == 0) gblock -= 16;      // ... or rather the block holding word end-1
 
-    // every kCheckEvery symbols: rows that are down to < kCheckEvery words get the next 32 (cold).  The first
-    // chunk of a stream only reaches down to the next 128-byte boundary and may be shorter than
-    // kCheckEvery words, hence the loop (it runs twice at most).
-    auto check_rows = [&]() {
-        unsigned mask = __ballot_sync(kFullMask, rptr < mark);
-        while (mask) {
-            const RefillResult u = ans_refill_rows_cold(mask, rows_addr, slots_addr, row_addr, rptr, mark, lane);
-            rptr = u.rptr;
-            mark = u.mark;
-            mask = __ballot_sync(kFullMask, rptr < mark);
-        }
+    // request the next block below (asynchronously); the first block of a stream may be partial at the top,
+    // the last one at the bottom
+    auto request_block = [&](uint32_t top_words) {
+        const uint32_t n = unstaged < top_words ? unstaged : top_words;
+        cp_async_16(ring | ((uint32_t)(uintptr_t)gblock & (kDecRingBytes - 1u)), gblock);
+        gblock -= 16;
+        unstaged -= n;
+        pending = n;
+    };
+    // every kCheckEvery symbols: the block requested at the previous check has landed; request the next
+    // one if there is room for it.  Invariant after the check: avail >= kCheckEvery or nothing is left.
+    auto top_up = [&]() {
+        cp_async_wait_all();
+        avail += pending;
+        pending = 0;
+        if (avail <= (uint32_t)(kDecRingWords - 4) && unstaged != 0u) request_block(4u);
+        cp_async_commit();
+    };
+    // start-up: stage at least 8 words (or the whole stream) synchronously
+    {
+        const uint32_t first = (end & 3u) ? (uint32_t)(end & 3u) : 4u;  // words of my stream in the top block
+        if (unstaged != 0u) request_block(first);
+        cp_async_commit();
+#pragma unroll 1
+        for (int i = 0; i < 3; ++i) top_up();
+        cp_async_wait_all();
+        avail += pending;
+        pending = 0;
+    }
+
+    auto pop_word = [&]() -> uint32_t {
+        pop_off -= 4u;
+        avail -= 1u;
+        return lds_u32(ring | (pop_off & (kDecRingBytes - 1u)));
     };
 
     // ---- initial state: stack.rs:299-318, 440-462 (from_compressed) or the caller's raw state ------
     uint32_t lo = 0, hi = 0;  // the coder state
     bool trailing_zero = false;
-    check_rows();
     if (raw) {
         if (valid && p.states_in) {
             const uint64_t s = p.states_in[k];
@@ -613,18 +537,21 @@ __global__ void __launch_bounds__((SHARED && !CONTIG) ? kDecBlockShared : kAnsBl
             hi = (uint32_t)(s >> 32);
         }
     } else {
-        if (rptr != row_addr) {
-            rptr -= 4u;
-            lo = lds_u32(rptr);
+        if (avail != 0u) {
+            lo = pop_word();
             trailing_zero = lo == 0u;
-            if (rptr != row_addr && lo != 0u) {
+            if (avail != 0u && lo != 0u) {
                 hi = lo;
-                rptr -= 4u;
-                lo = lds_u32(rptr);
+                lo = pop_word();
             }
         }
-        check_rows();
     }
+    top_up();
+
+    const uint32_t n_models = p.model.n_models;
+    uint32_t min_symbol = (uint32_t)p.model.min_symbol;
+    asm volatile("" : "+r"(min_symbol));
+    const uint32_t stream_model = (p.index_mode == 2) ? p.model_index[kc] : 0u;
 
     // one reference decode_symbol (stack.rs:1070-1100)
     auto decode_one = [&](uint32_t m) -> int32_t {
@@ -641,10 +568,9 @@ __global__ void __launch_bounds__((SHARED && !CONTIG) ? kDecBlockShared : kAnsBl
         const uint64_t t = (uint64_t)__funnelshift_r(lo, hi, kPrecision) * prob + (uint64_t)(q - left);
         hi = (uint32_t)(t >> 32) + (hi >> kPrecision) * prob;
         lo = (uint32_t)t;
-        if (hi == 0u && rptr != row_addr) {  // stack.rs:1091-1097
+        if (hi == 0u && avail != 0u) {  // stack.rs:1091-1097
             hi = lo;
-            rptr -= 4u;
-            lo = lds_u32(rptr);
+            lo = pop_word();
         }
         return (int32_t)(min_symbol + s);
     };
@@ -678,7 +604,7 @@ __global__ void __launch_bounds__((SHARED && !CONTIG) ? kDecBlockShared : kAnsBl
                         if (FULL || valid) st_stream_s32(reinterpret_cast<int32_t *>(po), sym);
                         po += row_bytes;
                     }
-                    check_rows();
+                    top_up();
                 }
                 while (rows_left > 0) {  // at most kCheckEvery-1 more symbols
                     uint32_t m = stream_model;
@@ -691,7 +617,7 @@ __global__ void __launch_bounds__((SHARED && !CONTIG) ? kDecBlockShared : kAnsBl
                     po += row_bytes;
                     rows_left -= 1;
                 }
-                check_rows();
+                top_up();
             };
             if (__all_sync(kFullMask, valid))
                 run_rows(std::true_type{});
@@ -715,7 +641,7 @@ __global__ void __launch_bounds__((SHARED && !CONTIG) ? kDecBlockShared : kAnsBl
             if (PERSYM) warp_fill_rows(have, idx_tile, p.model_index + o_k + done, c, lane);
             const uint32_t cmax = __reduce_max_sync(kFullMask, c);
             for (uint32_t s = 0; s < cmax; ++s) {
-                if ((s & (kCheckEvery - 1)) == 0) check_rows();
+                if ((s & (kCheckEvery - 1)) == 0) top_up();
                 if (s < c) {
                     const uint32_t m = PERSYM ? idx_tile[lane * kRowStride + s] : stream_model;
                     sym_tile[lane * kRowStride + s] = (uint32_t)decode_one(m);
@@ -726,9 +652,10 @@ __global__ void __launch_bounds__((SHARED && !CONTIG) ? kDecBlockShared : kAnsBl
         }
     }
 
+    cp_async_wait_all();
     if (valid) {
         if (p.states_out) p.states_out[k] = ((uint64_t)hi << 32) | lo;
-        if (p.words_left) p.words_left[k] = (uint64_t)cold_load(my_slot).z + (uint64_t)((rptr - row_addr) / 4u);
+        if (p.words_left) p.words_left[k] = (uint64_t)unstaged + pending + avail;
         if (trailing_zero) report_error(p.status, kErrTrailingZero, k);
     }
 }

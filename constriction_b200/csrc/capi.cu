@@ -460,13 +460,12 @@ bool use_shared_tables(const ctr_model_s *m, const ctr_layout *L) {
     return L->model_index_mode == CTR_INDEX_NONE && m->shared_ok;
 }
 
-size_t coder_smem_bytes(size_t table_bytes, const ctr_layout *L, int warps) {
+// dynamic shared memory of a coder kernel: per-warp word staging + tables + 32x32 transposition tiles
+size_t coder_smem_bytes(size_t table_bytes, const ctr_layout *L, int warps, size_t stage_words_per_warp) {
     const bool contig = L->sym_offsets_dev != nullptr;
-    int tiles = 0;  // 32x32 transposition tiles
+    int tiles = 0;
     if (contig) tiles += 1 + (L->model_index_mode == CTR_INDEX_PER_SYMBOL ? 1 : 0);
-    // the per-warp staging block is sized for the ANS kernels (35-word rows + cold slots); the range
-    // kernels use a 33-word-row tile of it
-    return table_bytes + (size_t)warps * kWarpStageWords * 4 + (size_t)tiles * warps * kTileWords * 4;
+    return table_bytes + (size_t)warps * stage_words_per_warp * 4 + (size_t)tiles * warps * kTileWords * 4;
 }
 
 // SHARED implies one model for the whole batch, hence no per-symbol index.
@@ -487,6 +486,7 @@ size_t coder_smem_bytes(size_t table_bytes, const ctr_layout *L, int warps) {
 
 struct AnsEncodeLauncher {
     static unsigned block_for(bool, bool) { return kAnsBlock; }
+    static size_t stage_words() { return 32 * (kEncRingWords + 4); }  // rings + parking slots
     static int run(bool shared, bool contig, bool persym, bool f64, const AnsParams &p, size_t smem, unsigned grid,
                    unsigned block, cudaStream_t s) {
 #define CTR_COMMA ,
@@ -496,6 +496,7 @@ struct AnsEncodeLauncher {
 };
 struct AnsDecodeLauncher {
     static unsigned block_for(bool shared, bool contig) { return (shared && !contig) ? kDecBlockShared : kAnsBlock; }
+    static size_t stage_words() { return 32 * kDecRingWords; }
     static int run(bool shared, bool contig, bool persym, bool, const AnsParams &p, size_t smem, unsigned grid,
                    unsigned block, cudaStream_t s) {
         if (shared && p.model.alphabet <= 256) CTR_DISPATCH(ans_decode_kernel, 1, CTR_COMMA true);
@@ -504,6 +505,7 @@ struct AnsDecodeLauncher {
 };
 struct RangeEncodeLauncher {
     static unsigned block_for(bool, bool) { return kAnsBlock; }
+    static size_t stage_words() { return kTileWords; }
     static int run(bool shared, bool contig, bool persym, bool, const AnsParams &p, size_t smem, unsigned grid,
                    unsigned block, cudaStream_t s) {
         CTR_DISPATCH(range_encode_kernel, 2);
@@ -511,6 +513,7 @@ struct RangeEncodeLauncher {
 };
 struct RangeDecodeLauncher {
     static unsigned block_for(bool, bool) { return kAnsBlock; }
+    static size_t stage_words() { return kTileWords; }
     static int run(bool shared, bool contig, bool persym, bool, const AnsParams &p, size_t smem, unsigned grid,
                    unsigned block, cudaStream_t s) {
         CTR_DISPATCH(range_decode_kernel, 3);
@@ -567,7 +570,8 @@ int encode_common(ctr_model_t model, const int32_t *symbols_dev, const ctr_layou
     const bool shared = use_shared_tables(model, L);
     const bool contig = L->sym_offsets_dev != nullptr;
     const unsigned block = EncLauncher::block_for(shared, contig);
-    const size_t smem = coder_smem_bytes(shared ? ((size_t)model->alphabet + 1) * 16 : 0, L, block / 32);
+    const size_t smem = coder_smem_bytes(shared ? ((size_t)model->alphabet + 1) * 16 : 0, L, block / 32,
+                                         EncLauncher::stage_words());
     return EncLauncher::run(shared, contig, L->model_index_mode == CTR_INDEX_PER_SYMBOL, model->enc_f64, p, smem,
                             grid_for(L->n_streams, block), block, s);
 }
@@ -580,6 +584,7 @@ int decode_common(ctr_model_t model, const uint32_t *words, const uint64_t *offs
     if (rc) return rc;
     if (!model || !offsets || (!symbols_out && L->n_symbols)) return CTR_ERR_BAD_ARGUMENT;
     if ((L->flags & CTR_FLAG_RAW) && !states_in) return CTR_ERR_BAD_ARGUMENT;
+    if (reinterpret_cast<uintptr_t>(words) % 16 != 0) return CTR_ERR_BAD_ARGUMENT;  // 16-byte vector loads
     if (ctr_device_count() == 0) return cuda_fail(cudaErrorNoDevice, "no CUDA device");
     cudaStream_t s = (cudaStream_t)stream;
     if (L->n_streams == 0) return CTR_OK;
@@ -597,7 +602,8 @@ int decode_common(ctr_model_t model, const uint32_t *words, const uint64_t *offs
     const bool shared = use_shared_tables(model, L);
     const bool contig = L->sym_offsets_dev != nullptr;
     const unsigned block = DecLauncher::block_for(shared, contig);
-    const size_t smem = coder_smem_bytes(shared ? (size_t)kLutBytes + model->dec_cdf_bytes : 0, L, block / 32);
+    const size_t smem = coder_smem_bytes(shared ? (size_t)kLutBytes + model->dec_cdf_bytes : 0, L, block / 32,
+                                         DecLauncher::stage_words());
     return DecLauncher::run(shared, contig, L->model_index_mode == CTR_INDEX_PER_SYMBOL, false, p, smem,
                             grid_for(L->n_streams, block), block, s);
 }

@@ -21,12 +21,14 @@ constexpr unsigned kFullMask = 0xffffffffu;
 constexpr int kRowWords = 32;
 constexpr int kRowStride = 33;
 constexpr int kTileWords = kWarp * kRowStride;  // 1056 words = 4224 B per warp
-// The coder kernels' word rows are longer: a row is flushed (refilled) in units of 32 words, but it is
-// only inspected every kCheckEvery symbols, during which a lane can push (pop) up to kCheckEvery words.
-// Stride 35 is odd, so lane-private and warp-wide accesses stay conflict free.
+// The ANS kernels keep each lane's compressed words in a small lane-private ring in shared memory and move
+// them to / from HBM 16 bytes at a time with lane-private vector accesses (no warp-cooperative phase): the
+// ring is inspected once per kCheckEvery symbols, during which a lane moves at most kCheckEvery words.
 constexpr int kCheckEvery = 4;
-constexpr int kWordRowStride = kRowWords + kCheckEvery - 1;  // 35 words
-constexpr int kWordRowsWords = kWarp * kWordRowStride;       // 1120 words = 4480 B per warp
+constexpr int kEncRingWords = 8;    // encoder: <= 3 leftover + 4 new words
+constexpr int kDecRingWords = 16;   // decoder: <= 12 unread + 4 arriving words
+constexpr uint32_t kEncRingBytes = kEncRingWords * 4u;
+constexpr uint32_t kDecRingBytes = kDecRingWords * 4u;
 
 // ---- explicit shared-memory accesses by 32-bit shared address ------------------------------------------
 // (generic pointers into shared memory cost 64-bit address arithmetic in the hot loops)
@@ -60,6 +62,21 @@ __device__ __forceinline__ uint32_t lds_table_u8(uint32_t addr) {
     asm("ld.shared.u8 %0, [%1];" : "=h"(v) : "r"(addr));
     return (uint32_t)v;
 }
+__device__ __forceinline__ uint4 lds_v4(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_stream_v4(void *p, const uint4 &v) {
+    asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+                 : "memory");
+}
+// 16-byte asynchronous copy global -> shared (LDGSTS), tracked by cp.async groups
+__device__ __forceinline__ void cp_async_16(uint32_t dst_smem, const void *src_gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src_gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ uint2 lds_table_v2(uint32_t addr) {
     uint2 v;
