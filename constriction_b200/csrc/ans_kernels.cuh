@@ -35,12 +35,14 @@
 namespace ctr {
 
 constexpr int kAnsBlock = 256;  // threads per CTA (8 warps)
-constexpr uint32_t kMaxSharedAlphabet = 4095;      // bigger alphabets use the global-table path
+constexpr uint32_t kMaxSharedAlphabet = 4095;      // decoder: bigger alphabets use the global-table path
+constexpr uint32_t kMaxSharedEncAlphabet = 511;    // encoder: its shared table is replicated 8x (128 B per entry)
 
 struct ModelView {
     const uint32_t *cdf;   // [n_models][alphabet + 1]
     const uint4 *enc;      // [n_models][alphabet + 1] {left, prob, reciprocal lo, hi}; entry [alphabet] is
                            // the all-zero sentinel that out-of-range symbols are clamped to
+    const uint4 *enc_rep;  // model 0 only: [alphabet + 1][8] -- each entry 8 times, one copy per 16-byte bank group
     const uint32_t *dec;   // model 0 only: quantile index uint2[kLutSize] ++ cdf u32[alphabet + 2] (padded to 16 B)
     uint32_t n_models;
     uint32_t alphabet;
@@ -205,15 +207,17 @@ __global__ void __launch_bounds__(kAnsBlock, 4) ans_encode_kernel(const AnsParam
     // tiles][index tiles].  The parking slot keeps values that are only needed again at the very end
     // (scratch base, capacity) out of the hot loop's registers.
     const uint32_t alphabet = p.model.alphabet;
-    const uint32_t table_words = SHARED ? (alphabet + 1) * 4 : 0;
+    const uint32_t table_words = SHARED ? (alphabet + 1) * 32 : 0;
     constexpr uint32_t kRingsWords = kAnsBlock * (kEncRingWords + 4);
     const uint32_t ring = smem_u32_pinned(smem) + threadIdx.x * kEncRingBytes;  // 32-byte aligned
     const uint32_t park = smem_u32(smem) + kAnsBlock * kEncRingBytes + threadIdx.x * 16u;
-    const uint32_t table_addr = smem_u32_pinned(smem + kRingsWords);
+    // lane l reads copy (l & 7) of an entry: the 8 lanes of a quarter-warp always hit 8 different 16-byte bank
+    // groups, so the random-index LDS.128 is conflict free
+    const uint32_t table_addr = smem_u32_pinned(smem + kRingsWords) + (uint32_t)(lane & 7) * 16u;
     uint32_t *sym_tile = smem + kRingsWords + table_words + warp_in_cta * kTileWords;
     uint32_t *idx_tile = sym_tile + kWarpsPerCta * kTileWords;
 
-    if (SHARED) stage_table(smem + kRingsWords, p.model.enc, (alphabet + 1) * 16u, &bar);
+    if (SHARED) stage_table(smem + kRingsWords, p.model.enc_rep, (alphabet + 1) * 128u, &bar);
 
     const uint64_t K = p.K, N = p.N;
     const uint32_t tile = take_tile_ticket(p.compact.ticket);  // which 256 streams this CTA codes
@@ -253,11 +257,12 @@ __global__ void __launch_bounds__(kAnsBlock, 4) ans_encode_kernel(const AnsParam
     const uint32_t min_symbol = (uint32_t)p.model.min_symbol;
 
     // one reference encode_symbol (stack.rs:1014-1048)
-    auto encode_one = [&](int32_t sym, uint32_t m) {
-        uint32_t idx = min((uint32_t)sym - min_symbol, alphabet);  // out of range -> sentinel entry
+    // symbol -> table index; out-of-range symbols map to the sentinel entry [alphabet]
+    auto index_of = [&](int32_t sym) -> uint32_t { return min((uint32_t)sym - min_symbol, alphabet); };
+    auto encode_idx = [&](uint32_t idx, uint32_t m) {
         uint4 e;
         if (SHARED) {
-            e = lds_table_v4(table_addr + idx * 16u);
+            e = lds_table_v4(table_addr + idx * 128u);
         } else {
             const bool ok = m < n_models;
             idx = ok ? idx : alphabet;
@@ -286,23 +291,26 @@ __global__ void __launch_bounds__(kAnsBlock, 4) ans_encode_kernel(const AnsParam
         q += fix ? 1u : 0u;
         state = (q << kPrecision) + (uint64_t)(e.x + r);  // stack.rs:1042-1045 (left + r < 2^24)
     };
+    auto encode_one = [&](int32_t sym, uint32_t m) { encode_idx(index_of(sym), m); };
 
     // every kCheckEvery symbols: a complete 16-byte group of my ring goes to my scratch region.  A lane
     // pushes at most kCheckEvery words in between, so one group per check keeps up with any input.
-    auto drain_ring = [&]() {
+    auto drain_store = [&](const uint4 &v) {
         if (pending >= 16u) {
-            const uint4 v = lds_v4(ring | ((pushed - pending) & (kEncRingBytes - 1u)));
             if (room >= 16u) {
                 st_stream_v4(gw, v);
                 gw += 16;
                 room -= 16u;
             } else {
-                room = 0u;  // words dropped: the stream is flagged at the end (room == 0 with words pending)
+                room = 0u;  // words dropped: the stream is flagged at the end
                 pushed |= 0x80000000u;
             }
             pending -= 16u;
         }
     };
+    // the oldest (possibly incomplete) 16-byte group of my ring; harmless to read when it is not yet complete
+    auto drain_load = [&]() -> uint4 { return lds_v4(ring | ((pushed - pending) & (kEncRingBytes - 16u))); };
+    auto drain_ring = [&]() { drain_store(drain_load()); };
 
     if (!CONTIG) {
         // ---- interleaved deal: row t holds symbols[t*K .. t*K+K); coded from the last row backwards ---
@@ -335,11 +343,46 @@ __global__ void __launch_bounds__(kAnsBlock, 4) ans_encode_kernel(const AnsParam
                     }
                 }
             };
+            // L2 prefetch kPrefetchBatches batches ahead: one instruction covers the warp's four 128-byte lines
+            // of a future batch (lanes 8j..8j+7 address row j of that batch)
+            constexpr int kPrefetchBatches = 6;
+            const char *pf = ps - ((uint64_t)kPrefetchBatches * kCheckEvery + (uint32_t)(lane >> 3)) * row_bytes;
+            const char *const pf_floor = reinterpret_cast<const char *>(p.symbols_in);
+            const uint64_t batch_bytes = row_bytes * kCheckEvery;
+            static_assert(kCheckEvery == 4, "code_batch is written for batches of four");
             auto code_batch = [&](int which, bool load_next) {
-                if (load_next) load_batch(which ^ 1);
-                drain_ring();
+                // Consume this batch's loads first (they were issued a whole batch ago), and only then
+                // issue the next batch's: a scoreboard wait on "my" loads must never cover loads that
+                // were issued a moment ago.  The empty asm statements pin that order.
+                uint32_t idx[kCheckEvery];
 #pragma unroll
-                for (int u = 0; u < kCheckEvery; ++u) encode_one(buf[which][u], mbuf[which][u]);
+                for (int u = 0; u < kCheckEvery; ++u) {
+                    idx[u] = index_of(buf[which][u]);
+                    asm volatile("" : "+r"(idx[u]));
+                }
+                if (load_next) load_batch(which ^ 1);
+                if (pf >= pf_floor) prefetch_l2(pf);
+                pf -= batch_bytes;
+                // drain: the 16-byte group is read from the ring now and stored two symbols later, so the
+                // shared-memory latency is covered by coding work.  The decision is taken now (a group that
+                // completes during this batch waits for the next check; the ring has room for that).
+                const bool full = pending >= 16u;
+                const uint4 oldest = drain_load();
+                encode_idx(idx[0], mbuf[which][0]);
+                encode_idx(idx[1], mbuf[which][1]);
+                if (full) {
+                    if (room >= 16u) {
+                        st_stream_v4(gw, oldest);
+                        gw += 16;
+                        room -= 16u;
+                    } else {
+                        room = 0u;
+                        pushed |= 0x80000000u;
+                    }
+                    pending -= 16u;
+                }
+                encode_idx(idx[2], mbuf[which][2]);
+                encode_idx(idx[3], mbuf[which][3]);
             };
             // (a stream of >= 2^34 symbols is split by the caller; 32-bit counters keep the loop lean)
             uint32_t batches = (uint32_t)(rows_total / kCheckEvery);

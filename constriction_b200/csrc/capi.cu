@@ -87,7 +87,8 @@ struct ctr_model_s {
     uint32_t n_models = 0, alphabet = 0;
     int32_t min_symbol = 0;
     uint32_t *d_cdf = nullptr;  // [n_models][alphabet+1]
-    uint4 *d_enc = nullptr;     // [n_models][alphabet], built on first encode
+    uint4 *d_enc = nullptr;     // [n_models][alphabet + 1], built on first encode
+    uint4 *d_enc_rep = nullptr; // model 0, every entry 8 times (small alphabets only)
     uint32_t *d_dec = nullptr;  // model 0: pairs + bucket index, built on first decode
     uint32_t dec_cdf_bytes = 0;  // (alphabet + 2) * 4 rounded up to 16: the cdf part of d_dec
     bool shared_ok = false;  // small enough for the shared-memory table kernels
@@ -135,6 +136,12 @@ int ensure_enc_table(ctr_model_s *m, cudaStream_t s) {
     build_enc_table_kernel<<<grid_for(entries, 256), 256, 0, s>>>(m->d_cdf, m->n_models, m->alphabet,
                                                                   m->enc_f64 ? 1 : 0, m->d_enc);
     LAUNCH_CHECK("build_enc_table_kernel");
+    if (m->alphabet <= kMaxSharedEncAlphabet) {
+        const uint32_t n = (m->alphabet + 1) * 8u;
+        CUDA_TRY(cudaMalloc(&m->d_enc_rep, (size_t)n * 16));
+        replicate_enc_table_kernel<<<grid_for(n, 256), 256, 0, s>>>(m->d_enc, m->alphabet, m->d_enc_rep);
+        LAUNCH_CHECK("replicate_enc_table_kernel");
+    }
     return CTR_OK;
 }
 
@@ -179,6 +186,7 @@ ModelView model_view(const ctr_model_s *m) {
     ModelView v;
     v.cdf = m->d_cdf;
     v.enc = m->d_enc;
+    v.enc_rep = m->d_enc_rep;
     v.dec = m->d_dec;
     v.n_models = m->n_models;
     v.alphabet = m->alphabet;
@@ -416,6 +424,7 @@ extern "C" int ctr_model_destroy(ctr_model_t m) {
     if (!m) return CTR_OK;
     if (m->d_cdf) cudaFree(m->d_cdf);
     if (m->d_enc) cudaFree(m->d_enc);
+    if (m->d_enc_rep) cudaFree(m->d_enc_rep);
     if (m->d_dec) cudaFree(m->d_dec);
     delete m;
     return CTR_OK;
@@ -459,6 +468,10 @@ namespace {
 bool use_shared_tables(const ctr_model_s *m, const ctr_layout *L) {
     return L->model_index_mode == CTR_INDEX_NONE && m->shared_ok;
 }
+// the ANS encoder's replicated table needs 128 B per entry
+bool use_shared_ans_enc_table(const ctr_model_s *m, const ctr_layout *L) {
+    return use_shared_tables(m, L) && m->alphabet <= kMaxSharedEncAlphabet;
+}
 
 // dynamic shared memory of a coder kernel: per-warp word staging + tables + 32x32 transposition tiles
 size_t coder_smem_bytes(size_t table_bytes, const ctr_layout *L, int warps, size_t stage_words_per_warp) {
@@ -485,6 +498,8 @@ size_t coder_smem_bytes(size_t table_bytes, const ctr_layout *L, int warps, size
     } while (0)
 
 struct AnsEncodeLauncher {
+    static bool shared(const ctr_model_s *m, const ctr_layout *L) { return use_shared_ans_enc_table(m, L); }
+    static size_t table_bytes(const ctr_model_s *m) { return ((size_t)m->alphabet + 1) * 128; }
     static unsigned block_for(bool, bool) { return kAnsBlock; }
     static size_t stage_words() { return 32 * (kEncRingWords + 4); }  // rings + parking slots
     static int run(bool shared, bool contig, bool persym, bool f64, const AnsParams &p, size_t smem, unsigned grid,
@@ -504,6 +519,8 @@ struct AnsDecodeLauncher {
     }
 };
 struct RangeEncodeLauncher {
+    static bool shared(const ctr_model_s *m, const ctr_layout *L) { return use_shared_tables(m, L); }
+    static size_t table_bytes(const ctr_model_s *m) { return ((size_t)m->alphabet + 1) * 16; }
     static unsigned block_for(bool, bool) { return kAnsBlock; }
     static size_t stage_words() { return kTileWords; }
     static int run(bool shared, bool contig, bool persym, bool, const AnsParams &p, size_t smem, unsigned grid,
@@ -567,10 +584,10 @@ int encode_common(ctr_model_t model, const int32_t *symbols_dev, const ctr_layou
     p.compact.offsets_out = offsets_out;
     CUDA_TRY(cudaMemsetAsync(ws + w.status_off, 0, w.total - w.status_off, s));
 
-    const bool shared = use_shared_tables(model, L);
+    const bool shared = EncLauncher::shared(model, L);
     const bool contig = L->sym_offsets_dev != nullptr;
     const unsigned block = EncLauncher::block_for(shared, contig);
-    const size_t smem = coder_smem_bytes(shared ? ((size_t)model->alphabet + 1) * 16 : 0, L, block / 32,
+    const size_t smem = coder_smem_bytes(shared ? EncLauncher::table_bytes(model) : 0, L, block / 32,
                                          EncLauncher::stage_words());
     return EncLauncher::run(shared, contig, L->model_index_mode == CTR_INDEX_PER_SYMBOL, model->enc_f64, p, smem,
                             grid_for(L->n_streams, block), block, s);

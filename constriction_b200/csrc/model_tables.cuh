@@ -123,6 +123,13 @@ __global__ void build_enc_table_kernel(const uint32_t *cdf, uint32_t n_models, u
     enc[tid] = make_uint4(left, prob, (uint32_t)rcp, (uint32_t)(rcp >> 32));
 }
 
+// model 0's encoder entries replicated 8 times each ([alphabet + 1][8] uint4): the ANS encoder stages this
+// layout in shared memory so that lane l can read copy (l & 7), which makes its LDS.128 conflict free
+__global__ void replicate_enc_table_kernel(const uint4 *enc, uint32_t alphabet, uint4 *rep) {
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid < (alphabet + 1) * 8u) rep[tid] = enc[tid >> 3];
+}
+
 // decoder table of model 0 (see lookup_shared in ans_kernels.cuh): quantile index uint2[kLutSize], then the
 // CDF row with one extra 2^24 entry.
 __global__ void build_dec_table_kernel(const uint32_t *cdf, uint32_t alphabet, uint32_t *dec) {
