@@ -46,7 +46,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
         raise RuntimeError("nvcc not found: cannot build libconstriction_b200.so")
-    cmd = [nvcc] + NVCC_FLAGS + ["-o", LIB, os.path.join(CSRC, "capi.cu")]
+    extra = os.environ.get("CTR_EXTRA_NVCC_FLAGS", "").split()  # experiments only (e.g. -DCTR_PF_BATCHES=8)
+    cmd = [nvcc] + NVCC_FLAGS + extra + ["-o", LIB, os.path.join(CSRC, "capi.cu")]
     proc = subprocess.run(cmd, capture_output=True, text=True)
     if proc.returncode != 0:
         sys.stderr.write(proc.stdout + proc.stderr)

@@ -279,17 +279,7 @@ __global__ void __launch_bounds__(kAnsBlock, 4) ans_encode_kernel(const AnsParam
             hi = 0u;
         }
         const uint64_t n = ((uint64_t)hi << 32) | lo;
-        uint64_t q;
-        if (F64DIV) {
-            q = __double2ull_rz(__ull2double_rz(n) * __hiloint2double((int)e.w, (int)e.z));
-        } else {
-            q = __umul64hi(n, ((uint64_t)e.w << 32) | e.z);
-        }
-        uint32_t r = lo - (uint32_t)q * e.y;  // remainder of the estimate, in [0, 2 prob)
-        const bool fix = r >= e.y;
-        r -= fix ? e.y : 0u;
-        q += fix ? 1u : 0u;
-        state = (q << kPrecision) + (uint64_t)(e.x + r);  // stack.rs:1042-1045 (left + r < 2^24)
+        state = ans_encode_recombine(n, ans_quotient_estimate<F64DIV>(n, e.z, e.w), e.x, e.y);
     };
     auto encode_one = [&](int32_t sym, uint32_t m) { encode_idx(index_of(sym), m); };
 
@@ -345,7 +335,10 @@ __global__ void __launch_bounds__(kAnsBlock, 4) ans_encode_kernel(const AnsParam
             };
             // L2 prefetch kPrefetchBatches batches ahead: one instruction covers the warp's four 128-byte lines
             // of a future batch (lanes 8j..8j+7 address row j of that batch)
-            constexpr int kPrefetchBatches = 6;
+#ifndef CTR_PF_BATCHES
+#define CTR_PF_BATCHES 6
+#endif
+            constexpr int kPrefetchBatches = CTR_PF_BATCHES;
             const char *pf = ps - ((uint64_t)kPrefetchBatches * kCheckEvery + (uint32_t)(lane >> 3)) * row_bytes;
             const char *const pf_floor = reinterpret_cast<const char *>(p.symbols_in);
             const uint64_t batch_bytes = row_bytes * kCheckEvery;
@@ -361,8 +354,10 @@ __global__ void __launch_bounds__(kAnsBlock, 4) ans_encode_kernel(const AnsParam
                     asm volatile("" : "+r"(idx[u]));
                 }
                 if (load_next) load_batch(which ^ 1);
-                if (pf >= pf_floor) prefetch_l2(pf);
-                pf -= batch_bytes;
+                if (kPrefetchBatches > 0) {
+                    if (pf >= pf_floor) prefetch_l2(pf);
+                    pf -= batch_bytes;
+                }
                 // drain: the 16-byte group is read from the ring now and stored two symbols later, so the
                 // shared-memory latency is covered by coding work.  The decision is taken now (a group that
                 // completes during this batch waits for the next check; the ring has room for that).

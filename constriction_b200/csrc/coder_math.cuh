@@ -12,7 +12,9 @@
 //   Range encode  src/stream/queue.rs:612-705        decode  src/stream/queue.rs:968-1035
 //   Range seal    src/stream/queue.rs:349-376,458-523
 #pragma once
+#include <math.h>
 #include <stdint.h>
+#include <string.h>
 
 #if defined(__CUDACC__)
 #define CTR_HD __host__ __device__ __forceinline__
@@ -74,12 +76,58 @@ CTR_HD bool ans_encode_needs_flush(uint64_t state, uint32_t prob) {
     return (uint32_t)(state >> (64 - kPrecision)) >= prob;  // state>>40 < 2^24, prob <= 2^24
 }
 
-// stack.rs:1042-1045 on the (already renormalised) state.
+// ---- the encoder's division: state / prob and state % prob without a divider --------------------------
+// Two interchangeable quotient estimates, both in {q - 1, q} for every n < prob * 2^40 (the renormalised
+// state), followed by the same exact correction:
+//   integer : mulhi64(n, floor((2^64-1)/prob))                       (see reciprocal_u64)
+//   FP64    : trunc(rz(double(n)) * ((1/prob) * (1 - 2^-50)))        3 instructions on the GPU
+//             every rounding involved is below 2^-52 relative and the bias is 2^-50, so the product never
+//             exceeds n/prob and falls short of it by less than 2^40 * 1.7 * 2^-50 < 1.
+CTR_HD uint64_t reciprocal_f64_bits(uint32_t d) {
+    if (d == 0) return 0ull;
+    const double r = (1.0 / (double)d) * (1.0 - 8.8817841970012523e-16);  // 2^-50
+    uint64_t b;
+#if defined(__CUDA_ARCH__)
+    b = (uint64_t)__double_as_longlong(r);
+#else
+    memcpy(&b, &r, 8);
+#endif
+    return b;
+}
+
+template <bool F64>
+CTR_HD uint64_t ans_quotient_estimate(uint64_t n, uint32_t rcp_lo, uint32_t rcp_hi) {
+    if (F64) {
+#if defined(__CUDA_ARCH__)
+        return __double2ull_rz(__ull2double_rz(n) * __hiloint2double((int)rcp_hi, (int)rcp_lo));
+#else
+        double nd = (double)n;  // round to nearest; step down if that rounded up (round toward zero)
+        if (nd >= 18446744073709551616.0 || (uint64_t)nd > n) nd = nextafter(nd, 0.0);
+        const uint64_t bits = ((uint64_t)rcp_hi << 32) | rcp_lo;
+        double r;
+        memcpy(&r, &bits, 8);
+        return (uint64_t)(nd * r);
+#endif
+    }
+    return mulhi64(n, ((uint64_t)rcp_hi << 32) | rcp_lo);
+}
+
+// stack.rs:1042-1045 on the (already renormalised) state n, given an estimate q_est in {q - 1, q}:
+// new state = (q << 24) | (left + n % prob).  With r = n - q_est * prob in [0, 2 prob) (its low 32 bits carry
+// it exactly since prob <= 2^24): if r >= prob the true quotient is q_est + 1 and the true remainder
+// r - prob, i.e. the new state is larger by 2^24 - prob.
+CTR_HD uint64_t ans_encode_recombine(uint64_t n, uint64_t q_est, uint32_t left, uint32_t prob) {
+    const uint32_t r = (uint32_t)n - (uint32_t)q_est * prob;
+    const uint32_t bump = r >= prob ? kTotal - prob : 0u;
+    return (q_est << kPrecision) + (uint64_t)(left + r + bump);
+}
+
 CTR_HD uint64_t ans_encode_update(uint64_t state, uint32_t left, uint32_t prob, uint64_t rcp) {
-    uint64_t prefix;
-    uint32_t remainder;
-    divmod_by_reciprocal(state, prob, rcp, prefix, remainder);
-    return (prefix << kPrecision) | (uint64_t)(left + remainder);
+    return ans_encode_recombine(state, ans_quotient_estimate<false>(state, (uint32_t)rcp, (uint32_t)(rcp >> 32)), left, prob);
+}
+CTR_HD uint64_t ans_encode_update_f64(uint64_t state, uint32_t left, uint32_t prob, uint64_t rcp_bits) {
+    return ans_encode_recombine(state, ans_quotient_estimate<true>(state, (uint32_t)rcp_bits, (uint32_t)(rcp_bits >> 32)),
+                                left, prob);
 }
 
 // stack.rs:1086

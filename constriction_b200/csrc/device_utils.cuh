@@ -165,7 +165,11 @@ __device__ __forceinline__ uint32_t ld_stream_u32(const uint32_t *p) {
 }
 __device__ __forceinline__ int32_t ld_stream_s32(const int32_t *p) {
     int32_t v;
+#ifdef CTR_LD_PLAIN
+    asm volatile("ld.global.s32 %0, [%1];" : "=r"(v) : "l"(p));
+#else
     asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
+#endif
     return v;
 }
 __device__ __forceinline__ void st_stream_u32(uint32_t *p, uint32_t v) {

@@ -113,13 +113,7 @@ __global__ void build_enc_table_kernel(const uint32_t *cdf, uint32_t n_models, u
     }
     const uint32_t *row = cdf + m * per;
     const uint32_t left = row[s], prob = row[s + 1] - row[s];
-    uint64_t rcp;
-    if (f64) {
-        const double r = (1.0 / (double)prob) * (1.0 - 8.8817841970012523e-16);  // 2^-50
-        rcp = prob ? (uint64_t)__double_as_longlong(r) : 0ull;
-    } else {
-        rcp = reciprocal_u64(prob);
-    }
+    const uint64_t rcp = f64 ? reciprocal_f64_bits(prob) : reciprocal_u64(prob);
     enc[tid] = make_uint4(left, prob, (uint32_t)rcp, (uint32_t)(rcp >> 32));
 }
 

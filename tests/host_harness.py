@@ -28,7 +28,9 @@ def load():
     L.h_divmod.restype = None
     L.h_divmod_check.argtypes = [u64p, u32p, C.c_uint64]
     L.h_divmod_check.restype = C.c_uint64
-    L.h_ans_encode.argtypes = [i32p, C.c_uint64, u32p, C.c_int32, C.c_uint64, u32p, u64p]
+    L.h_ans_encode.argtypes = [i32p, C.c_uint64, u32p, C.c_int32, C.c_uint64, u32p, u64p, C.c_int]
+    L.h_f64div_check.argtypes = [u64p, u32p, C.c_uint64]
+    L.h_f64div_check.restype = C.c_uint64
     L.h_ans_encode.restype = C.c_uint64
     L.h_ans_decode.argtypes = [u32p, C.c_uint64, i32p, C.c_uint64, u32p, C.c_uint32, C.c_int32]
     L.h_ans_decode.restype = None

@@ -30,9 +30,21 @@ uint64_t h_divmod_check(const uint64_t *n, const uint32_t *d, uint64_t count) {
     return bad;
 }
 
+// returns mismatches of the FP64-reciprocal division (estimate + exact correction) against native / and %
+// over `count` (n, d) pairs with n < d * 2^40 (the encoder's operand range)
+uint64_t h_f64div_check(const uint64_t *n, const uint32_t *d, uint64_t count) {
+    uint64_t bad = 0;
+    for (uint64_t i = 0; i < count; ++i) {
+        const uint64_t got = ans_encode_update_f64(n[i], 0u, d[i], reciprocal_f64_bits(d[i]));
+        const uint64_t want = ((n[i] / d[i]) << 24) | (n[i] % d[i]);
+        if (got != want) ++bad;
+    }
+    return bad;
+}
+
 // One ANS coder: encode symbols (reverse) with cdf; returns words (bulk ++ state).  out must hold n+2.
 uint64_t h_ans_encode(const int32_t *symbols, uint64_t n, const uint32_t *cdf, int32_t min_symbol,
-                      uint64_t init_state, uint32_t *out, uint64_t *state_out) {
+                      uint64_t init_state, uint32_t *out, uint64_t *state_out, int f64) {
     uint64_t state = init_state, len = 0;
     for (uint64_t i = n; i-- > 0;) {
         const uint32_t idx = (uint32_t)symbols[i] - (uint32_t)min_symbol;
@@ -41,7 +53,8 @@ uint64_t h_ans_encode(const int32_t *symbols, uint64_t n, const uint32_t *cdf, i
             out[len++] = (uint32_t)state;
             state >>= 32;
         }
-        state = ans_encode_update(state, left, prob, reciprocal_u64(prob));
+        state = f64 ? ans_encode_update_f64(state, left, prob, reciprocal_f64_bits(prob))
+                    : ans_encode_update(state, left, prob, reciprocal_u64(prob));
     }
     *state_out = state;
     const uint32_t ns = ans_state_words(state);

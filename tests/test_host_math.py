@@ -34,6 +34,11 @@ def test_division_by_reciprocal_is_exact(H):
     nn[n // 2 + 64: n // 2 + 128] = lim[n // 2 + 64: n // 2 + 128] - np.uint64(1)
     nn = np.ascontiguousarray(nn)
     assert H.h_divmod_check(P(nn, u64p), P(d, u32p), n) == 0
+    # the FP64-pipe estimate is only claimed for the encoder's operand range n < d * 2^40
+    m = np.ascontiguousarray(nn % lim)
+    m[:64] = lim[:64] - np.uint64(1)
+    m[64:128] = (lim[64:128] // np.uint64(2)) | np.uint64(1)
+    assert H.h_f64div_check(P(m, u64p), P(d, u32p), n) == 0
 
 
 def test_range_quantile_division_is_exact(H):
@@ -97,8 +102,9 @@ def test_ans_stream_matches_oracle(H, oracle, spec, n):
     want = oracle.ans_encode_iid(syms, cdf, lo)
     out = np.empty(n + 2, dtype=np.uint32)
     st = C.c_uint64()
-    m = H.h_ans_encode(P(syms, i32p), n, P(cdf, u32p), lo, 0, P(out, u32p), C.byref(st))
-    assert np.array_equal(out[:m], want)
+    for f64 in (0, 1):
+        m = H.h_ans_encode(P(syms, i32p), n, P(cdf, u32p), lo, 0, P(out, u32p), C.byref(st), f64)
+        assert np.array_equal(out[:m], want), f64
     dec = np.empty(n, dtype=np.int32)
     H.h_ans_decode(P(want, u32p), want.size, P(dec, i32p), n, P(cdf, u32p), cdf.size - 1, lo)
     assert np.array_equal(dec, syms)
