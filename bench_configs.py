@@ -1,0 +1,189 @@
+#!/usr/bin/env python
+"""bench_configs.py -- the other BASELINE.json configs, one JSON line each.
+
+`bench.py` is the contract benchmark (configs[1]).  This script times the remaining GPU configs on one
+B200 with the same hygiene (CUDA events, >= 3 warm-ups, device-resident inputs) and checks each result
+(round trip and/or oracle spot checks):
+
+  config 3  1e8 symbols, per-symbol Categorical models out of a pool of 1e6 256-bin CDFs (1.03 GB, streamed
+            from HBM / L2), ANS decode only
+  config 4  RangeEncoder, 122,070-symbol streams (the per-GPU shard of "1e9 symbols in 8192 streams on 8 GPUs"
+            is 1024 streams; also run with all 8192 streams on one GPU)
+  config 5  learned-image-compression shape: int32[64,192,32,32] latents, 192 per-channel QuantizedGaussian
+            models, one ANS stream per (image, channel)
+
+    python bench_configs.py [--configs 3,4,5] [--scale 1.0]
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def timed(fn, warmup=3, steps=5):
+    import torch
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+    ev[0].record()
+    for i in range(steps):
+        fn()
+        ev[i + 1].record()
+    torch.cuda.synchronize()
+    return ev[0].elapsed_time(ev[-1]) / steps  # ms
+
+
+def config3(scale):
+    """ANS decode with a per-symbol model index into a 1e6 x 256 CDF pool."""
+    import torch
+    from constriction_b200 import batch as B
+    from oracle import refapi as O
+    M, A = int(1_000_000 * scale), 256
+    n, k = int(100_000_000 * scale), 148 * 1024
+    g = torch.Generator(device="cuda")
+    g.manual_seed(3)
+    # Dirichlet(0.5) rows = normalised Gamma(0.5) draws, float32 (the pmf dtype decides the rounding)
+    gam = torch._standard_gamma(torch.full((M, A), 0.5, device="cuda"), generator=g).clamp_min_(1e-30)
+    pmf = (gam / gam.sum(dim=1, keepdim=True)).to(torch.float32)
+    del gam
+    model = B.ModelTable.categorical(pmf)
+    idx = torch.randint(0, M, (n,), device="cuda", dtype=torch.int32, generator=g)
+    # ANS decoding is surjective: decoding uniformly random words draws every symbol from its model, which is
+    # exactly "symbols sampled per row".  ~7 bits/symbol for these rows -> 0.25 words per symbol is ample.
+    words_per_stream = int(math.ceil(n / k * 0.25)) + 2
+    words = torch.randint(-2**31, 2**31 - 1, (k * words_per_stream,), device="cuda", dtype=torch.int32, generator=g)
+    words[words_per_stream - 1::words_per_stream] |= 1  # a valid ANS stream never ends in a zero word
+    offsets = (torch.arange(k + 1, device="cuda", dtype=torch.int64) * words_per_stream)
+    comp = B.Compressed(words, offsets, k, n, "ans")
+    bc = B.BatchCoder()
+    out = torch.empty(n, dtype=torch.int32, device="cuda")
+
+    ms = timed(lambda: bc.ans_decode(comp, model, model_index=idx, index_mode=1, out=out))
+    bc.check()
+    # parity: spot-check streams against the oracle's per-symbol-model decode
+    cdfs_dev = None
+    ok = True
+    cdf_rows = {}
+    for s in (0, 77, k - 1):
+        sl = slice(s, n, k)
+        ids = idx[sl].cpu().numpy().astype(np.uint32)
+        rows = np.unique(ids)
+        sub = B.ModelTable.categorical(pmf[torch.from_numpy(rows.astype(np.int64)).cuda()]).cdf()
+        remap = np.searchsorted(rows, ids).astype(np.uint32)
+        w = words[s * words_per_stream:(s + 1) * words_per_stream].cpu().numpy().view(np.uint32)
+        want = O.ans_decode_indexed(w, remap, sub, 0)
+        ok &= bool(np.array_equal(out[sl].cpu().numpy(), want))
+    # every decoded symbol reads its model's CDF row by binary search: 8 probes + the 2 interval ends
+    return {"config": 3, "workload": f"{n} symbols, {M} x {A} categorical pool ({M * (A + 1) * 4 / 1e9:.2f} GB), "
+                                     f"per-symbol model index, ANS decode, {k} streams",
+            "ms": ms, "Msymbols_per_s": n / ms / 1e3, "parity_spot_check": ok,
+            "bytes_per_symbol_if_rows_streamed": 4 * (A + 1) + 8 + 1, "note": "binary search touches <= 9 sectors"}
+
+
+def config4(scale, streams):
+    """Range coder, long contiguous streams."""
+    import torch
+    from constriction_b200 import batch as B
+    from oracle import refapi as O
+    per = int(122_070 * scale)
+    k, n = streams, streams * per
+    g = torch.Generator(device="cuda")
+    g.manual_seed(4)
+    syms = torch.clamp(torch.round(torch.randn(n, device="cuda", generator=g) * 9.6 + 3.2), -50, 50).to(torch.int32)
+    off = torch.arange(k + 1, device="cuda", dtype=torch.int64) * per
+    model = B.ModelTable.quantized_gaussian(-50, 50, [3.2], [9.6])
+    bc = B.BatchCoder()
+    state = {}
+
+    def enc():
+        state["c"] = bc.range_encode(syms, model, sym_offsets=off, out=state.get("c"))
+
+    ms_enc = timed(enc)
+    comp = state["c"]
+    out = torch.empty_like(syms)
+    ms_dec = timed(lambda: bc.range_decode(comp, model, out=out))
+    bc.check()
+    ok = bool(torch.equal(out, syms))
+    cdf = model.cdf()[0]
+    for s in (0, k - 1):
+        want = O.range_encode_iid(syms[s * per:(s + 1) * per].cpu().numpy(), cdf, -50)
+        ok &= bool(np.array_equal(comp.stream_words(s), want))
+    return {"config": 4, "workload": f"{k} RangeEncoder streams x {per} symbols (contiguous), QG(-50,50,3.2,9.6)",
+            "ms_encode": ms_enc, "ms_decode": ms_dec, "Msymbols_per_s_encode": n / ms_enc / 1e3,
+            "Msymbols_per_s_decode": n / ms_dec / 1e3, "Msymbols_per_s_round_trip": n / (ms_enc + ms_dec) / 1e3,
+            "parity": ok, "note": "one dependent chain per stream: latency-bound, not HBM-bound"}
+
+
+def config5(images=64):
+    """int32[images,192,32,32] latents, one QuantizedGaussian per channel, one ANS stream per (image, channel)."""
+    import torch
+    from constriction_b200 import batch as B
+    from oracle import refapi as O
+    rng = np.random.default_rng(5)
+    C_, HW = 192, 32 * 32
+    mu = rng.normal(0, 2, C_)
+    sigma = np.exp(rng.uniform(np.log(0.3), np.log(12), C_))
+    model = B.ModelTable.quantized_gaussian(-64, 64, mu, sigma)
+    g = torch.Generator(device="cuda")
+    g.manual_seed(5)
+    t_mu = torch.from_numpy(mu).cuda().float()[None, :, None]
+    t_sg = torch.from_numpy(sigma).cuda().float()[None, :, None]
+    lat = torch.clamp(torch.round(torch.randn(images, C_, HW, device="cuda", generator=g) * t_sg + t_mu), -64, 64)
+    syms = lat.to(torch.int32).reshape(-1).contiguous()
+    k, n = images * C_, images * C_ * HW
+    off = torch.arange(k + 1, device="cuda", dtype=torch.int64) * HW
+    sidx = torch.arange(C_, device="cuda", dtype=torch.int32).repeat(images)
+    bc = B.BatchCoder()
+    state = {}
+
+    def enc():
+        state["c"] = bc.ans_encode(syms, model, sym_offsets=off, model_index=sidx, index_mode=2, out=state.get("c"))
+
+    ms_enc = timed(enc)
+    comp = state["c"]
+    out = torch.empty_like(syms)
+    ms_dec = timed(lambda: bc.ans_decode(comp, model, model_index=sidx, index_mode=2, out=out))
+    bc.check()
+    ok = bool(torch.equal(out, syms))
+    cdfs = model.cdf()
+    for s in (0, 191, k - 1):
+        want = O.ans_encode_iid(syms[s * HW:(s + 1) * HW].cpu().numpy(), cdfs[s % C_], -64)
+        ok &= bool(np.array_equal(comp.stream_words(s), want))
+    return {"config": 5, "workload": f"latents int32[{images},192,32,32], 192 per-channel QuantizedGaussian(-64,64), "
+                                     f"{k} ANS streams x {HW} symbols",
+            "us_encode": ms_enc * 1e3, "us_decode": ms_dec * 1e3,
+            "Msymbols_per_s_round_trip": n / (ms_enc + ms_dec) / 1e3, "parity": ok,
+            "bits_per_symbol": 32.0 * comp.total_words() / n}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--configs", default="3,4,5")
+    ap.add_argument("--scale", type=float, default=1.0)
+    args = ap.parse_args()
+    import torch
+    assert torch.cuda.is_available(), "needs a CUDA device"
+    for c in [int(x) for x in args.configs.split(",")]:
+        if c == 3:
+            print(json.dumps(config3(args.scale)), flush=True)
+        elif c == 4:
+            print(json.dumps(config4(args.scale, 1024)), flush=True)
+            print(json.dumps(config4(args.scale, 8192)), flush=True)
+        elif c == 5:
+            print(json.dumps(config5(64)), flush=True)
+            print(json.dumps(config5(8)), flush=True)
+        torch.cuda.empty_cache()
+
+
+if __name__ == "__main__":
+    main()
