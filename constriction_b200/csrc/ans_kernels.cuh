@@ -87,16 +87,25 @@ __device__ __noinline__ void warp_flush_rows(unsigned mask, const uint32_t *rows
     __syncwarp();
 }
 
-// Fill row i with the `count_i` words at src_i, for every lane i in `mask`.
+// Fill row i with the `count_i` words at src_i, for every lane i in `mask` (count_i == 0 for the others).
+// Eight rows are in flight at a time: the loads of a group are all issued before the first store, so a
+// tile costs four global round trips instead of thirty-two.
 __device__ __noinline__ void warp_fill_rows(unsigned mask, uint32_t *rows, const uint32_t *src, uint32_t count,
                                             int lane) {
     __syncwarp();
-    while (mask) {
-        const int i = __ffs(mask) - 1;
-        mask &= mask - 1;
-        const uint32_t *s = (const uint32_t *)shfl_u64((uint64_t)src, i);
-        const uint32_t c = __shfl_sync(kFullMask, count, i);
-        if ((uint32_t)lane < c) rows[i * kRowStride + lane] = ld_stream_u32(s + lane);
+    for (int i0 = 0; i0 < 32; i0 += 8) {
+        if (((mask >> i0) & 0xffu) == 0u) continue;
+        uint32_t v[8], c[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const uint32_t *s = (const uint32_t *)shfl_u64((uint64_t)src, i0 + j);
+            c[j] = __shfl_sync(kFullMask, count, i0 + j);
+            v[j] = 0u;
+            if ((uint32_t)lane < c[j]) v[j] = ld_stream_u32(s + lane);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            if ((uint32_t)lane < c[j]) rows[(i0 + j) * kRowStride + lane] = v[j];
     }
     __syncwarp();
 }
