@@ -279,8 +279,16 @@ def run_ours(args):
     bytes_per_launch = 4.0 * n + 4.0 * total_words  # symbols in/out + compressed words out/in (same for both kernels)
     dom_name, dom_ms = ("ans_encode_kernel", enc_kernel_ms) if enc_kernel_ms >= dec_kernel_ms else ("ans_decode_kernel", dec_kernel_ms)
     achieved = bytes_per_launch / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
+    traffic = None  # DRAM bytes per launch of that kernel from the committed ncu capture (same workload only)
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            tj = json.load(f)
+        if tj["symbols"] == n and tj["streams"] == k:
+            traffic = tj["dram_bytes_per_launch"].get(dom_name)
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": bytes_per_launch,
                 "kernel_ms": {"ans_encode_kernel": enc_kernel_ms, "ans_decode_kernel": dec_kernel_ms},
                 "frac_of_step": {"ans_encode_kernel": enc_kernel_ms / ms_per_step, "ans_decode_kernel": dec_kernel_ms / ms_per_step}}
