@@ -43,6 +43,8 @@ struct ModelView {
     const uint4 *enc;      // [n_models][alphabet + 1] {left, prob, reciprocal lo, hi}; entry [alphabet] is
                            // the all-zero sentinel that out-of-range symbols are clamped to
     const uint4 *enc_rep;  // model 0 only: [alphabet + 1][8] -- each entry 8 times, one copy per 16-byte bank group
+    const uint8_t *cidx;   // [n_models][kCoarseSize + 1] u8 (alphabet <= 256) or u16: coarse quantile index for
+                           // decoding with global tables; cidx[m][b] = symbol of model m containing quantile b << 16
     const uint32_t *dec;   // model 0 only: quantile index uint2[kLutSize] ++ cdf u32[alphabet + 2] (padded to 16 B)
     uint32_t n_models;
     uint32_t alphabet;
@@ -158,11 +160,29 @@ __device__ __forceinline__ uint32_t lookup_shared(uint32_t lut_addr, uint32_t cd
     return s;
 }
 
-// decoder: binary search of a CDF row in global memory (through L1/L2):
-// the last index s with cdf[s] <= q  (categorical/contiguous.rs:628-665 partition point - 1)
-__device__ __forceinline__ uint32_t lookup_global(const uint32_t *row, uint32_t alphabet, uint32_t q, uint32_t &left,
-                                                  uint32_t &right) {
+// decoder with global tables (model sets that do not fit shared memory, read through L1/L2):
+// the last index s with cdf[s] <= q  (categorical/contiguous.rs:628-665: partition point - 1).
+// A 257-entry coarse index per model (cidx[b] = symbol containing quantile b << 16) narrows the binary search
+// to the symbols that intersect q's bucket, so a lookup costs ~3 dependent loads instead of log2(alphabet) + 2
+// -- for a 1 GB pool of CDF rows each of them is a DRAM round trip.
+constexpr int kCoarseBits = 8;
+constexpr int kCoarseSize = 1 << kCoarseBits;
+constexpr int kCoarseShift = kPrecision - kCoarseBits;
+
+__device__ __forceinline__ uint32_t lookup_global(const uint32_t *row, const uint8_t *cidx_row, bool wide,
+                                                  uint32_t alphabet, uint32_t q, uint32_t &left, uint32_t &right) {
     uint32_t lo = 0, hi = alphabet - 1;
+    if (cidx_row != nullptr) {
+        const uint32_t b = q >> kCoarseShift;
+        if (wide) {
+            const uint16_t *c = reinterpret_cast<const uint16_t *>(cidx_row);
+            lo = __ldg(c + b);
+            hi = __ldg(c + b + 1);
+        } else {
+            lo = __ldg(cidx_row + b);
+            hi = __ldg(cidx_row + b + 1);
+        }
+    }
     while (lo < hi) {
         const uint32_t mid = (lo + hi + 1) >> 1;
         if (__ldg(row + mid) <= q)
@@ -608,7 +628,10 @@ __global__ void __launch_bounds__((SHARED && !CONTIG) ? kDecBlockShared : kAnsBl
             s = lookup_shared<SMALL>(lut_addr, cdf_addr, alphabet, lo, q, left, right);
         } else {
             m = m < n_models ? m : n_models - 1;  // decoding cannot fail (stack.rs:1062-1065)
-            s = lookup_global(p.model.cdf + (uint64_t)m * (alphabet + 1), alphabet, q, left, right);
+            const uint32_t cstride = (alphabet > 256 ? 2u : 1u) * (kCoarseSize + 1);
+            s = lookup_global(p.model.cdf + (uint64_t)m * (alphabet + 1),
+                              p.model.cidx ? p.model.cidx + (uint64_t)m * cstride : nullptr, alphabet > 256, alphabet, q, left,
+                              right);
         }
         // state = (state >> 24) * prob + (q - left), in 32-bit pieces (state >> 24 has 40 bits)
         const uint32_t prob = right - left;

@@ -89,7 +89,8 @@ struct ctr_model_s {
     uint32_t *d_cdf = nullptr;  // [n_models][alphabet+1]
     uint4 *d_enc = nullptr;     // [n_models][alphabet + 1], built on first encode
     uint4 *d_enc_rep = nullptr; // model 0, every entry 8 times (small alphabets only)
-    uint32_t *d_dec = nullptr;  // model 0: pairs + bucket index, built on first decode
+    uint32_t *d_dec = nullptr;  // model 0: quantile index + cdf, for the shared-memory decoders
+    uint8_t *d_cidx = nullptr;  // coarse quantile index of every model, for the global-table decoders
     uint32_t dec_cdf_bytes = 0;  // (alphabet + 2) * 4 rounded up to 16: the cdf part of d_dec
     bool shared_ok = false;  // small enough for the shared-memory table kernels
     bool enc_f64 = false;    // d_enc holds double-precision reciprocals (CTR_DIV=f64)
@@ -154,6 +155,17 @@ int ensure_dec_table(ctr_model_s *m, cudaStream_t s) {
     return CTR_OK;
 }
 
+// coarse index for decoding with global tables (built on the first such decode; alphabets up to 65536)
+int ensure_coarse_index(ctr_model_s *m, cudaStream_t s) {
+    if (m->d_cidx || m->alphabet > 65536u) return CTR_OK;
+    const int wide = m->alphabet > 256 ? 1 : 0;
+    const uint64_t entries = (uint64_t)m->n_models * 257;
+    CUDA_TRY(cudaMalloc(&m->d_cidx, entries * (wide ? 2 : 1)));
+    build_coarse_index_kernel<<<grid_for(entries, 256), 256, 0, s>>>(m->d_cdf, m->n_models, m->alphabet, wide, m->d_cidx);
+    LAUNCH_CHECK("build_coarse_index_kernel");
+    return CTR_OK;
+}
+
 // runs the validation kernel, builds the derived tables (the encoder table only when it is small;
 // huge model pools get it on first encode) and turns device error bits into a status.
 // Synchronises `s`: model construction is not on the hot path.
@@ -187,6 +199,7 @@ ModelView model_view(const ctr_model_s *m) {
     v.cdf = m->d_cdf;
     v.enc = m->d_enc;
     v.enc_rep = m->d_enc_rep;
+    v.cidx = m->d_cidx;
     v.dec = m->d_dec;
     v.n_models = m->n_models;
     v.alphabet = m->alphabet;
@@ -425,6 +438,7 @@ extern "C" int ctr_model_destroy(ctr_model_t m) {
     if (m->d_cdf) cudaFree(m->d_cdf);
     if (m->d_enc) cudaFree(m->d_enc);
     if (m->d_enc_rep) cudaFree(m->d_enc_rep);
+    if (m->d_cidx) cudaFree(m->d_cidx);
     if (m->d_dec) cudaFree(m->d_dec);
     delete m;
     return CTR_OK;
@@ -606,6 +620,7 @@ int decode_common(ctr_model_t model, const uint32_t *words, const uint64_t *offs
     cudaStream_t s = (cudaStream_t)stream;
     if (L->n_streams == 0) return CTR_OK;
     if ((rc = ensure_dec_table(model, s))) return rc;
+    if (!use_shared_tables(model, L) && (rc = ensure_coarse_index(model, s))) return rc;
 
     AnsParams p = base_params(model, L);
     p.symbols_out = symbols_out;

@@ -117,6 +117,31 @@ __global__ void build_enc_table_kernel(const uint32_t *cdf, uint32_t n_models, u
     enc[tid] = make_uint4(left, prob, (uint32_t)rcp, (uint32_t)(rcp >> 32));
 }
 
+// coarse quantile index for decoding with global tables: cidx[m][b] = last symbol of model m whose left
+// cumulative is <= b << 16 (b = 0..256; the entry for b = 256 is the last symbol); u8 or u16 entries
+__global__ void build_coarse_index_kernel(const uint32_t *cdf, uint32_t n_models, uint32_t alphabet, int wide,
+                                          uint8_t *cidx) {
+    const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t per = 257;
+    if (tid >= (uint64_t)n_models * per) return;
+    const uint64_t m = tid / per;
+    const uint32_t b = (uint32_t)(tid % per);
+    const uint32_t *row = cdf + m * ((uint64_t)alphabet + 1);
+    const uint32_t q = b << 16;  // 2^24 for b == 256: every cdf[s] with s < alphabet is <= it
+    uint32_t lo = 0, hi = alphabet - 1;
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi + 1) >> 1;
+        if (row[mid] <= q)
+            lo = mid;
+        else
+            hi = mid - 1;
+    }
+    if (wide)
+        reinterpret_cast<uint16_t *>(cidx)[tid] = (uint16_t)lo;
+    else
+        cidx[tid] = (uint8_t)lo;
+}
+
 // model 0's encoder entries replicated 8 times each ([alphabet + 1][8] uint4): the ANS encoder stages this
 // layout in shared memory so that lane l can read copy (l & 7), which makes its LDS.128 conflict free
 __global__ void replicate_enc_table_kernel(const uint4 *enc, uint32_t alphabet, uint4 *rep) {

@@ -321,7 +321,10 @@ __global__ void __launch_bounds__(kAnsBlock) range_decode_kernel(const AnsParams
             s = lookup_shared<false>(lut_addr, cdf_addr, alphabet, q, q, left, right);
         } else {
             m = m < n_models ? m : n_models - 1;
-            s = lookup_global(p.model.cdf + (uint64_t)m * (alphabet + 1), alphabet, q, left, right);
+            const uint32_t cstride = (alphabet > 256 ? 2u : 1u) * (kCoarseSize + 1);
+            s = lookup_global(p.model.cdf + (uint64_t)m * (alphabet + 1),
+                              p.model.cidx ? p.model.cidx + (uint64_t)m * cstride : nullptr, alphabet > 256, alphabet, q, left,
+                              right);
         }
         if (range_decode_update(st, left, right - left)) {
             if (rptr != rend) st.point |= *rptr++;
