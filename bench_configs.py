@@ -124,6 +124,38 @@ def config4(scale, streams):
             "parity": ok, "note": "one dependent chain per stream: latency-bound, not HBM-bound"}
 
 
+def config2_range(scale):
+    """configs[1] workload with the range coder instead of ANS (interleaved deal, shared model)."""
+    import torch
+    from constriction_b200 import batch as B
+    from oracle import refapi as O
+    n, k = int(100_000_000 * scale), 148 * 1024
+    g = torch.Generator(device="cuda")
+    g.manual_seed(2)
+    syms = torch.clamp(torch.round(torch.randn(n, device="cuda", generator=g) * 9.6 + 3.2), -50, 50).to(torch.int32)
+    model = B.ModelTable.quantized_gaussian(-50, 50, [3.2], [9.6])
+    bc = B.BatchCoder()
+    state = {}
+
+    def enc():
+        state["c"] = bc.range_encode(syms, model, n_streams=k, out=state.get("c"))
+
+    ms_enc = timed(enc)
+    comp = state["c"]
+    out = torch.empty_like(syms)
+    ms_dec = timed(lambda: bc.range_decode(comp, model, out=out))
+    bc.check()
+    ok = bool(torch.equal(out, syms))
+    cdf = model.cdf()[0]
+    for s in (0, 1, k - 1):
+        want = O.range_encode_iid(syms[s::k].cpu().numpy(), cdf, -50)
+        ok &= bool(np.array_equal(comp.stream_words(s), want))
+    return {"config": "2-range", "workload": f"{n} i.i.d. symbols, QG(-50,50,3.2,9.6), {k} RangeEncoder streams (interleaved)",
+            "us_encode": ms_enc * 1e3, "us_decode": ms_dec * 1e3,
+            "Msymbols_per_s_round_trip": n / (ms_enc + ms_dec) / 1e3, "parity": ok,
+            "bits_per_symbol": 32.0 * comp.total_words() / n}
+
+
 def config5(images=64):
     """int32[images,192,32,32] latents, one QuantizedGaussian per channel, one ANS stream per (image, channel)."""
     import torch
@@ -174,7 +206,9 @@ def main():
     import torch
     assert torch.cuda.is_available(), "needs a CUDA device"
     for c in [int(x) for x in args.configs.split(",")]:
-        if c == 3:
+        if c == 2:
+            print(json.dumps(config2_range(args.scale)), flush=True)
+        elif c == 3:
             print(json.dumps(config3(args.scale)), flush=True)
         elif c == 4:
             print(json.dumps(config4(args.scale, 1024)), flush=True)

@@ -533,21 +533,22 @@ struct AnsDecodeLauncher {
     }
 };
 struct RangeEncodeLauncher {
-    static bool shared(const ctr_model_s *m, const ctr_layout *L) { return use_shared_tables(m, L); }
-    static size_t table_bytes(const ctr_model_s *m) { return ((size_t)m->alphabet + 1) * 16; }
+    static bool shared(const ctr_model_s *m, const ctr_layout *L) { return use_shared_ans_enc_table(m, L); }
+    static size_t table_bytes(const ctr_model_s *m) { return ((size_t)m->alphabet + 1) * 128; }
     static unsigned block_for(bool, bool) { return kAnsBlock; }
-    static size_t stage_words() { return kTileWords; }
+    static size_t stage_words() { return 32 * (kEncRingWords + 4); }
     static int run(bool shared, bool contig, bool persym, bool, const AnsParams &p, size_t smem, unsigned grid,
                    unsigned block, cudaStream_t s) {
         CTR_DISPATCH(range_encode_kernel, 2);
     }
 };
 struct RangeDecodeLauncher {
-    static unsigned block_for(bool, bool) { return kAnsBlock; }
-    static size_t stage_words() { return kTileWords; }
+    static unsigned block_for(bool shared, bool contig) { return (shared && !contig) ? kDecBlockShared : kAnsBlock; }
+    static size_t stage_words() { return 32 * kDecRingWords; }
     static int run(bool shared, bool contig, bool persym, bool, const AnsParams &p, size_t smem, unsigned grid,
                    unsigned block, cudaStream_t s) {
-        CTR_DISPATCH(range_decode_kernel, 3);
+        if (shared && p.model.alphabet <= 256) CTR_DISPATCH(range_decode_kernel, 3, CTR_COMMA true);
+        CTR_DISPATCH(range_decode_kernel, 3, CTR_COMMA false);
     }
 };
 

@@ -1,14 +1,17 @@
 // range_kernels.cuh -- batched range encode / decode kernels (K3 / K4), one lane per independent coder.
 //
-// Same execution model as ans_kernels.cuh (lane = coder, shared-memory rows for coalesced word I/O,
-// TMA-staged tables, uniform hot loops with the ragged last row peeled off), with queue semantics:
-// symbols are coded in forward order and words are read from the front.  The encoder's lazy carry
-// ("Inverted" situation, queue.rs:647-702) can release a burst of held-back words in one step; the
-// first word of a step goes through the normal (predicated) push, anything beyond it is drained by a
-// cold warp-uniform loop so that the cooperative row flush stays convergent.
+// Same execution model as ans_kernels.cuh: lane = coder with its state in registers, TMA-staged tables in
+// shared memory for a shared model, lane-private word rings that are drained (encoder: LDS.128 + STG.128
+// into the lane's scratch region) or topped up (decoder: asynchronous LDGSTS.128) 16 bytes at a time, uniform
+// hot loops with the ragged last row of the interleaved deal peeled off, fused compaction in the encoder's
+// tail.  Queue semantics: symbols are coded in forward order and words are read from the front.
 //
-// Per-stream results equal the reference's RangeEncoder / RangeDecoder (src/stream/queue.rs) word
-// for word, including the seal words (queue.rs:349-376,458-523).
+// The encoder's lazy carry ("Inverted" situation, queue.rs:647-702) can release a burst of held-back words in
+// one step; because the word path is lane-private, the (rare) burst is simply pushed by a lane-local loop that
+// drains the ring as it goes.
+//
+// Per-stream results equal the reference's RangeEncoder / RangeDecoder (src/stream/queue.rs) word for word,
+// including the seal words (queue.rs:349-376,458-523).
 //
 // Coder state on the wire (CTR_FLAG_RAW, states_in / states_out): 4 x u64 per stream,
 //   encoder {lower, range, num_inverted, first_inverted_word}, decoder {lower, range, point, 0}.
@@ -17,27 +20,29 @@
 
 namespace ctr {
 
-constexpr int kSymBatch = 4;  // symbols loaded per lane before they are coded
-
 template <bool SHARED, bool CONTIG, bool PERSYM>
-__global__ void __launch_bounds__(kAnsBlock) range_encode_kernel(const AnsParams p) {
-    extern __shared__ __align__(16) uint32_t smem[];
+__global__ void __launch_bounds__(kAnsBlock, 4) range_encode_kernel(const AnsParams p) {
+    extern __shared__ __align__(128) uint32_t smem[];
     __shared__ uint64_t bar;
 
     const int lane = threadIdx.x & 31;
     const int warp_in_cta = threadIdx.x >> 5;
     constexpr int kWarpsPerCta = kAnsBlock / 32;
 
-    const uint32_t table_words = SHARED ? (p.model.alphabet + 1) * 4 : 0;
-    const uint4 *s_enc = reinterpret_cast<const uint4 *>(smem);
-    uint32_t *rows = smem + table_words + warp_in_cta * kTileWords;
-    uint32_t *sym_tile = smem + table_words + (kWarpsPerCta + warp_in_cta) * kTileWords;
-    uint32_t *idx_tile = smem + table_words + (2 * kWarpsPerCta + warp_in_cta) * kTileWords;
+    // shared memory carve-up as in ans_encode_kernel: [rings + parking slots][replicated table][tiles]
+    const uint32_t alphabet = p.model.alphabet;
+    const uint32_t table_words = SHARED ? (alphabet + 1) * 32 : 0;
+    constexpr uint32_t kRingsWords = kAnsBlock * (kEncRingWords + 4);
+    const uint32_t ring = smem_u32_pinned(smem) + threadIdx.x * kEncRingBytes;
+    const uint32_t park = smem_u32(smem) + kAnsBlock * kEncRingBytes + threadIdx.x * 16u;
+    const uint32_t table_addr = smem_u32_pinned(smem + kRingsWords) + (uint32_t)(lane & 7) * 16u;
+    uint32_t *sym_tile = smem + kRingsWords + table_words + warp_in_cta * kTileWords;
+    uint32_t *idx_tile = sym_tile + kWarpsPerCta * kTileWords;
 
-    if (SHARED) stage_table(smem, p.model.enc, (p.model.alphabet + 1) * 16u, &bar);
+    if (SHARED) stage_table(smem + kRingsWords, p.model.enc_rep, (alphabet + 1) * 128u, &bar);
 
     const uint64_t K = p.K, N = p.N;
-    const uint32_t tile = take_tile_ticket(p.compact.ticket);  // which 256 streams this CTA codes
+    const uint32_t tile = take_tile_ticket(p.compact.ticket);
     const uint64_t k = (uint64_t)tile * kAnsBlock + threadIdx.x;
     const bool valid = k < K;
     const uint64_t kc = valid ? k : K - 1;
@@ -52,9 +57,16 @@ __global__ void __launch_bounds__(kAnsBlock) range_encode_kernel(const AnsParams
             o_k = interleaved_start(N, K, k);
         }
     }
-    uint32_t *gptr = p.scratch + scratch_start(o_k, k);
-    uint32_t *const gbegin = gptr;
-    uint32_t *const gend = valid ? p.scratch + scratch_start(o_k + n_k, k + 1) : gptr;
+    char *gw;
+    uint32_t room;
+    {
+        uint32_t *const gbegin = p.scratch + scratch_start(o_k, k);
+        const uint64_t r = valid ? scratch_start(o_k + n_k, k + 1) - scratch_start(o_k, k) : 0;
+        room = r > 0x3ffffff0u ? 0xffffffc0u : (uint32_t)r * 4u;
+        gw = reinterpret_cast<char *>(gbegin);
+        const uint64_t gb = (uint64_t)gbegin;
+        asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(park), "r"((uint32_t)gb), "r"((uint32_t)(gb >> 32)) : "memory");
+    }
 
     RangeEncState st = range_enc_init();
     if (valid && p.states_in) {
@@ -63,117 +75,123 @@ __global__ void __launch_bounds__(kAnsBlock) range_encode_kernel(const AnsParams
         st.num_inverted = (uint32_t)p.states_in[4 * k + 2];
         st.first_inverted = (uint32_t)p.states_in[4 * k + 3];
     }
-    uint32_t *const myrow = rows + lane * kRowStride;
-    uint32_t *wptr = myrow;
-    bool bad = false, overflow = false;
+    uint32_t pushed = 0, pending = 0;  // bytes pushed into my ring / not yet written to scratch
+    uint32_t min_prob = 0xffffffffu;
+    bool overflow = false;
     const uint32_t stream_model = (p.index_mode == 2) ? p.model_index[kc] : 0u;
-    const uint32_t alphabet = p.model.alphabet;
     const uint32_t n_models = p.model.n_models;
-    const int32_t min_symbol = p.model.min_symbol;
+    const uint32_t min_symbol = (uint32_t)p.model.min_symbol;
 
-    auto flush_full = [&]() {
-        const bool full = wptr == myrow + kRowWords;
-        const unsigned mask = __ballot_sync(kFullMask, full);
-        if (mask) {
-            const bool ok = !(full && gptr + kRowWords > gend);
-            const unsigned okmask = __ballot_sync(kFullMask, full && ok);
-            warp_flush_rows(okmask, rows, gptr, kRowWords, lane);
-            if (full) {
-                if (ok)
-                    gptr += kRowWords;
-                else
-                    overflow = true;
-                wptr = myrow;
+    auto push = [&](uint32_t w) {
+        sts_u32(ring | (pushed & (kEncRingBytes - 1u)), w);
+        pushed += 4u;
+        pending += 4u;
+    };
+    auto drain_ring = [&]() {
+        if (pending >= 16u) {
+            const uint4 v = lds_v4(ring | ((pushed - pending) & (kEncRingBytes - 16u)));
+            if (room >= 16u) {
+                st_stream_v4(gw, v);
+                gw += 16;
+                room -= 16u;
+            } else {
+                room = 0u;
+                overflow = true;
             }
+            pending -= 16u;
         }
     };
 
-    // push word_at(first .. pending) of every lane, one word per lane per round (cold unless pending > 1)
-    auto drain_from = [&](uint32_t first, uint32_t pending, auto word_at) {
-        uint32_t j = first;
-        while (__any_sync(kFullMask, j < pending)) {
-            if (j < pending) {
-                *wptr++ = word_at(j);
-                j += 1;
-            }
-            flush_full();
-        }
-    };
-
-    // one reference encode_symbol (queue.rs:612-705).  `act` is false for lanes that have no symbol in
-    // this step; impossible symbols are skipped and flagged.
-    auto encode_step = [&](bool act, int32_t sym, uint32_t m) {
-        uint32_t idx = (uint32_t)sym - (uint32_t)min_symbol;
-        bool ok = idx < alphabet;
+    // one reference encode_symbol (queue.rs:612-705); impossible symbols are skipped and flagged
+    auto encode_one = [&](int32_t sym, uint32_t m) {
+        uint32_t idx = min((uint32_t)sym - min_symbol, alphabet);  // out of range -> sentinel entry (prob 0)
         uint4 e;
         if (SHARED) {
-            idx = ok ? idx : 0u;
-            e = s_enc[idx];
+            e = lds_table_v4(table_addr + idx * 128u);
         } else {
-            ok = ok && m < n_models;
-            idx = ok ? idx : 0u;
+            const bool ok = m < n_models;
+            idx = ok ? idx : alphabet;
             m = ok ? m : 0u;
             e = __ldg(p.model.enc + (uint64_t)m * (alphabet + 1) + idx);
         }
-        ok = ok && e.y != 0u;
-        RangeEmit em;
-        em.n_burst = 0;
-        em.emit = false;
-        em.burst_first = em.burst_fill = em.word = 0;
-        if (act) {
-            if (ok)
-                ok = range_encode_step(st, e.x, e.y, em);
-            bad |= !ok;
+        min_prob = min(min_prob, e.y);
+        if (valid && e.y != 0u) {
+            RangeEmit em;
+            range_encode_step(st, e.x, e.y, em);
+            if (em.n_burst != 0u) {  // rare: a resolved Inverted situation releases its held-back words
+                for (uint32_t j = 0; j < em.n_burst; ++j) {
+                    push(j == 0 ? em.burst_first : em.burst_fill);
+                    drain_ring();
+                }
+            }
+            if (em.emit) push(em.word);
         }
-        const uint32_t pending = em.n_burst + (em.emit ? 1u : 0u);
-        auto word_at = [&](uint32_t j) { return j < em.n_burst ? (j == 0 ? em.burst_first : em.burst_fill) : em.word; };
-        if (pending) *wptr++ = word_at(0);
-        flush_full();
-        if (__any_sync(kFullMask, pending > 1)) drain_from(1, pending, word_at);
     };
 
     if (!CONTIG) {
         const Interleave g = interleave_of(N, K);
         if (g.T > 1) {
-            uint64_t rows_left = g.T - 1;  // full rows 0 .. T-2
-            const int32_t *ps = p.symbols_in + kc;
-            const uint32_t *pm = PERSYM ? p.model_index + kc : nullptr;
-            while (rows_left >= (uint64_t)kSymBatch) {
-                int32_t buf[kSymBatch];
-                uint32_t mbuf[kSymBatch];
+            const uint64_t rows_total = g.T - 1;  // full rows 0 .. T-2
+            const char *ps = reinterpret_cast<const char *>(p.symbols_in + kc);
+            const char *pm = PERSYM ? reinterpret_cast<const char *>(p.model_index + kc) : nullptr;
+            uint64_t row_bytes = K * 4u;
+            asm volatile("" : "+l"(row_bytes));
+            int32_t buf[2][kCheckEvery];
+            uint32_t mbuf[2][kCheckEvery];
+            auto load_batch = [&](int which) {
 #pragma unroll
-                for (int u = 0; u < kSymBatch; ++u) {
-                    buf[u] = ld_stream_s32(ps);
-                    ps += K;
+                for (int u = 0; u < kCheckEvery; ++u) {
+                    buf[which][u] = ld_stream_s32(reinterpret_cast<const int32_t *>(ps));
+                    ps += row_bytes;
                     if (PERSYM) {
-                        mbuf[u] = ld_stream_u32(pm);
-                        pm += K;
+                        mbuf[which][u] = ld_stream_u32(reinterpret_cast<const uint32_t *>(pm));
+                        pm += row_bytes;
                     } else {
-                        mbuf[u] = stream_model;
+                        mbuf[which][u] = stream_model;
                     }
                 }
+            };
+            auto code_batch = [&](int which, bool load_next) {
+                if (load_next) load_batch(which ^ 1);
+                drain_ring();
 #pragma unroll
-                for (int u = 0; u < kSymBatch; ++u) encode_step(valid, buf[u], mbuf[u]);
-                rows_left -= kSymBatch;
+                for (int u = 0; u < kCheckEvery; ++u) encode_one(buf[which][u], mbuf[which][u]);
+            };
+            uint32_t batches = (uint32_t)(rows_total / kCheckEvery);
+            uint32_t rows_left = (uint32_t)(rows_total - (uint64_t)batches * kCheckEvery);
+            if (batches > 0) {
+                load_batch(0);
+                while (batches > 2) {
+                    code_batch(0, true);
+                    code_batch(1, true);
+                    batches -= 2;
+                }
+                if (batches == 2) {
+                    code_batch(0, true);
+                    code_batch(1, false);
+                } else {
+                    code_batch(0, false);
+                }
             }
+            drain_ring();
             while (rows_left > 0) {
-                const int32_t sym = ld_stream_s32(ps);
-                ps += K;
+                const int32_t sym = ld_stream_s32(reinterpret_cast<const int32_t *>(ps));
+                ps += row_bytes;
                 uint32_t m = stream_model;
                 if (PERSYM) {
-                    m = ld_stream_u32(pm);
-                    pm += K;
+                    m = ld_stream_u32(reinterpret_cast<const uint32_t *>(pm));
+                    pm += row_bytes;
                 }
-                encode_step(valid, sym, m);
+                encode_one(sym, m);
                 rows_left -= 1;
             }
+            drain_ring();
         }
         if (g.T > 0) {  // ragged last row
-            const bool has = valid && k < g.last;
-            const uint64_t i = (g.T - 1) * K + (has ? k : 0);
-            const int32_t sym = has ? ld_stream_s32(p.symbols_in + i) : 0;
-            const uint32_t m = (has && PERSYM) ? ld_stream_u32(p.model_index + i) : stream_model;
-            encode_step(has, sym, m);
+            if (valid && k < g.last) {
+                const uint64_t i = (g.T - 1) * K + k;
+                encode_one(ld_stream_s32(p.symbols_in + i), PERSYM ? ld_stream_u32(p.model_index + i) : stream_model);
+            }
         }
     } else {
         uint64_t done = 0;
@@ -186,28 +204,35 @@ __global__ void __launch_bounds__(kAnsBlock) range_encode_kernel(const AnsParams
             if (PERSYM) warp_fill_rows(have, idx_tile, p.model_index + o_k + done, c, lane);
             const uint32_t cmax = __reduce_max_sync(kFullMask, c);
             for (uint32_t s = 0; s < cmax; ++s) {
-                const bool act = s < c;
-                const int32_t sym = act ? (int32_t)sym_tile[lane * kRowStride + s] : 0;
-                const uint32_t m = (act && PERSYM) ? idx_tile[lane * kRowStride + s] : stream_model;
-                encode_step(act, sym, m);
+                if ((s & (kCheckEvery - 1)) == 0) drain_ring();
+                if (s < c) {
+                    const int32_t sym = (int32_t)sym_tile[lane * kRowStride + s];
+                    const uint32_t m = PERSYM ? idx_tile[lane * kRowStride + s] : stream_model;
+                    encode_one(sym, m);
+                }
             }
             done += c;
         }
     }
 
     // ---- seal (queue.rs:349-355, 458-523) unless the caller keeps the raw state -----------------------
+    drain_ring();
     const bool raw = (p.flags & 1u) != 0;
+    const bool bad = min_prob == 0u;
     const uint32_t n_seal = (valid && !bad && !raw) ? range_num_seal_words(st) : 0u;
-    drain_from(0, n_seal, [&](uint32_t j) { return range_seal_word(st, j); });
-    uint32_t cnt = (uint32_t)(wptr - myrow);
-    {
-        const bool ok = gptr + cnt <= gend;
-        const unsigned mask = __ballot_sync(kFullMask, cnt > 0 && ok);
-        if (mask) warp_flush_rows(mask, rows, gptr, cnt, lane);
-        if (cnt > 0 && !ok) {
+    for (uint32_t j = 0; j < n_seal; ++j) {
+        push(range_seal_word(st, j));
+        drain_ring();
+    }
+    while (pending != 0u) {  // < 4 words, one at a time
+        if (room >= 4u) {
+            *reinterpret_cast<uint32_t *>(gw) = lds_u32(ring | ((pushed - pending) & (kEncRingBytes - 1u)));
+            gw += 4;
+            room -= 4u;
+        } else {
             overflow = true;
-            cnt = 0;
         }
+        pending -= 4u;
     }
     if (valid) {
         if (p.states_out) {
@@ -219,68 +244,88 @@ __global__ void __launch_bounds__(kAnsBlock) range_encode_kernel(const AnsParams
         if (bad) report_error(p.status, kErrImpossibleSymbol, k);
         if (overflow) report_error(p.status, kErrOutOfSpace, k);
     }
-    // ---- K6: place my stream in the dense container ---------------------------------------------------
-    compact_tail<kAnsBlock>(p.compact, tile, k, K, valid, gbegin, valid ? (uint32_t)(gptr - gbegin) + cnt : 0u, p.status);
+    uint32_t gb_lo, gb_hi;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(gb_lo), "=r"(gb_hi) : "r"(park) : "memory");
+    const uint32_t *gbegin = reinterpret_cast<const uint32_t *>(((uint64_t)gb_hi << 32) | gb_lo);
+    compact_tail<kAnsBlock>(p.compact, tile, k, K, valid, gbegin,
+                            (valid && !overflow) ? (uint32_t)((reinterpret_cast<const uint32_t *>(gw)) - gbegin) : 0u, p.status);
 }
 
-template <bool SHARED, bool CONTIG, bool PERSYM>
-__global__ void __launch_bounds__(kAnsBlock) range_decode_kernel(const AnsParams p) {
-    extern __shared__ __align__(16) uint32_t smem[];
+template <bool SHARED, bool CONTIG, bool PERSYM, bool SMALL>
+__global__ void __launch_bounds__((SHARED && !CONTIG) ? kDecBlockShared : kAnsBlock, (SHARED && !CONTIG) ? 1 : 2)
+    range_decode_kernel(const AnsParams p) {
+    extern __shared__ __align__(128) uint32_t smem[];
     __shared__ uint64_t bar;
 
+    constexpr int kBlock = (SHARED && !CONTIG) ? kDecBlockShared : kAnsBlock;
     const int lane = threadIdx.x & 31;
     const int warp_in_cta = threadIdx.x >> 5;
-    constexpr int kWarpsPerCta = kAnsBlock / 32;
+    constexpr int kWarpsPerCta = kBlock / 32;
 
+    const uint32_t alphabet = p.model.alphabet;
     const uint32_t table_words = SHARED ? (kLutBytes + p.model.dec_cdf_bytes) / 4 : 0;
-    const uint32_t lut_addr = smem_u32_pinned(smem);
-    const uint32_t cdf_addr = lut_addr + kLutBytes;
-    uint32_t *rows = smem + table_words + warp_in_cta * kTileWords;
-    uint32_t *sym_tile = smem + table_words + (kWarpsPerCta + warp_in_cta) * kTileWords;
-    uint32_t *idx_tile = smem + table_words + (2 * kWarpsPerCta + warp_in_cta) * kTileWords;
+    constexpr uint32_t kRingsWords = kBlock * kDecRingWords;
+    const uint32_t ring = smem_u32_pinned(smem) + threadIdx.x * kDecRingBytes;  // 64-byte aligned
+    const uint32_t lut_addr = smem_u32_pinned(smem + kRingsWords);
+    uint32_t cdf_addr = lut_addr + kLutBytes;
+    asm volatile("" : "+r"(cdf_addr));
+    uint32_t *sym_tile = smem + kRingsWords + table_words + warp_in_cta * kTileWords;
+    uint32_t *idx_tile = sym_tile + kWarpsPerCta * kTileWords;
 
-    if (SHARED) stage_table(smem, p.model.dec, kLutBytes + p.model.dec_cdf_bytes, &bar);
+    if (SHARED) stage_table(smem + kRingsWords, p.model.dec, kLutBytes + p.model.dec_cdf_bytes, &bar);
 
     const uint64_t K = p.K, N = p.N;
-    const uint64_t k = (uint64_t)blockIdx.x * kAnsBlock + threadIdx.x;
+    const uint64_t k = (uint64_t)blockIdx.x * kBlock + threadIdx.x;
     const bool valid = k < K;
     const uint64_t kc = valid ? k : K - 1;
     const bool raw = (p.flags & 1u) != 0;
 
+    // My stream is words[begin, end); I read from the front.  Ring slot of a word = its global address mod 64.
     uint64_t n_k = 0, o_k = 0;
-    const uint32_t *gnext = p.words;  // next word of my stream that is not yet staged
-    const uint32_t *gend = p.words;   // end of my stream
-    const uint32_t *gfirst = p.words;
+    uint64_t begin = 0, end = 0;
     if (valid) {
         if (CONTIG) {
             o_k = p.sym_off[k];
             n_k = p.sym_off[k + 1] - o_k;
         }
-        gfirst = gnext = p.words + p.offsets[k];
-        gend = p.words + p.offsets[k + 1];
+        begin = p.offsets[k];
+        end = p.offsets[k + 1];
     }
-    uint32_t *const myrow = rows + lane * kRowStride;
-    uint32_t *rptr = myrow, *rend = myrow;  // my row holds the unread words [rptr, rend)
-    const uint32_t alphabet = p.model.alphabet;
-    const uint32_t n_models = p.model.n_models;
-    const int32_t min_symbol = p.model.min_symbol;
-    const uint32_t stream_model = (p.index_mode == 2) ? p.model_index[kc] : 0u;
+    uint32_t pop_off = (uint32_t)(uintptr_t)(p.words + begin);  // low address bits of the next word to read
+    uint32_t avail = 0, pending = 0;
+    const uint32_t total_words = (uint32_t)(end - begin);
+    uint32_t unstaged = total_words;
+    const char *gblock = reinterpret_cast<const char *>(p.words) + ((begin * 4u) & ~(uint64_t)15);  // block holding word begin
 
-    // stage the next (up to) 32 words; chunks end on 128-byte boundaries of the global address space (cold)
-    auto refill = [&]() {
-        const bool need = rptr == rend && gnext != gend;
-        const unsigned mask = __ballot_sync(kFullMask, need);
-        if (mask) {
-            const uint32_t *line_end = (const uint32_t *)((((uint64_t)gnext) & ~(uint64_t)127) + 128);
-            const uint32_t *hi = line_end < gend ? line_end : gend;
-            const uint32_t c = need ? (uint32_t)(hi - gnext) : 0u;
-            warp_fill_rows(mask, rows, gnext, c, lane);
-            if (need) {
-                rptr = myrow;
-                rend = myrow + c;
-                gnext += c;
-            }
-        }
+    auto request_block = [&](uint32_t block_words) {
+        const uint32_t n = unstaged < block_words ? unstaged : block_words;
+        cp_async_16(ring | ((uint32_t)(uintptr_t)gblock & (kDecRingBytes - 1u)), gblock);
+        gblock += 16;
+        unstaged -= n;
+        pending = n;
+    };
+    auto top_up = [&]() {
+        cp_async_wait_all();
+        avail += pending;
+        pending = 0;
+        if (avail <= (uint32_t)(kDecRingWords - 4) && unstaged != 0u) request_block(4u);
+        cp_async_commit();
+    };
+    {
+        const uint32_t first = 4u - (uint32_t)(begin & 3u);  // words of my stream in the bottom block
+        if (unstaged != 0u) request_block(first);
+        cp_async_commit();
+#pragma unroll 1
+        for (int i = 0; i < 3; ++i) top_up();
+        cp_async_wait_all();
+        avail += pending;
+        pending = 0;
+    }
+    auto pop_word = [&]() -> uint32_t {
+        const uint32_t w = lds_u32(ring | (pop_off & (kDecRingBytes - 1u)));
+        pop_off += 4u;
+        avail -= 1u;
+        return w;
     };
 
     // ---- initial state: queue.rs:755-773 + read_point :847-868, or the caller's raw state -----------
@@ -289,7 +334,6 @@ __global__ void __launch_bounds__(kAnsBlock) range_decode_kernel(const AnsParams
     st.range = ~0ull;
     st.point = 0;
     bool invalid_data = false;
-    refill();
     if (raw) {
         if (valid) {
             st.lower = p.states_in[4 * k];
@@ -297,19 +341,17 @@ __global__ void __launch_bounds__(kAnsBlock) range_decode_kernel(const AnsParams
             st.point = p.states_in[4 * k + 2];
         }
     } else {
-        uint32_t got = 0;
-        if (rptr != rend) {
-            st.point = *rptr++;
-            got = 1;
+        if (avail != 0u) {
+            st.point = (uint64_t)pop_word() << 32;
+            if (avail != 0u) st.point |= pop_word();
         }
-        refill();
-        if (got == 1 && rptr != rend) {
-            st.point = (st.point << 32) | *rptr++;
-            got = 2;
-        }
-        refill();
-        if (got == 1) st.point <<= 32;
     }
+    top_up();
+
+    const uint32_t n_models = p.model.n_models;
+    uint32_t min_symbol = (uint32_t)p.model.min_symbol;
+    asm volatile("" : "+r"(min_symbol));
+    const uint32_t stream_model = (p.index_mode == 2) ? p.model_index[kc] : 0u;
 
     // one reference decode_symbol (queue.rs:968-1035); after invalid data the lane keeps running on a
     // clamped quantile (its symbols are garbage and the stream is flagged)
@@ -318,7 +360,7 @@ __global__ void __launch_bounds__(kAnsBlock) range_decode_kernel(const AnsParams
         invalid_data |= !range_peek_quantile(st, q);
         uint32_t left, right, s;
         if (SHARED) {
-            s = lookup_shared<false>(lut_addr, cdf_addr, alphabet, q, q, left, right);
+            s = lookup_shared<SMALL>(lut_addr, cdf_addr, alphabet, q, q, left, right);
         } else {
             m = m < n_models ? m : n_models - 1;
             const uint32_t cstride = (alphabet > 256 ? 2u : 1u) * (kCoarseSize + 1);
@@ -327,27 +369,58 @@ __global__ void __launch_bounds__(kAnsBlock) range_decode_kernel(const AnsParams
                               right);
         }
         if (range_decode_update(st, left, right - left)) {
-            if (rptr != rend) st.point |= *rptr++;
+            if (avail != 0u) st.point |= pop_word();
         }
-        return (int32_t)((uint32_t)min_symbol + s);
+        return (int32_t)(min_symbol + s);
     };
 
     if (!CONTIG) {
         const Interleave g = interleave_of(N, K);
         if (g.T > 1) {
-            int32_t *po = p.symbols_out + kc;
-            const uint32_t *pm = PERSYM ? p.model_index + kc : nullptr;
-            for (uint64_t t = 0; t + 1 < g.T; ++t) {
-                uint32_t m = stream_model;
-                if (PERSYM) {
-                    m = ld_stream_u32(pm);
-                    pm += K;
+            char *po = reinterpret_cast<char *>(p.symbols_out + kc);
+            const char *pm = PERSYM ? reinterpret_cast<const char *>(p.model_index + kc) : nullptr;
+            uint64_t row_bytes = K * 4u;
+            asm volatile("" : "+l"(row_bytes));
+            const uint64_t rows_total = g.T - 1;
+            auto run_rows = [&](auto full_tag) {
+                constexpr bool FULL = decltype(full_tag)::value;
+                uint32_t batches = (uint32_t)(rows_total / kCheckEvery);
+                uint32_t rows_left = (uint32_t)(rows_total - (uint64_t)batches * kCheckEvery);
+                for (; batches > 0; --batches) {
+                    uint32_t mbuf[kCheckEvery];
+#pragma unroll
+                    for (int u = 0; u < kCheckEvery; ++u) {
+                        mbuf[u] = stream_model;
+                        if (PERSYM) {
+                            mbuf[u] = ld_stream_u32(reinterpret_cast<const uint32_t *>(pm));
+                            pm += row_bytes;
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < kCheckEvery; ++u) {
+                        const int32_t sym = decode_one(mbuf[u]);
+                        if (FULL || valid) st_stream_s32(reinterpret_cast<int32_t *>(po), sym);
+                        po += row_bytes;
+                    }
+                    top_up();
                 }
-                const int32_t sym = decode_one(m);
-                if (valid) st_stream_s32(po, sym);
-                po += K;
-                refill();
-            }
+                while (rows_left > 0) {
+                    uint32_t m = stream_model;
+                    if (PERSYM) {
+                        m = ld_stream_u32(reinterpret_cast<const uint32_t *>(pm));
+                        pm += row_bytes;
+                    }
+                    const int32_t sym = decode_one(m);
+                    if (FULL || valid) st_stream_s32(reinterpret_cast<int32_t *>(po), sym);
+                    po += row_bytes;
+                    rows_left -= 1;
+                }
+                top_up();
+            };
+            if (__all_sync(kFullMask, valid))
+                run_rows(std::true_type{});
+            else
+                run_rows(std::false_type{});
         }
         if (g.T > 0) {
             if (valid && k < g.last) {
@@ -355,7 +428,6 @@ __global__ void __launch_bounds__(kAnsBlock) range_decode_kernel(const AnsParams
                 const int32_t sym = decode_one(PERSYM ? ld_stream_u32(p.model_index + i) : stream_model);
                 st_stream_s32(p.symbols_out + i, sym);
             }
-            refill();
         }
     } else {
         uint64_t done = 0;
@@ -367,17 +439,18 @@ __global__ void __launch_bounds__(kAnsBlock) range_decode_kernel(const AnsParams
             if (PERSYM) warp_fill_rows(have, idx_tile, p.model_index + o_k + done, c, lane);
             const uint32_t cmax = __reduce_max_sync(kFullMask, c);
             for (uint32_t s = 0; s < cmax; ++s) {
+                if ((s & (kCheckEvery - 1)) == 0) top_up();
                 if (s < c) {
                     const uint32_t m = PERSYM ? idx_tile[lane * kRowStride + s] : stream_model;
                     sym_tile[lane * kRowStride + s] = (uint32_t)decode_one(m);
                 }
-                refill();
             }
             warp_flush_rows(have, sym_tile, reinterpret_cast<uint32_t *>(p.symbols_out + o_k + done), c, lane);
             done += c;
         }
     }
 
+    cp_async_wait_all();
     if (valid) {
         if (p.states_out) {
             p.states_out[4 * k] = st.lower;
@@ -386,7 +459,7 @@ __global__ void __launch_bounds__(kAnsBlock) range_decode_kernel(const AnsParams
             p.states_out[4 * k + 3] = 0;
         }
         // words consumed so far (Pos::pos().0, queue.rs:182-196)
-        if (p.words_left) p.words_left[k] = (uint64_t)(gnext - gfirst) - (uint64_t)(rend - rptr);
+        if (p.words_left) p.words_left[k] = (uint64_t)(total_words - unstaged - pending - avail);
         if (invalid_data) report_error(p.status, kErrInvalidData, k);
     }
 }
