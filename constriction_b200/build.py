@@ -22,10 +22,12 @@ LIB = os.path.join(HERE, "libconstriction_b200.so")
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo", "-fmad=false",
-    "--shared", "-Xcompiler", "-fPIC,-ffp-contract=off,-fno-fast-math,-Wall",
+    "-Xcompiler", "-fPIC,-ffp-contract=off,-fno-fast-math,-Wall",
     "-Xptxas", "-v",
-    "-cudart", "shared",
 ]
+# one translation unit per kernel family (they compile in parallel); capi.cu holds the C ABI
+UNITS = ["capi", "ans_encode", "ans_decode", "range_encode", "range_decode"]
+OBJ_DIR = os.path.join(HERE, "_obj")
 
 
 def sources():
@@ -47,15 +49,32 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not os.path.exists(nvcc):
         raise RuntimeError("nvcc not found: cannot build libconstriction_b200.so")
     extra = os.environ.get("CTR_EXTRA_NVCC_FLAGS", "").split()  # experiments only (e.g. -DCTR_PF_BATCHES=8)
-    cmd = [nvcc] + NVCC_FLAGS + extra + ["-o", LIB, os.path.join(CSRC, "capi.cu")]
-    proc = subprocess.run(cmd, capture_output=True, text=True)
+    os.makedirs(OBJ_DIR, exist_ok=True)
+
+    def compile_unit(unit):
+        obj = os.path.join(OBJ_DIR, unit + ".o")
+        cmd = [nvcc] + NVCC_FLAGS + extra + ["-c", "-o", obj, os.path.join(CSRC, unit + ".cu")]
+        return unit, obj, subprocess.run(cmd, capture_output=True, text=True)
+
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=len(UNITS)) as pool:
+        results = list(pool.map(compile_unit, UNITS))
+    log = ""
+    for unit, _, proc in results:
+        log += f"==== {unit}.cu\n{proc.stderr}"
+        if proc.returncode != 0:
+            sys.stderr.write(proc.stdout + proc.stderr)
+            raise RuntimeError(f"nvcc failed compiling {unit}.cu")
+    link = [nvcc, "--shared", "-cudart", "shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + [
+        obj for _, obj, _ in results]
+    proc = subprocess.run(link, capture_output=True, text=True)
     if proc.returncode != 0:
         sys.stderr.write(proc.stdout + proc.stderr)
-        raise RuntimeError("nvcc failed building libconstriction_b200.so")
+        raise RuntimeError("nvcc failed linking libconstriction_b200.so")
     if verbose:
-        sys.stderr.write(proc.stderr)
+        sys.stderr.write(log)
     with open(os.path.join(HERE, "build_ptxas.log"), "w") as f:
-        f.write(proc.stderr)
+        f.write(log)
     return LIB
 
 

@@ -76,7 +76,7 @@ struct AnsParams {
 // ---- warp-cooperative tile I/O for the contiguous layout and the range kernels (generic pointers) ----
 
 // Write the first count_i words of row i to dst_i, for every lane i in `mask` (rows of kRowStride words).
-__device__ __noinline__ void warp_flush_rows(unsigned mask, const uint32_t *rows, uint32_t *dst, uint32_t count,
+static __device__ __noinline__ void warp_flush_rows(unsigned mask, const uint32_t *rows, uint32_t *dst, uint32_t count,
                                              int lane) {
     __syncwarp();
     while (mask) {
@@ -92,7 +92,7 @@ __device__ __noinline__ void warp_flush_rows(unsigned mask, const uint32_t *rows
 // Fill row i with the `count_i` words at src_i, for every lane i in `mask` (count_i == 0 for the others).
 // Eight rows are in flight at a time: the loads of a group are all issued before the first store, so a
 // tile costs four global round trips instead of thirty-two.
-__device__ __noinline__ void warp_fill_rows(unsigned mask, uint32_t *rows, const uint32_t *src, uint32_t count,
+static __device__ __noinline__ void warp_fill_rows(unsigned mask, uint32_t *rows, const uint32_t *src, uint32_t count,
                                             int lane) {
     __syncwarp();
     for (int i0 = 0; i0 < 32; i0 += 8) {
@@ -112,6 +112,19 @@ __device__ __noinline__ void warp_fill_rows(unsigned mask, uint32_t *rows, const
     __syncwarp();
 }
 
+// Asynchronous fill (LDGSTS, 4 bytes per lane): row i of the tile at shared address `rows` <- the count_i words
+// at src_i.  The caller commits the cp.async group and, before reading the tile, waits for it and
+// synchronises the warp (every lane writes into every row).
+__device__ __forceinline__ void warp_fill_rows_async(uint32_t rows, const uint32_t *src, uint32_t count, int lane) {
+    rows += (uint32_t)lane * 4u;
+#pragma unroll 8
+    for (int i = 0; i < 32; ++i) {
+        const uint32_t *s = (const uint32_t *)shfl_u64((uint64_t)src, i);
+        const uint32_t c = __shfl_sync(kFullMask, count, i);
+        if ((uint32_t)lane < c) cp_async_4(rows + (uint32_t)i * (kRowStride * 4u), s + lane);
+    }
+}
+
 // ---- model lookups ----------------------------------------------------------------------------------
 
 // Decoder table of a shared model (built by build_dec_table_kernel), staged in shared memory:
@@ -122,7 +135,7 @@ __device__ __noinline__ void warp_fill_rows(unsigned mask, uint32_t *rows, const
 //     only if that is not enough either (several tiny-probability symbols in one bucket) a cold binary
 //     search runs.
 //   cdf[0 .. alphabet] is the plain CDF row, cdf[alphabet + 1] = 2^24 pads the last probe.
-__device__ __noinline__ uint32_t lookup_far_cold(uint32_t cdf_addr, uint32_t alphabet, uint32_t s, uint32_t q) {
+static __device__ __noinline__ uint32_t lookup_far_cold(uint32_t cdf_addr, uint32_t alphabet, uint32_t s, uint32_t q) {
     uint32_t lo = s + 1, hi = alphabet - 1;  // cdf[s + 1] <= q is known
     while (lo < hi) {
         const uint32_t mid = (lo + hi + 1) >> 1;
@@ -223,47 +236,47 @@ __device__ __forceinline__ uint64_t warp_max_u64(uint64_t v, int lane) {
 //   CONTIG : stream k owns symbols[sym_off[k] .. sym_off[k+1]) (else interleaved deal)
 //   PERSYM : a model index per symbol (else one model per stream / model 0)
 //   F64DIV : the table holds double-precision reciprocals and the quotient estimate uses the FP64 pipe
-template <bool SHARED, bool CONTIG, bool PERSYM, bool F64DIV>
-__global__ void __launch_bounds__(kAnsBlock, 4) ans_encode_kernel(const AnsParams p) {
+//   BLOCK  : threads per CTA (kAnsBlock, or kSmallBlock for batches too small to fill the GPU with big CTAs)
+template <int BLOCK, bool SHARED, bool CONTIG, bool PERSYM, bool F64DIV>
+__global__ void __launch_bounds__(BLOCK, BLOCK >= 256 ? 4 : 8) ans_encode_kernel(const AnsParams p) {
     extern __shared__ __align__(128) uint32_t smem[];
     __shared__ uint64_t bar;
 
     const int lane = threadIdx.x & 31;
     const int warp_in_cta = threadIdx.x >> 5;
-    constexpr int kWarpsPerCta = kAnsBlock / 32;
+    constexpr int kWarpsPerCta = BLOCK / 32;
 
     // shared memory carve-up: [lane rings (32 B each) + per-thread parking slots (16 B each)][table][symbol
     // tiles][index tiles].  The parking slot keeps values that are only needed again at the very end
     // (scratch base, capacity) out of the hot loop's registers.
     const uint32_t alphabet = p.model.alphabet;
     const uint32_t table_words = SHARED ? (alphabet + 1) * 32 : 0;
-    constexpr uint32_t kRingsWords = kAnsBlock * (kEncRingWords + 4);
+    constexpr uint32_t kRingsWords = BLOCK * (kEncRingWords + 4);
     const uint32_t ring = smem_u32_pinned(smem) + threadIdx.x * kEncRingBytes;  // 32-byte aligned
-    const uint32_t park = smem_u32(smem) + kAnsBlock * kEncRingBytes + threadIdx.x * 16u;
+    const uint32_t park = smem_u32(smem) + BLOCK * kEncRingBytes + threadIdx.x * 16u;
     // lane l reads copy (l & 7) of an entry: the 8 lanes of a quarter-warp always hit 8 different 16-byte bank
     // groups, so the random-index LDS.128 is conflict free
     const uint32_t table_addr = smem_u32_pinned(smem + kRingsWords) + (uint32_t)(lane & 7) * 16u;
-    uint32_t *sym_tile = smem + kRingsWords + table_words + warp_in_cta * kTileWords;
-    uint32_t *idx_tile = sym_tile + kWarpsPerCta * kTileWords;
+    // contiguous layout: two symbol tiles per warp (double buffered), then one index tile per warp
+    uint32_t *sym_tile = smem + kRingsWords + table_words + warp_in_cta * (2 * kTileWords);
+    uint32_t *idx_tile = smem + kRingsWords + table_words + kWarpsPerCta * (2 * kTileWords) + warp_in_cta * kTileWords;
 
     if (SHARED) stage_table(smem + kRingsWords, p.model.enc_rep, (alphabet + 1) * 128u, &bar);
 
     const uint64_t K = p.K, N = p.N;
-    const uint32_t tile = take_tile_ticket(p.compact.ticket);  // which 256 streams this CTA codes
-    const uint64_t k = (uint64_t)tile * kAnsBlock + threadIdx.x;
+    const uint32_t tile = take_tile_ticket(p.compact.ticket);  // which BLOCK streams this CTA codes
+    const uint64_t k = (uint64_t)tile * BLOCK + threadIdx.x;
     const bool valid = k < K;
     const uint64_t kc = valid ? k : K - 1;  // lanes without a stream shadow the last one (loads only)
 
     // stream geometry and my scratch region
-    uint64_t n_k = 0, o_k = 0;
-    if (valid) {
-        if (CONTIG) {
-            o_k = p.sym_off[k];
-            n_k = p.sym_off[k + 1] - o_k;
-        } else {
-            n_k = interleaved_len(N, K, k);
-            o_k = interleaved_start(N, K, k);
-        }
+    uint64_t n_k, o_k;
+    if (CONTIG) {
+        o_k = p.sym_off[kc];
+        n_k = p.sym_off[kc + 1] - o_k;
+    } else {
+        n_k = interleaved_len(N, K, kc);
+        o_k = interleaved_start(N, K, kc);
     }
     char *gw;        // write cursor in my scratch region (128-byte aligned start)
     uint32_t room;   // bytes of scratch capacity left
@@ -288,16 +301,14 @@ __global__ void __launch_bounds__(kAnsBlock, 4) ans_encode_kernel(const AnsParam
     // one reference encode_symbol (stack.rs:1014-1048)
     // symbol -> table index; out-of-range symbols map to the sentinel entry [alphabet]
     auto index_of = [&](int32_t sym) -> uint32_t { return min((uint32_t)sym - min_symbol, alphabet); };
-    auto encode_idx = [&](uint32_t idx, uint32_t m) {
-        uint4 e;
-        if (SHARED) {
-            e = lds_table_v4(table_addr + idx * 128u);
-        } else {
-            const bool ok = m < n_models;
-            idx = ok ? idx : alphabet;
-            m = ok ? m : 0u;
-            e = __ldg(p.model.enc + (uint64_t)m * (alphabet + 1) + idx);
-        }
+    auto lookup = [&](uint32_t idx, uint32_t m) -> uint4 {
+        if (SHARED) return lds_table_v4(table_addr + idx * 128u);
+        const bool ok = m < n_models;
+        idx = ok ? idx : alphabet;
+        m = ok ? m : 0u;
+        return __ldg(p.model.enc + (uint64_t)m * (alphabet + 1) + idx);
+    };
+    auto encode_entry = [&](const uint4 &e) {
         min_prob = min(min_prob, e.y);
         uint32_t lo = (uint32_t)state, hi = (uint32_t)(state >> 32);
         if (shr_clamp(hi, push_shift) >= e.y) {  // stack.rs:1035-1040
@@ -310,6 +321,7 @@ __global__ void __launch_bounds__(kAnsBlock, 4) ans_encode_kernel(const AnsParam
         const uint64_t n = ((uint64_t)hi << 32) | lo;
         state = ans_encode_recombine(n, ans_quotient_estimate<F64DIV>(n, e.z, e.w), e.x, e.y);
     };
+    auto encode_idx = [&](uint32_t idx, uint32_t m) { encode_entry(lookup(idx, m)); };
     auto encode_one = [&](int32_t sym, uint32_t m) { encode_idx(index_of(sym), m); };
 
     // every kCheckEvery symbols: a complete 16-byte group of my ring goes to my scratch region.  A lane
@@ -330,6 +342,22 @@ __global__ void __launch_bounds__(kAnsBlock, 4) ans_encode_kernel(const AnsParam
     // the oldest (possibly incomplete) 16-byte group of my ring; harmless to read when it is not yet complete
     auto drain_load = [&]() -> uint4 { return lds_v4(ring | ((pushed - pending) & (kEncRingBytes - 16u))); };
     auto drain_ring = [&]() { drain_store(drain_load()); };
+    // split form: `full = pending >= 16` and `oldest = drain_load()` are taken at the check, the store is issued
+    // a couple of symbols later so that the shared-memory latency is covered by coding work (a group that
+    // completes in between waits for the next check; the ring has room for that)
+    auto drain_decided = [&](bool full, const uint4 &oldest) {
+        if (full) {
+            if (room >= 16u) {
+                st_stream_v4(gw, oldest);
+                gw += 16;
+                room -= 16u;
+            } else {
+                room = 0u;
+                pushed |= 0x80000000u;
+            }
+            pending -= 16u;
+        }
+    };
 
     if (!CONTIG) {
         // ---- interleaved deal: row t holds symbols[t*K .. t*K+K); coded from the last row backwards ---
@@ -394,17 +422,7 @@ __global__ void __launch_bounds__(kAnsBlock, 4) ans_encode_kernel(const AnsParam
                 const uint4 oldest = drain_load();
                 encode_idx(idx[0], mbuf[which][0]);
                 encode_idx(idx[1], mbuf[which][1]);
-                if (full) {
-                    if (room >= 16u) {
-                        st_stream_v4(gw, oldest);
-                        gw += 16;
-                        room -= 16u;
-                    } else {
-                        room = 0u;
-                        pushed |= 0x80000000u;
-                    }
-                    pending -= 16u;
-                }
+                drain_decided(full, oldest);
                 encode_idx(idx[2], mbuf[which][2]);
                 encode_idx(idx[3], mbuf[which][3]);
             };
@@ -440,23 +458,61 @@ __global__ void __launch_bounds__(kAnsBlock, 4) ans_encode_kernel(const AnsParam
         }
     } else {
         // ---- contiguous: 32x32 tiles, transposed through shared memory ---------------------------
-        uint64_t remaining = n_k;  // symbols of my stream not yet loaded (I consume from the end)
+        // The tile of the next round is filled asynchronously (LDGSTS) while this one is coded.  Within a
+        // tile, groups of four symbols are looked up first (independent of the coder state) and then coded,
+        // so that the loop-carried chain holds the state update only.
+        const uint32_t tiles_addr = smem_u32(sym_tile);
+        const uint32_t my_row = (uint32_t)lane * (kRowStride * 4u);
+        const uint32_t idx_row = smem_u32(idx_tile) + my_row;
+        uint64_t remaining = n_k;  // symbols of my stream not yet requested (I consume from the end)
         const uint64_t rounds = (warp_max_u64(n_k, lane) + 31) / 32;
+        uint32_t c_next = remaining < 32 ? (uint32_t)remaining : 32u;
+        remaining -= c_next;
+        warp_fill_rows_async(tiles_addr, reinterpret_cast<const uint32_t *>(p.symbols_in + o_k + remaining), c_next, lane);
+        cp_async_commit();
         for (uint64_t r = 0; r < rounds; ++r) {
-            const uint32_t c = remaining < 32 ? (uint32_t)remaining : 32u;
-            remaining -= c;
-            const unsigned have = __ballot_sync(kFullMask, c > 0);
-            warp_fill_rows(have, sym_tile, reinterpret_cast<const uint32_t *>(p.symbols_in + o_k + remaining), c, lane);
-            if (PERSYM) warp_fill_rows(have, idx_tile, p.model_index + o_k + remaining, c, lane);
-            const uint32_t cmax = __reduce_max_sync(kFullMask, c);
-            for (uint32_t s = 0; s < cmax; ++s) {
+            const uint32_t c = c_next;
+            const uint64_t first = remaining;  // my symbols of this round are [o_k + first, o_k + first + c)
+            const uint32_t row = tiles_addr + (uint32_t)(r & 1) * (kTileWords * 4u) + my_row;
+            c_next = remaining < 32 ? (uint32_t)remaining : 32u;
+            remaining -= c_next;
+            if (r + 1 < rounds)
+                warp_fill_rows_async(tiles_addr + (uint32_t)((r + 1) & 1) * (kTileWords * 4u),
+                                     reinterpret_cast<const uint32_t *>(p.symbols_in + o_k + remaining), c_next, lane);
+            cp_async_commit();
+            if (PERSYM) {
+                warp_fill_rows_async(smem_u32(idx_tile), p.model_index + o_k + first, c, lane);
+                cp_async_commit();
+                cp_async_wait_group<0>();
+            } else {
+                cp_async_wait_group<1>();
+            }
+            __syncwarp();
+            const uint32_t cmin = __reduce_min_sync(kFullMask, c), cmax = __reduce_max_sync(kFullMask, c);
+            uint32_t s = 0;
+            for (; s + kCheckEvery <= cmin; s += kCheckEvery) {  // every lane owns all four symbols
+                const bool full = pending >= 16u;
+                const uint4 oldest = drain_load();
+                uint4 e[kCheckEvery];
+#pragma unroll
+                for (int u = 0; u < kCheckEvery; ++u) {
+                    const uint32_t at = (c - 1u - s - (uint32_t)u) * 4u;
+                    e[u] = lookup(index_of((int32_t)lds_u32(row + at)), PERSYM ? lds_u32(idx_row + at) : stream_model);
+                }
+                encode_entry(e[0]);
+                encode_entry(e[1]);
+                drain_decided(full, oldest);
+                encode_entry(e[2]);
+                encode_entry(e[3]);
+            }
+            for (; s < cmax; ++s) {  // ragged end of the round
                 if ((s & (kCheckEvery - 1)) == 0) drain_ring();
                 if (s < c) {
-                    const int32_t sym = (int32_t)sym_tile[lane * kRowStride + (c - 1 - s)];
-                    const uint32_t m = PERSYM ? idx_tile[lane * kRowStride + (c - 1 - s)] : stream_model;
-                    encode_one(sym, m);
+                    const uint32_t at = (c - 1u - s) * 4u;
+                    encode_one((int32_t)lds_u32(row + at), PERSYM ? lds_u32(idx_row + at) : stream_model);
                 }
             }
+            __syncwarp();  // the tile is refilled by the next round's asynchronous fill
         }
     }
 
@@ -495,8 +551,8 @@ __global__ void __launch_bounds__(kAnsBlock, 4) ans_encode_kernel(const AnsParam
     uint32_t gb_lo, gb_hi;
     asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(gb_lo), "=r"(gb_hi) : "r"(park) : "memory");
     const uint32_t *gbegin = reinterpret_cast<const uint32_t *>(((uint64_t)gb_hi << 32) | gb_lo);
-    compact_tail<kAnsBlock>(p.compact, tile, k, K, valid, gbegin,
-                            (valid && !overflow) ? (uint32_t)((reinterpret_cast<const uint32_t *>(gw)) - gbegin) : 0u, p.status);
+    compact_tail<BLOCK>(p.compact, tile, k, K, valid, gbegin,
+                        (valid && !overflow) ? (uint32_t)((reinterpret_cast<const uint32_t *>(gw)) - gbegin) : 0u, p.status);
 }
 
 // =====================================================================================================
@@ -506,13 +562,12 @@ __global__ void __launch_bounds__(kAnsBlock, 4) ans_encode_kernel(const AnsParam
 // With a shared model and the interleaved layout the CTA is 1024 threads so that the 32 KB quantile index is
 // staged once per SM; otherwise (transposition tiles, or global tables: nothing to amortise) 256 threads.
 constexpr int kDecBlockShared = 1024;
-template <bool SHARED, bool CONTIG, bool PERSYM, bool SMALL>
-__global__ void __launch_bounds__((SHARED && !CONTIG) ? kDecBlockShared : kAnsBlock, (SHARED && !CONTIG) ? 1 : 2)
-    ans_decode_kernel(const AnsParams p) {
+template <int BLOCK, bool SHARED, bool CONTIG, bool PERSYM, bool SMALL>
+__global__ void __launch_bounds__(BLOCK, BLOCK >= 1024 ? 1 : (BLOCK >= 256 ? 2 : 8)) ans_decode_kernel(const AnsParams p) {
     extern __shared__ __align__(128) uint32_t smem[];
     __shared__ uint64_t bar;
 
-    constexpr int kBlock = (SHARED && !CONTIG) ? kDecBlockShared : kAnsBlock;
+    constexpr int kBlock = BLOCK;
     const int lane = threadIdx.x & 31;
     const int warp_in_cta = threadIdx.x >> 5;
     constexpr int kWarpsPerCta = kBlock / 32;
@@ -703,19 +758,27 @@ __global__ void __launch_bounds__((SHARED && !CONTIG) ? kDecBlockShared : kAnsBl
         }
     } else {
         uint64_t done = 0;  // symbols of my stream already produced
+        const uint32_t my_row = (uint32_t)lane * (kRowStride * 4u);
+        const uint32_t row = smem_u32(sym_tile) + my_row, idx_row = smem_u32(idx_tile) + my_row;
         const uint64_t rounds = (warp_max_u64(n_k, lane) + 31) / 32;
         for (uint64_t r = 0; r < rounds; ++r) {
             const uint64_t left_n = n_k - done;
             const uint32_t c = left_n < 32 ? (uint32_t)left_n : 32u;
             const unsigned have = __ballot_sync(kFullMask, c > 0);
             if (PERSYM) warp_fill_rows(have, idx_tile, p.model_index + o_k + done, c, lane);
-            const uint32_t cmax = __reduce_max_sync(kFullMask, c);
-            for (uint32_t s = 0; s < cmax; ++s) {
-                if ((s & (kCheckEvery - 1)) == 0) top_up();
-                if (s < c) {
-                    const uint32_t m = PERSYM ? idx_tile[lane * kRowStride + s] : stream_model;
-                    sym_tile[lane * kRowStride + s] = (uint32_t)decode_one(m);
+            const uint32_t cmin = __reduce_min_sync(kFullMask, c), cmax = __reduce_max_sync(kFullMask, c);
+            uint32_t s = 0;
+            for (; s + kCheckEvery <= cmin; s += kCheckEvery) {  // every lane owns all four symbols
+                top_up();
+#pragma unroll
+                for (int u = 0; u < kCheckEvery; ++u) {
+                    const uint32_t at = (s + (uint32_t)u) * 4u;
+                    sts_u32(row + at, (uint32_t)decode_one(PERSYM ? lds_u32(idx_row + at) : stream_model));
                 }
+            }
+            for (; s < cmax; ++s) {  // ragged end of the round
+                if ((s & (kCheckEvery - 1)) == 0) top_up();
+                if (s < c) sts_u32(row + s * 4u, (uint32_t)decode_one(PERSYM ? lds_u32(idx_row + s * 4u) : stream_model));
             }
             warp_flush_rows(have, sym_tile, reinterpret_cast<uint32_t *>(p.symbols_out + o_k + done), c, lane);
             done += c;

@@ -16,8 +16,8 @@
 #include "../../include/constriction_b200.h"
 #include "ans_kernels.cuh"
 #include "compact.cuh"
+#include "launch.cuh"
 #include "model_tables.cuh"
-#include "range_kernels.cuh"
 
 using namespace ctr;
 
@@ -228,17 +228,11 @@ struct EncodeWorkspace {
 EncodeWorkspace encode_workspace(const ctr_layout *L) {
     EncodeWorkspace w;
     w.scratch_words = scratch_start(L->n_symbols, L->n_streams) + 32;
-    w.n_tiles = (L->n_streams + kAnsBlock - 1) / kAnsBlock;
+    w.n_tiles = (L->n_streams + kSmallBlock - 1) / kSmallBlock;  // enough for either CTA size
     w.status_off = align_up((size_t)w.scratch_words * 4, 256);
     w.ticket_off = w.status_off + (size_t)w.n_tiles * 8;
     w.total = align_up(w.ticket_off + 8, 256);
     return w;
-}
-
-template <typename Kernel>
-int set_smem(Kernel kernel, size_t bytes) {
-    if (bytes > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-    return CTR_OK;
 }
 
 }  // namespace
@@ -482,75 +476,60 @@ namespace {
 bool use_shared_tables(const ctr_model_s *m, const ctr_layout *L) {
     return L->model_index_mode == CTR_INDEX_NONE && m->shared_ok;
 }
-// the ANS encoder's replicated table needs 128 B per entry
-bool use_shared_ans_enc_table(const ctr_model_s *m, const ctr_layout *L) {
+// the encoders' replicated table needs 128 B per entry
+bool use_shared_enc_table(const ctr_model_s *m, const ctr_layout *L) {
     return use_shared_tables(m, L) && m->alphabet <= kMaxSharedEncAlphabet;
 }
 
+// CTA size: big CTAs amortise the table staging, but a batch with fewer streams than one big CTA per SM is
+// latency-bound and wants its warps spread over as many SMs as possible.
+constexpr uint64_t kStreamsForBigCtas = 148ull * kAnsBlock;
+unsigned encode_block(const ctr_layout *L) { return L->n_streams < kStreamsForBigCtas ? kSmallBlock : kAnsBlock; }
+unsigned decode_block(const ctr_layout *L, bool shared, bool contig) {
+    if (L->n_streams < kStreamsForBigCtas) return kSmallBlock;
+    // shared model + interleaved deal: 1024-thread CTAs stage the 32 KB quantile index once per SM
+    if (shared && !contig && L->n_streams >= 148ull * kDecBlockShared) return kDecBlockShared;
+    return kAnsBlock;
+}
+
 // dynamic shared memory of a coder kernel: per-warp word staging + tables + 32x32 transposition tiles
-size_t coder_smem_bytes(size_t table_bytes, const ctr_layout *L, int warps, size_t stage_words_per_warp) {
+// (contiguous layout: the encoders double-buffer the symbol tile; one more tile for per-symbol model indices)
+size_t coder_smem_bytes(size_t table_bytes, const ctr_layout *L, int warps, size_t stage_words_per_warp, int sym_tiles) {
     const bool contig = L->sym_offsets_dev != nullptr;
     int tiles = 0;
-    if (contig) tiles += 1 + (L->model_index_mode == CTR_INDEX_PER_SYMBOL ? 1 : 0);
+    if (contig) tiles += sym_tiles + (L->model_index_mode == CTR_INDEX_PER_SYMBOL ? 1 : 0);
     return table_bytes + (size_t)warps * stage_words_per_warp * 4 + (size_t)tiles * warps * kTileWords * 4;
 }
 
-// SHARED implies one model for the whole batch, hence no per-symbol index.
-#define CTR_DISPATCH(KERNEL, SLOT, ...)                                                                    \
-    do {                                                                                                   \
-        auto launch = [&](auto kernel) -> int {                                                            \
-            int rc__ = set_smem(kernel, smem);                                                             \
-            if (rc__) return rc__;                                                                         \
-            ProfileScope prof(SLOT, s);                                                                    \
-            kernel<<<grid, block, smem, s>>>(p);                                                           \
-            LAUNCH_CHECK(#KERNEL);                                                                         \
-            return CTR_OK;                                                                                 \
-        };                                                                                                 \
-        if (shared) return contig ? launch(KERNEL<true, true, false __VA_ARGS__>) : launch(KERNEL<true, false, false __VA_ARGS__>); \
-        if (persym) return contig ? launch(KERNEL<false, true, true __VA_ARGS__>) : launch(KERNEL<false, false, true __VA_ARGS__>); \
-        return contig ? launch(KERNEL<false, true, false __VA_ARGS__>) : launch(KERNEL<false, false, false __VA_ARGS__>);          \
-    } while (0)
-
 struct AnsEncodeLauncher {
-    static bool shared(const ctr_model_s *m, const ctr_layout *L) { return use_shared_ans_enc_table(m, L); }
-    static size_t table_bytes(const ctr_model_s *m) { return ((size_t)m->alphabet + 1) * 128; }
-    static unsigned block_for(bool, bool) { return kAnsBlock; }
-    static size_t stage_words() { return 32 * (kEncRingWords + 4); }  // rings + parking slots
-    static int run(bool shared, bool contig, bool persym, bool f64, const AnsParams &p, size_t smem, unsigned grid,
-                   unsigned block, cudaStream_t s) {
-#define CTR_COMMA ,
-        if (f64) CTR_DISPATCH(ans_encode_kernel, 0, CTR_COMMA true);
-        CTR_DISPATCH(ans_encode_kernel, 0, CTR_COMMA false);
-    }
+    static constexpr int kSlot = 0;
+    static constexpr const char *kName = "ans_encode_kernel";
+    static cudaError_t run(const LaunchCfg &cfg, const AnsParams &p) { return launch_ans_encode(cfg, p); }
 };
 struct AnsDecodeLauncher {
-    static unsigned block_for(bool shared, bool contig) { return (shared && !contig) ? kDecBlockShared : kAnsBlock; }
-    static size_t stage_words() { return 32 * kDecRingWords; }
-    static int run(bool shared, bool contig, bool persym, bool, const AnsParams &p, size_t smem, unsigned grid,
-                   unsigned block, cudaStream_t s) {
-        if (shared && p.model.alphabet <= 256) CTR_DISPATCH(ans_decode_kernel, 1, CTR_COMMA true);
-        CTR_DISPATCH(ans_decode_kernel, 1, CTR_COMMA false);
-    }
+    static constexpr int kSlot = 1;
+    static constexpr const char *kName = "ans_decode_kernel";
+    static cudaError_t run(const LaunchCfg &cfg, const AnsParams &p) { return launch_ans_decode(cfg, p); }
 };
 struct RangeEncodeLauncher {
-    static bool shared(const ctr_model_s *m, const ctr_layout *L) { return use_shared_ans_enc_table(m, L); }
-    static size_t table_bytes(const ctr_model_s *m) { return ((size_t)m->alphabet + 1) * 128; }
-    static unsigned block_for(bool, bool) { return kAnsBlock; }
-    static size_t stage_words() { return 32 * (kEncRingWords + 4); }
-    static int run(bool shared, bool contig, bool persym, bool, const AnsParams &p, size_t smem, unsigned grid,
-                   unsigned block, cudaStream_t s) {
-        CTR_DISPATCH(range_encode_kernel, 2);
-    }
+    static constexpr int kSlot = 2;
+    static constexpr const char *kName = "range_encode_kernel";
+    static cudaError_t run(const LaunchCfg &cfg, const AnsParams &p) { return launch_range_encode(cfg, p); }
 };
 struct RangeDecodeLauncher {
-    static unsigned block_for(bool shared, bool contig) { return (shared && !contig) ? kDecBlockShared : kAnsBlock; }
-    static size_t stage_words() { return 32 * kDecRingWords; }
-    static int run(bool shared, bool contig, bool persym, bool, const AnsParams &p, size_t smem, unsigned grid,
-                   unsigned block, cudaStream_t s) {
-        if (shared && p.model.alphabet <= 256) CTR_DISPATCH(range_decode_kernel, 3, CTR_COMMA true);
-        CTR_DISPATCH(range_decode_kernel, 3, CTR_COMMA false);
-    }
+    static constexpr int kSlot = 3;
+    static constexpr const char *kName = "range_decode_kernel";
+    static cudaError_t run(const LaunchCfg &cfg, const AnsParams &p) { return launch_range_decode(cfg, p); }
 };
+
+template <class Launcher>
+int run_coder_kernel(const LaunchCfg &cfg, const AnsParams &p) {
+    ProfileScope prof(Launcher::kSlot, cfg.stream);
+    const cudaError_t e = Launcher::run(cfg, p);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    if (e != cudaSuccess) return cuda_fail(e, Launcher::kName);
+    return CTR_OK;
+}
 
 AnsParams base_params(const ctr_model_s *m, const ctr_layout *L) {
     AnsParams p;
@@ -599,13 +578,18 @@ int encode_common(ctr_model_t model, const int32_t *symbols_dev, const ctr_layou
     p.compact.offsets_out = offsets_out;
     CUDA_TRY(cudaMemsetAsync(ws + w.status_off, 0, w.total - w.status_off, s));
 
-    const bool shared = EncLauncher::shared(model, L);
-    const bool contig = L->sym_offsets_dev != nullptr;
-    const unsigned block = EncLauncher::block_for(shared, contig);
-    const size_t smem = coder_smem_bytes(shared ? EncLauncher::table_bytes(model) : 0, L, block / 32,
-                                         EncLauncher::stage_words());
-    return EncLauncher::run(shared, contig, L->model_index_mode == CTR_INDEX_PER_SYMBOL, model->enc_f64, p, smem,
-                            grid_for(L->n_streams, block), block, s);
+    LaunchCfg cfg;
+    cfg.shared = use_shared_enc_table(model, L);
+    cfg.contig = L->sym_offsets_dev != nullptr;
+    cfg.persym = L->model_index_mode == CTR_INDEX_PER_SYMBOL;
+    cfg.f64 = model->enc_f64;
+    cfg.block = encode_block(L);
+    cfg.grid = grid_for(L->n_streams, cfg.block);
+    // rings + parking slots; replicated table (128 B per entry); two symbol tiles
+    cfg.smem = coder_smem_bytes(cfg.shared ? ((size_t)model->alphabet + 1) * 128 : 0, L, cfg.block / 32,
+                                32 * (kEncRingWords + 4), 2);
+    cfg.stream = s;
+    return run_coder_kernel<EncLauncher>(cfg, p);
 }
 
 template <class DecLauncher>
@@ -632,13 +616,17 @@ int decode_common(ctr_model_t model, const uint32_t *words, const uint64_t *offs
     p.offsets = offsets;
     p.words_left = words_left;
 
-    const bool shared = use_shared_tables(model, L);
-    const bool contig = L->sym_offsets_dev != nullptr;
-    const unsigned block = DecLauncher::block_for(shared, contig);
-    const size_t smem = coder_smem_bytes(shared ? (size_t)kLutBytes + model->dec_cdf_bytes : 0, L, block / 32,
-                                         DecLauncher::stage_words());
-    return DecLauncher::run(shared, contig, L->model_index_mode == CTR_INDEX_PER_SYMBOL, false, p, smem,
-                            grid_for(L->n_streams, block), block, s);
+    LaunchCfg cfg;
+    cfg.shared = use_shared_tables(model, L);
+    cfg.contig = L->sym_offsets_dev != nullptr;
+    cfg.persym = L->model_index_mode == CTR_INDEX_PER_SYMBOL;
+    cfg.f64 = false;
+    cfg.block = decode_block(L, cfg.shared, cfg.contig);
+    cfg.grid = grid_for(L->n_streams, cfg.block);
+    cfg.smem = coder_smem_bytes(cfg.shared ? (size_t)kLutBytes + model->dec_cdf_bytes : 0, L, cfg.block / 32,
+                                32 * kDecRingWords, 1);
+    cfg.stream = s;
+    return run_coder_kernel<DecLauncher>(cfg, p);
 }
 
 }  // namespace

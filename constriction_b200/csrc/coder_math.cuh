@@ -143,87 +143,72 @@ CTR_HD uint32_t ans_state_words(uint64_t state) { return state == 0 ? 0u : ((sta
 
 // ---------------------------------------------------------------- Range (queue) --------------
 
+// ---- range encoder, "eager words, late carry" formulation --------------------------------------------
+//
+// The reference's encoder (queue.rs:612-705) holds words back while the coding interval straddles a multiple
+// of 2^64 (`EncoderSituation::Inverted(n, first)`) and releases them as `first, 0xffffffff x (n-1)` or, if the
+// interval ended up beyond the boundary, as `first + 1, 0 x (n-1)`.  The same words result from appending every
+// word the moment the interval is renormalised and, should `lower` later wrap around, adding one to the words
+// already written (a carry that ripples through the trailing 0xffffffff words into `first`):
+//   * a Normal interval [lower, lower + range) does not wrap and `scale * left < range`, so `lower` cannot wrap;
+//   * while Inverted, a renormalisation that leaves the interval wrapped has lower > 2^64 - 2^32, i.e. the
+//     word it appends is 0xffffffff -- exactly the fill word the reference will emit if no carry arrives;
+//   * `first <= 0xfffffffe` (the interval was not wrapped before its word was taken), so the carry stops there.
+// The situation is a function of (lower, range) alone -- Inverted <=> !(lower + range > lower) -- and the
+// number of held-back words is the run of trailing 0xffffffff words plus one, so the hot loop carries only
+// (lower, range) and the reference's 4-tuple is recovered when a caller asks for the raw state.
 struct RangeEncState {
     uint64_t lower;
-    uint64_t range;         // u64::MAX when empty (queue.rs:98-106)
-    uint32_t num_inverted;  // 0 == EncoderSituation::Normal
-    uint32_t first_inverted;
+    uint64_t range;  // u64::MAX when empty (queue.rs:98-106)
 };
 
 CTR_HD RangeEncState range_enc_init() {
     RangeEncState s;
     s.lower = 0;
     s.range = ~0ull;
-    s.num_inverted = 0;
-    s.first_inverted = 0;
     return s;
 }
 
-// Result of one encode step: up to `n_burst` words become final *before* `word` (the held-back
-// words of a resolved Inverted situation: `burst_first`, then n_burst-1 copies of `burst_fill`),
-// then `emit` says whether `word` is appended too.
-struct RangeEmit {
-    uint32_t n_burst;
-    uint32_t burst_first;
-    uint32_t burst_fill;
-    bool emit;
-    uint32_t word;
-};
+// EncoderSituation::Inverted <=> the interval wraps (queue.rs:647-666, 684-700)
+CTR_HD bool range_enc_inverted(const RangeEncState &s) { return !(s.lower + s.range > s.lower); }
 
-// queue.rs:612-705.  Returns false for an impossible symbol (range would collapse to zero).
-CTR_HD bool range_encode_step(RangeEncState &s, uint32_t left, uint32_t prob, RangeEmit &out) {
-    out.n_burst = 0;
-    out.emit = false;
+// One encode step (queue.rs:612-705).  Returns bit 0: add one to the words written so far (before `word`);
+// bit 1: append `word`.  prob == 0 (impossible symbol) must be rejected by the caller.
+CTR_HD uint32_t range_encode_step(RangeEncState &s, uint32_t left, uint32_t prob, uint32_t &word) {
     const uint64_t scale = s.range >> kPrecision;
-    const uint64_t new_range = scale * (uint64_t)prob;
-    if (new_range == 0) return false;
-    const uint64_t new_lower = s.lower + scale * (uint64_t)left;  // wrapping
-    if (s.num_inverted != 0) {
-        if (new_lower + new_range > new_lower) {  // interval no longer wraps: resolve
-            const bool carried = new_lower < s.lower;
-            out.n_burst = s.num_inverted;
-            out.burst_first = s.first_inverted + (carried ? 1u : 0u);
-            out.burst_fill = carried ? 0u : 0xffffffffu;
-            s.num_inverted = 0;
-        }
+    uint64_t range = scale * (uint64_t)prob;
+    uint64_t lower = s.lower + scale * (uint64_t)left;  // wrapping
+    uint32_t flags = lower < s.lower ? 1u : 0u;
+    if (range < (1ull << 32)) {
+        word = (uint32_t)(lower >> 32);
+        lower <<= 32;
+        range <<= 32;
+        flags |= 2u;
     }
-    s.lower = new_lower;
-    s.range = new_range;
-    if (s.range < (1ull << 32)) {
-        s.range <<= 32;
-        const uint32_t lower_word = (uint32_t)(s.lower >> 32);
-        s.lower <<= 32;
-        if (s.num_inverted != 0) {
-            s.num_inverted += 1;
-        } else if (s.lower + s.range > s.lower) {
-            out.emit = true;
-            out.word = lower_word;
-        } else {
-            s.num_inverted = 1;
-            s.first_inverted = lower_word;
-        }
-    }
-    return true;
+    s.lower = lower;
+    s.range = range;
+    return flags;
 }
 
-// queue.rs:357-376
-CTR_HD uint32_t range_num_seal_words(const RangeEncState &s) {
-    if (s.range == ~0ull) return 0;
-    const uint32_t point_word = (uint32_t)((s.lower + 0xffffffffull) >> 32);
-    const uint32_t upper_word = (uint32_t)((s.lower + s.range) >> 32);
-    return (upper_word == point_word ? 2u : 1u) + s.num_inverted;
-}
-
-// queue.rs:458-523: the i-th (0-based) of range_num_seal_words(s) seal words.
-CTR_HD uint32_t range_seal_word(const RangeEncState &s, uint32_t i) {
+// seal (queue.rs:349-376, 458-523): `carry` = add one to the words written so far; then `n` (0..2) words follow:
+// the point word, and a zero word iff the word above the interval's end equals the point word.
+struct RangeSeal {
+    bool carry;
+    uint32_t n;
+    uint32_t point_word;
+};
+CTR_HD RangeSeal range_seal(const RangeEncState &s) {
+    RangeSeal r;
+    r.carry = false;
+    r.n = 0;
+    r.point_word = 0;
+    if (s.range == ~0ull) return r;  // nothing was encoded
     const uint64_t point = s.lower + 0xffffffffull;
-    if (i < s.num_inverted) {
-        const bool carried = point < s.lower;
-        if (i == 0) return s.first_inverted + (carried ? 1u : 0u);
-        return carried ? 0u : 0xffffffffu;
-    }
-    if (i == s.num_inverted) return (uint32_t)(point >> 32);
-    return 0u;
+    r.carry = point < s.lower;
+    r.point_word = (uint32_t)(point >> 32);
+    const uint32_t upper_word = (uint32_t)((s.lower + s.range) >> 32);
+    r.n = upper_word == r.point_word ? 2u : 1u;
+    return r;
 }
 
 struct RangeDecState {

@@ -1,0 +1,35 @@
+// range_decode.cu -- instantiations of range_decode_kernel (K4) and their dispatch.
+#include "launch.cuh"
+#include "range_kernels.cuh"
+
+namespace ctr {
+
+// SMALL (alphabet <= 256) only matters for the shared-memory quantile index
+template <int BLOCK>
+static cudaError_t go(const LaunchCfg &cfg, const AnsParams &p) {
+    if (cfg.shared) {
+        if (p.model.alphabet <= 256)
+            return cfg.contig ? launch_kernel(range_decode_kernel<BLOCK, true, true, false, true>, cfg, p)
+                              : launch_kernel(range_decode_kernel<BLOCK, true, false, false, true>, cfg, p);
+        return cfg.contig ? launch_kernel(range_decode_kernel<BLOCK, true, true, false, false>, cfg, p)
+                          : launch_kernel(range_decode_kernel<BLOCK, true, false, false, false>, cfg, p);
+    }
+    if (cfg.persym)
+        return cfg.contig ? launch_kernel(range_decode_kernel<BLOCK, false, true, true, false>, cfg, p)
+                          : launch_kernel(range_decode_kernel<BLOCK, false, false, true, false>, cfg, p);
+    return cfg.contig ? launch_kernel(range_decode_kernel<BLOCK, false, true, false, false>, cfg, p)
+                      : launch_kernel(range_decode_kernel<BLOCK, false, false, false, false>, cfg, p);
+}
+
+cudaError_t launch_range_decode(const LaunchCfg &cfg, const AnsParams &p) {
+    if (cfg.block == (unsigned)kDecBlockShared) {  // shared model, interleaved deal, large batch
+        if (!cfg.shared || cfg.contig) return cudaErrorInvalidConfiguration;
+        return p.model.alphabet <= 256 ? launch_kernel(range_decode_kernel<kDecBlockShared, true, false, false, true>, cfg, p)
+                                       : launch_kernel(range_decode_kernel<kDecBlockShared, true, false, false, false>, cfg, p);
+    }
+    if (cfg.block == (unsigned)kSmallBlock) return go<kSmallBlock>(cfg, p);
+    if (cfg.block == (unsigned)kAnsBlock) return go<kAnsBlock>(cfg, p);
+    return cudaErrorInvalidConfiguration;
+}
+
+}  // namespace ctr

@@ -6,56 +6,59 @@
 // hot loops with the ragged last row of the interleaved deal peeled off, fused compaction in the encoder's
 // tail.  Queue semantics: symbols are coded in forward order and words are read from the front.
 //
-// The encoder's lazy carry ("Inverted" situation, queue.rs:647-702) can release a burst of held-back words in
-// one step; because the word path is lane-private, the (rare) burst is simply pushed by a lane-local loop that
-// drains the ring as it goes.
+// The encoder uses the "eager words, late carry" formulation of coder_math.cuh: a word is appended whenever
+// the interval is renormalised, and the reference's lazy carry ("Inverted" situation, queue.rs:647-702) becomes
+// an increment of the words already written -- a cold path that touches the lane's ring or, if the words
+// have been drained already, its scratch region.  The hot loop carries (lower, range) only and is branch-free
+// apart from that carry.
 //
 // Per-stream results equal the reference's RangeEncoder / RangeDecoder (src/stream/queue.rs) word for word,
 // including the seal words (queue.rs:349-376,458-523).
 //
 // Coder state on the wire (CTR_FLAG_RAW, states_in / states_out): 4 x u64 per stream,
 //   encoder {lower, range, num_inverted, first_inverted_word}, decoder {lower, range, point, 0}.
+// A raw-state encoder call returns the final words only: the held-back words of an unresolved Inverted
+// situation are stripped from the output and described by (num_inverted, first_inverted_word), exactly what
+// the reference's `pos()` reports; the next call writes them again before it continues.
 #pragma once
 #include "ans_kernels.cuh"
 
 namespace ctr {
 
-template <bool SHARED, bool CONTIG, bool PERSYM>
-__global__ void __launch_bounds__(kAnsBlock, 4) range_encode_kernel(const AnsParams p) {
+template <int BLOCK, bool SHARED, bool CONTIG, bool PERSYM>
+__global__ void __launch_bounds__(BLOCK, BLOCK >= 256 ? 4 : 8) range_encode_kernel(const AnsParams p) {
     extern __shared__ __align__(128) uint32_t smem[];
     __shared__ uint64_t bar;
 
     const int lane = threadIdx.x & 31;
     const int warp_in_cta = threadIdx.x >> 5;
-    constexpr int kWarpsPerCta = kAnsBlock / 32;
+    constexpr int kWarpsPerCta = BLOCK / 32;
 
     // shared memory carve-up as in ans_encode_kernel: [rings + parking slots][replicated table][tiles]
     const uint32_t alphabet = p.model.alphabet;
     const uint32_t table_words = SHARED ? (alphabet + 1) * 32 : 0;
-    constexpr uint32_t kRingsWords = kAnsBlock * (kEncRingWords + 4);
+    constexpr uint32_t kRingsWords = BLOCK * (kEncRingWords + 4);
     const uint32_t ring = smem_u32_pinned(smem) + threadIdx.x * kEncRingBytes;
-    const uint32_t park = smem_u32(smem) + kAnsBlock * kEncRingBytes + threadIdx.x * 16u;
+    const uint32_t park = smem_u32(smem) + BLOCK * kEncRingBytes + threadIdx.x * 16u;
     const uint32_t table_addr = smem_u32_pinned(smem + kRingsWords) + (uint32_t)(lane & 7) * 16u;
-    uint32_t *sym_tile = smem + kRingsWords + table_words + warp_in_cta * kTileWords;
-    uint32_t *idx_tile = sym_tile + kWarpsPerCta * kTileWords;
+    uint32_t *sym_tile = smem + kRingsWords + table_words + warp_in_cta * (2 * kTileWords);
+    uint32_t *idx_tile = smem + kRingsWords + table_words + kWarpsPerCta * (2 * kTileWords) + warp_in_cta * kTileWords;
 
     if (SHARED) stage_table(smem + kRingsWords, p.model.enc_rep, (alphabet + 1) * 128u, &bar);
 
     const uint64_t K = p.K, N = p.N;
     const uint32_t tile = take_tile_ticket(p.compact.ticket);
-    const uint64_t k = (uint64_t)tile * kAnsBlock + threadIdx.x;
+    const uint64_t k = (uint64_t)tile * BLOCK + threadIdx.x;
     const bool valid = k < K;
-    const uint64_t kc = valid ? k : K - 1;
+    const uint64_t kc = valid ? k : K - 1;  // lanes without a stream shadow the last one; nothing they push is stored
 
-    uint64_t n_k = 0, o_k = 0;
-    if (valid) {
-        if (CONTIG) {
-            o_k = p.sym_off[k];
-            n_k = p.sym_off[k + 1] - o_k;
-        } else {
-            n_k = interleaved_len(N, K, k);
-            o_k = interleaved_start(N, K, k);
-        }
+    uint64_t n_k, o_k;
+    if (CONTIG) {
+        o_k = p.sym_off[kc];
+        n_k = p.sym_off[kc + 1] - o_k;
+    } else {
+        n_k = interleaved_len(N, K, kc);
+        o_k = interleaved_start(N, K, kc);
     }
     char *gw;
     uint32_t room;
@@ -68,13 +71,7 @@ __global__ void __launch_bounds__(kAnsBlock, 4) range_encode_kernel(const AnsPar
         asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(park), "r"((uint32_t)gb), "r"((uint32_t)(gb >> 32)) : "memory");
     }
 
-    RangeEncState st = range_enc_init();
-    if (valid && p.states_in) {
-        st.lower = p.states_in[4 * k];
-        st.range = p.states_in[4 * k + 1];
-        st.num_inverted = (uint32_t)p.states_in[4 * k + 2];
-        st.first_inverted = (uint32_t)p.states_in[4 * k + 3];
-    }
+    uint64_t lower = 0, range = ~0ull;
     uint32_t pushed = 0, pending = 0;  // bytes pushed into my ring / not yet written to scratch
     uint32_t min_prob = 0xffffffffu;
     bool overflow = false;
@@ -101,32 +98,64 @@ __global__ void __launch_bounds__(kAnsBlock, 4) range_encode_kernel(const AnsPar
             pending -= 16u;
         }
     };
-
-    // one reference encode_symbol (queue.rs:612-705); impossible symbols are skipped and flagged
-    auto encode_one = [&](int32_t sym, uint32_t m) {
-        uint32_t idx = min((uint32_t)sym - min_symbol, alphabet);  // out of range -> sentinel entry (prob 0)
-        uint4 e;
-        if (SHARED) {
-            e = lds_table_v4(table_addr + idx * 128u);
-        } else {
-            const bool ok = m < n_models;
-            idx = ok ? idx : alphabet;
-            m = ok ? m : 0u;
-            e = __ldg(p.model.enc + (uint64_t)m * (alphabet + 1) + idx);
-        }
-        min_prob = min(min_prob, e.y);
-        if (valid && e.y != 0u) {
-            RangeEmit em;
-            range_encode_step(st, e.x, e.y, em);
-            if (em.n_burst != 0u) {  // rare: a resolved Inverted situation releases its held-back words
-                for (uint32_t j = 0; j < em.n_burst; ++j) {
-                    push(j == 0 ? em.burst_first : em.burst_fill);
-                    drain_ring();
-                }
+    // The word pushed when `pushed` was `pos`: still in my ring, or already in my scratch region.
+    auto word_in_ring = [&](uint32_t pos) { return pushed - pos <= pending; };
+    auto scratch_word = [&](uint32_t pos) { return reinterpret_cast<uint32_t *>(gw - (pushed - pending - pos)); };
+    // late carry (cold): add one to the words written so far -- the trailing 0xffffffff words wrap to zero and
+    // the word before them absorbs the carry (it is <= 0xfffffffe, see coder_math.cuh)
+    auto propagate_carry = [&]() {
+        uint32_t pos = pushed;
+        while (pos != 0u) {
+            pos -= 4u;
+            uint32_t w;
+            if (word_in_ring(pos)) {
+                const uint32_t a = ring | (pos & (kEncRingBytes - 1u));
+                w = lds_u32(a) + 1u;
+                sts_u32(a, w);
+            } else {
+                if (overflow) break;  // words were dropped: the stream is flagged anyway
+                uint32_t *g = scratch_word(pos);
+                w = __ldcg(g) + 1u;
+                __stcg(g, w);
             }
-            if (em.emit) push(em.word);
+            if (w != 0u) break;
         }
     };
+
+    if (valid && p.states_in) {  // resume (queue.rs:182-196): the held-back words are written again
+        lower = p.states_in[4 * k];
+        range = p.states_in[4 * k + 1];
+        const uint64_t held = p.states_in[4 * k + 2];
+        const uint32_t first = (uint32_t)p.states_in[4 * k + 3];
+        for (uint64_t j = 0; j < held; ++j) {
+            push(j == 0 ? first : 0xffffffffu);
+            drain_ring();
+        }
+    }
+
+    auto lookup = [&](int32_t sym, uint32_t m) -> uint2 {
+        uint32_t idx = min((uint32_t)sym - min_symbol, alphabet);  // out of range -> sentinel entry (prob 0)
+        if (SHARED) return lds_table_v2(table_addr + idx * 128u);
+        const bool ok = m < n_models;
+        idx = ok ? idx : alphabet;
+        m = ok ? m : 0u;
+        const uint4 e = __ldg(p.model.enc + (uint64_t)m * (alphabet + 1) + idx);
+        return make_uint2(e.x, e.y);
+    };
+    // one reference encode_symbol (queue.rs:612-705) on a looked-up (left, prob).  An impossible symbol
+    // (prob 0) collapses the range to zero: the words from there on are garbage and the stream is flagged.
+    auto encode_entry = [&](const uint2 &e) {
+        min_prob = min(min_prob, e.y);
+        const uint64_t scale = range >> kPrecision;
+        const uint64_t nr = scale * (uint64_t)e.y;
+        const uint64_t nl = lower + scale * (uint64_t)e.x;
+        if (nl < lower) propagate_carry();
+        const bool renorm = (uint32_t)(nr >> 32) == 0u;
+        if (renorm) push((uint32_t)(nl >> 32));
+        lower = renorm ? nl << 32 : nl;
+        range = renorm ? nr << 32 : nr;
+    };
+    auto encode_one = [&](int32_t sym, uint32_t m) { encode_entry(lookup(sym, m)); };
 
     if (!CONTIG) {
         const Interleave g = interleave_of(N, K);
@@ -151,11 +180,24 @@ __global__ void __launch_bounds__(kAnsBlock, 4) range_encode_kernel(const AnsPar
                     }
                 }
             };
+            // L2 prefetch a few batches ahead, as in ans_encode_kernel
+            constexpr int kPrefetchBatches = CTR_PF_BATCHES;
+            const char *pf = ps + ((uint64_t)kPrefetchBatches * kCheckEvery + (uint32_t)(lane >> 3)) * row_bytes;
+            const char *const pf_end = reinterpret_cast<const char *>(p.symbols_in + N);
+            const uint64_t batch_bytes = row_bytes * kCheckEvery;
             auto code_batch = [&](int which, bool load_next) {
+                // consume this batch's loads (issued a whole batch ago) before the next batch's are issued
+                uint2 e[kCheckEvery];
+#pragma unroll
+                for (int u = 0; u < kCheckEvery; ++u) e[u] = lookup(buf[which][u], mbuf[which][u]);
                 if (load_next) load_batch(which ^ 1);
+                if (kPrefetchBatches > 0) {
+                    if (pf < pf_end) prefetch_l2(pf);
+                    pf += batch_bytes;
+                }
                 drain_ring();
 #pragma unroll
-                for (int u = 0; u < kCheckEvery; ++u) encode_one(buf[which][u], mbuf[which][u]);
+                for (int u = 0; u < kCheckEvery; ++u) encode_entry(e[u]);
             };
             uint32_t batches = (uint32_t)(rows_total / kCheckEvery);
             uint32_t rows_left = (uint32_t)(rows_total - (uint64_t)batches * kCheckEvery);
@@ -194,34 +236,69 @@ __global__ void __launch_bounds__(kAnsBlock, 4) range_encode_kernel(const AnsPar
             }
         }
     } else {
-        uint64_t done = 0;
+        // contiguous: double-buffered asynchronous tiles, lookups of four symbols ahead of their coding
+        // (see ans_encode_kernel); queue order: symbols are consumed from the front
+        const uint32_t tiles_addr = smem_u32(sym_tile);
+        const uint32_t my_row = (uint32_t)lane * (kRowStride * 4u);
+        const uint32_t idx_row = smem_u32(idx_tile) + my_row;
+        uint64_t done = 0;  // symbols of my stream already requested
         const uint64_t rounds = (warp_max_u64(n_k, lane) + 31) / 32;
+        uint32_t c_next = n_k < 32 ? (uint32_t)n_k : 32u;
+        warp_fill_rows_async(tiles_addr, reinterpret_cast<const uint32_t *>(p.symbols_in + o_k), c_next, lane);
+        cp_async_commit();
         for (uint64_t r = 0; r < rounds; ++r) {
-            const uint64_t left_n = n_k - done;
-            const uint32_t c = left_n < 32 ? (uint32_t)left_n : 32u;
-            const unsigned have = __ballot_sync(kFullMask, c > 0);
-            warp_fill_rows(have, sym_tile, reinterpret_cast<const uint32_t *>(p.symbols_in + o_k + done), c, lane);
-            if (PERSYM) warp_fill_rows(have, idx_tile, p.model_index + o_k + done, c, lane);
-            const uint32_t cmax = __reduce_max_sync(kFullMask, c);
-            for (uint32_t s = 0; s < cmax; ++s) {
-                if ((s & (kCheckEvery - 1)) == 0) drain_ring();
-                if (s < c) {
-                    const int32_t sym = (int32_t)sym_tile[lane * kRowStride + s];
-                    const uint32_t m = PERSYM ? idx_tile[lane * kRowStride + s] : stream_model;
-                    encode_one(sym, m);
-                }
-            }
+            const uint32_t c = c_next;
+            const uint64_t first = done;
             done += c;
+            const uint32_t row = tiles_addr + (uint32_t)(r & 1) * (kTileWords * 4u) + my_row;
+            const uint64_t left_n = n_k - done;
+            c_next = left_n < 32 ? (uint32_t)left_n : 32u;
+            if (r + 1 < rounds)
+                warp_fill_rows_async(tiles_addr + (uint32_t)((r + 1) & 1) * (kTileWords * 4u),
+                                     reinterpret_cast<const uint32_t *>(p.symbols_in + o_k + done), c_next, lane);
+            cp_async_commit();
+            if (PERSYM) {
+                warp_fill_rows_async(smem_u32(idx_tile), p.model_index + o_k + first, c, lane);
+                cp_async_commit();
+                cp_async_wait_group<0>();
+            } else {
+                cp_async_wait_group<1>();
+            }
+            __syncwarp();
+            const uint32_t cmin = __reduce_min_sync(kFullMask, c), cmax = __reduce_max_sync(kFullMask, c);
+            uint32_t s = 0;
+            for (; s + kCheckEvery <= cmin; s += kCheckEvery) {  // every lane owns all four symbols
+                uint2 e[kCheckEvery];
+#pragma unroll
+                for (int u = 0; u < kCheckEvery; ++u) {
+                    const uint32_t at = (s + (uint32_t)u) * 4u;
+                    e[u] = lookup((int32_t)lds_u32(row + at), PERSYM ? lds_u32(idx_row + at) : stream_model);
+                }
+                drain_ring();
+#pragma unroll
+                for (int u = 0; u < kCheckEvery; ++u) encode_entry(e[u]);
+            }
+            for (; s < cmax; ++s) {  // ragged end of the round
+                if ((s & (kCheckEvery - 1)) == 0) drain_ring();
+                if (s < c) encode_one((int32_t)lds_u32(row + s * 4u), PERSYM ? lds_u32(idx_row + s * 4u) : stream_model);
+            }
+            __syncwarp();  // the tile is refilled by the next round's asynchronous fill
         }
     }
 
-    // ---- seal (queue.rs:349-355, 458-523) unless the caller keeps the raw state -----------------------
+    // ---- seal (queue.rs:349-355, 458-523), or hand the raw state back to the caller -----------------------
     drain_ring();
     const bool raw = (p.flags & 1u) != 0;
     const bool bad = min_prob == 0u;
-    const uint32_t n_seal = (valid && !bad && !raw) ? range_num_seal_words(st) : 0u;
-    for (uint32_t j = 0; j < n_seal; ++j) {
-        push(range_seal_word(st, j));
+    RangeEncState st;
+    st.lower = lower;
+    st.range = range;
+    if (valid && !bad && !raw) {
+        const RangeSeal seal = range_seal(st);
+        if (seal.carry) propagate_carry();
+        if (seal.n >= 1u) push(seal.point_word);
+        drain_ring();
+        if (seal.n == 2u) push(0u);
         drain_ring();
     }
     while (pending != 0u) {  // < 4 words, one at a time
@@ -234,30 +311,41 @@ __global__ void __launch_bounds__(kAnsBlock, 4) range_encode_kernel(const AnsPar
         }
         pending -= 4u;
     }
-    if (valid) {
-        if (p.states_out) {
-            p.states_out[4 * k] = st.lower;
-            p.states_out[4 * k + 1] = st.range;
-            p.states_out[4 * k + 2] = st.num_inverted;
-            p.states_out[4 * k + 3] = st.first_inverted;
-        }
-        if (bad) report_error(p.status, kErrImpossibleSymbol, k);
-        if (overflow) report_error(p.status, kErrOutOfSpace, k);
-    }
     uint32_t gb_lo, gb_hi;
     asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(gb_lo), "=r"(gb_hi) : "r"(park) : "memory");
     const uint32_t *gbegin = reinterpret_cast<const uint32_t *>(((uint64_t)gb_hi << 32) | gb_lo);
-    compact_tail<kAnsBlock>(p.compact, tile, k, K, valid, gbegin,
-                            (valid && !overflow) ? (uint32_t)((reinterpret_cast<const uint32_t *>(gw)) - gbegin) : 0u, p.status);
+    uint32_t n_words = (valid && !overflow) ? (uint32_t)((reinterpret_cast<const uint32_t *>(gw)) - gbegin) : 0u;
+    if (valid) {
+        if (p.states_out) {
+            // EncoderSituation (queue.rs:98-106) recovered from the words: Inverted(n, first) <=> the interval
+            // wraps; its held-back words are `first` followed by n-1 words 0xffffffff at the end of the stream
+            uint32_t held = 0, first = 0;
+            if (raw && !bad && !overflow && st.range != ~0ull && range_enc_inverted(st) && n_words != 0u) {
+                do {
+                    held += 1u;
+                    first = __ldcg(gbegin + (n_words - held));
+                } while (first == 0xffffffffu && held < n_words);
+                n_words -= held;
+            }
+            p.states_out[4 * k] = st.lower;
+            p.states_out[4 * k + 1] = st.range;
+            p.states_out[4 * k + 2] = held;
+            p.states_out[4 * k + 3] = first;
+        }
+        if (bad)
+            report_error(p.status, kErrImpossibleSymbol, k);
+        else if (overflow)
+            report_error(p.status, kErrOutOfSpace, k);
+    }
+    compact_tail<BLOCK>(p.compact, tile, k, K, valid, gbegin, n_words, p.status);
 }
 
-template <bool SHARED, bool CONTIG, bool PERSYM, bool SMALL>
-__global__ void __launch_bounds__((SHARED && !CONTIG) ? kDecBlockShared : kAnsBlock, (SHARED && !CONTIG) ? 1 : 2)
-    range_decode_kernel(const AnsParams p) {
+template <int BLOCK, bool SHARED, bool CONTIG, bool PERSYM, bool SMALL>
+__global__ void __launch_bounds__(BLOCK, BLOCK >= 1024 ? 1 : (BLOCK >= 256 ? 2 : 8)) range_decode_kernel(const AnsParams p) {
     extern __shared__ __align__(128) uint32_t smem[];
     __shared__ uint64_t bar;
 
-    constexpr int kBlock = (SHARED && !CONTIG) ? kDecBlockShared : kAnsBlock;
+    constexpr int kBlock = BLOCK;
     const int lane = threadIdx.x & 31;
     const int warp_in_cta = threadIdx.x >> 5;
     constexpr int kWarpsPerCta = kBlock / 32;
@@ -431,19 +519,27 @@ __global__ void __launch_bounds__((SHARED && !CONTIG) ? kDecBlockShared : kAnsBl
         }
     } else {
         uint64_t done = 0;
+        const uint32_t my_row = (uint32_t)lane * (kRowStride * 4u);
+        const uint32_t row = smem_u32(sym_tile) + my_row, idx_row = smem_u32(idx_tile) + my_row;
         const uint64_t rounds = (warp_max_u64(n_k, lane) + 31) / 32;
         for (uint64_t r = 0; r < rounds; ++r) {
             const uint64_t left_n = n_k - done;
             const uint32_t c = left_n < 32 ? (uint32_t)left_n : 32u;
             const unsigned have = __ballot_sync(kFullMask, c > 0);
             if (PERSYM) warp_fill_rows(have, idx_tile, p.model_index + o_k + done, c, lane);
-            const uint32_t cmax = __reduce_max_sync(kFullMask, c);
-            for (uint32_t s = 0; s < cmax; ++s) {
-                if ((s & (kCheckEvery - 1)) == 0) top_up();
-                if (s < c) {
-                    const uint32_t m = PERSYM ? idx_tile[lane * kRowStride + s] : stream_model;
-                    sym_tile[lane * kRowStride + s] = (uint32_t)decode_one(m);
+            const uint32_t cmin = __reduce_min_sync(kFullMask, c), cmax = __reduce_max_sync(kFullMask, c);
+            uint32_t s = 0;
+            for (; s + kCheckEvery <= cmin; s += kCheckEvery) {  // every lane owns all four symbols
+                top_up();
+#pragma unroll
+                for (int u = 0; u < kCheckEvery; ++u) {
+                    const uint32_t at = (s + (uint32_t)u) * 4u;
+                    sts_u32(row + at, (uint32_t)decode_one(PERSYM ? lds_u32(idx_row + at) : stream_model));
                 }
+            }
+            for (; s < cmax; ++s) {  // ragged end of the round
+                if ((s & (kCheckEvery - 1)) == 0) top_up();
+                if (s < c) sts_u32(row + s * 4u, (uint32_t)decode_one(PERSYM ? lds_u32(idx_row + s * 4u) : stream_model));
             }
             warp_flush_rows(have, sym_tile, reinterpret_cast<uint32_t *>(p.symbols_out + o_k + done), c, lane);
             done += c;

@@ -36,6 +36,8 @@ def load():
     L.h_ans_decode.restype = None
     L.h_range_encode.argtypes = [i32p, C.c_uint64, u32p, C.c_int32, u32p]
     L.h_range_encode.restype = C.c_uint64
+    L.h_range_encode_split.argtypes = [i32p, C.c_uint64, C.c_uint64, u32p, C.c_int32, u32p]
+    L.h_range_encode_split.restype = C.c_uint64
     L.h_range_decode.argtypes = [u32p, C.c_uint64, i32p, C.c_uint64, u32p, C.c_uint32, C.c_int32]
     L.h_range_quantile_check.argtypes = [u64p, u64p, C.c_uint64]
     L.h_range_quantile_check.restype = C.c_uint64

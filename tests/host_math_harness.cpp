@@ -84,19 +84,46 @@ void h_ans_decode(const uint32_t *words, uint64_t n_words, int32_t *symbols, uin
 }
 
 // One range encoder incl. seal.  out must hold n + 8 words.
-uint64_t h_range_encode(const int32_t *symbols, uint64_t n, const uint32_t *cdf, int32_t min_symbol, uint32_t *out) {
+static void carry_into(uint32_t *out, uint64_t len) {
+    while (len > 0) {
+        len -= 1;
+        if (++out[len] != 0u) break;
+    }
+}
+
+// One-shot encode when split >= n; otherwise the coder is suspended after `split` symbols the way the kernels
+// do it for a raw-state caller (held-back words stripped and described by (num_inverted, first)), and resumed.
+uint64_t h_range_encode_split(const int32_t *symbols, uint64_t n, uint64_t split, const uint32_t *cdf, int32_t min_symbol,
+                              uint32_t *out) {
     RangeEncState st = range_enc_init();
     uint64_t len = 0;
     for (uint64_t i = 0; i < n; ++i) {
+        if (i == split && range_enc_inverted(st) && st.range != ~0ull) {
+            uint64_t held = 1;
+            while (out[len - held] == 0xffffffffu) held += 1;
+            const uint32_t first = out[len - held];
+            len -= held;  // what a raw-state caller receives: the final words only
+            // resume: the held-back words are written again, speculatively
+            out[len++] = first;
+            for (uint64_t j = 1; j < held; ++j) out[len++] = 0xffffffffu;
+        }
         const uint32_t idx = (uint32_t)symbols[i] - (uint32_t)min_symbol;
-        RangeEmit em;
-        if (!range_encode_step(st, cdf[idx], cdf[idx + 1] - cdf[idx], em)) return ~0ull;
-        for (uint32_t j = 0; j < em.n_burst; ++j) out[len++] = j == 0 ? em.burst_first : em.burst_fill;
-        if (em.emit) out[len++] = em.word;
+        const uint32_t prob = cdf[idx + 1] - cdf[idx];
+        if (prob == 0) return ~0ull;
+        uint32_t word = 0;
+        const uint32_t flags = range_encode_step(st, cdf[idx], prob, word);
+        if (flags & 1u) carry_into(out, len);
+        if (flags & 2u) out[len++] = word;
     }
-    const uint32_t ns = range_num_seal_words(st);
-    for (uint32_t j = 0; j < ns; ++j) out[len++] = range_seal_word(st, j);
+    const RangeSeal seal = range_seal(st);
+    if (seal.carry) carry_into(out, len);
+    if (seal.n >= 1) out[len++] = seal.point_word;
+    if (seal.n == 2) out[len++] = 0u;
     return len;
+}
+
+uint64_t h_range_encode(const int32_t *symbols, uint64_t n, const uint32_t *cdf, int32_t min_symbol, uint32_t *out) {
+    return h_range_encode_split(symbols, n, ~0ull, cdf, min_symbol, out);
 }
 
 int h_range_decode(const uint32_t *words, uint64_t n_words, int32_t *symbols, uint64_t n, const uint32_t *cdf,

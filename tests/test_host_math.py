@@ -126,3 +126,20 @@ def test_range_stream_matches_oracle(H, oracle, spec, n):
     dec = np.empty(n, dtype=np.int32)
     assert H.h_range_decode(P(want, u32p), want.size, P(dec, i32p), n, P(cdf, u32p), cdf.size - 1, lo) == 0
     assert np.array_equal(dec, syms)
+
+
+@pytest.mark.parametrize("spec", MODELS[:2] + [(-20, 20, 0.0, 1e-3)])
+def test_range_encoder_suspend_resume_at_every_symbol(H, oracle, spec):
+    """The eager-word formulation recovers the reference's (num_inverted, first_inverted) from the words
+    written so far; suspending and resuming at any symbol must not change the stream."""
+    lo, hi, mean, std = spec
+    cdf = oracle.qgauss_cdf(lo, hi, mean, std)
+    rng = np.random.default_rng(77)
+    n = 1500
+    syms = _sample(rng, cdf, lo, n)
+    syms[::7] = rng.integers(lo, hi + 1, size=syms[::7].size)
+    want = oracle.range_encode_iid(syms, cdf, lo)
+    out = np.empty(n + 8, dtype=np.uint32)
+    for split in range(n + 1):
+        m = H.h_range_encode_split(P(syms, i32p), n, split, P(cdf, u32p), lo, P(out, u32p))
+        assert np.array_equal(out[:m], want), split
