@@ -50,7 +50,14 @@ struct ModelView {
     uint32_t alphabet;
     int32_t min_symbol;
     uint32_t dec_cdf_bytes;    // size of the cdf part of `dec`: (alphabet + 2) * 4 rounded up to 16
+    // pool decoders (a whole model set staged in shared memory): sizes of `cdf` and `cidx`, rounded up to 16
+    uint32_t pool_cdf_bytes, pool_cidx_bytes;
 };
+
+// where a decoder kernel finds its model tables
+constexpr int kTableGlobal = 0;  // read through L1/L2
+constexpr int kTableLut = 1;     // one model for the batch: quantile index + cdf in shared memory
+constexpr int kTablePool = 2;    // several models, all CDF rows + coarse indices in shared memory
 
 struct AnsParams {
     ModelView model;
@@ -206,6 +213,45 @@ __device__ __forceinline__ uint32_t lookup_global(const uint32_t *row, const uin
     left = __ldg(row + lo);
     right = __ldg(row + lo + 1);
     return lo;
+}
+
+// The same search on a model set staged in shared memory (`row` / `cidx_row` are shared addresses).  Two load
+// levels in the common case: the coarse index names the first symbol `lo` of q's bucket, then cdf[lo .. lo+2]
+// are read together and q is in symbol lo or lo + 1 unless three or more symbols share the bucket (cold).
+static __device__ __noinline__ uint32_t lookup_pool_cold(uint32_t row, uint32_t lo, uint32_t hi, uint32_t q) {
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi + 1) >> 1;
+        if (lds_table_u32(row + mid * 4u) <= q)
+            lo = mid;
+        else
+            hi = mid - 1;
+    }
+    return lo;
+}
+__device__ __forceinline__ uint32_t lookup_pool(uint32_t row, uint32_t cidx_row, bool wide, uint32_t q, uint32_t &left,
+                                                uint32_t &right) {
+    const uint32_t b = q >> kCoarseShift;
+    uint32_t lo, hi;
+    if (wide) {
+        lo = lds_table_u16(cidx_row + b * 2u);
+        hi = lds_table_u16(cidx_row + b * 2u + 2u);
+    } else {
+        lo = lds_table_u8(cidx_row + b);
+        hi = lds_table_u8(cidx_row + b + 1u);
+    }
+    // (cdf[lo + 2] may be one word past the row when lo is the last symbol; it is not used then)
+    const uint32_t at = row + lo * 4u;
+    const uint32_t c0 = lds_table_u32(at), c1 = lds_table_u32(at + 4u), c2 = lds_table_u32(at + 8u);
+    const bool second = q >= c1;
+    uint32_t s = lo + (second ? 1u : 0u);
+    left = second ? c1 : c0;
+    right = second ? c2 : c1;
+    if (second && hi > lo + 1u && q >= c2) {
+        s = lookup_pool_cold(row, lo + 2u, hi, q);
+        left = lds_table_u32(row + s * 4u);
+        right = lds_table_u32(row + s * 4u + 4u);
+    }
+    return s;
 }
 
 // Geometry of the interleaved deal shared by all kernels.
@@ -562,28 +608,36 @@ __global__ void __launch_bounds__(BLOCK, BLOCK >= 256 ? 4 : 8) ans_encode_kernel
 // With a shared model and the interleaved layout the CTA is 1024 threads so that the 32 KB quantile index is
 // staged once per SM; otherwise (transposition tiles, or global tables: nothing to amortise) 256 threads.
 constexpr int kDecBlockShared = 1024;
-template <int BLOCK, bool SHARED, bool CONTIG, bool PERSYM, bool SMALL>
-__global__ void __launch_bounds__(BLOCK, BLOCK >= 1024 ? 1 : (BLOCK >= 256 ? 2 : 8)) ans_decode_kernel(const AnsParams p) {
+//   BLOCK : threads per CTA; 0 = decided at launch (pool decoders: the CTA is sized so that the grid is one wave)
+//   TABLE : kTableGlobal / kTableLut / kTablePool
+template <int BLOCK, int TABLE, bool CONTIG, bool PERSYM, bool SMALL>
+__global__ void __launch_bounds__(BLOCK ? BLOCK : 1024, BLOCK == 0 || BLOCK >= 1024 ? 1 : (BLOCK >= 256 ? 2 : 8))
+    ans_decode_kernel(const AnsParams p) {
     extern __shared__ __align__(128) uint32_t smem[];
     __shared__ uint64_t bar;
 
-    constexpr int kBlock = BLOCK;
+    constexpr bool SHARED = TABLE == kTableLut, POOL = TABLE == kTablePool;
+    const uint32_t kBlock = BLOCK ? (uint32_t)BLOCK : blockDim.x;
     const int lane = threadIdx.x & 31;
     const int warp_in_cta = threadIdx.x >> 5;
-    constexpr int kWarpsPerCta = kBlock / 32;
+    const uint32_t kWarpsPerCta = kBlock / 32;
 
-    // shared memory carve-up: [lane rings (64 B each)][quantile index + cdf][symbol tiles][index tiles]
+    // shared memory carve-up: [lane rings (64 B each)][quantile index + cdf | model pool][symbol tiles][index tiles]
     const uint32_t alphabet = p.model.alphabet;
-    const uint32_t table_words = SHARED ? (kLutBytes + p.model.dec_cdf_bytes) / 4 : 0;
-    constexpr uint32_t kRingsWords = kBlock * kDecRingWords;
+    const uint32_t table_words = SHARED ? (kLutBytes + p.model.dec_cdf_bytes) / 4
+                                        : (POOL ? (p.model.pool_cdf_bytes + p.model.pool_cidx_bytes) / 4 : 0);
+    const uint32_t kRingsWords = kBlock * kDecRingWords;
     const uint32_t ring = smem_u32_pinned(smem) + threadIdx.x * kDecRingBytes;  // 64-byte aligned
     const uint32_t lut_addr = smem_u32_pinned(smem + kRingsWords);
-    uint32_t cdf_addr = lut_addr + kLutBytes;
+    uint32_t cdf_addr = lut_addr + (POOL ? 0u : kLutBytes);  // POOL: [n_models][alphabet + 1] starts the table area
     asm volatile("" : "+r"(cdf_addr));
     uint32_t *sym_tile = smem + kRingsWords + table_words + warp_in_cta * kTileWords;
     uint32_t *idx_tile = sym_tile + kWarpsPerCta * kTileWords;
 
     if (SHARED) stage_table(smem + kRingsWords, p.model.dec, kLutBytes + p.model.dec_cdf_bytes, &bar);
+    if (POOL)
+        stage_tables(smem + kRingsWords, p.model.cdf, p.model.pool_cdf_bytes, smem + kRingsWords + p.model.pool_cdf_bytes / 4,
+                     p.model.cidx, p.model.pool_cidx_bytes, &bar);
 
     const uint64_t K = p.K, N = p.N;
     const uint64_t k = (uint64_t)blockIdx.x * kBlock + threadIdx.x;
@@ -674,6 +728,9 @@ __global__ void __launch_bounds__(BLOCK, BLOCK >= 1024 ? 1 : (BLOCK >= 256 ? 2 :
     uint32_t min_symbol = (uint32_t)p.model.min_symbol;
     asm volatile("" : "+r"(min_symbol));
     const uint32_t stream_model = (p.index_mode == 2) ? p.model_index[kc] : 0u;
+    const uint32_t pool_row_bytes = (alphabet + 1) * 4u;
+    const uint32_t pool_cidx_stride = (alphabet > 256 ? 2u : 1u) * (kCoarseSize + 1);
+    const uint32_t pool_cidx_addr = cdf_addr + p.model.pool_cdf_bytes;
 
     // one reference decode_symbol (stack.rs:1070-1100)
     auto decode_one = [&](uint32_t m) -> int32_t {
@@ -681,6 +738,9 @@ __global__ void __launch_bounds__(BLOCK, BLOCK >= 1024 ? 1 : (BLOCK >= 256 ? 2 :
         uint32_t left, right, s;
         if (SHARED) {
             s = lookup_shared<SMALL>(lut_addr, cdf_addr, alphabet, lo, q, left, right);
+        } else if (POOL) {
+            m = m < n_models ? m : n_models - 1;
+            s = lookup_pool(cdf_addr + m * pool_row_bytes, pool_cidx_addr + m * pool_cidx_stride, alphabet > 256, q, left, right);
         } else {
             m = m < n_models ? m : n_models - 1;  // decoding cannot fail (stack.rs:1062-1065)
             const uint32_t cstride = (alphabet > 256 ? 2u : 1u) * (kCoarseSize + 1);

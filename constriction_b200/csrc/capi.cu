@@ -6,6 +6,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <atomic>
 #include <mutex>
 #include <new>
@@ -109,7 +110,8 @@ int model_alloc(uint32_t n_models, uint32_t alphabet, int32_t min_symbol, ctr_mo
     m->min_symbol = min_symbol;
     m->dec_cdf_bytes = (uint32_t)align_up(((size_t)alphabet + 2) * 4, 16);
     m->shared_ok = alphabet <= kMaxSharedAlphabet;
-    cudaError_t e = cudaMalloc(&m->d_cdf, (size_t)n_models * ((size_t)alphabet + 1) * 4);
+    // (rounded up to 16 bytes: the pool decoders bulk-copy the whole array into shared memory)
+    cudaError_t e = cudaMalloc(&m->d_cdf, align_up((size_t)n_models * ((size_t)alphabet + 1) * 4, 16));
     if (e != cudaSuccess) {
         delete m;
         return cuda_fail(e, "cudaMalloc(cdf)");
@@ -160,7 +162,7 @@ int ensure_coarse_index(ctr_model_s *m, cudaStream_t s) {
     if (m->d_cidx || m->alphabet > 65536u) return CTR_OK;
     const int wide = m->alphabet > 256 ? 1 : 0;
     const uint64_t entries = (uint64_t)m->n_models * 257;
-    CUDA_TRY(cudaMalloc(&m->d_cidx, entries * (wide ? 2 : 1)));
+    CUDA_TRY(cudaMalloc(&m->d_cidx, align_up(entries * (wide ? 2 : 1), 16)));
     build_coarse_index_kernel<<<grid_for(entries, 256), 256, 0, s>>>(m->d_cdf, m->n_models, m->alphabet, wide, m->d_cidx);
     LAUNCH_CHECK("build_coarse_index_kernel");
     return CTR_OK;
@@ -205,6 +207,7 @@ ModelView model_view(const ctr_model_s *m) {
     v.alphabet = m->alphabet;
     v.min_symbol = m->min_symbol;
     v.dec_cdf_bytes = m->dec_cdf_bytes;
+    v.pool_cdf_bytes = v.pool_cidx_bytes = 0;
     return v;
 }
 
@@ -492,6 +495,9 @@ unsigned decode_block(const ctr_layout *L, bool shared, bool contig) {
     return kAnsBlock;
 }
 
+// shared memory a pool decoder may use per CTA (227 KB is the limit; static shared memory needs a little)
+constexpr size_t kPoolSmemBudget = 220 * 1024;
+
 // dynamic shared memory of a coder kernel: per-warp word staging + tables + 32x32 transposition tiles
 // (contiguous layout: the encoders double-buffer the symbol tile; one more tile for per-symbol model indices)
 size_t coder_smem_bytes(size_t table_bytes, const ctr_layout *L, int warps, size_t stage_words_per_warp, int sym_tiles) {
@@ -579,6 +585,7 @@ int encode_common(ctr_model_t model, const int32_t *symbols_dev, const ctr_layou
     CUDA_TRY(cudaMemsetAsync(ws + w.status_off, 0, w.total - w.status_off, s));
 
     LaunchCfg cfg;
+    cfg.pool = false;
     cfg.shared = use_shared_enc_table(model, L);
     cfg.contig = L->sym_offsets_dev != nullptr;
     cfg.persym = L->model_index_mode == CTR_INDEX_PER_SYMBOL;
@@ -621,11 +628,32 @@ int decode_common(ctr_model_t model, const uint32_t *words, const uint64_t *offs
     cfg.contig = L->sym_offsets_dev != nullptr;
     cfg.persym = L->model_index_mode == CTR_INDEX_PER_SYMBOL;
     cfg.f64 = false;
+    cfg.stream = s;
+    cfg.pool = false;
+    if (!cfg.shared && model->d_cidx) {
+        // A model set that fits shared memory next to the rings and tiles is staged there once per CTA (every
+        // probe of the quantile search is then a shared-memory access instead of an L1/L2 round trip).  The
+        // CTA is as big as shared memory allows, but no bigger than what spreads the batch over all SMs.
+        const size_t cdf_bytes = align_up((size_t)model->n_models * ((size_t)model->alphabet + 1) * 4, 16);
+        const size_t cidx_bytes = align_up((size_t)model->n_models * 257 * (model->alphabet > 256 ? 2 : 1), 16);
+        const size_t per_warp = coder_smem_bytes(0, L, 1, 32 * kDecRingWords, 1);
+        if (cdf_bytes + cidx_bytes + per_warp <= kPoolSmemBudget) {
+            const uint64_t fit = (kPoolSmemBudget - cdf_bytes - cidx_bytes) / per_warp;
+            const uint64_t want = (L->n_streams + 148ull * 32 - 1) / (148ull * 32);  // warps per CTA for one wave
+            const uint64_t warps = std::max<uint64_t>(1, std::min<uint64_t>(std::min<uint64_t>(fit, want), 32));
+            cfg.pool = true;
+            cfg.block = (unsigned)warps * 32;
+            cfg.grid = grid_for(L->n_streams, cfg.block);
+            cfg.smem = coder_smem_bytes(cdf_bytes + cidx_bytes, L, (int)warps, 32 * kDecRingWords, 1);
+            p.model.pool_cdf_bytes = (uint32_t)cdf_bytes;
+            p.model.pool_cidx_bytes = (uint32_t)cidx_bytes;
+            return run_coder_kernel<DecLauncher>(cfg, p);
+        }
+    }
     cfg.block = decode_block(L, cfg.shared, cfg.contig);
     cfg.grid = grid_for(L->n_streams, cfg.block);
     cfg.smem = coder_smem_bytes(cfg.shared ? (size_t)kLutBytes + model->dec_cdf_bytes : 0, L, cfg.block / 32,
                                 32 * kDecRingWords, 1);
-    cfg.stream = s;
     return run_coder_kernel<DecLauncher>(cfg, p);
 }
 

@@ -165,6 +165,30 @@ __device__ __forceinline__ void stage_table(void *dst_smem, const void *src_gmem
     mbar_wait(bar, 0);
 }
 
+// Two tables on one barrier (byte counts multiples of 16; a zero-byte table is skipped).
+__device__ __forceinline__ void stage_tables(void *dst0, const void *src0, uint32_t bytes0, void *dst1, const void *src1,
+                                             uint32_t bytes1, uint64_t *bar) {
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        mbar_expect_tx(bar, bytes0 + bytes1);
+        for (int t = 0; t < 2; ++t) {
+            char *dst = (char *)(t ? dst1 : dst0);
+            const char *src = (const char *)(t ? src1 : src0);
+            const uint32_t bytes = t ? bytes1 : bytes0;
+            for (uint32_t done = 0; done < bytes;) {
+                const uint32_t piece = bytes - done < 32768u ? bytes - done : 32768u;
+                bulk_copy_g2s(dst + done, src + done, piece, bar);
+                done += piece;
+            }
+        }
+    }
+    mbar_wait(bar, 0);
+}
+
 // ---- streaming global accesses -----------------------------------------------------------------
 __device__ __forceinline__ uint32_t ld_stream_u32(const uint32_t *p) {
     uint32_t v;

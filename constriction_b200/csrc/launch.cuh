@@ -16,6 +16,7 @@ struct LaunchCfg {
     bool contig;   // contiguous layout (else interleaved deal)
     bool persym;   // a model index per symbol
     bool f64;      // ANS encoder: FP64 quotient estimate
+    bool pool;     // decoders: the whole model set is staged in shared memory (p.model.pool_*_bytes)
     unsigned grid, block;
     size_t smem;   // dynamic shared memory per CTA
     cudaStream_t stream;

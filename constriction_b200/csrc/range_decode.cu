@@ -9,23 +9,30 @@ template <int BLOCK>
 static cudaError_t go(const LaunchCfg &cfg, const AnsParams &p) {
     if (cfg.shared) {
         if (p.model.alphabet <= 256)
-            return cfg.contig ? launch_kernel(range_decode_kernel<BLOCK, true, true, false, true>, cfg, p)
-                              : launch_kernel(range_decode_kernel<BLOCK, true, false, false, true>, cfg, p);
-        return cfg.contig ? launch_kernel(range_decode_kernel<BLOCK, true, true, false, false>, cfg, p)
-                          : launch_kernel(range_decode_kernel<BLOCK, true, false, false, false>, cfg, p);
+            return cfg.contig ? launch_kernel(range_decode_kernel<BLOCK, kTableLut, true, false, true>, cfg, p)
+                              : launch_kernel(range_decode_kernel<BLOCK, kTableLut, false, false, true>, cfg, p);
+        return cfg.contig ? launch_kernel(range_decode_kernel<BLOCK, kTableLut, true, false, false>, cfg, p)
+                          : launch_kernel(range_decode_kernel<BLOCK, kTableLut, false, false, false>, cfg, p);
     }
     if (cfg.persym)
-        return cfg.contig ? launch_kernel(range_decode_kernel<BLOCK, false, true, true, false>, cfg, p)
-                          : launch_kernel(range_decode_kernel<BLOCK, false, false, true, false>, cfg, p);
-    return cfg.contig ? launch_kernel(range_decode_kernel<BLOCK, false, true, false, false>, cfg, p)
-                      : launch_kernel(range_decode_kernel<BLOCK, false, false, false, false>, cfg, p);
+        return cfg.contig ? launch_kernel(range_decode_kernel<BLOCK, kTableGlobal, true, true, false>, cfg, p)
+                          : launch_kernel(range_decode_kernel<BLOCK, kTableGlobal, false, true, false>, cfg, p);
+    return cfg.contig ? launch_kernel(range_decode_kernel<BLOCK, kTableGlobal, true, false, false>, cfg, p)
+                      : launch_kernel(range_decode_kernel<BLOCK, kTableGlobal, false, false, false>, cfg, p);
 }
 
 cudaError_t launch_range_decode(const LaunchCfg &cfg, const AnsParams &p) {
+    if (cfg.pool) {  // model set in shared memory, CTA size decided by the caller
+        if (cfg.persym)
+            return cfg.contig ? launch_kernel(range_decode_kernel<0, kTablePool, true, true, false>, cfg, p)
+                              : launch_kernel(range_decode_kernel<0, kTablePool, false, true, false>, cfg, p);
+        return cfg.contig ? launch_kernel(range_decode_kernel<0, kTablePool, true, false, false>, cfg, p)
+                          : launch_kernel(range_decode_kernel<0, kTablePool, false, false, false>, cfg, p);
+    }
     if (cfg.block == (unsigned)kDecBlockShared) {  // shared model, interleaved deal, large batch
         if (!cfg.shared || cfg.contig) return cudaErrorInvalidConfiguration;
-        return p.model.alphabet <= 256 ? launch_kernel(range_decode_kernel<kDecBlockShared, true, false, false, true>, cfg, p)
-                                       : launch_kernel(range_decode_kernel<kDecBlockShared, true, false, false, false>, cfg, p);
+        return p.model.alphabet <= 256 ? launch_kernel(range_decode_kernel<kDecBlockShared, kTableLut, false, false, true>, cfg, p)
+                                       : launch_kernel(range_decode_kernel<kDecBlockShared, kTableLut, false, false, false>, cfg, p);
     }
     if (cfg.block == (unsigned)kSmallBlock) return go<kSmallBlock>(cfg, p);
     if (cfg.block == (unsigned)kAnsBlock) return go<kAnsBlock>(cfg, p);

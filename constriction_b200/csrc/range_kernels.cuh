@@ -340,27 +340,34 @@ __global__ void __launch_bounds__(BLOCK, BLOCK >= 256 ? 4 : 8) range_encode_kern
     compact_tail<BLOCK>(p.compact, tile, k, K, valid, gbegin, n_words, p.status);
 }
 
-template <int BLOCK, bool SHARED, bool CONTIG, bool PERSYM, bool SMALL>
-__global__ void __launch_bounds__(BLOCK, BLOCK >= 1024 ? 1 : (BLOCK >= 256 ? 2 : 8)) range_decode_kernel(const AnsParams p) {
+template <int BLOCK, int TABLE, bool CONTIG, bool PERSYM, bool SMALL>
+__global__ void __launch_bounds__(BLOCK ? BLOCK : 1024, BLOCK == 0 || BLOCK >= 1024 ? 1 : (BLOCK >= 256 ? 2 : 8))
+    range_decode_kernel(const AnsParams p) {
     extern __shared__ __align__(128) uint32_t smem[];
     __shared__ uint64_t bar;
 
-    constexpr int kBlock = BLOCK;
+    constexpr bool SHARED = TABLE == kTableLut, POOL = TABLE == kTablePool;
+    const uint32_t kBlock = BLOCK ? (uint32_t)BLOCK : blockDim.x;
     const int lane = threadIdx.x & 31;
     const int warp_in_cta = threadIdx.x >> 5;
-    constexpr int kWarpsPerCta = kBlock / 32;
+    const uint32_t kWarpsPerCta = kBlock / 32;
 
+    // shared memory carve-up as in ans_decode_kernel
     const uint32_t alphabet = p.model.alphabet;
-    const uint32_t table_words = SHARED ? (kLutBytes + p.model.dec_cdf_bytes) / 4 : 0;
-    constexpr uint32_t kRingsWords = kBlock * kDecRingWords;
+    const uint32_t table_words = SHARED ? (kLutBytes + p.model.dec_cdf_bytes) / 4
+                                        : (POOL ? (p.model.pool_cdf_bytes + p.model.pool_cidx_bytes) / 4 : 0);
+    const uint32_t kRingsWords = kBlock * kDecRingWords;
     const uint32_t ring = smem_u32_pinned(smem) + threadIdx.x * kDecRingBytes;  // 64-byte aligned
     const uint32_t lut_addr = smem_u32_pinned(smem + kRingsWords);
-    uint32_t cdf_addr = lut_addr + kLutBytes;
+    uint32_t cdf_addr = lut_addr + (POOL ? 0u : kLutBytes);
     asm volatile("" : "+r"(cdf_addr));
     uint32_t *sym_tile = smem + kRingsWords + table_words + warp_in_cta * kTileWords;
     uint32_t *idx_tile = sym_tile + kWarpsPerCta * kTileWords;
 
     if (SHARED) stage_table(smem + kRingsWords, p.model.dec, kLutBytes + p.model.dec_cdf_bytes, &bar);
+    if (POOL)
+        stage_tables(smem + kRingsWords, p.model.cdf, p.model.pool_cdf_bytes, smem + kRingsWords + p.model.pool_cdf_bytes / 4,
+                     p.model.cidx, p.model.pool_cidx_bytes, &bar);
 
     const uint64_t K = p.K, N = p.N;
     const uint64_t k = (uint64_t)blockIdx.x * kBlock + threadIdx.x;
@@ -440,6 +447,9 @@ __global__ void __launch_bounds__(BLOCK, BLOCK >= 1024 ? 1 : (BLOCK >= 256 ? 2 :
     uint32_t min_symbol = (uint32_t)p.model.min_symbol;
     asm volatile("" : "+r"(min_symbol));
     const uint32_t stream_model = (p.index_mode == 2) ? p.model_index[kc] : 0u;
+    const uint32_t pool_row_bytes = (alphabet + 1) * 4u;
+    const uint32_t pool_cidx_stride = (alphabet > 256 ? 2u : 1u) * (kCoarseSize + 1);
+    const uint32_t pool_cidx_addr = cdf_addr + p.model.pool_cdf_bytes;
 
     // one reference decode_symbol (queue.rs:968-1035); after invalid data the lane keeps running on a
     // clamped quantile (its symbols are garbage and the stream is flagged)
@@ -449,6 +459,9 @@ __global__ void __launch_bounds__(BLOCK, BLOCK >= 1024 ? 1 : (BLOCK >= 256 ? 2 :
         uint32_t left, right, s;
         if (SHARED) {
             s = lookup_shared<SMALL>(lut_addr, cdf_addr, alphabet, q, q, left, right);
+        } else if (POOL) {
+            m = m < n_models ? m : n_models - 1;
+            s = lookup_pool(cdf_addr + m * pool_row_bytes, pool_cidx_addr + m * pool_cidx_stride, alphabet > 256, q, left, right);
         } else {
             m = m < n_models ? m : n_models - 1;
             const uint32_t cstride = (alphabet > 256 ? 2u : 1u) * (kCoarseSize + 1);

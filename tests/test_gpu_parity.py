@@ -88,7 +88,9 @@ def test_uniform_and_cdf_tables(env):
 # ANS / range, interleaved layout, one shared model (BASELINE configs 1, 2)
 # ---------------------------------------------------------------------------------------------------
 SHAPES = [(0, 1), (1, 1), (5, 1), (100_000, 1), (1000, 32), (1000, 33), (31, 64), (100_003, 4096), (50_000, 777),
-          (200_000, 128 * 3 + 5)]
+          (200_000, 128 * 3 + 5),
+          # CTA sizes: < 37,888 streams -> 64-thread CTAs; up to 151,552 -> 256; beyond -> 1024-thread decoders
+          (400_000, 40_001), (1_000_000, 151_552 + 7)]
 
 
 @pytest.mark.parametrize("coder", ["ans", "range"])
@@ -207,6 +209,68 @@ def test_per_stream_gaussian_models(env, coder):
         want = (O.ans_encode_iid if coder == "ans" else O.range_encode_iid)(seg, cdfs[sidx[s]], -64)
         assert np.array_equal(words[int(o[s]):int(o[s + 1])], want), s
     out = (bc.ans_decode if coder == "ans" else bc.range_decode)(comp, model, model_index=d_idx, index_mode=2)
+    bc.check()
+    assert np.array_equal(out.cpu().numpy(), syms)
+
+
+@pytest.mark.parametrize("coder", ["ans", "range"])
+def test_contiguous_many_streams_big_ctas(env, coder):
+    """>= 37,888 streams: the 256-thread CTA variants of the contiguous kernels."""
+    B, O, bc, torch = env["B"], env["O"], env["bc"], env["torch"]
+    rng = np.random.default_rng(23)
+    lens = rng.integers(0, 20, size=40_000)
+    lens[::1000] = rng.integers(100, 400, size=lens[::1000].size)
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+    n, k = int(off[-1]), lens.size
+    syms = gauss_symbols(rng, n)
+    model = B.ModelTable.quantized_gaussian(*BASE[:2], [BASE[2]], [BASE[3]])
+    cdf = model.cdf()[0]
+    enc_o = O.multi_ans_encode if coder == "ans" else O.multi_range_encode
+    want_words, want_off = enc_o(syms, k, cdf, -50, sym_offsets=off, threads=8)
+    d_off = torch.from_numpy(off.astype(np.int64)).cuda()
+    comp = (bc.ans_encode if coder == "ans" else bc.range_encode)(dev(env, syms), model, sym_offsets=d_off)
+    words, o = comp.to_host()
+    bc.check()
+    assert np.array_equal(o, want_off)
+    assert np.array_equal(words, want_words)
+    out = (bc.ans_decode if coder == "ans" else bc.range_decode)(comp, model)
+    bc.check()
+    assert np.array_equal(out.cpu().numpy(), syms)
+
+
+@pytest.mark.parametrize("coder", ["ans", "range"])
+@pytest.mark.parametrize("M,A,contig", [(40, 256, False), (40, 256, True), (7, 1000, True), (500, 256, True)])
+def test_model_sets_in_shared_memory_and_global(env, coder, M, A, contig):
+    """Per-symbol model index: model sets that fit shared memory are decoded by the pool kernels
+    (M = 40, or 7 models with a wide coarse index), bigger ones through L1/L2 (M = 500); both layouts."""
+    B, O, bc, torch = env["B"], env["O"], env["bc"], env["torch"]
+    rng = np.random.default_rng(M * 7 + A)
+    n, k = 30_000, 50
+    pmf = rng.dirichlet(0.3 * np.ones(A), size=M).astype(np.float32)
+    model = B.ModelTable.categorical(pmf)
+    cdfs = model.cdf()
+    idx = rng.integers(0, M, size=n).astype(np.uint32)
+    u = rng.integers(0, 1 << 24, size=n)
+    syms = np.array([np.searchsorted(cdfs[m], q, side="right") - 1 for m, q in zip(idx, u)], dtype=np.int32)
+    d_idx = dev(env, idx.view(np.int32))
+    if contig:
+        lens = rng.multinomial(n, np.ones(k) / k)
+        lens[3] += lens[4]
+        lens[4] = 0
+        off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+        layout = dict(sym_offsets=torch.from_numpy(off).cuda())
+        pieces = [slice(int(off[s]), int(off[s + 1])) for s in range(k)]
+    else:
+        layout = dict(n_streams=k)
+        pieces = [slice(s, n, k) for s in range(k)]
+    comp = (bc.ans_encode if coder == "ans" else bc.range_encode)(dev(env, syms), model, model_index=d_idx, index_mode=1,
+                                                                  **layout)
+    words, o = comp.to_host()
+    bc.check()
+    for s in (0, 3, 4, 17, k - 1):
+        want = _indexed_oracle_encode(O, coder, syms[pieces[s]], idx[pieces[s]], cdfs, 0)
+        assert np.array_equal(words[int(o[s]):int(o[s + 1])], want), s
+    out = (bc.ans_decode if coder == "ans" else bc.range_decode)(comp, model, model_index=d_idx, index_mode=1)
     bc.check()
     assert np.array_equal(out.cpu().numpy(), syms)
 
