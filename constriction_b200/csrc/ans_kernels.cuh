@@ -27,6 +27,8 @@
 //
 // Per-stream results equal the reference's `AnsCoder` (src/stream/stack.rs:1014-1100) word for word.
 #pragma once
+#include <cuda.h>
+
 #include <type_traits>
 
 #include "compact.cuh"
@@ -35,6 +37,16 @@
 namespace ctr {
 
 constexpr int kAnsBlock = 256;  // threads per CTA (8 warps)
+// Interleaved deal with one model per stream: symbols move between HBM and shared memory as 2-D TMA boxes of
+// kBoxRows rows x 32 streams per warp (device_utils.cuh), kEncBoxSlots / kDecBoxSlots boxes in flight per warp.
+#ifndef CTR_ENC_BOX_SLOTS
+#define CTR_ENC_BOX_SLOTS 3
+#endif
+#ifndef CTR_DEC_BOX_SLOTS
+#define CTR_DEC_BOX_SLOTS 2
+#endif
+constexpr int kEncBoxSlots = CTR_ENC_BOX_SLOTS;
+constexpr int kDecBoxSlots = CTR_DEC_BOX_SLOTS;
 constexpr uint32_t kMaxSharedAlphabet = 4095;      // decoder: bigger alphabets use the global-table path
 constexpr uint32_t kMaxSharedEncAlphabet = 511;    // encoder: its shared table is replicated 8x (128 B per entry)
 
@@ -78,6 +90,9 @@ struct AnsParams {
     const uint32_t *words;
     const uint64_t *offsets;
     uint64_t *words_left;
+    // interleaved deal: the symbol array as a [full rows][K] int32 tensor (boxes of kBoxRows x 32), if use_tma
+    uint32_t use_tma;
+    alignas(64) CUtensorMap tmap;
 };
 
 // ---- warp-cooperative tile I/O for the contiguous layout and the range kernels (generic pointers) ----
@@ -284,9 +299,10 @@ __device__ __forceinline__ uint64_t warp_max_u64(uint64_t v, int lane) {
 //   F64DIV : the table holds double-precision reciprocals and the quotient estimate uses the FP64 pipe
 //   BLOCK  : threads per CTA (kAnsBlock, or kSmallBlock for batches too small to fill the GPU with big CTAs)
 template <int BLOCK, bool SHARED, bool CONTIG, bool PERSYM, bool F64DIV>
-__global__ void __launch_bounds__(BLOCK, BLOCK >= 256 ? 4 : 8) ans_encode_kernel(const AnsParams p) {
+__global__ void __launch_bounds__(BLOCK, BLOCK >= 256 ? 4 : 8) ans_encode_kernel(const __grid_constant__ AnsParams p) {
     extern __shared__ __align__(128) uint32_t smem[];
     __shared__ uint64_t bar;
+    __shared__ uint64_t tma_bar[BLOCK / 32][kEncBoxSlots];
 
     const int lane = threadIdx.x & 31;
     const int warp_in_cta = threadIdx.x >> 5;
@@ -414,6 +430,71 @@ __global__ void __launch_bounds__(BLOCK, BLOCK >= 256 ? 4 : 8) ans_encode_kernel
                 encode_one(ld_stream_s32(p.symbols_in + i), PERSYM ? ld_stream_u32(p.model_index + i) : stream_model);
             }
         }
+        if (!PERSYM && p.use_tma && g.T > 1) {
+            // ---- TMA path: the warp's column strip arrives as boxes of kBoxRows rows (one UTMALDG by lane 0 per
+            // box, completion on a per-slot mbarrier); lanes read their column with LDS.  kEncBoxSlots boxes
+            // are in flight per warp, which covers the HBM latency without holding any register.
+            const uint64_t rows_total = g.T - 1;  // full rows T-2 .. 0
+            uint32_t nbox = (uint32_t)(rows_total / kBoxRows);
+            const uint32_t top_rows = (uint32_t)(rows_total - (uint64_t)nbox * kBoxRows);
+            {  // the rows above the highest box, one at a time
+                const int32_t *ps = p.symbols_in + (g.T - 2) * K + kc;
+                for (uint32_t j = 0; j < top_rows; ++j) {
+                    if ((j & (kCheckEvery - 1)) == 0) drain_ring();
+                    encode_one(ld_stream_s32(ps), stream_model);
+                    ps -= K;
+                }
+                drain_ring();
+            }
+            const uint32_t bars = smem_u32(&tma_bar[warp_in_cta][0]);
+            const uint32_t boxes = smem_u32_pinned(smem + kRingsWords + table_words) + (uint32_t)warp_in_cta * (kEncBoxSlots * kBoxBytes);
+            const int32_t x0 = (int32_t)((uint32_t)tile * BLOCK + (uint32_t)warp_in_cta * 32u);  // my warp's first stream
+            if (lane == 0) {
+#pragma unroll
+                for (int sl = 0; sl < kEncBoxSlots; ++sl) mbar_init_addr(bars + 8u * sl, 1);
+                fence_mbar_init();
+            }
+            __syncwarp();
+            uint32_t next = nbox;  // boxes [0, next) are not requested yet; they are taken from the top
+            auto request_box = [&](uint32_t slot) {
+                if (next != 0u) {
+                    next -= 1u;
+                    if (lane == 0) {
+                        mbar_expect_tx_addr(bars + 8u * slot, kBoxBytes);
+                        tma_load_box(boxes + slot * kBoxBytes, &p.tmap, x0, (int32_t)(next * kBoxRows), bars + 8u * slot);
+                    }
+                }
+            };
+#pragma unroll
+            for (int sl = 0; sl < kEncBoxSlots; ++sl) request_box(sl);
+            uint32_t slot = 0, parity = 0;
+            const uint32_t my_col = boxes + (uint32_t)lane * 4u;
+            for (; nbox > 0; --nbox) {
+                mbar_wait_addr(bars + 8u * slot, parity);
+                const uint32_t box = my_col + slot * kBoxBytes;
+#pragma unroll
+                for (int half = 1; half >= 0; --half) {  // rows 7..4, then 3..0
+                    uint32_t idx[kCheckEvery];
+#pragma unroll
+                    for (int u = 0; u < kCheckEvery; ++u)
+                        idx[u] = index_of((int32_t)lds_u32(box + (uint32_t)(half * kCheckEvery + (kCheckEvery - 1 - u)) * 128u));
+                    const bool full = pending >= 16u;
+                    const uint4 oldest = drain_load();
+                    encode_idx(idx[0], stream_model);
+                    encode_idx(idx[1], stream_model);
+                    drain_decided(full, oldest);
+                    encode_idx(idx[2], stream_model);
+                    encode_idx(idx[3], stream_model);
+                }
+                __syncwarp();  // every lane has read the box: its slot is requested again
+                request_box(slot);
+                if (++slot == kEncBoxSlots) {
+                    slot = 0;
+                    parity ^= 1u;
+                }
+            }
+            drain_ring();
+        } else
         if (g.T > 1) {
             const uint64_t rows_total = g.T - 1;  // full rows T-2 .. 0
             const char *ps = reinterpret_cast<const char *>(p.symbols_in + (g.T - 2) * K + kc);
@@ -426,7 +507,11 @@ __global__ void __launch_bounds__(BLOCK, BLOCK >= 256 ? 4 : 8) ans_encode_kernel
             auto load_batch = [&](int which) {
 #pragma unroll
                 for (int u = 0; u < kCheckEvery; ++u) {
+#ifdef CTR_DBG_NO_LOAD
+                    buf[which][u] = (int32_t)(((uint32_t)(uintptr_t)ps >> 7) % 23u) - 8;
+#else
                     buf[which][u] = ld_stream_s32(reinterpret_cast<const int32_t *>(ps));
+#endif
                     ps -= row_bytes;
                     if (PERSYM) {
                         mbuf[which][u] = ld_stream_u32(reinterpret_cast<const uint32_t *>(pm));
@@ -442,7 +527,13 @@ __global__ void __launch_bounds__(BLOCK, BLOCK >= 256 ? 4 : 8) ans_encode_kernel
 #define CTR_PF_BATCHES 6
 #endif
             constexpr int kPrefetchBatches = CTR_PF_BATCHES;
+#ifdef CTR_PF_FULL
+            // lanes 8j..8j+7 address row j of the future batch, two lanes per 32-byte sector of the warp's line
+            const char *pf = ps - (uint32_t)lane * 4u + (((uint32_t)lane >> 1) & 3u) * 32u -
+                             ((uint64_t)kPrefetchBatches * kCheckEvery + (uint32_t)(lane >> 3)) * row_bytes;
+#else
             const char *pf = ps - ((uint64_t)kPrefetchBatches * kCheckEvery + (uint32_t)(lane >> 3)) * row_bytes;
+#endif
             const char *const pf_floor = reinterpret_cast<const char *>(p.symbols_in);
             const uint64_t batch_bytes = row_bytes * kCheckEvery;
             static_assert(kCheckEvery == 4, "code_batch is written for batches of four");
@@ -597,6 +688,9 @@ __global__ void __launch_bounds__(BLOCK, BLOCK >= 256 ? 4 : 8) ans_encode_kernel
     uint32_t gb_lo, gb_hi;
     asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(gb_lo), "=r"(gb_hi) : "r"(park) : "memory");
     const uint32_t *gbegin = reinterpret_cast<const uint32_t *>(((uint64_t)gb_hi << 32) | gb_lo);
+#ifdef CTR_DBG_NO_TAIL
+    if (threadIdx.x == 0x7fffffff)
+#endif
     compact_tail<BLOCK>(p.compact, tile, k, K, valid, gbegin,
                         (valid && !overflow) ? (uint32_t)((reinterpret_cast<const uint32_t *>(gw)) - gbegin) : 0u, p.status);
 }
@@ -612,7 +706,7 @@ constexpr int kDecBlockShared = 1024;
 //   TABLE : kTableGlobal / kTableLut / kTablePool
 template <int BLOCK, int TABLE, bool CONTIG, bool PERSYM, bool SMALL>
 __global__ void __launch_bounds__(BLOCK ? BLOCK : 1024, BLOCK == 0 || BLOCK >= 1024 ? 1 : (BLOCK >= 256 ? 2 : 8))
-    ans_decode_kernel(const AnsParams p) {
+    ans_decode_kernel(const __grid_constant__ AnsParams p) {
     extern __shared__ __align__(128) uint32_t smem[];
     __shared__ uint64_t bar;
 

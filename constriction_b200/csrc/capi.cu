@@ -537,6 +537,45 @@ int run_coder_kernel(const LaunchCfg &cfg, const AnsParams &p) {
     return CTR_OK;
 }
 
+// The interleaved symbol array as a 2-D tensor [full rows][K] of int32 for the TMA paths of the coder kernels
+// (boxes of kBoxRows rows x 32 streams).  Returns false when the array cannot be described (K not a multiple of
+// 4: row pitch must be a multiple of 16 bytes; misaligned base; fewer than kBoxRows full rows; no driver entry
+// point), in which case the kernels use their per-row load / store paths.
+using EncodeTiledFn = CUresult (*)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled_fn() {
+    static const EncodeTiledFn fn = [] {
+        if (const char *e = getenv("CTR_TMA"))
+            if (strcmp(e, "0") == 0) return (EncodeTiledFn) nullptr;
+        void *f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess) {
+            cudaGetLastError();
+            return (EncodeTiledFn) nullptr;
+        }
+        return (EncodeTiledFn)f;
+    }();
+    return fn;
+}
+bool make_symbol_tensor_map(CUtensorMap *out, const void *symbols, const ctr_layout *L) {
+    const uint64_t K = L->n_streams;
+    if (K == 0 || K % 4 != 0 || K > 0xffffffffull) return false;
+    const uint64_t full_rows = L->n_symbols / K;
+    if (full_rows < (uint64_t)kBoxRows + 1 || full_rows > 0x7fffffffull) return false;
+    if (reinterpret_cast<uintptr_t>(symbols) % 16 != 0) return false;
+    const EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn) return false;
+    const cuuint64_t dims[2] = {K, full_rows};
+    const cuuint64_t strides[1] = {K * 4};  // bytes between rows
+    const cuuint32_t box[2] = {32, (cuuint32_t)kBoxRows};
+    const cuuint32_t elem_strides[2] = {1, 1};
+    return fn(out, CU_TENSOR_MAP_DATA_TYPE_INT32, 2, const_cast<void *>(symbols), dims, strides, box, elem_strides,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 AnsParams base_params(const ctr_model_s *m, const ctr_layout *L) {
     AnsParams p;
     memset(&p, 0, sizeof p);
@@ -595,6 +634,10 @@ int encode_common(ctr_model_t model, const int32_t *symbols_dev, const ctr_layou
     // rings + parking slots; replicated table (128 B per entry); two symbol tiles
     cfg.smem = coder_smem_bytes(cfg.shared ? ((size_t)model->alphabet + 1) * 128 : 0, L, cfg.block / 32,
                                 32 * (kEncRingWords + 4), 2);
+    if (!cfg.contig && !cfg.persym && make_symbol_tensor_map(&p.tmap, symbols_dev, L)) {
+        p.use_tma = 1;
+        cfg.smem += (size_t)(cfg.block / 32) * kEncBoxSlots * kBoxBytes;  // TMA boxes
+    }
     cfg.stream = s;
     return run_coder_kernel<EncLauncher>(cfg, p);
 }

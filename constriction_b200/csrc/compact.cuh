@@ -4,7 +4,8 @@
 // worst-case-sized scratch region.  When a CTA has finished its 256 streams it
 //   1. prefix-sums their lengths inside the CTA,
 //   2. obtains the total length of all preceding streams with a single-pass "decoupled look-back"
-//      over per-CTA status words (aggregate published first, inclusive prefix as soon as it is known),
+//      over per-CTA status words (aggregate published first, inclusive prefix as soon as it is known;
+//      the whole CTA looks back, one predecessor per thread and round),
 //   3. writes the container's `offsets` (u64[K+1]) and gathers its streams' words from scratch (still
 //      L2-resident: this CTA wrote them microseconds ago) into the dense `words` buffer, so that
 //      words[offsets[k] .. offsets[k+1]) is stream k's `get_compressed()` (stack.rs:537-547,
@@ -77,7 +78,6 @@ __device__ __forceinline__ void compact_tail(const CompactParams &c, uint32_t ti
                                              const uint32_t *src, uint32_t len, uint32_t *status) {
     constexpr int kWarps = BLOCK / 32;
     __shared__ uint64_t s_warp_totals[kWarps];
-    __shared__ uint64_t s_tile_base;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
     // 1. offsets inside the CTA
@@ -92,11 +92,15 @@ __device__ __forceinline__ void compact_tail(const CompactParams &c, uint32_t ti
         tile_total += t;
     }
 
-    // 2. decoupled look-back by warp 0: lane j inspects tile (tile - 1 - j - 32 * round)
-    if (warp == 0) {
-        if (lane == 0) st_volatile_u64(c.tile_status + tile, (tile == 0 ? kTilePrefix : kTileAggregate) | tile_total);
-        uint64_t exclusive = 0;
-        int64_t idx = (int64_t)tile - 1 - lane;
+    // 2. decoupled look-back by the whole CTA: in round r thread j inspects tile (tile - 1 - j - BLOCK * r), so
+    //    the statuses of BLOCK predecessors are fetched with one L2 round trip.  The nearest predecessor that
+    //    has published an inclusive prefix ends the walk; nearer ones contribute their aggregates.
+    __shared__ uint64_t s_round_sum[kWarps];
+    __shared__ uint32_t s_round_has[kWarps];
+    if (threadIdx.x == 0) st_volatile_u64(c.tile_status + tile, (tile == 0 ? kTilePrefix : kTileAggregate) | tile_total);
+    uint64_t exclusive = 0;
+    {
+        int64_t idx = (int64_t)tile - 1 - (int64_t)threadIdx.x;
         bool done = tile == 0;
         while (!done) {
             uint64_t v = kTilePrefix;  // tiles before the first one contribute a prefix of 0
@@ -106,19 +110,26 @@ __device__ __forceinline__ void compact_tail(const CompactParams &c, uint32_t ti
                 } while ((v >> 62) == 0);
             }
             const unsigned has_prefix = __ballot_sync(kFullMask, (v >> 62) == 2);
-            // nearest predecessor with a full prefix ends the walk; nearer ones contribute their aggregates
             const int stop = has_prefix ? __ffs(has_prefix) - 1 : 31;
-            exclusive += warp_sum_u64(lane <= stop ? (v & kTileValueMask) : 0ull, lane);
-            done = has_prefix != 0;
-            idx -= 32;
-        }
-        if (lane == 0) {
-            if (tile != 0) st_volatile_u64(c.tile_status + tile, kTilePrefix | (exclusive + tile_total));
-            s_tile_base = exclusive;
+            const uint64_t wsum = warp_sum_u64(lane <= stop ? (v & kTileValueMask) : 0ull, lane);
+            if (lane == 0) {
+                s_round_sum[warp] = wsum;
+                s_round_has[warp] = has_prefix;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int w = 0; w < kWarps; ++w) {
+                if (!done) {
+                    exclusive += s_round_sum[w];
+                    done = s_round_has[w] != 0u;
+                }
+            }
+            __syncthreads();
+            idx -= BLOCK;
         }
     }
-    __syncthreads();
-    const uint64_t my_off = s_tile_base + before + inc - len;
+    if (threadIdx.x == 0 && tile != 0) st_volatile_u64(c.tile_status + tile, kTilePrefix | (exclusive + tile_total));
+    const uint64_t my_off = exclusive + before + inc - len;
 
     // 3. offsets + gather
     if (valid) {
@@ -130,6 +141,9 @@ __device__ __forceinline__ void compact_tail(const CompactParams &c, uint32_t ti
     const uint32_t n = (valid && fits) ? len : 0u;
     const uint32_t n_max = __reduce_max_sync(kFullMask, n);
     if (n_max == 0) return;
+#ifdef CTR_DBG_NO_GATHER
+    if (n_max != 0xffffffffu) return;
+#endif
     uint32_t *dst = c.words_out + my_off;
     __syncwarp();
     // The copy is latency-bound (one L2 round trip per batch of loads), so the loads of kGroup streams are

@@ -67,17 +67,31 @@ __device__ __forceinline__ uint4 lds_v4(uint32_t addr) {
     asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
     return v;
 }
+__device__ __forceinline__ uint64_t l2_policy_evict_last();
 __device__ __forceinline__ void st_stream_v4(void *p, const uint4 &v) {
+#if defined(CTR_L2_POLICY)
+    asm volatile("st.global.L1::no_allocate.L2::cache_hint.v4.u32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(p), "r"(v.x), "r"(v.y),
+                 "r"(v.z), "r"(v.w), "l"(l2_policy_evict_last())
+                 : "memory");
+#else
     asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
                  : "memory");
+#endif
 }
 // 16-byte asynchronous copy global -> shared (LDGSTS), tracked by cp.async groups
 __device__ __forceinline__ void cp_async_16(uint32_t dst_smem, const void *src_gmem) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src_gmem) : "memory");
 }
 // 4-byte variant (any 4-byte aligned source): used to fill transposition tiles asynchronously
+__device__ __forceinline__ uint64_t l2_policy_evict_first();
 __device__ __forceinline__ void cp_async_4(uint32_t dst_smem, const void *src_gmem) {
+#if defined(CTR_L2_POLICY)
+    asm volatile("cp.async.ca.shared.global.L2::cache_hint [%0], [%1], 4, %2;" ::"r"(dst_smem), "l"(src_gmem),
+                 "l"(l2_policy_evict_first())
+                 : "memory");
+#else
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst_smem), "l"(src_gmem) : "memory");
+#endif
 }
 template <int N>
 __device__ __forceinline__ void cp_async_wait_group() {
@@ -144,6 +158,53 @@ __device__ __forceinline__ void bulk_copy_g2s(void *dst_smem, const void *src_gm
                  : "memory");
 }
 
+// ---- 2-D tiled TMA (cp.async.bulk.tensor, SASS UTMALDG / UTMASTG) ------------------------------------
+// The interleaved symbol array is a [rows][K] int32 matrix; a warp's 32 streams are a 128-byte wide column
+// strip of it.  One instruction moves a box of kBoxRows rows x 32 columns between HBM and shared memory
+// (row pitch in shared memory: 128 bytes), instead of one load / store instruction and one 64-bit address
+// update per row.  `tmap` is the address of a CUtensorMap (kernel parameter, __grid_constant__).
+constexpr int kBoxRows = 8;                       // rows per box (two batches of kCheckEvery)
+constexpr uint32_t kBoxBytes = kBoxRows * 128u;   // 1 KiB
+__device__ __forceinline__ void mbar_init_addr(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx_addr(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_addr(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
+// box at column x, row y of the tensor -> shared memory at `dst` (128-byte aligned); completes on `bar`
+__device__ __forceinline__ void tma_load_box(uint32_t dst, const void *tmap, int32_t x, int32_t y, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+                 "l"(tmap), "r"(x), "r"(y), "r"(bar)
+                 : "memory");
+}
+// shared memory at `src` -> box at column x, row y of the tensor (columns / rows outside the tensor are clipped)
+__device__ __forceinline__ void tma_store_box(const void *tmap, int32_t x, int32_t y, uint32_t src) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(tmap), "r"(x), "r"(y), "r"(src)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// waits until at most N of this thread's bulk groups still read their shared-memory source
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() {
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// generic-proxy writes to shared memory become visible to the async proxy (before a TMA store reads them)
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 // Stage `bytes` (multiple of 16) of table data into shared memory; all threads of the CTA call it
 // and may read the data when it returns.  One elected thread drives the TMA engine.
 __device__ __forceinline__ void stage_table(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
@@ -195,10 +256,22 @@ __device__ __forceinline__ uint32_t ld_stream_u32(const uint32_t *p) {
     asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
     return v;
 }
+// L2 eviction policies (CTR_L2_POLICY): the symbol stream is read once (evict first), the encoders' scratch words
+// are read back by the fused compaction at the end of the kernel (evict last)
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t pol;
+    asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t pol;
+    asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
 __device__ __forceinline__ int32_t ld_stream_s32(const int32_t *p) {
     int32_t v;
-#ifdef CTR_LD_PLAIN
-    asm volatile("ld.global.s32 %0, [%1];" : "=r"(v) : "l"(p));
+#if defined(CTR_L2_POLICY)
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(l2_policy_evict_first()));
 #else
     asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
 #endif
