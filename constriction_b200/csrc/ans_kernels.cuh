@@ -40,7 +40,7 @@ constexpr int kAnsBlock = 256;  // threads per CTA (8 warps)
 // Interleaved deal with one model per stream: symbols move between HBM and shared memory as 2-D TMA boxes of
 // kBoxRows rows x 32 streams per warp (device_utils.cuh), kEncBoxSlots / kDecBoxSlots boxes in flight per warp.
 #ifndef CTR_ENC_BOX_SLOTS
-#define CTR_ENC_BOX_SLOTS 3
+#define CTR_ENC_BOX_SLOTS 2
 #endif
 #ifndef CTR_DEC_BOX_SLOTS
 #define CTR_DEC_BOX_SLOTS 2
@@ -299,7 +299,10 @@ __device__ __forceinline__ uint64_t warp_max_u64(uint64_t v, int lane) {
 //   F64DIV : the table holds double-precision reciprocals and the quotient estimate uses the FP64 pipe
 //   BLOCK  : threads per CTA (kAnsBlock, or kSmallBlock for batches too small to fill the GPU with big CTAs)
 template <int BLOCK, bool SHARED, bool CONTIG, bool PERSYM, bool F64DIV>
-__global__ void __launch_bounds__(BLOCK, BLOCK >= 256 ? 4 : 8) ans_encode_kernel(const __grid_constant__ AnsParams p) {
+#ifndef CTR_ENC_MIN_CTAS
+#define CTR_ENC_MIN_CTAS 4
+#endif
+__global__ void __launch_bounds__(BLOCK, BLOCK >= 256 ? CTR_ENC_MIN_CTAS : 8) ans_encode_kernel(const __grid_constant__ AnsParams p) {
     extern __shared__ __align__(128) uint32_t smem[];
     __shared__ uint64_t bar;
     __shared__ uint64_t tma_bar[BLOCK / 32][kEncBoxSlots];
@@ -352,8 +355,8 @@ __global__ void __launch_bounds__(BLOCK, BLOCK >= 256 ? 4 : 8) ans_encode_kernel
     }
 
     uint64_t state = (valid && p.states_in) ? p.states_in[k] : 0;
-    uint32_t pushed = 0;             // bytes pushed into my ring so far (ring slot = pushed & 31)
-    uint32_t pending = 0;            // bytes in my ring that are not yet written to scratch
+    uint32_t pushed = 0;             // bytes pushed into my ring so far (ring slot = pushed & 31); bit 31: words dropped
+    uint32_t drained = 0;            // bytes of my ring already written to scratch
     uint32_t min_prob = 0xffffffffu; // running minimum of the probabilities used (0 <=> impossible symbol)
     const uint32_t push_shift = valid ? 8u : 32u;  // (state >> 32) >> 32 == 0: lanes without a stream never push
     const uint32_t stream_model = (p.index_mode == 2) ? p.model_index[kc] : 0u;
@@ -376,7 +379,6 @@ __global__ void __launch_bounds__(BLOCK, BLOCK >= 256 ? 4 : 8) ans_encode_kernel
         if (shr_clamp(hi, push_shift) >= e.y) {  // stack.rs:1035-1040
             sts_u32(ring | (pushed & (kEncRingBytes - 1u)), lo);
             pushed += 4u;
-            pending += 4u;
             lo = hi;
             hi = 0u;
         }
@@ -388,8 +390,10 @@ __global__ void __launch_bounds__(BLOCK, BLOCK >= 256 ? 4 : 8) ans_encode_kernel
 
     // every kCheckEvery symbols: a complete 16-byte group of my ring goes to my scratch region.  A lane
     // pushes at most kCheckEvery words in between, so one group per check keeps up with any input.
+    // bytes in my ring that are not yet written to scratch
+    auto in_ring = [&]() -> uint32_t { return (pushed - drained) & 0x7fffffffu; };
     auto drain_store = [&](const uint4 &v) {
-        if (pending >= 16u) {
+        if (in_ring() >= 16u) {
             if (room >= 16u) {
                 st_stream_v4(gw, v);
                 gw += 16;
@@ -398,13 +402,13 @@ __global__ void __launch_bounds__(BLOCK, BLOCK >= 256 ? 4 : 8) ans_encode_kernel
                 room = 0u;  // words dropped: the stream is flagged at the end
                 pushed |= 0x80000000u;
             }
-            pending -= 16u;
+            drained += 16u;
         }
     };
     // the oldest (possibly incomplete) 16-byte group of my ring; harmless to read when it is not yet complete
-    auto drain_load = [&]() -> uint4 { return lds_v4(ring | ((pushed - pending) & (kEncRingBytes - 16u))); };
+    auto drain_load = [&]() -> uint4 { return lds_v4(ring | (drained & (kEncRingBytes - 16u))); };
     auto drain_ring = [&]() { drain_store(drain_load()); };
-    // split form: `full = pending >= 16` and `oldest = drain_load()` are taken at the check, the store is issued
+    // split form: `full = in_ring() >= 16` and `oldest = drain_load()` are taken at the check, the store is issued
     // a couple of symbols later so that the shared-memory latency is covered by coding work (a group that
     // completes in between waits for the next check; the ring has room for that)
     auto drain_decided = [&](bool full, const uint4 &oldest) {
@@ -417,7 +421,7 @@ __global__ void __launch_bounds__(BLOCK, BLOCK >= 256 ? 4 : 8) ans_encode_kernel
                 room = 0u;
                 pushed |= 0x80000000u;
             }
-            pending -= 16u;
+            drained += 16u;
         }
     };
 
@@ -459,10 +463,12 @@ __global__ void __launch_bounds__(BLOCK, BLOCK >= 256 ? 4 : 8) ans_encode_kernel
             auto request_box = [&](uint32_t slot) {
                 if (next != 0u) {
                     next -= 1u;
+#ifndef CTR_DBG_NO_LOAD
                     if (lane == 0) {
                         mbar_expect_tx_addr(bars + 8u * slot, kBoxBytes);
                         tma_load_box(boxes + slot * kBoxBytes, &p.tmap, x0, (int32_t)(next * kBoxRows), bars + 8u * slot);
                     }
+#endif
                 }
             };
 #pragma unroll
@@ -470,15 +476,17 @@ __global__ void __launch_bounds__(BLOCK, BLOCK >= 256 ? 4 : 8) ans_encode_kernel
             uint32_t slot = 0, parity = 0;
             const uint32_t my_col = boxes + (uint32_t)lane * 4u;
             for (; nbox > 0; --nbox) {
+#ifndef CTR_DBG_NO_LOAD
                 mbar_wait_addr(bars + 8u * slot, parity);
+#endif
                 const uint32_t box = my_col + slot * kBoxBytes;
 #pragma unroll
-                for (int half = 1; half >= 0; --half) {  // rows 7..4, then 3..0
+                for (int half = kBoxRows / kCheckEvery - 1; half >= 0; --half) {  // batches of rows, top down
                     uint32_t idx[kCheckEvery];
 #pragma unroll
                     for (int u = 0; u < kCheckEvery; ++u)
                         idx[u] = index_of((int32_t)lds_u32(box + (uint32_t)(half * kCheckEvery + (kCheckEvery - 1 - u)) * 128u));
-                    const bool full = pending >= 16u;
+                    const bool full = in_ring() >= 16u;
                     const uint4 oldest = drain_load();
                     encode_idx(idx[0], stream_model);
                     encode_idx(idx[1], stream_model);
@@ -555,7 +563,7 @@ __global__ void __launch_bounds__(BLOCK, BLOCK >= 256 ? 4 : 8) ans_encode_kernel
                 // drain: the 16-byte group is read from the ring now and stored two symbols later, so the
                 // shared-memory latency is covered by coding work.  The decision is taken now (a group that
                 // completes during this batch waits for the next check; the ring has room for that).
-                const bool full = pending >= 16u;
+                const bool full = in_ring() >= 16u;
                 const uint4 oldest = drain_load();
                 encode_idx(idx[0], mbuf[which][0]);
                 encode_idx(idx[1], mbuf[which][1]);
@@ -628,7 +636,7 @@ __global__ void __launch_bounds__(BLOCK, BLOCK >= 256 ? 4 : 8) ans_encode_kernel
             const uint32_t cmin = __reduce_min_sync(kFullMask, c), cmax = __reduce_max_sync(kFullMask, c);
             uint32_t s = 0;
             for (; s + kCheckEvery <= cmin; s += kCheckEvery) {  // every lane owns all four symbols
-                const bool full = pending >= 16u;
+                const bool full = in_ring() >= 16u;
                 const uint4 oldest = drain_load();
                 uint4 e[kCheckEvery];
 #pragma unroll
@@ -660,24 +668,22 @@ __global__ void __launch_bounds__(BLOCK, BLOCK >= 256 ? 4 : 8) ans_encode_kernel
     if (n_state >= 1) {
         sts_u32(ring | (pushed & (kEncRingBytes - 1u)), (uint32_t)state);
         pushed += 4u;
-        pending += 4u;
     }
     if (n_state == 2) {
         sts_u32(ring | (pushed & (kEncRingBytes - 1u)), (uint32_t)(state >> 32));
         pushed += 4u;
-        pending += 4u;
     }
     drain_ring();
     bool overflow = (pushed & 0x80000000u) != 0u;
-    while (pending != 0u) {  // < 4 words, one at a time
+    while (in_ring() != 0u) {  // < 4 words, one at a time
         if (room >= 4u) {
-            *reinterpret_cast<uint32_t *>(gw) = lds_u32(ring | ((pushed - pending) & (kEncRingBytes - 1u)));
+            *reinterpret_cast<uint32_t *>(gw) = lds_u32(ring | (drained & (kEncRingBytes - 1u)));
             gw += 4;
             room -= 4u;
         } else {
             overflow = true;
         }
-        pending -= 4u;
+        drained += 4u;
     }
     if (valid) {
         if (p.states_out) p.states_out[k] = state;
@@ -854,7 +860,49 @@ __global__ void __launch_bounds__(BLOCK ? BLOCK : 1024, BLOCK == 0 || BLOCK >= 1
         return (int32_t)(min_symbol + s);
     };
 
-    if (!CONTIG) {
+    if (!CONTIG && !PERSYM && p.use_tma) {
+        // ---- TMA path: decoded symbols are collected in shared-memory boxes of kBoxRows rows x 32 streams and
+        // leave as one UTMASTG per box (columns beyond K are clipped by the tensor map)
+        const Interleave g = interleave_of(N, K);
+        const uint64_t rows_total = g.T - 1;  // full rows 0 .. T-2
+        const uint32_t nbox = (uint32_t)(rows_total / kBoxRows);
+        // (the tables end on a 16-byte boundary; boxes need 128)
+        const uint32_t boxes = ((smem_u32_pinned(smem + kRingsWords + table_words) + 127u) & ~127u) + (uint32_t)warp_in_cta * (kDecBoxSlots * kBoxBytes);
+        const uint32_t my_col = boxes + (uint32_t)lane * 4u;
+        const int32_t x0 = (int32_t)(blockIdx.x * kBlock + (uint32_t)warp_in_cta * 32u);
+        uint32_t slot = 0;
+        for (uint32_t b = 0; b < nbox; ++b) {
+            // the store that last read this slot (kDecBoxSlots boxes ago) must have read it
+            if (lane == 0) tma_store_wait_read<kDecBoxSlots - 1>();
+            __syncwarp();
+            const uint32_t box = my_col + slot * kBoxBytes;
+#pragma unroll
+            for (int half = 0; half < kBoxRows / kCheckEvery; ++half) {
+#pragma unroll
+                for (int u = 0; u < kCheckEvery; ++u)
+                    sts_u32(box + (uint32_t)(half * kCheckEvery + u) * 128u, (uint32_t)decode_one(stream_model));
+                top_up();
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+                tma_store_box(&p.tmap, x0, (int32_t)(b * kBoxRows), boxes + slot * kBoxBytes);
+                tma_store_commit();
+            }
+            if (++slot == kDecBoxSlots) slot = 0;
+        }
+        {  // the rows after the last box, then the ragged last row
+            int32_t *po = p.symbols_out + (uint64_t)nbox * kBoxRows * K + kc;
+            for (uint64_t r = (uint64_t)nbox * kBoxRows; r < rows_total; ++r) {
+                const int32_t sym = decode_one(stream_model);
+                if (valid) st_stream_s32(po, sym);
+                po += K;
+                top_up();
+            }
+            if (valid && k < g.last) st_stream_s32(p.symbols_out + (g.T - 1) * K + k, decode_one(stream_model));
+        }
+        if (lane == 0) tma_store_wait_all();
+    } else if (!CONTIG) {
         const Interleave g = interleave_of(N, K);
         if (g.T > 1) {
             char *po = reinterpret_cast<char *>(p.symbols_out + kc);

@@ -43,7 +43,11 @@ __device__ __forceinline__ void st_volatile_u64(uint64_t *p, uint64_t v) {
 }
 __device__ __forceinline__ uint32_t ld_cg_u32(const uint32_t *p) {
     uint32_t v;
+#if defined(CTR_L2_POLICY) && defined(CTR_L2_GATHER_FIRST)
+    asm volatile("ld.global.cg.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(l2_policy_evict_first()) : "memory");
+#else
     asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+#endif
     return v;
 }
 
@@ -74,7 +78,7 @@ __device__ __forceinline__ uint64_t warp_sum_u64(uint64_t v, int lane) {
 //   tile    : this CTA's tile index (stream k = tile * blockDim.x + threadIdx.x)
 //   src/len : my stream's words in scratch (len = 0 for threads without a stream)
 template <int BLOCK>
-__device__ __forceinline__ void compact_tail(const CompactParams &c, uint32_t tile, uint64_t k, uint64_t K, bool valid,
+__device__ __noinline__ void compact_tail(const CompactParams &c, uint32_t tile, uint64_t k, uint64_t K, bool valid,
                                              const uint32_t *src, uint32_t len, uint32_t *status) {
     constexpr int kWarps = BLOCK / 32;
     __shared__ uint64_t s_warp_totals[kWarps];
@@ -149,7 +153,10 @@ __device__ __forceinline__ void compact_tail(const CompactParams &c, uint32_t ti
     // The copy is latency-bound (one L2 round trip per batch of loads), so the loads of kGroup streams are
     // put in flight together: lane l moves words l, l+32, ... of each stream; kSlots chunks per stream cover
     // streams of up to 32*kSlots words in one pass (longer ones loop).
-    constexpr int kGroup = 4, kSlots = 4;
+#ifndef CTR_GATHER_GROUP
+#define CTR_GATHER_GROUP 4
+#endif
+    constexpr int kGroup = CTR_GATHER_GROUP, kSlots = 4;
     for (int i0 = 0; i0 < 32; i0 += kGroup) {
         uint32_t ni[kGroup];
         const uint32_t *si[kGroup];

@@ -163,7 +163,10 @@ __device__ __forceinline__ void bulk_copy_g2s(void *dst_smem, const void *src_gm
 // strip of it.  One instruction moves a box of kBoxRows rows x 32 columns between HBM and shared memory
 // (row pitch in shared memory: 128 bytes), instead of one load / store instruction and one 64-bit address
 // update per row.  `tmap` is the address of a CUtensorMap (kernel parameter, __grid_constant__).
-constexpr int kBoxRows = 8;                       // rows per box (two batches of kCheckEvery)
+#ifndef CTR_BOX_ROWS
+#define CTR_BOX_ROWS 8
+#endif
+constexpr int kBoxRows = CTR_BOX_ROWS;            // rows per box (a multiple of kCheckEvery)
 constexpr uint32_t kBoxBytes = kBoxRows * 128u;   // 1 KiB
 __device__ __forceinline__ void mbar_init_addr(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
@@ -185,10 +188,19 @@ __device__ __forceinline__ void mbar_wait_addr(uint32_t bar, uint32_t parity) {
         : "memory");
 }
 // box at column x, row y of the tensor -> shared memory at `dst` (128-byte aligned); completes on `bar`
+__device__ __forceinline__ uint64_t l2_policy_evict_first();
 __device__ __forceinline__ void tma_load_box(uint32_t dst, const void *tmap, int32_t x, int32_t y, uint32_t bar) {
+#if defined(CTR_L2_POLICY)
+    // the symbol stream is read once: first candidate for eviction, so that it does not displace the scratch words
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3}], [%4], %5;" ::"r"(dst),
+        "l"(tmap), "r"(x), "r"(y), "r"(bar), "l"(l2_policy_evict_first())
+        : "memory");
+#else
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
                  "l"(tmap), "r"(x), "r"(y), "r"(bar)
                  : "memory");
+#endif
 }
 // shared memory at `src` -> box at column x, row y of the tensor (columns / rows outside the tensor are clipped)
 __device__ __forceinline__ void tma_store_box(const void *tmap, int32_t x, int32_t y, uint32_t src) {
