@@ -78,7 +78,7 @@ __device__ __forceinline__ uint64_t warp_sum_u64(uint64_t v, int lane) {
 //   tile    : this CTA's tile index (stream k = tile * blockDim.x + threadIdx.x)
 //   src/len : my stream's words in scratch (len = 0 for threads without a stream)
 template <int BLOCK>
-__device__ __noinline__ void compact_tail(const CompactParams &c, uint32_t tile, uint64_t k, uint64_t K, bool valid,
+__device__ __forceinline__ void compact_tail(const CompactParams &c, uint32_t tile, uint64_t k, uint64_t K, bool valid,
                                              const uint32_t *src, uint32_t len, uint32_t *status) {
     constexpr int kWarps = BLOCK / 32;
     __shared__ uint64_t s_warp_totals[kWarps];
