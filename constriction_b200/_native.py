@@ -65,6 +65,12 @@ SIGNATURES = {
     "ctr_range_max_compressed_words": (C.c_uint64, [C.POINTER(Layout)]),
     "ctr_range_encode": (C.c_int, [vp, vp, C.POINTER(Layout), vp, vp, C.c_size_t, vp, C.c_uint64, vp, vp, vp, vp]),
     "ctr_range_decode": (C.c_int, [vp, vp, vp, C.POINTER(Layout), vp, vp, vp, vp, vp, vp]),
+    "ctr_ans_encode_reverse_gaussian": (C.c_int, [C.c_int32, C.c_int32, vp, vp, vp, C.POINTER(Layout), vp, vp, C.c_size_t,
+                                                  vp, C.c_uint64, vp, vp, vp, vp]),
+    "ctr_ans_decode_gaussian": (C.c_int, [C.c_int32, C.c_int32, vp, vp, vp, vp, C.POINTER(Layout), vp, vp, vp, vp, vp, vp]),
+    "ctr_range_encode_gaussian": (C.c_int, [C.c_int32, C.c_int32, vp, vp, vp, C.POINTER(Layout), vp, vp, C.c_size_t,
+                                            vp, C.c_uint64, vp, vp, vp, vp]),
+    "ctr_range_decode_gaussian": (C.c_int, [C.c_int32, C.c_int32, vp, vp, vp, vp, C.POINTER(Layout), vp, vp, vp, vp, vp, vp]),
     "ctr_ans_encode_reverse_host": (C.c_int, [vp, vp, C.c_uint64, C.c_uint64, vp, vp, C.c_int32, vp, C.c_uint64, vp,
                                               C.POINTER(C.c_int), u64p]),
     "ctr_ans_decode_host": (C.c_int, [vp, vp, vp, C.c_uint64, C.c_uint64, vp, vp, C.c_int32, vp, C.POINTER(C.c_int), u64p]),

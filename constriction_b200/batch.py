@@ -145,6 +145,35 @@ class ModelTable:
         return out
 
 
+class GaussianParams:
+    """Per-symbol QuantizedGaussian parameters on the device: means[i], stds[i] (float64, laid out like the symbols)
+    over the support [min_symbol, max_symbol].  Passed to the BatchCoder methods in place of a ModelTable, it
+    selects the table-free kernels (ctr_*_gaussian in include/constriction_b200.h): the reference's lazily
+    evaluated per-symbol models (pybindings/stream/model/internals.rs:188-249, quantize.rs:525-568,580-779)."""
+
+    def __init__(self, min_symbol: int, max_symbol: int, means, stds, device=None):
+        _require_cuda()
+        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+
+        def col(x):
+            t = x if isinstance(x, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(np.asarray(x, dtype=np.float64)))
+            t = t.to(device=dev, dtype=torch.float64).contiguous()
+            if t.dim() != 1:
+                raise ValueError("means and stds must be 1-D")
+            return t
+
+        self.min_symbol, self.max_symbol = int(min_symbol), int(max_symbol)
+        if not self.max_symbol > self.min_symbol:
+            raise ValueError("max_symbol must be greater than min_symbol")
+        self.means, self.stds = col(means), col(stds)
+        if self.means.numel() != self.stds.numel():
+            raise ValueError("Model parameters have unequal shape")
+        self.device = dev
+
+    def __len__(self):
+        return self.means.numel()
+
+
 @dataclass
 class Compressed:
     """Container of a batch: dense `words` (u32 stored in an int32 tensor) + `offsets` (int64[K+1])."""
@@ -240,10 +269,18 @@ class BatchCoder:
         states_out = None
         if want_states:
             states_out = torch.empty(n_streams * state_words, dtype=torch.int64, device=self.device)
-        fn = lib.ctr_ans_encode_reverse if kind == "ans" else lib.ctr_range_encode
         with torch.cuda.device(self.device):
-            rc = fn(model.handle, symbols.data_ptr(), C.byref(L), _ptr(states_in), ws.data_ptr(), ws.numel(),
-                    words.data_ptr(), cap, offsets.data_ptr(), _ptr(states_out), self.status.data_ptr(), _stream_ptr())
+            if isinstance(model, GaussianParams):
+                if len(model) != n:
+                    raise ValueError("`symbols` argument has wrong length.")
+                fn = lib.ctr_ans_encode_reverse_gaussian if kind == "ans" else lib.ctr_range_encode_gaussian
+                rc = fn(model.min_symbol, model.max_symbol, model.means.data_ptr(), model.stds.data_ptr(),
+                        symbols.data_ptr(), C.byref(L), _ptr(states_in), ws.data_ptr(), ws.numel(), words.data_ptr(), cap,
+                        offsets.data_ptr(), _ptr(states_out), self.status.data_ptr(), _stream_ptr())
+            else:
+                fn = lib.ctr_ans_encode_reverse if kind == "ans" else lib.ctr_range_encode
+                rc = fn(model.handle, symbols.data_ptr(), C.byref(L), _ptr(states_in), ws.data_ptr(), ws.numel(),
+                        words.data_ptr(), cap, offsets.data_ptr(), _ptr(states_out), self.status.data_ptr(), _stream_ptr())
         N.raise_for(rc)
         return Compressed(words, offsets, n_streams, n, kind, sym_offsets, states_out)
 
@@ -274,10 +311,18 @@ class BatchCoder:
         state_words = 1 if kind == "ans" else 4
         states_out = torch.empty(n_streams * state_words, dtype=torch.int64, device=self.device) if want_states else None
         pos = torch.empty(n_streams, dtype=torch.int64, device=self.device) if want_pos else None
-        fn = self._lib.ctr_ans_decode if kind == "ans" else self._lib.ctr_range_decode
         with torch.cuda.device(self.device):
-            rc = fn(model.handle, words.data_ptr(), offsets.data_ptr(), C.byref(L), _ptr(states_in), out.data_ptr(),
-                    _ptr(states_out), _ptr(pos), self.status.data_ptr(), _stream_ptr())
+            if isinstance(model, GaussianParams):
+                if len(model) != n_symbols:
+                    raise ValueError("the number of model parameters differs from the number of symbols")
+                fn = self._lib.ctr_ans_decode_gaussian if kind == "ans" else self._lib.ctr_range_decode_gaussian
+                rc = fn(model.min_symbol, model.max_symbol, model.means.data_ptr(), model.stds.data_ptr(), words.data_ptr(),
+                        offsets.data_ptr(), C.byref(L), _ptr(states_in), out.data_ptr(), _ptr(states_out), _ptr(pos),
+                        self.status.data_ptr(), _stream_ptr())
+            else:
+                fn = self._lib.ctr_ans_decode if kind == "ans" else self._lib.ctr_range_decode
+                rc = fn(model.handle, words.data_ptr(), offsets.data_ptr(), C.byref(L), _ptr(states_in), out.data_ptr(),
+                        _ptr(states_out), _ptr(pos), self.status.data_ptr(), _stream_ptr())
         N.raise_for(rc)
         if want_states or want_pos:
             return out, states_out, pos

@@ -21,6 +21,15 @@ static cudaError_t go(const LaunchCfg &cfg, const AnsParams &p) {
 }
 
 cudaError_t launch_ans_decode(const LaunchCfg &cfg, const AnsParams &p) {
+    if (cfg.gauss) {  // per-symbol Gaussian parameters (gauss_kernels.cuh); always a model index per symbol
+        if (cfg.block == (unsigned)kSmallBlock)
+            return cfg.contig ? launch_kernel(ans_decode_kernel<kSmallBlock, kTableGauss, true, true, false>, cfg, p)
+                              : launch_kernel(ans_decode_kernel<kSmallBlock, kTableGauss, false, true, false>, cfg, p);
+        if (cfg.block == (unsigned)kAnsBlock)
+            return cfg.contig ? launch_kernel(ans_decode_kernel<kAnsBlock, kTableGauss, true, true, false>, cfg, p)
+                              : launch_kernel(ans_decode_kernel<kAnsBlock, kTableGauss, false, true, false>, cfg, p);
+        return cudaErrorInvalidConfiguration;
+    }
     if (cfg.pool) {  // model set in shared memory, CTA size decided by the caller
         if (cfg.persym)
             return cfg.contig ? launch_kernel(ans_decode_kernel<0, kTablePool, true, true, false>, cfg, p)

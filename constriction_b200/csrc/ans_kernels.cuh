@@ -33,6 +33,7 @@
 
 #include "compact.cuh"
 #include "device_utils.cuh"
+#include "gauss_kernels.cuh"
 
 namespace ctr {
 
@@ -70,6 +71,7 @@ struct ModelView {
 constexpr int kTableGlobal = 0;  // read through L1/L2
 constexpr int kTableLut = 1;     // one model for the batch: quantile index + cdf in shared memory
 constexpr int kTablePool = 2;    // several models, all CDF rows + coarse indices in shared memory
+constexpr int kTableGauss = 3;   // no table: model_index[i] names the (mean, std) pair of symbol i (gauss_kernels.cuh)
 
 struct AnsParams {
     ModelView model;
@@ -90,6 +92,9 @@ struct AnsParams {
     const uint32_t *words;
     const uint64_t *offsets;
     uint64_t *words_left;
+    // kTableGauss decoders: per-symbol Gaussian parameters and the quantiser's free weight (quantize.rs:284-308)
+    const double *gauss_means, *gauss_stds;
+    double gauss_free_weight;
     // interleaved deal: the symbol array as a [full rows][K] int32 tensor (boxes of kBoxRows x 32), if use_tma
     uint32_t use_tma;
     alignas(64) CUtensorMap tmap;
@@ -716,7 +721,7 @@ __global__ void __launch_bounds__(BLOCK ? BLOCK : 1024, BLOCK == 0 || BLOCK >= 1
     extern __shared__ __align__(128) uint32_t smem[];
     __shared__ uint64_t bar;
 
-    constexpr bool SHARED = TABLE == kTableLut, POOL = TABLE == kTablePool;
+    constexpr bool SHARED = TABLE == kTableLut, POOL = TABLE == kTablePool, GAUSS = TABLE == kTableGauss;
     const uint32_t kBlock = BLOCK ? (uint32_t)BLOCK : blockDim.x;
     const int lane = threadIdx.x & 31;
     const int warp_in_cta = threadIdx.x >> 5;
@@ -832,12 +837,18 @@ __global__ void __launch_bounds__(BLOCK ? BLOCK : 1024, BLOCK == 0 || BLOCK >= 1
     const uint32_t pool_cidx_stride = (alphabet > 256 ? 2u : 1u) * (kCoarseSize + 1);
     const uint32_t pool_cidx_addr = cdf_addr + p.model.pool_cdf_bytes;
 
+    bool bad_model = false;  // GAUSS: a std that is not > 0 (the symbols decoded with it are garbage)
     // one reference decode_symbol (stack.rs:1070-1100)
     auto decode_one = [&](uint32_t m) -> int32_t {
         const uint32_t q = lo & kQuantileMask;
         uint32_t left, right, s;
         if (SHARED) {
             s = lookup_shared<SMALL>(lut_addr, cdf_addr, alphabet, lo, q, left, right);
+        } else if (GAUSS) {
+            m = m < n_models ? m : n_models - 1;
+            const double mean = __ldg(p.gauss_means + m), std = __ldg(p.gauss_stds + m);
+            bad_model |= !(std > 0.0);
+            s = gauss_quantile(q, mean, std, p.gauss_free_weight, p.model.min_symbol, alphabet, left, right);
         } else if (POOL) {
             m = m < n_models ? m : n_models - 1;
             s = lookup_pool(cdf_addr + m * pool_row_bytes, pool_cidx_addr + m * pool_cidx_stride, alphabet > 256, q, left, right);
@@ -992,6 +1003,7 @@ __global__ void __launch_bounds__(BLOCK ? BLOCK : 1024, BLOCK == 0 || BLOCK >= 1
         if (p.states_out) p.states_out[k] = ((uint64_t)hi << 32) | lo;
         if (p.words_left) p.words_left[k] = (uint64_t)unstaged + pending + avail;
         if (trailing_zero) report_error(p.status, kErrTrailingZero, k);
+        if (GAUSS && bad_model) report_error(p.status, kErrBadModel, k);
     }
 }
 

@@ -17,6 +17,7 @@
 #include "../../include/constriction_b200.h"
 #include "ans_kernels.cuh"
 #include "compact.cuh"
+#include "gauss_kernels.cuh"
 #include "launch.cuh"
 #include "model_tables.cuh"
 
@@ -95,6 +96,9 @@ struct ctr_model_s {
     uint32_t dec_cdf_bytes = 0;  // (alphabet + 2) * 4 rounded up to 16: the cdf part of d_dec
     bool shared_ok = false;  // small enough for the shared-memory table kernels
     bool enc_f64 = false;    // d_enc holds double-precision reciprocals (CTR_DIV=f64)
+    // transient "model" of the ctr_*_gaussian entry points: no tables, (mean, std) per symbol
+    const double *lazy_means = nullptr, *lazy_stds = nullptr;
+    double lazy_free_weight = 0.0;
 };
 
 namespace {
@@ -638,6 +642,7 @@ int encode_common(ctr_model_t model, const int32_t *symbols_dev, const ctr_layou
 
     LaunchCfg cfg;
     cfg.pool = false;
+    cfg.gauss = false;
     cfg.shared = use_shared_enc_table(model, L);
     cfg.contig = L->sym_offsets_dev != nullptr;
     cfg.persym = L->model_index_mode == CTR_INDEX_PER_SYMBOL;
@@ -667,8 +672,11 @@ int decode_common(ctr_model_t model, const uint32_t *words, const uint64_t *offs
     if (ctr_device_count() == 0) return cuda_fail(cudaErrorNoDevice, "no CUDA device");
     cudaStream_t s = (cudaStream_t)stream;
     if (L->n_streams == 0) return CTR_OK;
-    if ((rc = ensure_dec_table(model, s))) return rc;
-    if (!use_shared_tables(model, L) && (rc = ensure_coarse_index(model, s))) return rc;
+    const bool lazy_gauss = model->lazy_means != nullptr;
+    if (!lazy_gauss) {
+        if ((rc = ensure_dec_table(model, s))) return rc;
+        if (!use_shared_tables(model, L) && (rc = ensure_coarse_index(model, s))) return rc;
+    }
 
     AnsParams p = base_params(model, L);
     p.symbols_out = symbols_out;
@@ -686,6 +694,18 @@ int decode_common(ctr_model_t model, const uint32_t *words, const uint64_t *offs
     cfg.f64 = false;
     cfg.stream = s;
     cfg.pool = false;
+    cfg.gauss = lazy_gauss;
+    if (lazy_gauss) {  // gauss_kernels.cuh: the lane searches its symbol's Gaussian; no tables, no staging
+        if (!cfg.persym) return CTR_ERR_BAD_ARGUMENT;
+        p.gauss_means = model->lazy_means;
+        p.gauss_stds = model->lazy_stds;
+        p.gauss_free_weight = model->lazy_free_weight;
+        cfg.shared = false;
+        cfg.block = L->n_streams < kStreamsForBigCtas ? kSmallBlock : kAnsBlock;
+        cfg.grid = grid_for(L->n_streams, cfg.block);
+        cfg.smem = coder_smem_bytes(0, L, cfg.block / 32, 32 * kDecRingWords, 1);
+        return run_coder_kernel<DecLauncher>(cfg, p);
+    }
     // interleaved deal, one model per stream: decoded symbols leave as TMA boxes (kDecBoxSlots per warp)
     size_t box_bytes_per_warp = 0;
     if (DecLauncher::kTma && tma_decode_enabled() && !cfg.contig && !cfg.persym && make_symbol_tensor_map(&p.tmap, symbols_out, L)) {
@@ -758,6 +778,137 @@ extern "C" int ctr_range_decode(ctr_model_t model, const uint32_t *words_dev, co
                                 void *stream) {
     return decode_common<RangeDecodeLauncher>(model, words_dev, offsets_dev, layout, states_in_dev, symbols_out_dev,
                                               states_out_dev, words_read_dev, status_dev, stream);
+}
+
+// =====================================================================================================
+// per-symbol Gaussian parameters (no tables)
+// =====================================================================================================
+namespace {
+
+struct PoolBuf {  // stream-ordered scratch allocation, released (stream-ordered) when the call returns
+    void *p = nullptr;
+    cudaStream_t s = nullptr;
+    int alloc(size_t bytes, cudaStream_t stream) {
+        s = stream;
+        CUDA_TRY(cudaMallocAsync(&p, bytes ? bytes : 16, stream));
+        return CTR_OK;
+    }
+    ~PoolBuf() {
+        if (p) cudaFreeAsync(p, s);
+    }
+};
+
+int check_gaussian_args(int32_t min_symbol, int32_t max_symbol, const double *means, const double *stds,
+                        const ctr_layout *L, double *free_weight) {
+    int rc = check_layout(L);
+    if (rc) return rc;
+    if (L->model_index_mode != CTR_INDEX_NONE) return CTR_ERR_BAD_ARGUMENT;  // the parameters are the per-symbol model
+    if ((!means || !stds) && L->n_symbols) return CTR_ERR_BAD_ARGUMENT;
+    if (L->n_symbols > 0xffffffffull) return CTR_ERR_BAD_ARGUMENT;
+    if (!mm::leaky_free_weight(min_symbol, max_symbol, *free_weight)) return CTR_ERR_BAD_MODEL;
+    if (ctr_device_count() == 0) return cuda_fail(cudaErrorNoDevice, "no CUDA device");
+    return CTR_OK;
+}
+
+// the transient model + layout the table-free paths hand to encode_common / decode_common
+void lazy_model(ctr_model_s *m, ctr_layout *L2, const ctr_layout *L, int32_t min_symbol, int32_t max_symbol,
+                const uint32_t *iota) {
+    m->n_models = (uint32_t)(L->n_symbols ? L->n_symbols : 1);
+    m->min_symbol = min_symbol;
+    m->shared_ok = false;
+    *L2 = *L;
+    L2->model_index_dev = iota;
+    L2->model_index_mode = CTR_INDEX_PER_SYMBOL;
+    (void)max_symbol;
+}
+
+template <class EncLauncher>
+int encode_gaussian(int32_t min_symbol, int32_t max_symbol, const double *means, const double *stds,
+                    const int32_t *symbols, const ctr_layout *L, const uint64_t *states_in, void *workspace,
+                    size_t workspace_bytes, uint32_t *words_out, uint64_t capacity, uint64_t *offsets_out,
+                    uint64_t *states_out, uint32_t *status, void *stream) {
+    double free_weight;
+    int rc = check_gaussian_args(min_symbol, max_symbol, means, stds, L, &free_weight);
+    if (rc) return rc;
+    if (!symbols && L->n_symbols) return CTR_ERR_BAD_ARGUMENT;
+    cudaStream_t s = (cudaStream_t)stream;
+    const uint64_t n = L->n_symbols;
+    PoolBuf entries, iota;
+    if ((rc = entries.alloc(n * 16, s)) || (rc = iota.alloc(n * 4, s))) return rc;
+    ctr_model_s m;
+    ctr_layout L2;
+    lazy_model(&m, &L2, L, min_symbol, max_symbol, static_cast<uint32_t *>(iota.p));
+    m.alphabet = 0;  // every symbol maps to entry 0 of "its" model: enc[i * 1 + 0]
+    m.d_enc = static_cast<uint4 *>(entries.p);
+    m.enc_f64 = use_f64_division();
+    if (n) {
+        qgauss_entries_kernel<<<grid_for(n, 128), 128, 0, s>>>(min_symbol, max_symbol, means, stds, symbols, n,
+                                                              m.enc_f64 ? 1 : 0, m.d_enc, static_cast<uint32_t *>(iota.p), status);
+        LAUNCH_CHECK("qgauss_entries_kernel");
+    }
+    return encode_common<EncLauncher>(&m, symbols, &L2, states_in, workspace, workspace_bytes, words_out, capacity,
+                                      offsets_out, states_out, status, stream);
+}
+
+template <class DecLauncher>
+int decode_gaussian(int32_t min_symbol, int32_t max_symbol, const double *means, const double *stds,
+                    const uint32_t *words, const uint64_t *offsets, const ctr_layout *L, const uint64_t *states_in,
+                    int32_t *symbols_out, uint64_t *states_out, uint64_t *words_left, uint32_t *status, void *stream) {
+    double free_weight;
+    int rc = check_gaussian_args(min_symbol, max_symbol, means, stds, L, &free_weight);
+    if (rc) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    const uint64_t n = L->n_symbols;
+    PoolBuf iota;
+    if ((rc = iota.alloc(n * 4, s))) return rc;
+    if (n) {
+        iota_kernel<<<grid_for(n, 256), 256, 0, s>>>(static_cast<uint32_t *>(iota.p), n);
+        LAUNCH_CHECK("iota_kernel");
+    }
+    ctr_model_s m;
+    ctr_layout L2;
+    lazy_model(&m, &L2, L, min_symbol, max_symbol, static_cast<uint32_t *>(iota.p));
+    m.alphabet = (uint32_t)max_symbol - (uint32_t)min_symbol + 1u;
+    m.lazy_means = means ? means : reinterpret_cast<const double *>(iota.p);
+    m.lazy_stds = stds;
+    m.lazy_free_weight = free_weight;
+    return decode_common<DecLauncher>(&m, words, offsets, &L2, states_in, symbols_out, states_out, words_left, status,
+                                      stream);
+}
+
+}  // namespace
+
+extern "C" int ctr_ans_encode_reverse_gaussian(int32_t min_symbol, int32_t max_symbol, const double *means_dev,
+    const double *stds_dev, const int32_t *symbols_dev, const ctr_layout *layout, const uint64_t *states_in_dev,
+    void *workspace_dev, size_t workspace_bytes, uint32_t *words_out_dev, uint64_t words_capacity,
+    uint64_t *offsets_out_dev, uint64_t *states_out_dev, uint32_t *status_dev, void *stream) {
+    return encode_gaussian<AnsEncodeLauncher>(min_symbol, max_symbol, means_dev, stds_dev, symbols_dev, layout,
+                                              states_in_dev, workspace_dev, workspace_bytes, words_out_dev,
+                                              words_capacity, offsets_out_dev, states_out_dev, status_dev, stream);
+}
+extern "C" int ctr_range_encode_gaussian(int32_t min_symbol, int32_t max_symbol, const double *means_dev,
+    const double *stds_dev, const int32_t *symbols_dev, const ctr_layout *layout, const uint64_t *states_in_dev,
+    void *workspace_dev, size_t workspace_bytes, uint32_t *words_out_dev, uint64_t words_capacity,
+    uint64_t *offsets_out_dev, uint64_t *states_out_dev, uint32_t *status_dev, void *stream) {
+    return encode_gaussian<RangeEncodeLauncher>(min_symbol, max_symbol, means_dev, stds_dev, symbols_dev, layout,
+                                                states_in_dev, workspace_dev, workspace_bytes, words_out_dev,
+                                                words_capacity, offsets_out_dev, states_out_dev, status_dev, stream);
+}
+extern "C" int ctr_ans_decode_gaussian(int32_t min_symbol, int32_t max_symbol, const double *means_dev,
+    const double *stds_dev, const uint32_t *words_dev, const uint64_t *offsets_dev, const ctr_layout *layout,
+    const uint64_t *states_in_dev, int32_t *symbols_out_dev, uint64_t *states_out_dev, uint64_t *words_left_dev,
+    uint32_t *status_dev, void *stream) {
+    return decode_gaussian<AnsDecodeLauncher>(min_symbol, max_symbol, means_dev, stds_dev, words_dev, offsets_dev, layout,
+                                              states_in_dev, symbols_out_dev, states_out_dev, words_left_dev, status_dev,
+                                              stream);
+}
+extern "C" int ctr_range_decode_gaussian(int32_t min_symbol, int32_t max_symbol, const double *means_dev,
+    const double *stds_dev, const uint32_t *words_dev, const uint64_t *offsets_dev, const ctr_layout *layout,
+    const uint64_t *states_in_dev, int32_t *symbols_out_dev, uint64_t *states_out_dev, uint64_t *words_read_dev,
+    uint32_t *status_dev, void *stream) {
+    return decode_gaussian<RangeDecodeLauncher>(min_symbol, max_symbol, means_dev, stds_dev, words_dev, offsets_dev,
+                                                layout, states_in_dev, symbols_out_dev, states_out_dev, words_read_dev,
+                                                status_dev, stream);
 }
 
 // =====================================================================================================

@@ -33,6 +33,7 @@ constexpr uint32_t kOk = 0;
 constexpr uint32_t kErrImpossibleSymbol = 1;  // lib.rs:376  -> KeyError
 constexpr uint32_t kErrInvalidData = 2;       // queue.rs:1401 -> AssertionError
 constexpr uint32_t kErrTrailingZero = 3;      // stack.rs:1555 -> ValueError
+constexpr uint32_t kErrBadModel = 5;          // invalid model parameter (std <= 0)          -> ValueError
 constexpr uint32_t kErrOutOfSpace = 7;        // backends.rs:1512 BoundedWriteError::OutOfSpace
 
 CTR_HD uint64_t mulhi64(uint64_t a, uint64_t b) {

@@ -17,6 +17,7 @@ struct LaunchCfg {
     bool persym;   // a model index per symbol
     bool f64;      // ANS encoder: FP64 quotient estimate
     bool pool;     // decoders: the whole model set is staged in shared memory (p.model.pool_*_bytes)
+    bool gauss;    // decoders: per-symbol Gaussian parameters instead of tables (p.gauss_*; implies persym)
     unsigned grid, block;
     size_t smem;   // dynamic shared memory per CTA
     cudaStream_t stream;

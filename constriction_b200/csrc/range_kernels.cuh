@@ -346,7 +346,7 @@ __global__ void __launch_bounds__(BLOCK ? BLOCK : 1024, BLOCK == 0 || BLOCK >= 1
     extern __shared__ __align__(128) uint32_t smem[];
     __shared__ uint64_t bar;
 
-    constexpr bool SHARED = TABLE == kTableLut, POOL = TABLE == kTablePool;
+    constexpr bool SHARED = TABLE == kTableLut, POOL = TABLE == kTablePool, GAUSS = TABLE == kTableGauss;
     const uint32_t kBlock = BLOCK ? (uint32_t)BLOCK : blockDim.x;
     const int lane = threadIdx.x & 31;
     const int warp_in_cta = threadIdx.x >> 5;
@@ -453,12 +453,18 @@ __global__ void __launch_bounds__(BLOCK ? BLOCK : 1024, BLOCK == 0 || BLOCK >= 1
 
     // one reference decode_symbol (queue.rs:968-1035); after invalid data the lane keeps running on a
     // clamped quantile (its symbols are garbage and the stream is flagged)
+    bool bad_model = false;  // GAUSS: a std that is not > 0
     auto decode_one = [&](uint32_t m) -> int32_t {
         uint32_t q = kQuantileMask;
         invalid_data |= !range_peek_quantile(st, q);
         uint32_t left, right, s;
         if (SHARED) {
             s = lookup_shared<SMALL>(lut_addr, cdf_addr, alphabet, q, q, left, right);
+        } else if (GAUSS) {
+            m = m < n_models ? m : n_models - 1;
+            const double mean = __ldg(p.gauss_means + m), std = __ldg(p.gauss_stds + m);
+            bad_model |= !(std > 0.0);
+            s = gauss_quantile(q, mean, std, p.gauss_free_weight, p.model.min_symbol, alphabet, left, right);
         } else if (POOL) {
             m = m < n_models ? m : n_models - 1;
             s = lookup_pool(cdf_addr + m * pool_row_bytes, pool_cidx_addr + m * pool_cidx_stride, alphabet > 256, q, left, right);
@@ -570,6 +576,7 @@ __global__ void __launch_bounds__(BLOCK ? BLOCK : 1024, BLOCK == 0 || BLOCK >= 1
         // words consumed so far (Pos::pos().0, queue.rs:182-196)
         if (p.words_left) p.words_left[k] = (uint64_t)(total_words - unstaged - pending - avail);
         if (invalid_data) report_error(p.status, kErrInvalidData, k);
+        if (GAUSS && bad_model) report_error(p.status, kErrBadModel, k);
     }
 }
 

@@ -6,6 +6,8 @@ parameters deferred to per-symbol arrays passed to `encode*` / `decode`: one CDF
 tabulated on the device in one launch, then addressed by a per-symbol model index)."""
 from __future__ import annotations
 
+import os
+
 import numpy as np
 
 from .. import batch as B
@@ -70,7 +72,10 @@ class QuantizedGaussian(Model):
         means, stds = self._split(params)
         if not np.all(stds > 0.0):
             raise ValueError("Invalid model parameter: `std` must be positive.")
-        return B.ModelTable.quantized_gaussian(self._lo, self._hi, means, stds)
+        if os.environ.get("CTR_GAUSS_TABLES") == "1":  # one tabulated CDF row per symbol (tests compare both paths)
+            return B.ModelTable.quantized_gaussian(self._lo, self._hi, means, stds)
+        # default: parameters go to the device as they are and the kernels evaluate them (no table per symbol)
+        return B.GaussianParams(self._lo, self._hi, means, stds)
 
 
 class Categorical(Model):

@@ -7,6 +7,7 @@ import numpy as np
 import torch
 
 from .. import _native as N
+from ..batch import GaussianParams
 from ..batch import Compressed
 from ._common import coder, from_dev_u64, is_scalar, symbols_array, to_dev_i32, to_dev_u64
 
@@ -31,6 +32,7 @@ class RangeEncoder:
         bc = coder()
         n = symbols.size
         sym = to_dev_i32(symbols) if n else torch.zeros(1, dtype=torch.int32, device=bc.device)[:0]
+        per_symbol = per_symbol and not isinstance(table, GaussianParams)  # table-free kernels need no index
         idx = torch.arange(n, dtype=torch.int32, device=bc.device) if per_symbol else None
         comp = bc.range_encode(sym, table, n_streams=1, model_index=idx,
                                index_mode=N.INDEX_PER_SYMBOL if per_symbol else N.INDEX_NONE,
@@ -112,6 +114,7 @@ class RangeDecoder:
         rest = self._words[self._pos:]
         words = to_dev_i32(rest) if rest.size else torch.zeros(1, dtype=torch.int32, device=bc.device)
         offsets = torch.tensor([0, rest.size], dtype=torch.int64, device=bc.device)
+        per_symbol = per_symbol and not isinstance(table, GaussianParams)  # table-free kernels need no index
         idx = torch.arange(n, dtype=torch.int32, device=bc.device) if per_symbol else None
         comp = Compressed(words, offsets, 1, n, "range")
         out, st, pos = bc.range_decode(comp, table, n_symbols=n, model_index=idx,

@@ -7,6 +7,7 @@ import numpy as np
 import torch
 
 from .. import _native as N
+from ..batch import GaussianParams
 from ._common import coder, from_dev_u64, is_scalar, symbols_array, to_dev_i32, to_dev_u64
 
 _MASK32 = 0xFFFFFFFF
@@ -91,6 +92,7 @@ class AnsCoder:
     def _encode(self, symbols: np.ndarray, table, per_symbol: bool):
         bc = coder()
         n = symbols.size
+        per_symbol = per_symbol and not isinstance(table, GaussianParams)  # table-free kernels need no index
         idx = torch.arange(n, dtype=torch.int32, device=bc.device) if per_symbol else None
         comp = bc.ans_encode(to_dev_i32(symbols), table, n_streams=1, model_index=idx,
                              index_mode=N.INDEX_PER_SYMBOL if per_symbol else N.INDEX_NONE,
@@ -120,6 +122,7 @@ class AnsCoder:
         bc = coder()
         words = to_dev_i32(self._bulk) if self._bulk.size else torch.zeros(1, dtype=torch.int32, device=bc.device)
         offsets = torch.tensor([0, self._bulk.size], dtype=torch.int64, device=bc.device)
+        per_symbol = per_symbol and not isinstance(table, GaussianParams)  # table-free kernels need no index
         idx = torch.arange(n, dtype=torch.int32, device=bc.device) if per_symbol else None
         from ..batch import Compressed
         comp = Compressed(words, offsets, 1, n, "ans")

@@ -175,6 +175,43 @@ int ctr_range_decode(ctr_model_t model, const uint32_t *words_dev, const uint64_
                      const ctr_layout *layout, const uint64_t *states_in_dev, int32_t *symbols_out_dev,
                      uint64_t *states_out_dev, uint64_t *words_read_dev, uint32_t *status_dev, void *stream);
 
+/* ---- QuantizedGaussian with per-symbol parameters, evaluated on the device (no tables) -----------
+ * What Python callers write as  coder.encode_reverse(symbols, QuantizedGaussian(lo, hi), means, stds)
+ * / coder.decode(QuantizedGaussian(lo, hi), means, stds): the reference builds one
+ * LeakilyQuantizedDistribution per symbol (src/pybindings/stream/model/internals.rs:188-249) and
+ * evaluates it lazily -- encode: left_cumulative_and_probability, two Gaussian CDFs per symbol
+ * (src/stream/model/quantize.rs:525-568); decode: quantile_function (quantize.rs:580-779).  Here the
+ * encoders run a parallel pre-pass (thread per symbol) that produces the (left, probability) pairs, and
+ * the decoders search the symbol's cumulative function inside the coder kernel; results are
+ * word-for-word those of the table path (ctr_model_quantized_gaussian with one model per symbol), without
+ * its O(alphabet) memory per symbol.
+ *   means_dev / stds_dev  f64[N], laid out like the symbols (means[i], stds[i] belong to symbols[i]);
+ *                         f32 parameters are widened by the caller, as the reference does
+ *                         (pybindings/stream/model/internals.rs:169-174)
+ *   layout                model_index_mode must be CTR_INDEX_NONE; N < 2^32
+ * Data-level errors: CTR_ERR_BAD_MODEL if a std is not > 0 (pybindings/stream/model.rs:654-657),
+ * CTR_ERR_IMPOSSIBLE_SYMBOL for a symbol outside [min_symbol, max_symbol].  Workspace and capacity as
+ * for the table entry points (ctr_ans_encode_workspace_bytes, ctr_ans_max_compressed_words); scratch
+ * for the pre-pass comes from the stream-ordered CUDA memory pool (no host synchronisation). */
+int ctr_ans_encode_reverse_gaussian(int32_t min_symbol, int32_t max_symbol, const double *means_dev,
+                                    const double *stds_dev, const int32_t *symbols_dev, const ctr_layout *layout,
+                                    const uint64_t *states_in_dev, void *workspace_dev, size_t workspace_bytes,
+                                    uint32_t *words_out_dev, uint64_t words_capacity, uint64_t *offsets_out_dev,
+                                    uint64_t *states_out_dev, uint32_t *status_dev, void *stream);
+int ctr_ans_decode_gaussian(int32_t min_symbol, int32_t max_symbol, const double *means_dev, const double *stds_dev,
+                            const uint32_t *words_dev, const uint64_t *offsets_dev, const ctr_layout *layout,
+                            const uint64_t *states_in_dev, int32_t *symbols_out_dev, uint64_t *states_out_dev,
+                            uint64_t *words_left_dev, uint32_t *status_dev, void *stream);
+int ctr_range_encode_gaussian(int32_t min_symbol, int32_t max_symbol, const double *means_dev,
+                              const double *stds_dev, const int32_t *symbols_dev, const ctr_layout *layout,
+                              const uint64_t *states_in_dev, void *workspace_dev, size_t workspace_bytes,
+                              uint32_t *words_out_dev, uint64_t words_capacity, uint64_t *offsets_out_dev,
+                              uint64_t *states_out_dev, uint32_t *status_dev, void *stream);
+int ctr_range_decode_gaussian(int32_t min_symbol, int32_t max_symbol, const double *means_dev, const double *stds_dev,
+                              const uint32_t *words_dev, const uint64_t *offsets_dev, const ctr_layout *layout,
+                              const uint64_t *states_in_dev, int32_t *symbols_out_dev, uint64_t *states_out_dev,
+                              uint64_t *words_read_dev, uint32_t *status_dev, void *stream);
+
 /* ---- host-buffer entry points (the reference-facing call: host in, host out) ------------------
  * Same semantics with HOST buffers (pinned memory makes the copies asynchronous DMA): device memory
  * comes from the stream-ordered CUDA memory pool, inputs are copied in, the kernels run, results are
