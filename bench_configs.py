@@ -11,6 +11,8 @@ B200 with the same hygiene (CUDA events, >= 3 warm-ups, device-resident inputs) 
             is 1024 streams; also run with all 8192 streams on one GPU)
   config 5  learned-image-compression shape: int32[64,192,32,32] latents, 192 per-channel QuantizedGaussian
             models, one ANS stream per (image, channel)
+  config 6  (not in BASELINE.json) the same latents with one (mean, std) pair per latent,
+            evaluated on the device by the table-free Gaussian kernels
 
     python bench_configs.py [--configs 3,4,5] [--scale 1.0]
 """
@@ -198,6 +200,54 @@ def config5(images=64):
             "bits_per_symbol": 32.0 * comp.total_words() / n}
 
 
+def config6(images=64, coder="ans"):
+    """Config 5's latents with a (mean, std) pair per latent (hyperprior models): the table-free Gaussian kernels
+    (SURVEY.md 8f rank 1).  Also reports the pre-pass on its own and the CPU oracle on a sample."""
+    import time
+
+    import torch
+    from constriction_b200 import batch as B
+    from oracle import refapi as O
+    C_, HW = 192, 32 * 32
+    k, n = images * C_, images * C_ * HW
+    g = torch.Generator(device="cuda")
+    g.manual_seed(6)
+    means = torch.randn(n, device="cuda", generator=g, dtype=torch.float64) * 2.0
+    stds = torch.exp(torch.rand(n, device="cuda", generator=g, dtype=torch.float64) * 3.7 - 1.2)  # 0.3 .. 12
+    syms = torch.clamp(torch.round(means + stds * torch.randn(n, device="cuda", generator=g, dtype=torch.float64)), -64, 64).to(torch.int32)
+    model = B.GaussianParams(-64, 64, means, stds)
+    off = torch.arange(k + 1, device="cuda", dtype=torch.int64) * HW
+    bc = B.BatchCoder()
+    enc_fn, dec_fn = (bc.ans_encode, bc.ans_decode) if coder == "ans" else (bc.range_encode, bc.range_decode)
+    state = {}
+
+    def enc():
+        state["c"] = enc_fn(syms, model, sym_offsets=off, out=state.get("c"))
+
+    ms_enc = timed(enc)
+    comp = state["c"]
+    out = torch.empty_like(syms)
+    ms_dec = timed(lambda: dec_fn(comp, model, out=out))
+    bc.check()
+    ok = bool(torch.equal(out, syms))
+    # oracle: stream 0 and the last one, one quantised Gaussian per symbol
+    t_cpu = 0.0
+    for s in (0, k - 1):
+        sl = slice(s * HW, (s + 1) * HW)
+        hm, hs, hy = means[sl].cpu().numpy(), stds[sl].cpu().numpy(), syms[sl].cpu().numpy()
+        t0 = time.perf_counter()
+        cdfs = np.stack([O.qgauss_cdf(-64, 64, float(a), float(b)) for a, b in zip(hm, hs)])
+        t_cpu += time.perf_counter() - t0
+        if coder == "ans":
+            ok &= bool(np.array_equal(comp.stream_words(s), O.ans_encode_indexed(hy, np.arange(HW), cdfs, -64)))
+    return {"config": f"6-{coder}", "workload": f"latents int32[{images},192,32,32], one QuantizedGaussian(-64,64,mean,std) per latent "
+                                              f"(f64 parameters on the device, no tables), {k} {coder} streams x {HW} symbols",
+            "us_encode": ms_enc * 1e3, "us_decode": ms_dec * 1e3,
+            "Msymbols_per_s_encode": n / ms_enc / 1e3, "Msymbols_per_s_decode": n / ms_dec / 1e3,
+            "Msymbols_per_s_round_trip": n / (ms_enc + ms_dec) / 1e3, "parity": ok,
+            "bits_per_symbol": 32.0 * comp.total_words() / n}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--configs", default="3,4,5")
@@ -216,6 +266,10 @@ def main():
         elif c == 5:
             print(json.dumps(config5(64)), flush=True)
             print(json.dumps(config5(8)), flush=True)
+        elif c == 6:
+            print(json.dumps(config6(64, "ans")), flush=True)
+            print(json.dumps(config6(64, "range")), flush=True)
+            print(json.dumps(config6(8, "ans")), flush=True)
         torch.cuda.empty_cache()
 
 
