@@ -23,6 +23,7 @@ ERR_CUDA = 9
 
 INDEX_NONE, INDEX_PER_SYMBOL, INDEX_PER_STREAM = 0, 1, 2
 FLAG_RAW = 1
+FLAG_CHECKPOINTS = 2
 
 u32p = C.POINTER(C.c_uint32)
 i32p = C.POINTER(C.c_int32)
@@ -39,6 +40,10 @@ class Layout(C.Structure):
         ("model_index_dev", vp),
         ("model_index_mode", C.c_int32),
         ("flags", C.c_uint32),
+        ("checkpoint_every", C.c_uint32),
+        ("reserved", C.c_uint32),
+        ("ckpt_offsets_dev", vp),
+        ("checkpoints_dev", vp),
     ]
 
 
@@ -65,6 +70,8 @@ SIGNATURES = {
     "ctr_range_max_compressed_words": (C.c_uint64, [C.POINTER(Layout)]),
     "ctr_range_encode": (C.c_int, [vp, vp, C.POINTER(Layout), vp, vp, C.c_size_t, vp, C.c_uint64, vp, vp, vp, vp]),
     "ctr_range_decode": (C.c_int, [vp, vp, vp, C.POINTER(Layout), vp, vp, vp, vp, vp, vp]),
+    "ctr_checkpoint_max_records": (C.c_uint64, [C.POINTER(Layout)]),
+    "ctr_checkpoint_offsets": (C.c_int, [C.POINTER(Layout), vp, vp]),
     "ctr_ans_encode_reverse_gaussian": (C.c_int, [C.c_int32, C.c_int32, vp, vp, vp, C.POINTER(Layout), vp, vp, C.c_size_t,
                                                   vp, C.c_uint64, vp, vp, vp, vp]),
     "ctr_ans_decode_gaussian": (C.c_int, [C.c_int32, C.c_int32, vp, vp, vp, vp, C.POINTER(Layout), vp, vp, vp, vp, vp, vp]),
@@ -108,7 +115,7 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)  # AttributeError here = header and library out of sync
         fn.restype = res
         fn.argtypes = args
-    if lib.ctr_abi_version() != 1:
+    if lib.ctr_abi_version() != 2:
         raise RuntimeError("libconstriction_b200.so: ABI version mismatch")
     _LIB = lib
     return lib

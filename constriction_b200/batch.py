@@ -184,6 +184,10 @@ class Compressed:
     coder: str
     sym_offsets: Optional[torch.Tensor] = None
     states: Optional[torch.Tensor] = None
+    # checkpoints (CTR_FLAG_CHECKPOINTS): records every `checkpoint_every` symbols, see include/constriction_b200.h
+    checkpoint_every: int = 0
+    ckpt_offsets: Optional[torch.Tensor] = None
+    checkpoints: Optional[torch.Tensor] = None
 
     def total_words(self) -> int:
         return int(self.offsets[-1].item())
@@ -210,7 +214,7 @@ class BatchCoder:
         self.status = torch.zeros(4, dtype=torch.int32, device=self.device)
 
     # -- helpers -----------------------------------------------------------------------------------
-    def _layout(self, n_symbols, n_streams, sym_offsets, model_index, index_mode, raw) -> N.Layout:
+    def _layout(self, n_symbols, n_streams, sym_offsets, model_index, index_mode, raw, ckpt=None) -> N.Layout:
         if index_mode is None:
             index_mode = N.INDEX_NONE if model_index is None else (
                 N.INDEX_PER_STREAM if model_index.numel() == n_streams and n_streams != n_symbols else N.INDEX_PER_SYMBOL)
@@ -221,6 +225,12 @@ class BatchCoder:
         L.model_index_dev = _ptr(model_index)
         L.model_index_mode = int(index_mode)
         L.flags = N.FLAG_RAW if raw else 0
+        if ckpt is not None:
+            every, ckpt_off, records = ckpt
+            L.flags |= N.FLAG_CHECKPOINTS
+            L.checkpoint_every = int(every)
+            L.ckpt_offsets_dev = _ptr(ckpt_off)
+            L.checkpoints_dev = _ptr(records)
         return L
 
     def _check_inputs(self, sym_offsets, model_index, n_streams):
@@ -246,7 +256,7 @@ class BatchCoder:
 
     # -- encode ------------------------------------------------------------------------------------
     def _encode(self, kind, symbols, model, n_streams, sym_offsets, model_index, index_mode, states_in, raw,
-                want_states, out: Optional[Compressed]):
+                want_states, out: Optional[Compressed], checkpoint_every=0):
         if symbols.dtype != torch.int32 or not symbols.is_cuda or not symbols.is_contiguous() or symbols.dim() != 1:
             raise TypeError("symbols must be a contiguous 1-D CUDA int32 tensor")
         n = symbols.numel()
@@ -257,6 +267,17 @@ class BatchCoder:
         self._check_inputs(sym_offsets, model_index, n_streams)
         L = self._layout(n, n_streams, sym_offsets, model_index, index_mode, raw)
         lib = self._lib
+        ckpt_off = records = None
+        if checkpoint_every:
+            if sym_offsets is None:
+                raise ValueError("checkpoints need the contiguous layout (sym_offsets)")
+            L.checkpoint_every = int(checkpoint_every)
+            ckpt_off = torch.empty(n_streams + 1, dtype=torch.int64, device=self.device)
+            with torch.cuda.device(self.device):
+                N.raise_for(lib.ctr_checkpoint_offsets(C.byref(L), ckpt_off.data_ptr(), _stream_ptr()))
+            records = torch.empty(int(lib.ctr_checkpoint_max_records(C.byref(L))) * (2 if kind == "ans" else 4),
+                                  dtype=torch.int64, device=self.device)
+            L = self._layout(n, n_streams, sym_offsets, model_index, index_mode, raw, (checkpoint_every, ckpt_off, records))
         ws_bytes = lib.ctr_ans_encode_workspace_bytes(C.byref(L))
         cap = lib.ctr_ans_max_compressed_words(C.byref(L))
         ws = self._workspace(ws_bytes)
@@ -282,30 +303,32 @@ class BatchCoder:
                 rc = fn(model.handle, symbols.data_ptr(), C.byref(L), _ptr(states_in), ws.data_ptr(), ws.numel(),
                         words.data_ptr(), cap, offsets.data_ptr(), _ptr(states_out), self.status.data_ptr(), _stream_ptr())
         N.raise_for(rc)
-        return Compressed(words, offsets, n_streams, n, kind, sym_offsets, states_out)
+        return Compressed(words, offsets, n_streams, n, kind, sym_offsets, states_out, int(checkpoint_every), ckpt_off, records)
 
     def ans_encode(self, symbols, model: ModelTable, n_streams=None, sym_offsets=None, model_index=None,
-                   index_mode=None, states_in=None, raw=False, want_states=False, out=None) -> Compressed:
-        """Every stream encodes its symbols in reverse order (AnsCoder.encode_reverse on K coders)."""
+                   index_mode=None, states_in=None, raw=False, want_states=False, out=None, checkpoint_every=0) -> Compressed:
+        """Every stream encodes its symbols in reverse order (AnsCoder.encode_reverse on K coders).
+        checkpoint_every=C (multiple of 32, contiguous layout): also record the coder positions every C symbols, so
+        that `ans_decode` can decode every chunk on its own lane."""
         return self._encode("ans", symbols, model, n_streams, sym_offsets, model_index, index_mode, states_in, raw,
-                            want_states, out)
+                            want_states, out, checkpoint_every)
 
     def range_encode(self, symbols, model: ModelTable, n_streams=None, sym_offsets=None, model_index=None,
-                     index_mode=None, states_in=None, raw=False, want_states=False, out=None) -> Compressed:
+                     index_mode=None, states_in=None, raw=False, want_states=False, out=None, checkpoint_every=0) -> Compressed:
         """Every stream encodes its symbols in forward order (RangeEncoder.encode on K coders)."""
         return self._encode("range", symbols, model, n_streams, sym_offsets, model_index, index_mode, states_in, raw,
-                            want_states, out)
+                            want_states, out, checkpoint_every)
 
     # -- decode ------------------------------------------------------------------------------------
     def _decode(self, kind, words, offsets, model, n_symbols, sym_offsets, model_index, index_mode, states_in, raw,
-                want_states, want_pos, out):
+                want_states, want_pos, out, ckpt=None):
         n_streams = offsets.numel() - 1
         if offsets.dtype != torch.int64 or not offsets.is_cuda:
             raise TypeError("offsets must be a CUDA int64 tensor")
         if words.dtype != torch.int32 or not words.is_cuda or not words.is_contiguous():
             raise TypeError("words must be a contiguous CUDA int32 tensor (u32 bit patterns)")
         self._check_inputs(sym_offsets, model_index, n_streams)
-        L = self._layout(n_symbols, n_streams, sym_offsets, model_index, index_mode, raw)
+        L = self._layout(n_symbols, n_streams, sym_offsets, model_index, index_mode, raw, ckpt)
         if out is None:
             out = torch.empty(n_symbols, dtype=torch.int32, device=self.device)
         state_words = 1 if kind == "ans" else 4
@@ -329,18 +352,26 @@ class BatchCoder:
         return out
 
     def ans_decode(self, compressed: Compressed, model: ModelTable, n_symbols=None, model_index=None,
-                   index_mode=None, states_in=None, raw=False, want_states=False, want_pos=False, out=None):
+                   index_mode=None, states_in=None, raw=False, want_states=False, want_pos=False, out=None,
+                   use_checkpoints=True):
         """Every stream decodes its symbols in forward order (AnsCoder.decode on K coders)."""
         n = compressed.n_symbols if n_symbols is None else n_symbols
+        ckpt = None
+        if use_checkpoints and compressed.checkpoint_every and not raw:
+            ckpt = (compressed.checkpoint_every, compressed.ckpt_offsets, compressed.checkpoints)
         return self._decode("ans", compressed.words, compressed.offsets, model, n, compressed.sym_offsets,
-                            model_index, index_mode, states_in, raw, want_states, want_pos, out)
+                            model_index, index_mode, states_in, raw, want_states, want_pos, out, ckpt)
 
     def range_decode(self, compressed: Compressed, model: ModelTable, n_symbols=None, model_index=None,
-                     index_mode=None, states_in=None, raw=False, want_states=False, want_pos=False, out=None):
+                     index_mode=None, states_in=None, raw=False, want_states=False, want_pos=False, out=None,
+                   use_checkpoints=True):
         """Every stream decodes its symbols in forward order (RangeDecoder.decode on K coders)."""
         n = compressed.n_symbols if n_symbols is None else n_symbols
+        ckpt = None
+        if use_checkpoints and compressed.checkpoint_every and not raw:
+            ckpt = (compressed.checkpoint_every, compressed.ckpt_offsets, compressed.checkpoints)
         return self._decode("range", compressed.words, compressed.offsets, model, n, compressed.sym_offsets,
-                            model_index, index_mode, states_in, raw, want_states, want_pos, out)
+                            model_index, index_mode, states_in, raw, want_states, want_pos, out, ckpt)
 
 
 def kernel_launch_count() -> int:

@@ -92,6 +92,14 @@ struct AnsParams {
     const uint32_t *words;
     const uint64_t *offsets;
     uint64_t *words_left;
+    // checkpoints (contiguous layout): the encoders record their coder position every ckpt_every symbols
+    // (Pos::pos, stack.rs:1107-1115 / queue.rs:182-196) so that one stream can be decoded by many lanes;
+    // ckpt_off[k] = index of stream k's first record in ckpt_out (u64[K+1])
+    uint32_t ckpt_every;  // multiple of 32; 0 = none
+    const uint64_t *ckpt_off;
+    uint64_t *ckpt_out;   // ANS: {words pushed, state} per record; range: {words pushed, lower, range, 0}
+    // decoders: stream k's words end at ends[k] instead of offsets[k + 1] (virtual streams of a chunked decode)
+    const uint64_t *ends;
     // kTableGauss decoders: per-symbol Gaussian parameters and the quantiser's free weight (quantize.rs:284-308)
     const double *gauss_means, *gauss_stds;
     double gauss_free_weight;
@@ -615,6 +623,9 @@ __global__ void __launch_bounds__(BLOCK, BLOCK >= 256 ? CTR_ENC_MIN_CTAS : 8) an
         const uint32_t my_row = (uint32_t)lane * (kRowStride * 4u);
         const uint32_t idx_row = smem_u32(idx_tile) + my_row;
         uint64_t remaining = n_k;  // symbols of my stream not yet requested (I consume from the end)
+        const uint32_t ckpt_every = valid ? p.ckpt_every : 0u;
+        const uint64_t ckpt_base = ckpt_every ? p.ckpt_off[k] : 0;
+        uint32_t to_ckpt = ckpt_every;  // symbols until the next checkpoint
         const uint64_t rounds = (warp_max_u64(n_k, lane) + 31) / 32;
         uint32_t c_next = remaining < 32 ? (uint32_t)remaining : 32u;
         remaining -= c_next;
@@ -660,6 +671,17 @@ __global__ void __launch_bounds__(BLOCK, BLOCK >= 256 ? CTR_ENC_MIN_CTAS : 8) an
                 if (s < c) {
                     const uint32_t at = (c - 1u - s) * 4u;
                     encode_one((int32_t)lds_u32(row + at), PERSYM ? lds_u32(idx_row + at) : stream_model);
+                }
+            }
+            // checkpoint: every symbol from `first` on is coded.  Record j (decode order) starts the chunk of
+            // symbols [first, ...): j = ceil(first / ckpt_every); boundaries are counted from the stream's end.
+            if (ckpt_every != 0u && c != 0u) {
+                to_ckpt -= c;
+                if (to_ckpt == 0u || first == 0u) {
+                    uint64_t *rec = p.ckpt_out + 2u * (ckpt_base + (first + ckpt_every - 1u) / ckpt_every);
+                    rec[0] = (pushed & 0x7fffffffu) >> 2;
+                    rec[1] = state;
+                    to_ckpt = ckpt_every;
                 }
             }
             __syncwarp();  // the tile is refilled by the next round's asynchronous fill
@@ -761,7 +783,7 @@ __global__ void __launch_bounds__(BLOCK ? BLOCK : 1024, BLOCK == 0 || BLOCK >= 1
             n_k = p.sym_off[k + 1] - o_k;
         }
         begin = p.offsets[k];
-        end = p.offsets[k + 1];
+        end = p.ends ? p.ends[k] : p.offsets[k + 1];
     }
     // low 32 bits of the global byte address just past the next word to pop
     uint32_t pop_off = (uint32_t)(uintptr_t)(p.words + end);

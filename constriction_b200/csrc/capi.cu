@@ -222,6 +222,10 @@ int check_layout(const ctr_layout *L) {
     if (L->model_index_mode < 0 || L->model_index_mode > 2) return CTR_ERR_BAD_ARGUMENT;
     if (L->model_index_mode != CTR_INDEX_NONE && !L->model_index_dev) return CTR_ERR_BAD_ARGUMENT;
     if (L->n_streams == 0 && L->n_symbols != 0) return CTR_ERR_BAD_ARGUMENT;
+    if (L->flags & CTR_FLAG_CHECKPOINTS) {  // contiguous layout, C a multiple of 32, both arrays present
+        if (!L->sym_offsets_dev || L->checkpoint_every == 0 || L->checkpoint_every % 32 != 0) return CTR_ERR_BAD_ARGUMENT;
+        if (!L->ckpt_offsets_dev || !L->checkpoints_dev) return CTR_ERR_BAD_ARGUMENT;
+    }
     return CTR_OK;
 }
 
@@ -603,6 +607,11 @@ AnsParams base_params(const ctr_model_s *m, const ctr_layout *L) {
     p.model_index = L->model_index_dev;
     p.index_mode = L->model_index_mode;
     p.flags = L->flags;
+    if (L->flags & CTR_FLAG_CHECKPOINTS) {
+        p.ckpt_every = L->checkpoint_every;
+        p.ckpt_off = L->ckpt_offsets_dev;
+        p.ckpt_out = L->checkpoints_dev;
+    }
     return p;
 }
 
@@ -610,6 +619,83 @@ AnsParams base_params(const ctr_model_s *m, const ctr_layout *L) {
 int empty_offsets(uint64_t *offsets, uint64_t K, cudaStream_t s) {
     CUDA_TRY(cudaMemsetAsync(offsets, 0, (size_t)(K + 1) * 8, s));
     return CTR_OK;
+}
+
+// ---- checkpoints ------------------------------------------------------------------------------------------
+// records per stream: J_k = ceil(n_k / C); exclusive prefix sums by one CTA (K is the number of *real* streams)
+__global__ void checkpoint_offsets_kernel(const uint64_t *sym_off, uint64_t K, uint32_t every, uint64_t *out) {
+    __shared__ uint64_t s_carry, s_warp[32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (uint64_t base = 0; base < K; base += blockDim.x) {
+        const uint64_t k = base + threadIdx.x;
+        const uint64_t j = k < K ? (sym_off[k + 1] - sym_off[k] + every - 1) / every : 0;
+        const uint64_t inc = warp_inclusive_scan_u64(j, lane);
+        if (lane == 31) s_warp[warp] = inc;
+        __syncthreads();
+        uint64_t before = s_carry;
+        for (int w = 0; w < warp; ++w) before += s_warp[w];
+        if (k < K) out[k] = before + inc - j;
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) s_carry = before + inc;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[K] = s_carry;
+}
+
+// Virtual streams of a chunk-parallel decode: chunk j of stream k becomes stream v = ckpt_off[k] + j with its own
+// word range, symbol range and raw start state; entries beyond the last real chunk (the arrays are sized by an
+// upper bound) are empty streams.  RANGE: 4 state words and the decoder's `point` is read from the words
+// (RangeDecoder::seek -> read_point, queue.rs:847-868,911-928).
+template <bool RANGE>
+__global__ void expand_checkpoints_kernel(const uint64_t *sym_off, const uint64_t *offsets, const uint32_t *words,
+                                          const uint64_t *ckpt_off, const uint64_t *ckpt, uint32_t every, uint64_t K,
+                                          uint64_t V_max, uint64_t N, const uint32_t *stream_index, uint64_t *v_begin,
+                                          uint64_t *v_end, uint64_t *v_sym_off, uint64_t *v_state, uint32_t *v_index) {
+    const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t V = ckpt_off[K];
+    if (k < K) {
+        const uint64_t o = sym_off[k], n = sym_off[k + 1] - o;
+        const uint64_t J = (n + every - 1) / every;
+        const uint64_t base = offsets[k], stream_end = offsets[k + 1];
+        const uint64_t v0 = ckpt_off[k];
+        for (uint64_t j = 0; j < J; ++j) {
+            const uint64_t v = v0 + j;
+            if (v >= V_max) break;
+            if (RANGE) {
+                const uint64_t *rec = ckpt + 4 * v;
+                const uint64_t pos = base + rec[0];
+                uint64_t point = 0;
+                if (pos < stream_end) point = (uint64_t)words[pos] << 32;
+                if (pos + 1 < stream_end) point |= words[pos + 1];
+                v_sym_off[v] = o + j * every;
+                v_begin[v] = pos + 2 < stream_end ? pos + 2 : stream_end;
+                v_end[v] = stream_end;
+                v_state[4 * v] = rec[1];
+                v_state[4 * v + 1] = rec[2];
+                v_state[4 * v + 2] = point;
+                v_state[4 * v + 3] = 0;
+            } else {
+                const uint64_t *rec = ckpt + 2 * v;
+                v_sym_off[v] = j == 0 ? o : o + n - (J - j) * every;
+                v_end[v] = base + rec[0];
+                v_begin[v] = j + 1 < J ? base + ckpt[2 * (v + 1)] : base;
+                v_state[v] = rec[1];
+            }
+            if (v_index) v_index[v] = stream_index[k];
+        }
+    }
+    // padding entries [V, V_max] : empty streams at the end of the symbol array
+    for (uint64_t v = V + k; v <= V_max; v += (uint64_t)gridDim.x * blockDim.x) {
+        v_sym_off[v] = N;
+        if (v < V_max) {
+            v_begin[v] = 0;
+            v_end[v] = 0;
+            for (int i = 0; i < (RANGE ? 4 : 1); ++i) v_state[(RANGE ? 4 : 1) * v + i] = RANGE && i == 1 ? ~0ull : 0;
+            if (v_index) v_index[v] = 0;
+        }
+    }
 }
 
 template <class EncLauncher>
@@ -663,7 +749,7 @@ int encode_common(ctr_model_t model, const int32_t *symbols_dev, const ctr_layou
 template <class DecLauncher>
 int decode_common(ctr_model_t model, const uint32_t *words, const uint64_t *offsets, const ctr_layout *L,
                   const uint64_t *states_in, int32_t *symbols_out, uint64_t *states_out, uint64_t *words_left,
-                  uint32_t *status, void *stream) {
+                  uint32_t *status, void *stream, const uint64_t *ends = nullptr) {
     int rc = check_layout(L);
     if (rc) return rc;
     if (!model || !offsets || (!symbols_out && L->n_symbols)) return CTR_ERR_BAD_ARGUMENT;
@@ -678,6 +764,41 @@ int decode_common(ctr_model_t model, const uint32_t *words, const uint64_t *offs
         if (!use_shared_tables(model, L) && (rc = ensure_coarse_index(model, s))) return rc;
     }
 
+    if (L->flags & CTR_FLAG_CHECKPOINTS) {
+        // chunk-parallel decode: expand the records into virtual streams (one per chunk) and decode those from
+        // their raw states; no per-stream outputs (a chunk is not a stream)
+        if (states_in || states_out || words_left || (L->flags & CTR_FLAG_RAW)) return CTR_ERR_BAD_ARGUMENT;
+        constexpr bool kRange = DecLauncher::kSlot == 3;
+        const uint64_t V_max = ctr_checkpoint_max_records(L);
+        struct Pool {
+            void *p = nullptr;
+            cudaStream_t s;
+            ~Pool() {
+                if (p) cudaFreeAsync(p, s);
+            }
+        } pool;
+        pool.s = s;
+        const size_t state_words = kRange ? 4 : 1;
+        const size_t bytes = (V_max * (2 + state_words) + (V_max + 1)) * 8 + V_max * 4;
+        CUDA_TRY(cudaMallocAsync(&pool.p, bytes, s));
+        uint64_t *v_begin = static_cast<uint64_t *>(pool.p);
+        uint64_t *v_end = v_begin + V_max, *v_sym_off = v_end + V_max, *v_state = v_sym_off + V_max + 1;
+        uint32_t *v_index = reinterpret_cast<uint32_t *>(v_state + V_max * state_words);
+        const bool per_stream = L->model_index_mode == CTR_INDEX_PER_STREAM;
+        expand_checkpoints_kernel<kRange><<<grid_for(L->n_streams, 128), 128, 0, s>>>(
+            L->sym_offsets_dev, offsets, words, L->ckpt_offsets_dev, L->checkpoints_dev, L->checkpoint_every, L->n_streams,
+            V_max, L->n_symbols, per_stream ? L->model_index_dev : nullptr, v_begin, v_end, v_sym_off, v_state,
+            per_stream ? v_index : nullptr);
+        LAUNCH_CHECK("expand_checkpoints_kernel");
+        ctr_layout L2 = *L;
+        L2.n_streams = V_max;
+        L2.sym_offsets_dev = v_sym_off;
+        if (per_stream) L2.model_index_dev = v_index;
+        L2.flags = (L->flags & ~CTR_FLAG_CHECKPOINTS) | CTR_FLAG_RAW;
+        return decode_common<DecLauncher>(model, words, v_begin, &L2, v_state, symbols_out, nullptr, nullptr, status, stream,
+                                          v_end);
+    }
+
     AnsParams p = base_params(model, L);
     p.symbols_out = symbols_out;
     p.states_in = states_in;
@@ -685,6 +806,7 @@ int decode_common(ctr_model_t model, const uint32_t *words, const uint64_t *offs
     p.status = status;
     p.words = words;
     p.offsets = offsets;
+    p.ends = ends;
     p.words_left = words_left;
 
     LaunchCfg cfg;
@@ -778,6 +900,23 @@ extern "C" int ctr_range_decode(ctr_model_t model, const uint32_t *words_dev, co
                                 void *stream) {
     return decode_common<RangeDecodeLauncher>(model, words_dev, offsets_dev, layout, states_in_dev, symbols_out_dev,
                                               states_out_dev, words_read_dev, status_dev, stream);
+}
+
+// =====================================================================================================
+// checkpoints
+// =====================================================================================================
+extern "C" uint64_t ctr_checkpoint_max_records(const ctr_layout *L) {
+    if (!L || L->checkpoint_every == 0) return 0;
+    return L->n_symbols / L->checkpoint_every + L->n_streams;
+}
+
+extern "C" int ctr_checkpoint_offsets(const ctr_layout *L, uint64_t *out, void *stream) {
+    if (!L || !out || !L->sym_offsets_dev || L->checkpoint_every == 0 || L->checkpoint_every % 32 != 0)
+        return CTR_ERR_BAD_ARGUMENT;
+    if (ctr_device_count() == 0) return cuda_fail(cudaErrorNoDevice, "no CUDA device");
+    checkpoint_offsets_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(L->sym_offsets_dev, L->n_streams, L->checkpoint_every, out);
+    LAUNCH_CHECK("checkpoint_offsets_kernel");
+    return CTR_OK;
 }
 
 // =====================================================================================================

@@ -246,10 +246,25 @@ __global__ void __launch_bounds__(BLOCK, BLOCK >= 256 ? 4 : 8) range_encode_kern
         uint32_t c_next = n_k < 32 ? (uint32_t)n_k : 32u;
         warp_fill_rows_async(tiles_addr, reinterpret_cast<const uint32_t *>(p.symbols_in + o_k), c_next, lane);
         cp_async_commit();
+        const uint32_t ckpt_every = valid ? p.ckpt_every : 0u;
+        const uint64_t ckpt_base = ckpt_every ? p.ckpt_off[k] : 0;
+        uint32_t to_ckpt = 0;  // symbols until the next checkpoint (the first one is at symbol 0)
         for (uint64_t r = 0; r < rounds; ++r) {
             const uint32_t c = c_next;
             const uint64_t first = done;
             done += c;
+            // checkpoint j = first / ckpt_every: the coder's position before symbol `first` (queue.rs:182-196)
+            if (ckpt_every != 0u && c != 0u) {
+                if (to_ckpt == 0u) {
+                    uint64_t *rec = p.ckpt_out + 4u * (ckpt_base + first / ckpt_every);
+                    rec[0] = pushed >> 2;
+                    rec[1] = lower;
+                    rec[2] = range;
+                    rec[3] = 0;
+                    to_ckpt = ckpt_every;
+                }
+                to_ckpt -= c;
+            }
             const uint32_t row = tiles_addr + (uint32_t)(r & 1) * (kTileWords * 4u) + my_row;
             const uint64_t left_n = n_k - done;
             c_next = left_n < 32 ? (uint32_t)left_n : 32u;
@@ -384,7 +399,7 @@ __global__ void __launch_bounds__(BLOCK ? BLOCK : 1024, BLOCK == 0 || BLOCK >= 1
             n_k = p.sym_off[k + 1] - o_k;
         }
         begin = p.offsets[k];
-        end = p.offsets[k + 1];
+        end = p.ends ? p.ends[k] : p.offsets[k + 1];
     }
     uint32_t pop_off = (uint32_t)(uintptr_t)(p.words + begin);  // low address bits of the next word to read
     uint32_t avail = 0, pending = 0;

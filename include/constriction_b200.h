@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define CTR_ABI_VERSION 1
+#define CTR_ABI_VERSION 2
 
 /* call-level and data-level status codes */
 #define CTR_OK 0
@@ -67,6 +67,13 @@ extern "C" {
                            appended to / parsed from the words (Pos/Seek, stack.rs:1107-1139,      \
                            queue.rs:182-196,911-928; from_raw_parts / into_raw_parts)              */
 
+#define CTR_FLAG_CHECKPOINTS 2u /* contiguous layout only.  Encoders also record their position (Pos::pos,    \
+                                   stack.rs:1107-1115, queue.rs:182-196) every `checkpoint_every` symbols;      \
+                                   decoders use the records to decode every chunk of every stream on its own   \
+                                   lane (Seek::seek, stack.rs:1117-1139, queue.rs:911-928): a long stream no    \
+                                   longer decodes at the speed of one dependent chain.  The words are           \
+                                   unchanged: any stream is still one stock-constriction stream.               */
+
 typedef struct ctr_model_s *ctr_model_t; /* opaque: device-resident 24-bit CDF tables of M models */
 
 typedef struct {
@@ -76,6 +83,16 @@ typedef struct {
     const uint32_t *model_index_dev; /* u32[N] / u32[K] / NULL according to model_index_mode  */
     int32_t model_index_mode;        /* CTR_INDEX_*                                           */
     uint32_t flags;                  /* CTR_FLAG_*                                            */
+    /* CTR_FLAG_CHECKPOINTS (all zero otherwise).  Stream k of n_k symbols has J_k = ceil(n_k / C) records,
+     * record j (decode order) describing the coder where the chunk of symbols starting at
+     *   ANS:   s_0 = 0, s_j = n_k - (J_k - j) C   (boundaries counted from the stream's end: ANS is a stack)
+     *   range: s_j = j C
+     * begins: ANS {words pushed so far, state} (2 x u64), range {words pushed so far, lower, range, 0}
+     * (4 x u64) -- the values AnsCoder::pos() / RangeEncoder::pos() return at that moment.             */
+    uint32_t checkpoint_every;        /* C, a multiple of 32                                           */
+    uint32_t reserved;
+    const uint64_t *ckpt_offsets_dev; /* u64[K+1]: index of stream k's first record (ctr_checkpoint_offsets) */
+    uint64_t *checkpoints_dev;        /* records; capacity ctr_checkpoint_max_records(layout)           */
 } ctr_layout;
 
 /* ---- library ------------------------------------------------------------------------------ */
@@ -174,6 +191,12 @@ int ctr_range_encode(ctr_model_t model, const int32_t *symbols_dev, const ctr_la
 int ctr_range_decode(ctr_model_t model, const uint32_t *words_dev, const uint64_t *offsets_dev,
                      const ctr_layout *layout, const uint64_t *states_in_dev, int32_t *symbols_out_dev,
                      uint64_t *states_out_dev, uint64_t *words_read_dev, uint32_t *status_dev, void *stream);
+
+/* ---- checkpoints -------------------------------------------------------------------------------
+ * upper bound on the number of records of a batch: n_symbols / C + n_streams */
+uint64_t ctr_checkpoint_max_records(const ctr_layout *layout);
+/* fills ckpt_offsets_out_dev (u64[K+1]) from layout->sym_offsets_dev and layout->checkpoint_every */
+int ctr_checkpoint_offsets(const ctr_layout *layout, uint64_t *ckpt_offsets_out_dev, void *stream);
 
 /* ---- QuantizedGaussian with per-symbol parameters, evaluated on the device (no tables) -----------
  * What Python callers write as  coder.encode_reverse(symbols, QuantizedGaussian(lo, hi), means, stds)

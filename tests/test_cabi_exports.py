@@ -21,7 +21,7 @@ def test_library_exports_every_declared_symbol():
     for name in names:
         assert hasattr(lib, name), f"{name} declared in the header but not exported"
     assert set(names) == set(N.SIGNATURES), set(names) ^ set(N.SIGNATURES)
-    assert lib.ctr_abi_version() == 1
+    assert lib.ctr_abi_version() == 2
     assert lib.ctr_status_string(1).decode().startswith("Tried to encode symbol")
 
 
