@@ -66,86 +66,101 @@ def synth_symbols_numpy(n, seed):
 # ----------------------------------------------------------------------------------------------------
 # clocks sampling (B200_PROFILING.md recipe)
 # ----------------------------------------------------------------------------------------------------
+_SAMPLER_SRC = r"""
+import json, os, sys, time
+idx = int(sys.argv[1])
+samples, max_mhz, source = [], None, "nvml"
+try:
+    import pynvml as nv
+    nv.nvmlInit()
+    h = nv.nvmlDeviceGetHandleByIndex(idx)
+    max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+    get = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+    def bit(a, b, d):
+        return getattr(nv, a, getattr(nv, b, d))
+    bits = [bit("nvmlClocksEventReasonHwSlowdown", "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+            bit("nvmlClocksEventReasonHwThermalSlowdown", "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+            bit("nvmlClocksEventReasonSwThermalSlowdown", "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+            bit("nvmlClocksEventReasonSwPowerCap", "nvmlClocksThrottleReasonSwPowerCap", 0x4)]
+    def sample():
+        r = int(get(h))
+        return [time.time(), float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)), [bool(r & b) for b in bits]]
+except Exception:
+    import subprocess
+    source = "nvidia-smi"
+    F = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    def sample():
+        global max_mhz
+        o = subprocess.run(["nvidia-smi", "--id=%d" % idx, "--query-gpu=" + F, "--format=csv,noheader,nounits"],
+                           capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+        max_mhz = float(o[1])
+        return [time.time(), float(o[0]), [x.strip().lower().startswith("active") for x in o[2:6]]]
+print("ready", flush=True)
+os.set_blocking(0, False)
+while True:
+    try:
+        samples.append(sample())
+    except Exception:
+        pass
+    try:
+        if os.read(0, 16):
+            break
+    except BlockingIOError:
+        pass
+    except Exception:
+        break
+    if len(samples) > 2000000:
+        break
+print(json.dumps({"samples": samples, "max": max_mhz, "source": source}), flush=True)
+"""
+
+
 class ClockSampler:
-    """SM clock and throttle reasons sampled DURING the timed region.  NVML (pynvml) is polled every millisecond,
-    so even a timed region of a few milliseconds gets samples; nvidia-smi (one query per ~50 ms) is the fallback."""
-    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-              "clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled DURING the timed region by a child process that polls NVML
+    back to back (one query takes ~0.1 ms, so a timed region of a few milliseconds gets tens of samples;
+    a thread of this process would compete with the launch loop for the GIL).  nvidia-smi is the fallback."""
     NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, gpu_index: int):
-        self.gpu = gpu_index
-        self.samples = []   # (sm_mhz, [reason flags])
-        self.max_mhz = None
-        self.source = None
-        self._stop = threading.Event()
-        self._thread = None
-        self._nvml = None
+        phys = gpu_index
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:  # NVML enumerates physical devices
+            ids = [v.strip() for v in vis.split(",") if v.strip()]
+            if gpu_index < len(ids) and ids[gpu_index].isdigit():
+                phys = int(ids[gpu_index])
+        self.result = None
+        self.t0 = self.t1 = None
         try:
-            import pynvml
-            pynvml.nvmlInit()
-            # NVML enumerates physical devices: honour CUDA_VISIBLE_DEVICES if it is a plain index list
-            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
-            phys = gpu_index
-            if vis:
-                ids = [v.strip() for v in vis.split(",") if v.strip()]
-                if gpu_index < len(ids) and ids[gpu_index].isdigit():
-                    phys = int(ids[gpu_index])
-            self._handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
-            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self._handle, pynvml.NVML_CLOCK_SM))
-            self._nvml = pynvml
-            self.source = "nvml"
+            self.proc = subprocess.Popen([sys.executable, "-c", _SAMPLER_SRC, str(phys)], stdin=subprocess.PIPE,
+                                         stdout=subprocess.PIPE, text=True)
+            self.proc.stdout.readline()  # "ready": NVML is initialised, sampling has started
         except Exception:
-            self._nvml = None
-            self.source = "nvidia-smi"
-
-    def _run_nvml(self):
-        nv = self._nvml
-        bits = [getattr(nv, "nvmlClocksEventReasonHwSlowdown", getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8)),
-                getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40)),
-                getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20)),
-                getattr(nv, "nvmlClocksEventReasonSwPowerCap", getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4))]
-        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
-        while not self._stop.is_set():
-            try:
-                mhz = float(nv.nvmlDeviceGetClockInfo(self._handle, nv.NVML_CLOCK_SM))
-                r = int(get_reasons(self._handle))
-                self.samples.append((mhz, [bool(r & b) for b in bits]))
-            except Exception:
-                pass
-            self._stop.wait(0.001)
-
-    def _run_smi(self):
-        while not self._stop.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.FIELDS}",
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                parts = [p.strip() for p in out.strip().split(",")]
-                if len(parts) >= 7 and parts[0].replace(".", "").isdigit():
-                    self.samples.append((float(parts[0]), [parts[3 + i].lower().startswith("active") for i in range(4)]))
-                    if parts[1].replace(".", "").isdigit():
-                        self.max_mhz = float(parts[1])
-            except Exception:
-                pass
-            self._stop.wait(0.05)
+            self.proc = None
 
     def __enter__(self):
-        self._thread = threading.Thread(target=self._run_nvml if self._nvml else self._run_smi, daemon=True)
-        self._thread.start()
+        self.t0 = time.time()
         return self
 
     def __exit__(self, *exc):
-        self._stop.set()
-        self._thread.join(timeout=10)
+        self.t1 = time.time()
+        if self.proc is None:
+            return
+        try:
+            out, _ = self.proc.communicate("stop\n", timeout=30)
+            self.result = json.loads(out.strip().splitlines()[-1])
+        except Exception:
+            self.proc.kill()
 
     def summary(self):
-        if not self.samples:
-            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["no samples"], "source": self.source}
-        sm = sorted(s[0] for s in self.samples)
-        reasons = [n for i, n in enumerate(self.NAMES) if any(s[1][i] for s in self.samples)]
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.max_mhz, "reasons": reasons, "samples": len(self.samples),
-                "source": self.source}
+        if not self.result or not self.result["samples"]:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        inside = [s for s in self.result["samples"] if self.t0 <= s[0] <= self.t1]
+        used = inside or self.result["samples"][-3:]
+        sm = sorted(s[1] for s in used)
+        reasons = [n for i, n in enumerate(self.NAMES) if any(s[2][i] for s in used)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.result["max"], "reasons": reasons,
+                "samples": len(inside), "source": self.result["source"]}
 
 
 # ----------------------------------------------------------------------------------------------------
@@ -266,6 +281,7 @@ def run_ours(args):
             dist.barrier()
             torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank)  # started before the warm-up so that the GPU is not idle right before the timed steps
     for _ in range(max(args.warmup, 3)):
         step()
     torch.cuda.synchronize()
@@ -283,13 +299,16 @@ def run_ours(args):
         del check, mine
 
     # ---- timed region: device-resident inputs --------------------------------------------------------
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    sync_all()
+    for _ in range(3):  # the checks above left the GPU idle for a moment
+        step()
+    sync_all()
     lib.ctr_profile_enable(1)
     lib.ctr_profile_read(0, None, None)
     lib.ctr_profile_read(1, None, None)
     launches0 = B.kernel_launch_count()
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
-    sync_all()
-    with ClockSampler(local_rank) as clocks:
+    with sampler as clocks:
         ev[0].record()
         for i in range(args.steps):
             step()

@@ -81,6 +81,22 @@ int cuda_fail(cudaError_t e, const char *what) {
     } while (0)
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// Scratch memory of the entry points that need some (per-symbol Gaussian entries, virtual streams of a chunked
+// decode, the host-buffer calls) comes from the device's stream-ordered memory pool.  By default the pool gives
+// freed memory back to the driver at every synchronisation, which makes the next call pay for a fresh mapping
+// (milliseconds); keep it instead.
+void keep_pool_memory() {
+    static thread_local int configured_device = -1;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev == configured_device) return;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        uint64_t threshold = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold);
+    }
+    configured_device = dev;
+}
 inline unsigned grid_for(uint64_t n, unsigned block) { return (unsigned)((n + block - 1) / block); }
 
 }  // namespace
@@ -780,6 +796,7 @@ int decode_common(ctr_model_t model, const uint32_t *words, const uint64_t *offs
         pool.s = s;
         const size_t state_words = kRange ? 4 : 1;
         const size_t bytes = (V_max * (2 + state_words) + (V_max + 1)) * 8 + V_max * 4;
+        keep_pool_memory();
         CUDA_TRY(cudaMallocAsync(&pool.p, bytes, s));
         uint64_t *v_begin = static_cast<uint64_t *>(pool.p);
         uint64_t *v_end = v_begin + V_max, *v_sym_off = v_end + V_max, *v_state = v_sym_off + V_max + 1;
@@ -929,6 +946,7 @@ struct PoolBuf {  // stream-ordered scratch allocation, released (stream-ordered
     cudaStream_t s = nullptr;
     int alloc(size_t bytes, cudaStream_t stream) {
         s = stream;
+        keep_pool_memory();
         CUDA_TRY(cudaMallocAsync(&p, bytes ? bytes : 16, stream));
         return CTR_OK;
     }
@@ -1076,13 +1094,7 @@ cudaStream_t host_stream() {
     static thread_local cudaStream_t s = nullptr;
     if (!s) {
         cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking);
-        // keep freed blocks in the pool instead of returning them to the driver at every sync
-        int dev = 0;
-        cudaMemPool_t pool;
-        if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-            uint64_t threshold = ~0ull;
-            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold);
-        }
+        keep_pool_memory();
     }
     return s;
 }

@@ -43,11 +43,7 @@ __device__ __forceinline__ void st_volatile_u64(uint64_t *p, uint64_t v) {
 }
 __device__ __forceinline__ uint32_t ld_cg_u32(const uint32_t *p) {
     uint32_t v;
-#if defined(CTR_L2_POLICY) && defined(CTR_L2_GATHER_FIRST)
-    asm volatile("ld.global.cg.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(l2_policy_evict_first()) : "memory");
-#else
     asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-#endif
     return v;
 }
 

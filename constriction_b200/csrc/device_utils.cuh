@@ -67,31 +67,17 @@ __device__ __forceinline__ uint4 lds_v4(uint32_t addr) {
     asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
     return v;
 }
-__device__ __forceinline__ uint64_t l2_policy_evict_last();
 __device__ __forceinline__ void st_stream_v4(void *p, const uint4 &v) {
-#if defined(CTR_L2_POLICY)
-    asm volatile("st.global.L1::no_allocate.L2::cache_hint.v4.u32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(p), "r"(v.x), "r"(v.y),
-                 "r"(v.z), "r"(v.w), "l"(l2_policy_evict_last())
-                 : "memory");
-#else
     asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
                  : "memory");
-#endif
 }
 // 16-byte asynchronous copy global -> shared (LDGSTS), tracked by cp.async groups
 __device__ __forceinline__ void cp_async_16(uint32_t dst_smem, const void *src_gmem) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src_gmem) : "memory");
 }
 // 4-byte variant (any 4-byte aligned source): used to fill transposition tiles asynchronously
-__device__ __forceinline__ uint64_t l2_policy_evict_first();
 __device__ __forceinline__ void cp_async_4(uint32_t dst_smem, const void *src_gmem) {
-#if defined(CTR_L2_POLICY)
-    asm volatile("cp.async.ca.shared.global.L2::cache_hint [%0], [%1], 4, %2;" ::"r"(dst_smem), "l"(src_gmem),
-                 "l"(l2_policy_evict_first())
-                 : "memory");
-#else
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst_smem), "l"(src_gmem) : "memory");
-#endif
 }
 template <int N>
 __device__ __forceinline__ void cp_async_wait_group() {
@@ -188,19 +174,10 @@ __device__ __forceinline__ void mbar_wait_addr(uint32_t bar, uint32_t parity) {
         : "memory");
 }
 // box at column x, row y of the tensor -> shared memory at `dst` (128-byte aligned); completes on `bar`
-__device__ __forceinline__ uint64_t l2_policy_evict_first();
 __device__ __forceinline__ void tma_load_box(uint32_t dst, const void *tmap, int32_t x, int32_t y, uint32_t bar) {
-#if defined(CTR_L2_POLICY)
-    // the symbol stream is read once: first candidate for eviction, so that it does not displace the scratch words
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3}], [%4], %5;" ::"r"(dst),
-        "l"(tmap), "r"(x), "r"(y), "r"(bar), "l"(l2_policy_evict_first())
-        : "memory");
-#else
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
                  "l"(tmap), "r"(x), "r"(y), "r"(bar)
                  : "memory");
-#endif
 }
 // shared memory at `src` -> box at column x, row y of the tensor (columns / rows outside the tensor are clipped)
 __device__ __forceinline__ void tma_store_box(const void *tmap, int32_t x, int32_t y, uint32_t src) {
@@ -268,25 +245,9 @@ __device__ __forceinline__ uint32_t ld_stream_u32(const uint32_t *p) {
     asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
     return v;
 }
-// L2 eviction policies (CTR_L2_POLICY): the symbol stream is read once (evict first), the encoders' scratch words
-// are read back by the fused compaction at the end of the kernel (evict last)
-__device__ __forceinline__ uint64_t l2_policy_evict_first() {
-    uint64_t pol;
-    asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-    return pol;
-}
-__device__ __forceinline__ uint64_t l2_policy_evict_last() {
-    uint64_t pol;
-    asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
-    return pol;
-}
 __device__ __forceinline__ int32_t ld_stream_s32(const int32_t *p) {
     int32_t v;
-#if defined(CTR_L2_POLICY)
-    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(l2_policy_evict_first()));
-#else
     asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
-#endif
     return v;
 }
 __device__ __forceinline__ void st_stream_u32(uint32_t *p, uint32_t v) {
