@@ -241,6 +241,11 @@ def run_ours(args):
         raise SystemExit("bench.py --impl ours needs a CUDA device (no CPU fallback)")
     torch.cuda.set_device(local_rank)
     if world > 1:
+        # NCCL prints its version banner to stdout when the first communicator is created; stdout must carry
+        # exactly one JSON line, so file descriptor 1 points to stderr until the warm-up is over
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     lib = N.load()
     n, k = args.symbols, args.streams
@@ -257,23 +262,52 @@ def run_ours(args):
 
     side = torch.cuda.Stream() if world > 1 else None
     gathered = {}
+    comps = [None, None]       # N > 1: two containers, so that step i+1 can encode while step i's container is gathered
+    pipe = {"i": 0, "prev": None}
 
     def step():
-        # N == 1: encode -> decode.  N > 1: encode -> (all-gather of the containers || decode of the own
-        # shard) -> join: the exchange runs on a side stream and overlaps the decode kernel; the gathered
-        # container is checked against the local one outside the timed region.
+        # N == 1: encode -> decode.
+        # N > 1: encode -> decode of the own shard on the main stream; on a side stream the all-gather of the
+        # containers: sizes first (16 bytes per rank, the host waits for them while the decode runs), then the
+        # words and offset tables.  The gather of step i is joined at the end of step i+1 (it only has to be done
+        # before its source container is overwritten by the encode of step i+2), so in steady state a step costs
+        # max(encode + decode, gather); drain() joins the last one inside the timed region.
         nonlocal comp
-        comp = bc.ans_encode(syms, model, n_streams=k, out=comp)
-        if world > 1:
-            encoded = torch.cuda.Event()
-            encoded.record()
+        if world == 1:
+            comp = bc.ans_encode(syms, model, n_streams=k, out=comp)
             bc.ans_decode(comp, model, out=out)
-            with torch.cuda.stream(side):
-                side.wait_event(encoded)
-                gathered["gc"] = D.all_gather_compressed(comp.words, comp.offsets, stream_counts=[k] * world)
-            torch.cuda.current_stream().wait_stream(side)
-        else:
-            bc.ans_decode(comp, model, out=out)
+            return
+        buf = pipe["i"] & 1
+        pipe["i"] += 1
+        comp = comps[buf] = bc.ans_encode(syms, model, n_streams=k, out=comps[buf])
+        encoded = torch.cuda.Event()
+        encoded.record()
+        if pipe.get("pg") is None and os.environ.get("CTR_GATHER", "peer") == "peer":
+            torch.cuda.synchronize()  # (set-up, first warm-up step only)
+            pipe["pg"] = D.PeerGather(comp.words.numel(), [k] * world)
+        pg = pipe.get("pg")
+        with torch.cuda.stream(side):
+            side.wait_event(encoded)
+            pending = (pg.gather_begin(comp.words, comp.offsets) if pg else
+                       D.all_gather_compressed_begin(comp.words, comp.offsets, stream_counts=[k] * world))
+        bc.ans_decode(comp, model, out=out)
+        with torch.cuda.stream(side):
+            gathered["gc"] = pg.gather_end(pending) if pg else D.all_gather_compressed_end(pending)
+            done = torch.cuda.Event()
+            done.record()
+        join()
+        pipe["prev"] = (done, gathered["gc"])
+
+    def join():  # the previous step's gather: wait for it on the main stream and finalise its offset table
+        if pipe["prev"] is not None:
+            done, gc = pipe["prev"]
+            torch.cuda.current_stream().wait_event(done)
+            if pipe.get("pg") is not None:
+                pipe["pg"].finish(gc)
+            pipe["prev"] = None
+
+    def drain():
+        join()
 
     def sync_all():
         torch.cuda.synchronize()
@@ -284,7 +318,12 @@ def run_ours(args):
     sampler = ClockSampler(local_rank)  # started before the warm-up so that the GPU is not idle right before the timed steps
     for _ in range(max(args.warmup, 3)):
         step()
+    drain()
     torch.cuda.synchronize()
+    if world > 1:
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        os.close(saved_stdout)
     bc.check()
     assert torch.equal(out, syms), "decode(encode(x)) != x"
     total_words = comp.total_words()
@@ -303,6 +342,7 @@ def run_ours(args):
     sync_all()
     for _ in range(3):  # the checks above left the GPU idle for a moment
         step()
+    drain()
     sync_all()
     lib.ctr_profile_enable(1)
     lib.ctr_profile_read(0, None, None)
@@ -312,6 +352,8 @@ def run_ours(args):
         ev[0].record()
         for i in range(args.steps):
             step()
+            if i + 1 == args.steps:
+                drain()
             ev[i + 1].record()
         sync_all()
     launches = B.kernel_launch_count() - launches0
@@ -389,6 +431,7 @@ def run_ours(args):
            "ms_per_step": e2e_s * 1e3, "steps": args.e2e_steps,
            "api": "ctr_ans_encode_reverse_host + ctr_ans_decode_host (pinned host buffers)"}
 
+    gather_kind = None if world == 1 else ("copy-engine pushes into peer-mapped containers over NVLink, ordered by stream memory operations (no kernel)" if pipe.get("pg") else "NCCL all-gather")
     if rank == 0:
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
@@ -403,7 +446,9 @@ def run_ours(args):
                        "bits_per_symbol": 32.0 * total_words / n,
                        "l2": "inputs (400 MB symbols) larger than the 126 MB L2; no flush between steps",
                        "step": "ANS encode (kernel with fused compaction) -> ANS decode; N>1: the NCCL all-gather of the "
-                               "containers runs on a side stream, overlapped with the decode, and is joined before the step ends"},
+                               "containers runs on a side stream, overlapped with the decode and the next step's encode "
+                               "(double-buffered containers), every gather joined inside the timed region",
+                       "gather": gather_kind},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
             "clocks": clocks.summary(),
         }

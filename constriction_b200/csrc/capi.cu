@@ -920,6 +920,44 @@ extern "C" int ctr_range_decode(ctr_model_t model, const uint32_t *words_dev, co
 }
 
 // =====================================================================================================
+// stream memory operations (SM-free signalling between the GPUs of a node, see constriction_b200/dist.py)
+// =====================================================================================================
+namespace {
+using StreamValue32Fn = CUresult (*)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+StreamValue32Fn stream_value_fn(const char *name) {
+    void *f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint(name, &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return (StreamValue32Fn)f;
+}
+}  // namespace
+
+extern "C" int ctr_stream_write_value32(void *addr, uint32_t value, void *stream) {
+    static const StreamValue32Fn fn = stream_value_fn("cuStreamWriteValue32");
+    if (!fn || !addr) return CTR_ERR_BAD_ARGUMENT;
+    const CUresult r = fn((CUstream)stream, (CUdeviceptr)(uintptr_t)addr, value, CU_STREAM_WRITE_VALUE_DEFAULT);
+    if (r != CUDA_SUCCESS) {
+        g_last_cuda_error = "cuStreamWriteValue32 failed (" + std::to_string((int)r) + ")";
+        return CTR_ERR_CUDA;
+    }
+    return CTR_OK;
+}
+
+extern "C" int ctr_stream_wait_value32(void *addr, uint32_t value, void *stream) {
+    static const StreamValue32Fn fn = stream_value_fn("cuStreamWaitValue32");
+    if (!fn || !addr) return CTR_ERR_BAD_ARGUMENT;
+    const CUresult r = fn((CUstream)stream, (CUdeviceptr)(uintptr_t)addr, value, CU_STREAM_WAIT_VALUE_GEQ);
+    if (r != CUDA_SUCCESS) {
+        g_last_cuda_error = "cuStreamWaitValue32 failed (" + std::to_string((int)r) + ")";
+        return CTR_ERR_CUDA;
+    }
+    return CTR_OK;
+}
+
+// =====================================================================================================
 // checkpoints
 // =====================================================================================================
 extern "C" uint64_t ctr_checkpoint_max_records(const ctr_layout *L) {

@@ -40,37 +40,61 @@ class GatheredContainer:
     word_base: List[int]       # first global word index of each rank
 
 
-def all_gather_compressed(words: torch.Tensor, offsets: torch.Tensor, group: Optional[dist.ProcessGroup] = None,
-                          stream_counts: Optional[Sequence[int]] = None) -> GatheredContainer:
-    """Concatenates every rank's container (words[:offsets[-1]], offsets) into one global container that
-    every rank holds.  `stream_counts[r]` = number of streams of rank r if the caller knows them (e.g. from
-    `shard_bounds`); otherwise they are exchanged together with the word counts.
-    `words` may be longer than offsets[-1] (capacity-sized buffers are fine; the slack is not sent)."""
+@dataclass
+class PendingGather:
+    """Handle between `all_gather_compressed_begin` and `all_gather_compressed_end`."""
+    words: torch.Tensor
+    offsets: torch.Tensor
+    group: Optional[dist.ProcessGroup]
+    metas: torch.Tensor                 # int64[world * 2] on the device: (total words, streams) of every rank
+    metas_host: Optional[torch.Tensor]  # pinned copy (CUDA) -- valid once `ready` has fired
+    ready: Optional["torch.cuda.Event"]
+    stream_counts: Optional[Sequence[int]]
+
+
+def all_gather_compressed_begin(words: torch.Tensor, offsets: torch.Tensor, group: Optional[dist.ProcessGroup] = None,
+                                stream_counts: Optional[Sequence[int]] = None) -> PendingGather:
+    """First half of the exchange: enqueues the 16-byte size exchange and its copy to pinned host memory on the
+    current stream and returns at once.  The caller can enqueue independent work (the decode of its own shard, the
+    next encode) before it calls `all_gather_compressed_end`, whose only host wait is then for these 16 bytes."""
+    world = dist.get_world_size(group)
+    dev = words.device
+    k_local = offsets.numel() - 1
+    meta = torch.stack([offsets[-1], torch.tensor(k_local, dtype=torch.int64, device=dev)])
+    metas = torch.empty(world * 2, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(metas, meta, group=group)
+    metas_host, ready = None, None
+    if dev.type == "cuda":
+        metas_host = torch.empty(world * 2, dtype=torch.int64).pin_memory()
+        metas_host.copy_(metas, non_blocking=True)
+        ready = torch.cuda.Event()
+        ready.record()
+    return PendingGather(words, offsets, group, metas, metas_host, ready, stream_counts)
+
+
+def all_gather_compressed_end(p: PendingGather) -> GatheredContainer:
+    """Second half: waits (host) for the sizes, then enqueues the all-gather of the words with per-rank sizes --
+    every rank's slice lands at its final place in the dense buffer -- and of the rebased offset tables."""
+    words, offsets, group = p.words, p.offsets, p.group
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
     dev = words.device
     k_local = offsets.numel() - 1
-
-    # 1. word counts (and stream counts if unknown): the one host synchronisation of the exchange
-    if stream_counts is not None:
-        totals = torch.empty(world, dtype=torch.int64, device=dev)
-        dist.all_gather_into_tensor(totals, offsets[-1:], group=group)
-        lens = [int(x) for x in totals.cpu()]
-        ks = [int(x) for x in stream_counts]
+    if p.ready is not None:
+        p.ready.synchronize()
+        metas_host = p.metas_host.view(world, 2)
     else:
-        meta = torch.stack([offsets[-1], torch.tensor(k_local, dtype=torch.int64, device=dev)])
-        metas = torch.empty(world * 2, dtype=torch.int64, device=dev)
-        dist.all_gather_into_tensor(metas, meta, group=group)
-        metas_host = metas.view(world, 2).cpu()
-        lens = [int(x) for x in metas_host[:, 0]]
-        ks = [int(x) for x in metas_host[:, 1]]
-        totals = metas.view(world, 2)[:, 0]
+        metas_host = p.metas.view(world, 2).cpu()
+    lens = [int(x) for x in metas_host[:, 0]]
+    ks = [int(x) for x in metas_host[:, 1]]
+    if p.stream_counts is not None and [int(x) for x in p.stream_counts] != ks:
+        raise ValueError("stream_counts does not match the ranks' containers")
     word_base, stream_base = [0], [0]
     for r in range(world):
         word_base.append(word_base[-1] + lens[r])
         stream_base.append(stream_base[-1] + ks[r])
 
-    # 2. words: every rank's slice lands at its final place in the dense buffer
+    # words: every rank's slice lands at its final place in the dense buffer
     dense = torch.empty(max(word_base[-1], 1), dtype=words.dtype, device=dev)
     views = [dense[word_base[r]:word_base[r + 1]] for r in range(world)]
     if all(n == lens[0] for n in lens):
@@ -87,7 +111,7 @@ def all_gather_compressed(words: torch.Tensor, offsets: torch.Tensor, group: Opt
         for r in range(world):
             views[r].copy_(padded[r * max_len:r * max_len + lens[r]])
 
-    # 3. offsets: gather the (equal-length padded) tables, rebase by each rank's first word, drop the padding
+    # offsets: gather the (equal-length padded) tables, rebase by each rank's first word, drop the padding
     max_k = max(ks)
     if k_local == max_k:
         off_send = offsets
@@ -96,11 +120,159 @@ def all_gather_compressed(words: torch.Tensor, offsets: torch.Tensor, group: Opt
     off_all = torch.empty(world * (max_k + 1), dtype=torch.int64, device=dev)
     dist.all_gather_into_tensor(off_all, off_send.contiguous(), group=group)
     view = off_all.view(world, max_k + 1)
-    for r in range(1, world):  # rebase in place by each rank's first word (host-known after step 1)
-        view[r].add_(word_base[r])
+    base = torch.tensor(word_base[:world], dtype=torch.int64).to(dev, non_blocking=True)
+    view += base[:, None]  # rebase by each rank's first word (one kernel)
     if all(k == max_k for k in ks):
         # the padded table is [world][k + 1]; dropping each rank's last entry except the final one makes it dense
         g_off = torch.cat([view[:, :max_k].reshape(-1), view[world - 1, max_k:]])
     else:
         g_off = torch.cat([view[r, :ks[r]] for r in range(world)] + [view[world - 1, ks[world - 1]:ks[world - 1] + 1]])
     return GatheredContainer(dense, g_off, stream_base[:-1], word_base[:-1])
+
+
+def all_gather_compressed(words: torch.Tensor, offsets: torch.Tensor, group: Optional[dist.ProcessGroup] = None,
+                          stream_counts: Optional[Sequence[int]] = None) -> GatheredContainer:
+    """Concatenates every rank's container (words[:offsets[-1]], offsets) into one global container that
+    every rank holds.  `stream_counts[r]` = number of streams of rank r if the caller knows them (checked).
+    `words` may be longer than offsets[-1] (capacity-sized buffers are fine; the slack is not sent).
+    The one host synchronisation of the exchange is for the 16 bytes of sizes per rank; callers that have other
+    work to enqueue meanwhile use the `_begin` / `_end` pair."""
+    return all_gather_compressed_end(all_gather_compressed_begin(words, offsets, group, stream_counts))
+
+
+class PeerGather:
+    """The same exchange without any SM: every rank *pushes* its words and offsets straight into every peer's
+    dense container with copy-engine transfers over NVLink, ordered by stream memory operations
+    (cuStreamWriteValue32 / cuStreamWaitValue32 on flags in peer memory), so the gather runs concurrently with
+    coder kernels that occupy every SM of the GPU.  (Any kernel-based collective -- an NCCL all-gather, even an
+    8-byte one -- has to wait for a free SM, and the ANS encode kernel holds all registers of all SMs for its
+    whole run: with NCCL the exchange and the coders serialise.)  The receive buffers are symmetric memory
+    (`torch.distributed._symmetric_memory`: every rank's buffer is mapped into every rank's address space).
+
+    Protocol of one gather (sequence number q, all on the caller's side stream, no kernel launches):
+      begin:  my total -> meta[me] of every rank (8-byte copies); flag A[me] := q on every rank;
+              wait until A[r] >= q for all r; meta -> pinned host memory; event
+      end:    (host waits for the event: it needs the sizes to issue copies)  my words -> words[base_me ..] and my
+              offsets -> offsets[K_me ..] of every rank; flag B[me] := q on every rank; wait until B[r] >= q for all r
+      finish: (on the consumer's stream, after the gather's event) offsets of rank r += base_r   (one small kernel)
+
+    One node, one process per GPU.  Receive buffers are allocated and exchanged once (`capacity_words` per rank
+    and buffer); `n_buffers` of them are used round-robin, so that a container gathered in step i stays valid
+    while step i+1 is being gathered."""
+
+    def __init__(self, capacity_words: int, stream_counts: Sequence[int], group: Optional[dist.ProcessGroup] = None,
+                 n_buffers: int = 2, dtype=torch.int32):
+        import torch.distributed._symmetric_memory as symm_mem
+
+        from . import _native as N
+        self._lib = N.load()
+        self.group = group
+        pg = group if group is not None else dist.group.WORLD
+        self.world = world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.ks = [int(x) for x in stream_counts]
+        self.stream_base = [0]
+        for kk in self.ks:
+            self.stream_base.append(self.stream_base[-1] + kk)
+        dev = torch.device("cuda", torch.cuda.current_device())
+        self.dev = dev
+        cap = torch.tensor([int(capacity_words)], dtype=torch.int64, device=dev)
+        dist.all_reduce(cap, op=dist.ReduceOp.MAX, group=group)  # symmetric buffers: same size on every rank
+        self.cap = int(cap.item())
+        self.n_buffers = n_buffers
+        n_words, n_off = world * self.cap, self.stream_base[-1] + 1
+        self.dense, self.g_off, self._handles = [], [], []
+        self.peer_dense = [[None] * n_buffers for _ in range(world)]
+        self.peer_off = [[None] * n_buffers for _ in range(world)]
+        for b in range(n_buffers):
+            d = symm_mem.empty(n_words, dtype=dtype, device=dev)
+            o = symm_mem.empty(n_off, dtype=torch.int64, device=dev)
+            hd, ho = symm_mem.rendezvous(d, pg), symm_mem.rendezvous(o, pg)
+            self._handles += [hd, ho]
+            self.dense.append(d)
+            self.g_off.append(o)
+            for r in range(world):
+                self.peer_dense[r][b] = d if r == self.rank else hd.get_buffer(r, (n_words,), dtype, 0)
+                self.peer_off[r][b] = o if r == self.rank else ho.get_buffer(r, (n_off,), torch.int64, 0)
+        # sizes and flags: meta int64[world]; flags int32[2 * world] (A then B), zero-initialised
+        self.meta = symm_mem.empty(world, dtype=torch.int64, device=dev)
+        self.flags = symm_mem.empty(2 * world, dtype=torch.int32, device=dev)
+        self.meta.zero_()
+        self.flags.zero_()
+        torch.cuda.synchronize()
+        hm, hf = symm_mem.rendezvous(self.meta, pg), symm_mem.rendezvous(self.flags, pg)
+        self._handles += [hm, hf]
+        self.peer_meta = [self.meta if r == self.rank else hm.get_buffer(r, (world,), torch.int64, 0) for r in range(world)]
+        self.flag_ptrs = [int(x) for x in hf.buffer_ptrs]  # flags of rank r, mapped here
+        self.meta_host = torch.empty(world, dtype=torch.int64).pin_memory()
+        counts = torch.tensor(self.ks, dtype=torch.int64)
+        counts[-1] += 1  # the final entry of the table belongs to the last rank
+        self._owner = torch.repeat_interleave(torch.arange(world), counts).to(dev)  # rank that supplies each entry
+        self._seq = 0
+        self._turn = 0
+        dist.barrier(group=group)
+        torch.cuda.synchronize()
+
+    # -- stream memory operations on the current stream ------------------------------------------------
+    def _signal_all(self, slot: int, value: int) -> None:
+        stream = torch.cuda.current_stream().cuda_stream
+        for step in range(self.world):
+            dst = (self.rank + step) % self.world
+            rc = self._lib.ctr_stream_write_value32(self.flag_ptrs[dst] + 4 * (slot * self.world + self.rank), value, stream)
+            if rc:
+                raise RuntimeError("ctr_stream_write_value32 failed: " + self._lib.ctr_last_cuda_error().decode())
+
+    def _wait_all(self, slot: int, value: int) -> None:
+        stream = torch.cuda.current_stream().cuda_stream
+        for r in range(self.world):
+            rc = self._lib.ctr_stream_wait_value32(self.flag_ptrs[self.rank] + 4 * (slot * self.world + r), value, stream)
+            if rc:
+                raise RuntimeError("ctr_stream_wait_value32 failed: " + self._lib.ctr_last_cuda_error().decode())
+
+    def gather_begin(self, words: torch.Tensor, offsets: torch.Tensor) -> PendingGather:
+        self._seq += 1
+        q = self._seq
+        for step in range(self.world):
+            dst = (self.rank + step) % self.world
+            self.peer_meta[dst][self.rank:self.rank + 1].copy_(offsets[-1:], non_blocking=True)
+        self._signal_all(0, q)
+        self._wait_all(0, q)
+        self.meta_host.copy_(self.meta, non_blocking=True)
+        ready = torch.cuda.Event()
+        ready.record()
+        return PendingGather(words, offsets, self.group, self.meta, self.meta_host, ready, self.ks)
+
+    def gather_end(self, p: PendingGather) -> GatheredContainer:
+        world, rank = self.world, self.rank
+        p.ready.synchronize()
+        lens = [int(x) for x in p.metas_host]
+        if max(lens) > self.cap:
+            raise MemoryError("PeerGather: a rank's container exceeds the receive capacity")
+        word_base = [0]
+        for n in lens:
+            word_base.append(word_base[-1] + n)
+        b = self._turn
+        self._turn = (self._turn + 1) % self.n_buffers
+        wb, n = word_base[rank], lens[rank]
+        sb, k = self.stream_base[rank], self.ks[rank]
+        n_off = k + 1 if rank == world - 1 else k  # the last rank also supplies the final entry
+        for step in range(world):  # start with myself, then my right neighbour, ...: spreads the load over the links
+            dst = (rank + step) % world
+            self.peer_dense[dst][b][wb:wb + n].copy_(p.words[:n], non_blocking=True)
+            self.peer_off[dst][b][sb:sb + n_off].copy_(p.offsets[:n_off], non_blocking=True)
+        self._signal_all(1, self._seq)
+        self._wait_all(1, self._seq)
+        total = word_base[-1]
+        gc = GatheredContainer(self.dense[b][:max(total, 1)], self.g_off[b], self.stream_base[:-1], word_base[:-1])
+        gc._rebase = torch.tensor(word_base[:world], dtype=torch.int64)
+        return gc
+
+    def finish(self, gc: GatheredContainer) -> GatheredContainer:
+        """Rebases the gathered offset table (rank r's entries += first word of rank r) on the current stream; call
+        it once, after waiting for the event recorded behind `gather_end`.  Until then `gc.offsets` holds the
+        ranks' local offsets."""
+        base = getattr(gc, "_rebase", None)
+        if base is not None:
+            gc.offsets += base.pin_memory().to(gc.offsets.device, non_blocking=True)[self._owner]
+            gc._rebase = None
+        return gc

@@ -262,6 +262,13 @@ int ctr_range_decode_host(ctr_model_t model, const uint32_t *words_host, const u
                           const uint32_t *model_index_host, int32_t model_index_mode, int32_t *symbols_out_host,
                           int *data_status, uint64_t *failing_stream);
 
+/* ---- stream-ordered signalling without any SM (multi-GPU exchange, constriction_b200/dist.py) ----
+ * cuStreamWriteValue32 / cuStreamWaitValue32 (>=) on `stream`: `addr` is a 4-byte aligned device address, which may
+ * be a peer GPU's memory mapped into this process (symmetric memory).  Used to order copy-engine pushes between
+ * the GPUs of a node while coder kernels occupy every SM (an NCCL barrier kernel would have to wait for them). */
+int ctr_stream_write_value32(void *addr, uint32_t value, void *stream);
+int ctr_stream_wait_value32(void *addr, uint32_t value, void *stream);
+
 /* ---- launch accounting and kernel timing (bench.py's `gpu_launches` and `roofline`) ----------
  * With profiling enabled the library brackets every main coder kernel (not the compaction helpers)
  * with CUDA events on the launching stream.  ctr_profile_read synchronises those events and returns

@@ -39,4 +39,16 @@ timeit("words all_gather (uneven list)", lambda: dist.all_gather(views, words[:l
 off_all = torch.empty(world * (k + 1), dtype=torch.int64, device="cuda")
 timeit("offsets all_gather_into_tensor (1.2 MB)", lambda: dist.all_gather_into_tensor(off_all, offsets))
 timeit("full all_gather_compressed", lambda: D.all_gather_compressed(words, offsets, stream_counts=[k] * world))
+pg = D.PeerGather(words.numel(), [k] * world)
+peer = (rank + 1) % world
+n = lens[rank]
+timeit("raw push: peer_dense[peer][0][:n].copy_(words[:n])", lambda: pg.peer_dense[peer][0][:n].copy_(words[:n], non_blocking=True))
+timeit("raw self copy: dense[0][:n].copy_(words[:n])", lambda: pg.dense[0][:n].copy_(words[:n], non_blocking=True))
+timeit("PeerGather begin+end+finish", lambda: pg.finish(pg.gather_end(pg.gather_begin(words, offsets))))
+gc = pg.finish(pg.gather_end(pg.gather_begin(words, offsets)))
+ref = D.all_gather_compressed(words, offsets, stream_counts=[k] * world)
+torch.cuda.synchronize()
+assert torch.equal(gc.offsets, ref.offsets) and torch.equal(gc.words[:ref.words.numel()], ref.words), "PeerGather != NCCL gather"
+if rank == 0:
+    print("PeerGather result equals the NCCL all-gather", flush=True)
 dist.destroy_process_group()
