@@ -386,8 +386,7 @@ __global__ void __launch_bounds__(BLOCK, BLOCK >= 256 ? CTR_ENC_MIN_CTAS : 8) an
         m = ok ? m : 0u;
         return __ldg(p.model.enc + (uint64_t)m * (alphabet + 1) + idx);
     };
-    auto encode_entry = [&](const uint4 &e) {
-        min_prob = min(min_prob, e.y);
+    auto encode_entry_nomin = [&](const uint4 &e) {
         uint32_t lo = (uint32_t)state, hi = (uint32_t)(state >> 32);
         if (shr_clamp(hi, push_shift) >= e.y) {  // stack.rs:1035-1040
             sts_u32(ring | (pushed & (kEncRingBytes - 1u)), lo);
@@ -397,6 +396,17 @@ __global__ void __launch_bounds__(BLOCK, BLOCK >= 256 ? CTR_ENC_MIN_CTAS : 8) an
         }
         const uint64_t n = ((uint64_t)hi << 32) | lo;
         state = ans_encode_recombine(n, ans_quotient_estimate<F64DIV>(n, e.z, e.w), e.x, e.y);
+    };
+    auto encode_entry = [&](const uint4 &e) {
+        min_prob = min(min_prob, e.y);
+        encode_entry_nomin(e);
+    };
+    // two symbols, one three-input minimum for the impossible-symbol check
+    auto encode_pair = [&](uint32_t idx0, uint32_t idx1, uint32_t m) {
+        const uint4 e0 = lookup(idx0, m), e1 = lookup(idx1, m);
+        encode_entry_nomin(e0);
+        encode_entry_nomin(e1);
+        min_prob = __vimin3_u32(min_prob, e0.y, e1.y);
     };
     auto encode_idx = [&](uint32_t idx, uint32_t m) { encode_entry(lookup(idx, m)); };
     auto encode_one = [&](int32_t sym, uint32_t m) { encode_idx(index_of(sym), m); };
@@ -501,11 +511,9 @@ __global__ void __launch_bounds__(BLOCK, BLOCK >= 256 ? CTR_ENC_MIN_CTAS : 8) an
                         idx[u] = index_of((int32_t)lds_u32(box + (uint32_t)(half * kCheckEvery + (kCheckEvery - 1 - u)) * 128u));
                     const bool full = in_ring() >= 16u;
                     const uint4 oldest = drain_load();
-                    encode_idx(idx[0], stream_model);
-                    encode_idx(idx[1], stream_model);
+                    encode_pair(idx[0], idx[1], stream_model);
                     drain_decided(full, oldest);
-                    encode_idx(idx[2], stream_model);
-                    encode_idx(idx[3], stream_model);
+                    encode_pair(idx[2], idx[3], stream_model);
                 }
                 __syncwarp();  // every lane has read the box: its slot is requested again
                 request_box(slot);

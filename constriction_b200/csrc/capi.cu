@@ -596,7 +596,7 @@ bool tma_decode_enabled() {
     }();
     return on;
 }
-bool make_symbol_tensor_map(CUtensorMap *out, const void *symbols, const ctr_layout *L) {
+bool make_symbol_tensor_map(CUtensorMap *out, const void *symbols, const ctr_layout *L, uint32_t box_streams = 32) {
     const uint64_t K = L->n_streams;
     if (K == 0 || K % 4 != 0 || K > 0xffffffffull) return false;
     const uint64_t full_rows = L->n_symbols / K;
@@ -606,7 +606,7 @@ bool make_symbol_tensor_map(CUtensorMap *out, const void *symbols, const ctr_lay
     if (!fn) return false;
     const cuuint64_t dims[2] = {K, full_rows};
     const cuuint64_t strides[1] = {K * 4};  // bytes between rows
-    const cuuint32_t box[2] = {32, (cuuint32_t)kBoxRows};
+    const cuuint32_t box[2] = {box_streams, (cuuint32_t)kBoxRows};
     const cuuint32_t elem_strides[2] = {1, 1};
     return fn(out, CU_TENSOR_MAP_DATA_TYPE_INT32, 2, const_cast<void *>(symbols), dims, strides, box, elem_strides,
               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,

@@ -144,10 +144,50 @@ class Uniform(Model):
         return self._table
 
 
+class Bernoulli(Model):
+    """pybindings/stream/model.rs:985-1060 with perfect=False: a two-symbol categorical model over [1 - p, p]
+    quantised by `fast_quantized_cdf` in f64 (categorical.rs:16-54); `p` fixed, or one `p` per symbol."""
+
+    def __init__(self, p=None, perfect=None):
+        if perfect is None or perfect:
+            raise NotImplementedError(
+                "Bernoulli(perfect=True) is outside the accelerated path (SURVEY.md 8f rank 4); use perfect=False")
+        self._p = None if p is None else float(p)
+        self._nparams = 1 if p is None else 0
+        if self._p is not None:
+            self._table = self._make(np.array([[1.0 - self._p, self._p]], dtype=np.float64))
+
+    @staticmethod
+    def _make(pmf):
+        try:
+            return B.ModelTable.categorical(pmf)
+        except ValueError:
+            raise ValueError("`p` must be >= 0.0 and <= 1.0.") from None
+
+    def _concrete_table(self):
+        if self._p is None:
+            raise ValueError("No model parameters specified.")
+        return self._table
+
+    def _params(self, params):
+        if self._p is not None:
+            raise ValueError("Model parameters were specified but the model is already fully parameterized.")
+        if len(params) != 1:
+            raise ValueError(f"Wrong number of model parameters: expected 1, got {len(params)}.")
+        return _float_param(params[0])
+
+    def _family_len(self, params):
+        return self._params(params).size
+
+    def _family_table(self, params):
+        p = self._params(params)
+        return self._make(np.ascontiguousarray(np.stack([1.0 - p, p], axis=1)))
+
+
 def _unsupported(name):
     def ctor(*_a, **_k):
         raise NotImplementedError(f"{name} is outside the accelerated path (SURVEY.md 8f); "
-                                  "QuantizedGaussian, Categorical(perfect=False) and Uniform are provided")
+                                  "QuantizedGaussian, Categorical(perfect=False), Bernoulli(perfect=False) and Uniform are provided")
     ctor.__name__ = name
     return ctor
 
@@ -155,6 +195,5 @@ def _unsupported(name):
 QuantizedLaplace = _unsupported("QuantizedLaplace")
 QuantizedCauchy = _unsupported("QuantizedCauchy")
 Binomial = _unsupported("Binomial")
-Bernoulli = _unsupported("Bernoulli")
 CustomModel = _unsupported("CustomModel")
 ScipyModel = _unsupported("ScipyModel")

@@ -169,3 +169,29 @@ def test_learned_compression_shape(env):
         out = dec(comp, lazy)
         bc.check()
         assert torch.equal(out, syms)
+
+
+def test_bernoulli_mirror(env):
+    """Bernoulli(perfect=False) = two-symbol categorical [1 - p, p] (pybindings/stream/model.rs:985-1060)."""
+    import constriction_b200.stream as S
+    O = env["O"]
+    rng = np.random.default_rng(12)
+    n = 4000
+    ps = rng.uniform(0.0, 1.0, size=n)
+    ps[:3] = [0.0, 1.0, 0.5]
+    bits = (rng.uniform(size=n) < ps).astype(np.int32)
+    a = S.stack.AnsCoder()
+    a.encode_reverse(bits, S.model.Bernoulli(perfect=False), ps)
+    oa = O.AnsCoder()
+    oa.encode_reverse(bits, O.Categorical(perfect=False), np.stack([1.0 - ps, ps], axis=1))
+    assert np.array_equal(a.get_compressed(), oa.get_compressed())
+    assert np.array_equal(a.decode(S.model.Bernoulli(perfect=False), ps), bits)
+    m = S.model.Bernoulli(0.2, perfect=False)
+    r = S.queue.RangeEncoder()
+    r.encode(bits, m)
+    orr = O.RangeEncoder()
+    orr.encode(bits, O.Categorical(np.array([0.8, 0.2]), perfect=False))
+    assert np.array_equal(r.get_compressed(), orr.get_compressed())
+    assert np.array_equal(S.queue.RangeDecoder(r.get_compressed()).decode(m, n), bits)
+    with pytest.raises(ValueError):
+        S.model.Bernoulli(1.5, perfect=False)

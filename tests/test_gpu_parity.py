@@ -90,7 +90,10 @@ def test_uniform_and_cdf_tables(env):
 SHAPES = [(0, 1), (1, 1), (5, 1), (100_000, 1), (1000, 32), (1000, 33), (31, 64), (100_003, 4096), (50_000, 777),
           (200_000, 128 * 3 + 5),
           # CTA sizes: < 37,888 streams -> 64-thread CTAs; up to 151,552 -> 256; beyond -> 1024-thread decoders
-          (400_000, 40_001), (1_000_000, 151_552 + 7)]
+          (400_000, 40_001), (1_000_000, 151_552 + 7),
+          # TMA symbol boxes (K a multiple of 4): last warp partly outside the tensor, rows above the highest box,
+          # exactly one box, one row short of a box (per-row path)
+          (300_000, 100), (2_000_003, 148 * 256 + 4), (9 * 64, 64), (8 * 64 + 5, 64)]
 
 
 @pytest.mark.parametrize("coder", ["ans", "range"])
@@ -115,6 +118,25 @@ def test_interleaved_iid_matches_oracle(env, coder, n, k):
     bc.check()
     assert np.array_equal(out.cpu().numpy(), syms)
     assert np.array_equal(dec_o(want_words, want_off, n, k, cdf, -50, threads=8), syms)
+
+
+def test_interleaved_unaligned_symbol_buffer(env):
+    """A symbol array that does not start on a 16-byte boundary cannot be a TMA tensor: per-row path, same words."""
+    B, bc, torch = env["B"], env["bc"], env["torch"]
+    rng = np.random.default_rng(77)
+    n, k = 200_000, 256
+    syms = gauss_symbols(rng, n + 1)
+    model = B.ModelTable.quantized_gaussian(*BASE[:2], [BASE[2]], [BASE[3]])
+    whole = dev(env, syms)
+    aligned = whole[1:].clone()
+    a = bc.ans_encode(aligned, model, n_streams=k)
+    b = bc.ans_encode(whole[1:], model, n_streams=k)  # data pointer = base + 4 bytes
+    bc.check()
+    assert whole[1:].data_ptr() % 16 != 0 and aligned.data_ptr() % 16 == 0
+    assert np.array_equal(a.to_host()[0], b.to_host()[0]) and np.array_equal(a.to_host()[1], b.to_host()[1])
+    out = torch.empty(n + 1, dtype=torch.int32, device="cuda")
+    bc.ans_decode(a, model, out=out[1:])
+    assert torch.equal(out[1:], whole[1:])
 
 
 # ---------------------------------------------------------------------------------------------------
