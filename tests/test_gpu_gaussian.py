@@ -193,5 +193,8 @@ def test_bernoulli_mirror(env):
     orr.encode(bits, O.Categorical(np.array([0.8, 0.2]), perfect=False))
     assert np.array_equal(r.get_compressed(), orr.get_compressed())
     assert np.array_equal(S.queue.RangeDecoder(r.get_compressed()).decode(m, n), bits)
+    # like the reference's fast quantiser, p outside [0, 1] is only rejected when it breaks the normalisation
+    # (categorical.rs:38-41); [-0.5, 1.5] sums to one and quantises to a valid model
+    S.model.Bernoulli(1.5, perfect=False)
     with pytest.raises(ValueError):
-        S.model.Bernoulli(1.5, perfect=False)
+        S.model.Bernoulli(float("nan"), perfect=False)
