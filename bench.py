@@ -284,7 +284,17 @@ def run_ours(args):
         encoded.record()
         if pipe.get("pg") is None and os.environ.get("CTR_GATHER", "peer") == "peer":
             torch.cuda.synchronize()  # (set-up, first warm-up step only)
-            pipe["pg"] = D.PeerGather(comp.words.numel(), [k] * world)
+            try:
+                pipe["pg"] = D.PeerGather(comp.words.numel(), [k] * world)
+                ok = 1
+            except Exception as exc:  # no symmetric memory / stream memory operations here: NCCL all-gather instead
+                sys.stderr.write(f"rank {rank}: PeerGather unavailable ({exc}); using the NCCL all-gather\n")
+                ok = 0
+            flag = torch.tensor([ok], device="cuda")
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)  # all ranks take the same path
+            if int(flag.item()) == 0:
+                pipe["pg"] = None
+                os.environ["CTR_GATHER"] = "nccl"
         pg = pipe.get("pg")
         with torch.cuda.stream(side):
             side.wait_event(encoded)

@@ -210,11 +210,20 @@ def config5(images=64):
     for s in (0, 191, k - 1):
         want = O.ans_encode_iid(syms[s * HW:(s + 1) * HW].cpu().numpy(), cdfs[s % C_], -64)
         ok &= bool(np.array_equal(comp.stream_words(s), want))
+    # checkpoints every 128 symbols: the same words, 8 lanes per (image, channel) stream in the decoder
+    ck = bc.ans_encode(syms, model, sym_offsets=off, model_index=sidx, index_mode=2, checkpoint_every=128)
+    ok &= bool(torch.equal(ck.words[:ck.total_words()], comp.words[:comp.total_words()]))
+    out.zero_()
+    ms_dec_ck = timed(lambda: bc.ans_decode(ck, model, model_index=sidx, index_mode=2, out=out))
+    bc.check()
+    ok &= bool(torch.equal(out, syms))
     return {"config": 5, "workload": f"latents int32[{images},192,32,32], 192 per-channel QuantizedGaussian(-64,64), "
                                      f"{k} ANS streams x {HW} symbols",
             "us_encode": ms_enc * 1e3, "us_decode": ms_dec * 1e3,
-            "Msymbols_per_s_round_trip": n / (ms_enc + ms_dec) / 1e3, "parity": ok,
-            "bits_per_symbol": 32.0 * comp.total_words() / n}
+            "Msymbols_per_s_round_trip": n / (ms_enc + ms_dec) / 1e3,
+            "checkpoints_every_128": {"us_decode": ms_dec_ck * 1e3, "Msymbols_per_s_decode": n / ms_dec_ck / 1e3,
+                                      "extra_bytes_per_symbol": 16.0 / 128},
+            "parity": ok, "bits_per_symbol": 32.0 * comp.total_words() / n}
 
 
 def config6(images=64, coder="ans"):

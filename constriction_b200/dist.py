@@ -210,6 +210,11 @@ class PeerGather:
         self._owner = torch.repeat_interleave(torch.arange(world), counts).to(dev)  # rank that supplies each entry
         self._seq = 0
         self._turn = 0
+        # self-test of the stream memory operations on peer memory (value 0: leaves the protocol untouched); raises
+        # here, where callers can still fall back to the NCCL path, rather than in the first gather
+        self._signal_all(0, 0)
+        self._wait_all(0, 0)
+        torch.cuda.synchronize()
         dist.barrier(group=group)
         torch.cuda.synchronize()
 
