@@ -86,6 +86,9 @@ SIGNATURES = {
     "ctr_range_decode_host": (C.c_int, [vp, vp, vp, C.c_uint64, C.c_uint64, vp, vp, C.c_int32, vp, C.POINTER(C.c_int), u64p]),
     "ctr_stream_write_value32": (C.c_int, [vp, C.c_uint32, vp]),
     "ctr_stream_wait_value32": (C.c_int, [vp, C.c_uint32, vp]),
+    "ctr_stream_write_value32_many": (C.c_int, [vp, C.c_uint32, C.c_uint32, C.c_uint32, vp]),
+    "ctr_stream_wait_value32_many": (C.c_int, [vp, C.c_uint32, C.c_uint32, vp]),
+    "ctr_peer_push": (C.c_int, [vp, C.c_uint32, C.c_uint32, C.c_uint64, vp, C.c_uint64, vp]),
     "ctr_kernel_launch_count": (C.c_uint64, []),
     "ctr_profile_enable": (None, [C.c_int]),
     "ctr_profile_read": (C.c_int, [C.c_int, C.POINTER(C.c_double), u64p]),

@@ -957,6 +957,34 @@ extern "C" int ctr_stream_wait_value32(void *addr, uint32_t value, void *stream)
     return CTR_OK;
 }
 
+// One call for a whole phase of the exchange (the Python side would otherwise spend more time issuing the
+// copies and flags one by one than the GPUs spend executing them).
+extern "C" int ctr_peer_push(void *const *dst_bases, uint32_t n_dst, uint32_t first, uint64_t dst_offset_bytes,
+                             const void *src, uint64_t bytes, void *stream) {
+    if (!dst_bases || n_dst == 0 || (!src && bytes)) return CTR_ERR_BAD_ARGUMENT;
+    for (uint32_t i = 0; i < n_dst && bytes; ++i) {
+        char *dst = static_cast<char *>(dst_bases[(first + i) % n_dst]) + dst_offset_bytes;
+        CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    }
+    return CTR_OK;
+}
+
+extern "C" int ctr_stream_write_value32_many(void *const *addrs, uint32_t n, uint32_t first, uint32_t value, void *stream) {
+    for (uint32_t i = 0; i < n; ++i) {
+        const int rc = ctr_stream_write_value32(addrs[(first + i) % n], value, stream);
+        if (rc) return rc;
+    }
+    return CTR_OK;
+}
+
+extern "C" int ctr_stream_wait_value32_many(void *const *addrs, uint32_t n, uint32_t value, void *stream) {
+    for (uint32_t i = 0; i < n; ++i) {
+        const int rc = ctr_stream_wait_value32(addrs[i], value, stream);
+        if (rc) return rc;
+    }
+    return CTR_OK;
+}
+
 // =====================================================================================================
 // checkpoints
 // =====================================================================================================

@@ -10,6 +10,7 @@ tables are all-gathered and rebased with one fused tensor expression.  `torch.di
 """
 from __future__ import annotations
 
+import ctypes
 from dataclasses import dataclass
 from typing import List, Optional, Sequence, Tuple
 
@@ -182,6 +183,7 @@ class PeerGather:
         self.n_buffers = n_buffers
         n_words, n_off = world * self.cap, self.stream_base[-1] + 1
         self.dense, self.g_off, self._handles = [], [], []
+        self._dense_ptrs, self._off_ptrs = [], []
         self.peer_dense = [[None] * n_buffers for _ in range(world)]
         self.peer_off = [[None] * n_buffers for _ in range(world)]
         for b in range(n_buffers):
@@ -194,6 +196,8 @@ class PeerGather:
             for r in range(world):
                 self.peer_dense[r][b] = d if r == self.rank else hd.get_buffer(r, (n_words,), dtype, 0)
                 self.peer_off[r][b] = o if r == self.rank else ho.get_buffer(r, (n_off,), torch.int64, 0)
+            self._dense_ptrs.append((ctypes.c_void_p * world)(*[int(x) for x in hd.buffer_ptrs]))
+            self._off_ptrs.append((ctypes.c_void_p * world)(*[int(x) for x in ho.buffer_ptrs]))
         # sizes and flags: meta int64[world]; flags int32[2 * world] (A then B), zero-initialised
         self.meta = symm_mem.empty(world, dtype=torch.int64, device=dev)
         self.flags = symm_mem.empty(2 * world, dtype=torch.int32, device=dev)
@@ -204,6 +208,12 @@ class PeerGather:
         self._handles += [hm, hf]
         self.peer_meta = [self.meta if r == self.rank else hm.get_buffer(r, (world,), torch.int64, 0) for r in range(world)]
         self.flag_ptrs = [int(x) for x in hf.buffer_ptrs]  # flags of rank r, mapped here
+        self._meta_ptrs = (ctypes.c_void_p * world)(*[int(x) for x in hm.buffer_ptrs])
+        # flag (slot, me) in every rank's array; flags (slot, r) in mine
+        self._signal_ptrs = [(ctypes.c_void_p * world)(*[self.flag_ptrs[d] + 4 * (slot * world + self.rank) for d in range(world)])
+                             for slot in range(2)]
+        self._wait_ptrs = [(ctypes.c_void_p * world)(*[self.flag_ptrs[self.rank] + 4 * (slot * world + r) for r in range(world)])
+                           for slot in range(2)]
         self.meta_host = torch.empty(world, dtype=torch.int64).pin_memory()
         counts = torch.tensor(self.ks, dtype=torch.int64)
         counts[-1] += 1  # the final entry of the table belongs to the last rank
@@ -219,27 +229,23 @@ class PeerGather:
         torch.cuda.synchronize()
 
     # -- stream memory operations on the current stream ------------------------------------------------
+    def _check(self, rc: int) -> None:
+        if rc:
+            raise RuntimeError("PeerGather: " + self._lib.ctr_status_string(rc).decode() + " " + self._lib.ctr_last_cuda_error().decode())
+
     def _signal_all(self, slot: int, value: int) -> None:
-        stream = torch.cuda.current_stream().cuda_stream
-        for step in range(self.world):
-            dst = (self.rank + step) % self.world
-            rc = self._lib.ctr_stream_write_value32(self.flag_ptrs[dst] + 4 * (slot * self.world + self.rank), value, stream)
-            if rc:
-                raise RuntimeError("ctr_stream_write_value32 failed: " + self._lib.ctr_last_cuda_error().decode())
+        self._check(self._lib.ctr_stream_write_value32_many(self._signal_ptrs[slot], self.world, (self.rank + 1) % self.world, value,
+                                                           torch.cuda.current_stream().cuda_stream))
 
     def _wait_all(self, slot: int, value: int) -> None:
-        stream = torch.cuda.current_stream().cuda_stream
-        for r in range(self.world):
-            rc = self._lib.ctr_stream_wait_value32(self.flag_ptrs[self.rank] + 4 * (slot * self.world + r), value, stream)
-            if rc:
-                raise RuntimeError("ctr_stream_wait_value32 failed: " + self._lib.ctr_last_cuda_error().decode())
+        self._check(self._lib.ctr_stream_wait_value32_many(self._wait_ptrs[slot], self.world, value,
+                                                          torch.cuda.current_stream().cuda_stream))
 
     def gather_begin(self, words: torch.Tensor, offsets: torch.Tensor) -> PendingGather:
         self._seq += 1
         q = self._seq
-        for step in range(self.world):
-            dst = (self.rank + step) % self.world
-            self.peer_meta[dst][self.rank:self.rank + 1].copy_(offsets[-1:], non_blocking=True)
+        self._check(self._lib.ctr_peer_push(self._meta_ptrs, self.world, (self.rank + 1) % self.world, 8 * self.rank,
+                                            offsets[-1:].data_ptr(), 8, torch.cuda.current_stream().cuda_stream))
         self._signal_all(0, q)
         self._wait_all(0, q)
         self.meta_host.copy_(self.meta, non_blocking=True)
@@ -261,10 +267,10 @@ class PeerGather:
         wb, n = word_base[rank], lens[rank]
         sb, k = self.stream_base[rank], self.ks[rank]
         n_off = k + 1 if rank == world - 1 else k  # the last rank also supplies the final entry
-        for step in range(world):  # start with myself, then my right neighbour, ...: spreads the load over the links
-            dst = (rank + step) % world
-            self.peer_dense[dst][b][wb:wb + n].copy_(p.words[:n], non_blocking=True)
-            self.peer_off[dst][b][sb:sb + n_off].copy_(p.offsets[:n_off], non_blocking=True)
+        stream = torch.cuda.current_stream().cuda_stream
+        first = (rank + 1) % world  # start with my right neighbour: in every round the destinations form a permutation
+        self._check(self._lib.ctr_peer_push(self._dense_ptrs[b], world, first, 4 * wb, p.words.data_ptr(), 4 * n, stream))
+        self._check(self._lib.ctr_peer_push(self._off_ptrs[b], world, first, 8 * sb, p.offsets.data_ptr(), 8 * n_off, stream))
         self._signal_all(1, self._seq)
         self._wait_all(1, self._seq)
         total = word_base[-1]

@@ -268,6 +268,12 @@ int ctr_range_decode_host(ctr_model_t model, const uint32_t *words_host, const u
  * the GPUs of a node while coder kernels occupy every SM (an NCCL barrier kernel would have to wait for them). */
 int ctr_stream_write_value32(void *addr, uint32_t value, void *stream);
 int ctr_stream_wait_value32(void *addr, uint32_t value, void *stream);
+/* the same for a list of addresses (written in the order first, first+1, ... mod n), and a copy-engine push of one
+ * device buffer to the same offset of n_dst (peer-mapped) destination buffers, starting with destination `first` */
+int ctr_stream_write_value32_many(void *const *addrs, uint32_t n, uint32_t first, uint32_t value, void *stream);
+int ctr_stream_wait_value32_many(void *const *addrs, uint32_t n, uint32_t value, void *stream);
+int ctr_peer_push(void *const *dst_bases, uint32_t n_dst, uint32_t first, uint64_t dst_offset_bytes, const void *src,
+                  uint64_t bytes, void *stream);
 
 /* ---- launch accounting and kernel timing (bench.py's `gpu_launches` and `roofline`) ----------
  * With profiling enabled the library brackets every main coder kernel (not the compaction helpers)
