@@ -486,12 +486,10 @@ __global__ void __launch_bounds__(BLOCK, BLOCK >= 256 ? CTR_ENC_MIN_CTAS : 8) an
             auto request_box = [&](uint32_t slot) {
                 if (next != 0u) {
                     next -= 1u;
-#ifndef CTR_DBG_NO_LOAD
                     if (lane == 0) {
                         mbar_expect_tx_addr(bars + 8u * slot, kBoxBytes);
                         tma_load_box(boxes + slot * kBoxBytes, &p.tmap, x0, (int32_t)(next * kBoxRows), bars + 8u * slot);
                     }
-#endif
                 }
             };
 #pragma unroll
@@ -499,9 +497,7 @@ __global__ void __launch_bounds__(BLOCK, BLOCK >= 256 ? CTR_ENC_MIN_CTAS : 8) an
             uint32_t slot = 0, parity = 0;
             const uint32_t my_col = boxes + (uint32_t)lane * 4u;
             for (; nbox > 0; --nbox) {
-#ifndef CTR_DBG_NO_LOAD
                 mbar_wait_addr(bars + 8u * slot, parity);
-#endif
                 const uint32_t box = my_col + slot * kBoxBytes;
 #pragma unroll
                 for (int half = kBoxRows / kCheckEvery - 1; half >= 0; --half) {  // batches of rows, top down
@@ -556,13 +552,7 @@ __global__ void __launch_bounds__(BLOCK, BLOCK >= 256 ? CTR_ENC_MIN_CTAS : 8) an
 #define CTR_PF_BATCHES 6
 #endif
             constexpr int kPrefetchBatches = CTR_PF_BATCHES;
-#ifdef CTR_PF_FULL
-            // lanes 8j..8j+7 address row j of the future batch, two lanes per 32-byte sector of the warp's line
-            const char *pf = ps - (uint32_t)lane * 4u + (((uint32_t)lane >> 1) & 3u) * 32u -
-                             ((uint64_t)kPrefetchBatches * kCheckEvery + (uint32_t)(lane >> 3)) * row_bytes;
-#else
             const char *pf = ps - ((uint64_t)kPrefetchBatches * kCheckEvery + (uint32_t)(lane >> 3)) * row_bytes;
-#endif
             const char *const pf_floor = reinterpret_cast<const char *>(p.symbols_in);
             const uint64_t batch_bytes = row_bytes * kCheckEvery;
             static_assert(kCheckEvery == 4, "code_batch is written for batches of four");

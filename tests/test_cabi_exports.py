@@ -56,3 +56,44 @@ def test_product_never_imports_the_oracle():
                 assert not pattern.search(text), (dirpath, f)
     header = open(os.path.join(ROOT, "include", "constriction_b200.h")).read()
     assert not pattern.search(header)
+
+
+def test_call_level_argument_checks():
+    """Call-level errors of the newer entry points are reported before any device work (so they can be checked
+    here): checkpoints need the contiguous layout and a multiple of 32; the table-free Gaussian entry points take
+    no model index, a non-empty support and fewer than 2^32 symbols."""
+    from constriction_b200 import _native as N
+    lib = N.load()
+    one = C.c_void_p(16)  # a non-null dummy pointer; none of these calls may dereference it
+
+    def layout(**kw):
+        L = N.Layout()
+        L.n_streams, L.n_symbols = 4, 4096
+        for k, v in kw.items():
+            setattr(L, k, v)
+        return L
+
+    enc_args = (None, one, 1 << 20, one, 1 << 20, one, None, None, None)
+    # checkpoints: interleaved layout / C not a multiple of 32 / missing record arrays
+    for L in (layout(flags=N.FLAG_CHECKPOINTS, checkpoint_every=64, ckpt_offsets_dev=16, checkpoints_dev=16),
+              layout(flags=N.FLAG_CHECKPOINTS, sym_offsets_dev=16, checkpoint_every=48, ckpt_offsets_dev=16, checkpoints_dev=16),
+              layout(flags=N.FLAG_CHECKPOINTS, sym_offsets_dev=16, checkpoint_every=64)):
+        assert lib.ctr_ans_encode_reverse(one, one, C.byref(L), *enc_args) == N.ERR_BAD_ARGUMENT
+        assert lib.ctr_range_decode(one, one, one, C.byref(L), None, one, None, None, None, None) == N.ERR_BAD_ARGUMENT
+    assert lib.ctr_checkpoint_offsets(C.byref(layout(checkpoint_every=64)), one, None) == N.ERR_BAD_ARGUMENT  # no sym_offsets
+    assert lib.ctr_checkpoint_offsets(C.byref(layout(sym_offsets_dev=16, checkpoint_every=33)), one, None) == N.ERR_BAD_ARGUMENT
+    assert lib.ctr_checkpoint_max_records(C.byref(layout(checkpoint_every=64))) == 4096 // 64 + 4
+    assert lib.ctr_checkpoint_max_records(C.byref(layout())) == 0
+    # table-free Gaussian entry points
+    g_enc = (one, one, one)
+    L = layout(model_index_dev=16, model_index_mode=N.INDEX_PER_SYMBOL)
+    assert lib.ctr_ans_encode_reverse_gaussian(-5, 5, *g_enc, C.byref(L), *enc_args) == N.ERR_BAD_ARGUMENT
+    L = layout()
+    assert lib.ctr_ans_encode_reverse_gaussian(5, 5, *g_enc, C.byref(L), *enc_args) == N.ERR_BAD_MODEL
+    assert lib.ctr_range_decode_gaussian(7, -7, one, one, one, one, C.byref(L), None, one, None, None, None, None) == N.ERR_BAD_MODEL
+    assert lib.ctr_ans_decode_gaussian(-5, 5, None, one, one, one, C.byref(L), None, one, None, None, None, None) == N.ERR_BAD_ARGUMENT
+    big = layout(n_symbols=1 << 32)
+    assert lib.ctr_range_encode_gaussian(-5, 5, *g_enc, C.byref(big), *enc_args) == N.ERR_BAD_ARGUMENT
+    # stream memory operations: null address
+    assert lib.ctr_stream_write_value32(None, 1, None) == N.ERR_BAD_ARGUMENT
+    assert lib.ctr_peer_push(None, 0, 0, 0, None, 0, None) == N.ERR_BAD_ARGUMENT
