@@ -544,7 +544,7 @@ struct AnsDecodeLauncher {
     static cudaError_t run(const LaunchCfg &cfg, const AnsParams &p) { return launch_ans_decode(cfg, p); }
 };
 struct RangeEncodeLauncher {
-    static constexpr bool kTma = false;  // (the range kernels still use their per-row paths)
+    static constexpr bool kTma = true;
     static constexpr int kSlot = 2;
     static constexpr const char *kName = "range_encode_kernel";
     static cudaError_t run(const LaunchCfg &cfg, const AnsParams &p) { return launch_range_encode(cfg, p); }

@@ -26,9 +26,10 @@
 namespace ctr {
 
 template <int BLOCK, bool SHARED, bool CONTIG, bool PERSYM>
-__global__ void __launch_bounds__(BLOCK, BLOCK >= 256 ? 4 : 8) range_encode_kernel(const AnsParams p) {
+__global__ void __launch_bounds__(BLOCK, BLOCK >= 256 ? 4 : 8) range_encode_kernel(const __grid_constant__ AnsParams p) {
     extern __shared__ __align__(128) uint32_t smem[];
     __shared__ uint64_t bar;
+    __shared__ uint64_t tma_bar[BLOCK / 32][kEncBoxSlots];
 
     const int lane = threadIdx.x & 31;
     const int warp_in_cta = threadIdx.x >> 5;
@@ -157,7 +158,66 @@ __global__ void __launch_bounds__(BLOCK, BLOCK >= 256 ? 4 : 8) range_encode_kern
     };
     auto encode_one = [&](int32_t sym, uint32_t m) { encode_entry(lookup(sym, m)); };
 
-    if (!CONTIG) {
+    if (!CONTIG && !PERSYM && p.use_tma) {
+        // ---- TMA path (see ans_encode_kernel): the warp's column strip arrives as boxes of kBoxRows rows, queue order
+        const Interleave g = interleave_of(N, K);
+        const uint64_t rows_total = g.T - 1;  // full rows 0 .. T-2
+        const uint32_t nbox = (uint32_t)(rows_total / kBoxRows);
+        const uint32_t bars = smem_u32(&tma_bar[warp_in_cta][0]);
+        const uint32_t boxes = smem_u32_pinned(smem + kRingsWords + table_words) + (uint32_t)warp_in_cta * (kEncBoxSlots * kBoxBytes);
+        const int32_t x0 = (int32_t)((uint32_t)tile * BLOCK + (uint32_t)warp_in_cta * 32u);
+        if (lane == 0) {
+#pragma unroll
+            for (int sl = 0; sl < kEncBoxSlots; ++sl) mbar_init_addr(bars + 8u * sl, 1);
+            fence_mbar_init();
+        }
+        __syncwarp();
+        uint32_t next = 0;  // boxes [next, nbox) are not requested yet
+        auto request_box = [&](uint32_t slot) {
+            if (next < nbox) {
+                if (lane == 0) {
+                    mbar_expect_tx_addr(bars + 8u * slot, kBoxBytes);
+                    tma_load_box(boxes + slot * kBoxBytes, &p.tmap, x0, (int32_t)(next * kBoxRows), bars + 8u * slot);
+                }
+                next += 1u;
+            }
+        };
+#pragma unroll
+        for (int sl = 0; sl < kEncBoxSlots; ++sl) request_box(sl);
+        uint32_t slot = 0, parity = 0;
+        const uint32_t my_col = boxes + (uint32_t)lane * 4u;
+        for (uint32_t b = 0; b < nbox; ++b) {
+            mbar_wait_addr(bars + 8u * slot, parity);
+            const uint32_t box = my_col + slot * kBoxBytes;
+#pragma unroll
+            for (int half = 0; half < kBoxRows / kCheckEvery; ++half) {
+                uint2 e[kCheckEvery];
+#pragma unroll
+                for (int u = 0; u < kCheckEvery; ++u)
+                    e[u] = lookup((int32_t)lds_u32(box + (uint32_t)(half * kCheckEvery + u) * 128u), stream_model);
+                drain_ring();
+#pragma unroll
+                for (int u = 0; u < kCheckEvery; ++u) encode_entry(e[u]);
+            }
+            __syncwarp();  // every lane has read the box: its slot is requested again
+            request_box(slot);
+            if (++slot == kEncBoxSlots) {
+                slot = 0;
+                parity ^= 1u;
+            }
+        }
+        {  // the rows after the last box, then the ragged last row
+            const int32_t *ps = p.symbols_in + (uint64_t)nbox * kBoxRows * K + kc;
+            uint32_t j = 0;
+            for (uint64_t r = (uint64_t)nbox * kBoxRows; r < rows_total; ++r, ++j) {
+                if ((j & (kCheckEvery - 1)) == 0) drain_ring();
+                encode_one(ld_stream_s32(ps), stream_model);
+                ps += K;
+            }
+            drain_ring();
+            if (valid && k < g.last) encode_one(ld_stream_s32(p.symbols_in + (g.T - 1) * K + k), stream_model);
+        }
+    } else if (!CONTIG) {
         const Interleave g = interleave_of(N, K);
         if (g.T > 1) {
             const uint64_t rows_total = g.T - 1;  // full rows 0 .. T-2
