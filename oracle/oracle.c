@@ -16,8 +16,8 @@
  *   musl).  orc_erf / orc_exp restate that published algorithm (Sun
  *   Microsystems 1993 rational approximations), operation for operation.  The
  *   coefficients were cross-checked (decimal vs. IEEE hex form) and the result
- *   is within 1 ulp of glibc's erf/exp over 2e7 random points
- *   (tests/test_oracle_math.py).  Parity of erf at the last-ulp level against
+ *   is within 1 ulp of glibc's erf/exp on random and special arguments
+ *   (tests/test_host_math.py, 1.4e5 points).  Parity of erf at the last-ulp level against
  *   the real Rust build is pinned only through the goldens (G1-G8).
  */
 #include "oracle.h"
