@@ -352,6 +352,11 @@ __global__ void __launch_bounds__(BLOCK, BLOCK >= 256 ? CTR_ENC_MIN_CTAS : 8) an
     if (CONTIG) {
         o_k = p.sym_off[kc];
         n_k = p.sym_off[kc + 1] - o_k;
+        if (o_k > N || n_k > N - o_k) {  // offsets outside the symbol array (or decreasing): flag, code nothing
+            if (valid) report_error(p.status, kErrBadArgument, k);
+            o_k = 0;
+            n_k = 0;
+        }
     } else {
         n_k = interleaved_len(N, K, kc);
         o_k = interleaved_start(N, K, kc);
@@ -779,6 +784,11 @@ __global__ void __launch_bounds__(BLOCK ? BLOCK : 1024, BLOCK == 0 || BLOCK >= 1
         if (CONTIG) {
             o_k = p.sym_off[k];
             n_k = p.sym_off[k + 1] - o_k;
+            if (o_k > N || n_k > N - o_k) {  // offsets outside the symbol array (or decreasing): flag, decode nothing
+                report_error(p.status, kErrBadArgument, k);
+                o_k = 0;
+                n_k = 0;
+            }
         }
         begin = p.offsets[k];
         end = p.ends ? p.ends[k] : p.offsets[k + 1];

@@ -35,6 +35,7 @@ constexpr uint32_t kErrInvalidData = 2;       // queue.rs:1401 -> AssertionError
 constexpr uint32_t kErrTrailingZero = 3;      // stack.rs:1555 -> ValueError
 constexpr uint32_t kErrBadModel = 5;          // invalid model parameter (std <= 0)          -> ValueError
 constexpr uint32_t kErrOutOfSpace = 7;        // backends.rs:1512 BoundedWriteError::OutOfSpace
+constexpr uint32_t kErrBadArgument = 8;       // sym_offsets that do not describe slices of the symbol array -> ValueError
 
 CTR_HD uint64_t mulhi64(uint64_t a, uint64_t b) {
 #if defined(__CUDA_ARCH__)

@@ -300,6 +300,27 @@ def test_model_sets_in_shared_memory_and_global(env, coder, M, A, contig):
 # ---------------------------------------------------------------------------------------------------
 # data errors
 # ---------------------------------------------------------------------------------------------------
+def test_offsets_outside_the_symbol_array_are_rejected(env):
+    """sym_offsets that reach beyond the symbol tensor (or decrease) must not be followed: ValueError, no access."""
+    B, bc, torch = env["B"], env["bc"], env["torch"]
+    model = B.ModelTable.quantized_gaussian(*BASE[:2], [BASE[2]], [BASE[3]])
+    syms = dev(env, gauss_symbols(np.random.default_rng(1), 10_000))
+    good = torch.arange(0, 11, device="cuda", dtype=torch.int64) * 1000
+    comp = bc.ans_encode(syms, model, sym_offsets=good)
+    bc.check()
+    for bad in (good * 200, torch.flip(good, dims=[0])):
+        for enc in (bc.ans_encode, bc.range_encode):
+            enc(syms, model, sym_offsets=bad, checkpoint_every=64)
+            with pytest.raises(ValueError):
+                bc.check()
+        comp.sym_offsets = bad
+        bc.ans_decode(comp, model)
+        with pytest.raises(ValueError):
+            bc.check()
+    comp.sym_offsets = good
+    assert torch.equal(bc.ans_decode(comp, model), syms)
+
+
 def test_data_errors(env):
     B, bc, torch = env["B"], env["bc"], env["torch"]
     model = B.ModelTable.quantized_gaussian(*BASE[:2], [BASE[2]], [BASE[3]])

@@ -27,8 +27,8 @@ decoded = bc.ans_decode(comp, model)
 bc.check()
 assert torch.equal(decoded, symbols)
 
-offsets = torch.arange(0, 1025, device="cuda") * 122_070
-latents = symbols[: 1024 * 122_070]
+offsets = torch.arange(0, 801, device="cuda") * 122_070
+latents = symbols[: 800 * 122_070]
 comp = bc.range_encode(latents, model, sym_offsets=offsets, checkpoint_every=1024)
 decoded = bc.range_decode(comp, model)
 bc.check()
