@@ -404,42 +404,95 @@ def run_ours(args):
                 "frac_of_step": {"ans_encode_kernel": enc_kernel_ms / ms_per_step, "ans_decode_kernel": dec_kernel_ms / ms_per_step}}
 
     # ---- e2e: host buffers through the C ABI, copies inside the timed region ---------------------------
-    h_syms = torch.empty(n, dtype=torch.int32).pin_memory()
-    h_syms.copy_(syms)
-    L = N.Layout()
-    L.n_streams, L.n_symbols = k, n
-    cap = int(lib.ctr_ans_max_compressed_words(C.byref(L)))
-    h_words = torch.empty(cap, dtype=torch.int32).pin_memory()
-    h_off = torch.empty(k + 1, dtype=torch.int64).pin_memory()
-    h_out = torch.empty(n, dtype=torch.int32).pin_memory()
-    status, bad = C.c_int(), C.c_uint64()
+    # The batch goes through the host-buffer entry points as two halves (k/2 streams, n/2 symbols each), each half
+    # on its own host thread: encode_host(half) -> decode_host(half), every step.  The calls are synchronous and
+    # PCIe-bound in one direction at a time (encode: 4 bytes per symbol host->device, decode: 4 bytes per symbol
+    # device->host), so the second thread starts when the first has finished its first encode and from then on
+    # one half uploads while the other downloads: both directions of the bus are busy.  `serial_ms_per_step` is
+    # the same work issued from one thread, one call after the other.
+    halves = []
+    for h in range(2):
+        k_h = k // 2 if h == 0 else k - k // 2
+        n_h = n // 2 if h == 0 else n - n // 2
+        hs = torch.empty(n_h, dtype=torch.int32).pin_memory()
+        hs.copy_(syms[:n_h] if h == 0 else syms[n // 2:])
+        Lh = N.Layout()
+        Lh.n_streams, Lh.n_symbols = k_h, n_h
+        cap_h = int(lib.ctr_ans_max_compressed_words(C.byref(Lh)))
+        halves.append(dict(k=k_h, n=n_h, syms=hs, cap=cap_h, words=torch.empty(cap_h, dtype=torch.int32).pin_memory(),
+                           off=torch.empty(k_h + 1, dtype=torch.int64).pin_memory(),
+                           out=torch.empty(n_h, dtype=torch.int32).pin_memory(), status=C.c_int(), bad=C.c_uint64()))
 
-    def e2e_step():
-        rc = lib.ctr_ans_encode_reverse_host(model.handle, h_syms.data_ptr(), n, k, None, None, 0, h_words.data_ptr(), cap,
-                                             h_off.data_ptr(), C.byref(status), C.byref(bad))
-        assert rc == 0 and status.value == 0, (rc, status.value)
-        rc = lib.ctr_ans_decode_host(model.handle, h_words.data_ptr(), h_off.data_ptr(), n, k, None, None, 0,
-                                     h_out.data_ptr(), C.byref(status), C.byref(bad))
-        assert rc == 0 and status.value == 0, (rc, status.value)
+    def enc_half(H):
+        rc = lib.ctr_ans_encode_reverse_host(model.handle, H["syms"].data_ptr(), H["n"], H["k"], None, None, 0,
+                                             H["words"].data_ptr(), H["cap"], H["off"].data_ptr(), C.byref(H["status"]),
+                                             C.byref(H["bad"]))
+        assert rc == 0 and H["status"].value == 0, (rc, H["status"].value)
 
-    e2e_step()
-    e2e_step()
-    assert torch.equal(h_out, h_syms)
+    def dec_half(H):
+        rc = lib.ctr_ans_decode_host(model.handle, H["words"].data_ptr(), H["off"].data_ptr(), H["n"], H["k"], None, None, 0,
+                                     H["out"].data_ptr(), C.byref(H["status"]), C.byref(H["bad"]))
+        assert rc == 0 and H["status"].value == 0, (rc, H["status"].value)
+
+    def e2e_serial_step():
+        for H in halves:
+            enc_half(H)
+            dec_half(H)
+
+    def e2e_pipelined(steps):
+        first_encoded = threading.Event()
+        errors = []
+
+        def worker(H, lead):
+            try:
+                torch.cuda.set_device(local_rank)
+                if not lead:
+                    first_encoded.wait()
+                for i in range(steps):
+                    enc_half(H)
+                    if lead and i == 0:
+                        first_encoded.set()
+                    dec_half(H)
+            except BaseException as exc:  # noqa: BLE001
+                errors.append(exc)
+                first_encoded.set()
+
+        threads = [threading.Thread(target=worker, args=(halves[0], True)), threading.Thread(target=worker, args=(halves[1], False))]
+        t0 = time.perf_counter()
+        for th in threads:
+            th.start()
+        for th in threads:
+            th.join()
+        dt = time.perf_counter() - t0
+        if errors:
+            raise errors[0]
+        return dt
+
+    e2e_serial_step()
+    e2e_pipelined(1)
+    for H in halves:
+        assert torch.equal(H["out"], H["syms"])
+        H["out"].zero_()
     sync_all()
     t0 = time.perf_counter()
     for _ in range(args.e2e_steps):
-        e2e_step()
-    e2e_s = (time.perf_counter() - t0) / max(args.e2e_steps, 1)
-    t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+        e2e_serial_step()
+    serial_s = (time.perf_counter() - t0) / max(args.e2e_steps, 1)
+    sync_all()
+    e2e_s = e2e_pipelined(args.e2e_steps) / max(args.e2e_steps, 1) if args.e2e_steps else 0.0
+    for H in halves:
+        assert torch.equal(H["out"], H["syms"])
+    t = torch.tensor([e2e_s, serial_s], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_s = float(t.item())
-    words_bytes = 4 * int(h_off[-1].item())
+    e2e_s, serial_s = float(t[0].item()), float(t[1].item())
+    words_bytes = 4 * sum(int(H["off"][-1].item()) for H in halves)
     e2e = {"value": world * n / e2e_s / 1e6 if args.e2e_steps else None, "unit": "Msymbols/s",
-           "h2d_bytes_per_step": 4 * n + words_bytes + 8 * (k + 1),
-           "d2h_bytes_per_step": words_bytes + 8 * (k + 1) + 4 * n + 32,
-           "ms_per_step": e2e_s * 1e3, "steps": args.e2e_steps,
-           "api": "ctr_ans_encode_reverse_host + ctr_ans_decode_host (pinned host buffers)"}
+           "h2d_bytes_per_step": 4 * n + words_bytes + 8 * (k + 2),
+           "d2h_bytes_per_step": words_bytes + 8 * (k + 2) + 4 * n + 64,
+           "ms_per_step": e2e_s * 1e3, "steps": args.e2e_steps, "serial_ms_per_step": serial_s * 1e3,
+           "api": "ctr_ans_encode_reverse_host + ctr_ans_decode_host (pinned host buffers); the batch as two halves of "
+                  "k/2 streams on two host threads, one uploading while the other downloads (PCIe full duplex)"}
 
     gather_kind = None if world == 1 else ("copy-engine pushes into peer-mapped containers over NVLink, ordered by stream memory operations (no kernel)" if pipe.get("pg") else "NCCL all-gather")
     if rank == 0:
