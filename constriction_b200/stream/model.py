@@ -131,17 +131,48 @@ class Categorical(Model):
 
 
 class Uniform(Model):
-    """pybindings/stream/model.rs Uniform; uniform.rs:44-146 (concrete form only)."""
+    """pybindings/stream/model.rs:570-600; uniform.rs:44-146: every bin 2^24 // size, the last one takes the
+    remainder.  `size` fixed, or one int32 `size` per symbol: the rows are then padded to the largest alphabet with
+    zero-probability symbols, which can neither be encoded (KeyError, like a symbol >= size in the reference) nor
+    come out of the decoder."""
 
     def __init__(self, size=None):
-        if size is None:
-            raise NotImplementedError("Uniform with a per-symbol `size` is outside the accelerated path")
-        self._size = int(size)
+        self._size = None if size is None else int(size)
+        self._nparams = 1 if size is None else 0
 
     def _concrete_table(self):
+        if self._size is None:
+            raise ValueError("No model parameters specified.")
         if self._table is None:
             self._table = B.ModelTable.uniform(self._size)
         return self._table
+
+    def _sizes(self, params):
+        if self._size is not None:
+            raise ValueError("Model parameters were specified but the model is already fully parameterized.")
+        if len(params) != 1:
+            raise ValueError(f"Wrong number of model parameters: expected 1, got {len(params)}.")
+        sizes = np.asarray(params[0])
+        if sizes.ndim != 1 or sizes.dtype != np.int32:
+            raise TypeError("size must be a rank-1 numpy array with dtype int32")
+        return sizes
+
+    def _family_len(self, params):
+        return self._sizes(params).size
+
+    def _family_table(self, params):
+        sizes = self._sizes(params).astype(np.int64)
+        if sizes.size == 0:
+            return B.ModelTable.uniform(2)
+        if sizes.min() < 2 or sizes.max() > (1 << 24):
+            raise ValueError("Invalid model parameter: `size` must be at least 2 and at most 2^24.")
+        widest = int(sizes.max())
+        if widest * sizes.size > (1 << 28):
+            raise NotImplementedError("Uniform with per-symbol sizes: table too large (alphabet x symbols > 2^28)")
+        per_bin = (1 << 24) // sizes
+        i = np.arange(widest + 1, dtype=np.int64)[None, :]
+        rows = np.where(i < sizes[:, None], i * per_bin[:, None], 1 << 24).astype(np.uint32)
+        return B.ModelTable.from_cdf(rows)
 
 
 class Bernoulli(Model):

@@ -198,3 +198,29 @@ def test_bernoulli_mirror(env):
     S.model.Bernoulli(1.5, perfect=False)
     with pytest.raises(ValueError):
         S.model.Bernoulli(float("nan"), perfect=False)
+
+
+def test_uniform_family_mirror(env):
+    """Uniform() with one int32 `size` per symbol (pybindings/stream/model.rs:570-600, uniform.rs:44-146)."""
+    import constriction_b200.stream as S
+    O = env["O"]
+    rng = np.random.default_rng(13)
+    n = 3000
+    sizes = rng.integers(2, 300, size=n).astype(np.int32)
+    sizes[:3] = [2, 299, 7]
+    syms = (rng.uniform(size=n) * sizes).astype(np.int32)
+    syms[:3] = [1, 298, 0]
+    a, oa = S.stack.AnsCoder(), O.AnsCoder()
+    a.encode_reverse(syms, S.model.Uniform(), sizes)
+    oa.encode_reverse(syms, O.Uniform(), sizes)
+    assert np.array_equal(a.get_compressed(), oa.get_compressed())
+    assert np.array_equal(a.decode(S.model.Uniform(), sizes), syms)
+    r, orr = S.queue.RangeEncoder(), O.RangeEncoder()
+    r.encode(syms, S.model.Uniform(), sizes)
+    orr.encode(syms, O.Uniform(), sizes)
+    assert np.array_equal(r.get_compressed(), orr.get_compressed())
+    assert np.array_equal(S.queue.RangeDecoder(r.get_compressed()).decode(S.model.Uniform(), sizes), syms)
+    bad = syms.copy()
+    bad[5] = sizes[5]  # one past the symbol's alphabet
+    with pytest.raises(KeyError):
+        S.stack.AnsCoder().encode_reverse(bad, S.model.Uniform(), sizes)
