@@ -73,8 +73,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
         raise RuntimeError("nvcc failed linking libconstriction_b200.so")
     if verbose:
         sys.stderr.write(log)
-    with open(os.path.join(HERE, "build_ptxas.log"), "w") as f:
-        f.write(log)
+    with open(os.path.join(HERE, "build_ptxas.log"), "w") as f:  # register / spill report (compile times vary: dropped)
+        f.write("".join(line for line in log.splitlines(keepends=True) if "Compile time" not in line))
     return LIB
 
 
