@@ -101,6 +101,13 @@ inline unsigned grid_for(uint64_t n, unsigned block) { return (unsigned)((n + bl
 
 }  // namespace
 
+// build state of one lazily built table (see ctr_model_s)
+struct LazyTable {
+    cudaEvent_t built = nullptr;       // recorded behind the build kernel(s)
+    cudaStream_t builder = nullptr;    // the stream they were enqueued on
+    std::atomic<bool> complete{false};  // the event has been observed complete: no further waits needed
+};
+
 struct ctr_model_s {
     uint32_t n_models = 0, alphabet = 0;
     int32_t min_symbol = 0;
@@ -115,6 +122,11 @@ struct ctr_model_s {
     // transient "model" of the ctr_*_gaussian entry points: no tables, (mean, std) per symbol
     const double *lazy_means = nullptr, *lazy_stds = nullptr;
     double lazy_free_weight = 0.0;
+    // Derived tables are built on first use, on the stream of the call that needs them.  A pointer is published
+    // only after its build kernel is enqueued (under `lazy_mutex`) together with an event recorded behind it;
+    // calls on other streams / host threads wait for that event before their kernel reads the table.
+    std::mutex lazy_mutex;
+    LazyTable enc_ready, dec_ready, cidx_ready;
 };
 
 namespace {
@@ -151,41 +163,74 @@ bool use_f64_division() {
     return on;
 }
 
-int ensure_enc_table(ctr_model_s *m, cudaStream_t s) {
-    if (m->d_enc) return CTR_OK;
-    const uint64_t entries = (uint64_t)m->n_models * ((uint64_t)m->alphabet + 1);
-    CUDA_TRY(cudaMalloc(&m->d_enc, entries * 16));
-    m->enc_f64 = use_f64_division();
-    build_enc_table_kernel<<<grid_for(entries, 256), 256, 0, s>>>(m->d_cdf, m->n_models, m->alphabet,
-                                                                  m->enc_f64 ? 1 : 0, m->d_enc);
-    LAUNCH_CHECK("build_enc_table_kernel");
-    if (m->alphabet <= kMaxSharedEncAlphabet) {
-        const uint32_t n = (m->alphabet + 1) * 8u;
-        CUDA_TRY(cudaMalloc(&m->d_enc_rep, (size_t)n * 16));
-        replicate_enc_table_kernel<<<grid_for(n, 256), 256, 0, s>>>(m->d_enc, m->alphabet, m->d_enc_rep);
-        LAUNCH_CHECK("replicate_enc_table_kernel");
+// Makes the calling stream wait for a table that another stream built (no-op once the build is known complete).
+int join_lazy_table(LazyTable &t, cudaStream_t s) {
+    if (t.complete.load(std::memory_order_acquire) || !t.built) return CTR_OK;
+    if (cudaEventQuery(t.built) == cudaSuccess) {
+        t.complete.store(true, std::memory_order_release);
+        return CTR_OK;
     }
+    cudaGetLastError();  // cudaErrorNotReady is not an error
+    if (s != t.builder) CUDA_TRY(cudaStreamWaitEvent(s, t.built, 0));
+    return CTR_OK;
+}
+int publish_lazy_table(LazyTable &t, cudaStream_t s) {
+    CUDA_TRY(cudaEventCreateWithFlags(&t.built, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventRecord(t.built, s));
+    t.builder = s;
     return CTR_OK;
 }
 
+int ensure_enc_table(ctr_model_s *m, cudaStream_t s) {
+    std::lock_guard<std::mutex> lock(m->lazy_mutex);
+    if (m->d_enc) return join_lazy_table(m->enc_ready, s);
+    const uint64_t entries = (uint64_t)m->n_models * ((uint64_t)m->alphabet + 1);
+    uint4 *d_enc = nullptr, *d_rep = nullptr;
+    CUDA_TRY(cudaMalloc(&d_enc, entries * 16));
+    m->enc_f64 = use_f64_division();
+    build_enc_table_kernel<<<grid_for(entries, 256), 256, 0, s>>>(m->d_cdf, m->n_models, m->alphabet,
+                                                                  m->enc_f64 ? 1 : 0, d_enc);
+    LAUNCH_CHECK("build_enc_table_kernel");
+    if (m->alphabet <= kMaxSharedEncAlphabet) {
+        const uint32_t n = (m->alphabet + 1) * 8u;
+        CUDA_TRY(cudaMalloc(&d_rep, (size_t)n * 16));
+        replicate_enc_table_kernel<<<grid_for(n, 256), 256, 0, s>>>(d_enc, m->alphabet, d_rep);
+        LAUNCH_CHECK("replicate_enc_table_kernel");
+    }
+    const int rc = publish_lazy_table(m->enc_ready, s);
+    m->d_enc_rep = d_rep;
+    m->d_enc = d_enc;
+    return rc;
+}
+
 int ensure_dec_table(ctr_model_s *m, cudaStream_t s) {
-    if (m->d_dec || !m->shared_ok) return CTR_OK;
-    CUDA_TRY(cudaMalloc(&m->d_dec, kLutBytes + m->dec_cdf_bytes));
+    if (!m->shared_ok) return CTR_OK;
+    std::lock_guard<std::mutex> lock(m->lazy_mutex);
+    if (m->d_dec) return join_lazy_table(m->dec_ready, s);
+    uint32_t *d_dec = nullptr;
+    CUDA_TRY(cudaMalloc(&d_dec, kLutBytes + m->dec_cdf_bytes));
     const uint32_t threads = m->alphabet + 2 > (uint32_t)kLutSize ? m->alphabet + 2 : (uint32_t)kLutSize;
-    build_dec_table_kernel<<<grid_for(threads, 256), 256, 0, s>>>(m->d_cdf, m->alphabet, m->d_dec);
+    build_dec_table_kernel<<<grid_for(threads, 256), 256, 0, s>>>(m->d_cdf, m->alphabet, d_dec);
     LAUNCH_CHECK("build_dec_table_kernel");
-    return CTR_OK;
+    const int rc = publish_lazy_table(m->dec_ready, s);
+    m->d_dec = d_dec;
+    return rc;
 }
 
 // coarse index for decoding with global tables (built on the first such decode; alphabets up to 65536)
 int ensure_coarse_index(ctr_model_s *m, cudaStream_t s) {
-    if (m->d_cidx || m->alphabet > 65536u) return CTR_OK;
+    if (m->alphabet > 65536u) return CTR_OK;
+    std::lock_guard<std::mutex> lock(m->lazy_mutex);
+    if (m->d_cidx) return join_lazy_table(m->cidx_ready, s);
     const int wide = m->alphabet > 256 ? 1 : 0;
     const uint64_t entries = (uint64_t)m->n_models * 257;
-    CUDA_TRY(cudaMalloc(&m->d_cidx, align_up(entries * (wide ? 2 : 1), 16)));
-    build_coarse_index_kernel<<<grid_for(entries, 256), 256, 0, s>>>(m->d_cdf, m->n_models, m->alphabet, wide, m->d_cidx);
+    uint8_t *d_cidx = nullptr;
+    CUDA_TRY(cudaMalloc(&d_cidx, align_up(entries * (wide ? 2 : 1), 16)));
+    build_coarse_index_kernel<<<grid_for(entries, 256), 256, 0, s>>>(m->d_cdf, m->n_models, m->alphabet, wide, d_cidx);
     LAUNCH_CHECK("build_coarse_index_kernel");
-    return CTR_OK;
+    const int rc = publish_lazy_table(m->cidx_ready, s);
+    m->d_cidx = d_cidx;
+    return rc;
 }
 
 // runs the validation kernel, builds the derived tables (the encoder table only when it is small;
@@ -201,6 +246,8 @@ int model_finish(ctr_model_s *m, uint32_t *d_err, int strict, cudaStream_t s) {
     uint32_t h_err = 0;
     CUDA_TRY(cudaMemcpyAsync(&h_err, d_err, 4, cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaStreamSynchronize(s));
+    if (m->d_enc) m->enc_ready.complete.store(true, std::memory_order_release);
+    if (m->d_dec) m->dec_ready.complete.store(true, std::memory_order_release);
     return h_err ? CTR_ERR_BAD_MODEL : CTR_OK;
 }
 
@@ -461,6 +508,8 @@ extern "C" int ctr_model_destroy(ctr_model_t m) {
     if (m->d_enc_rep) cudaFree(m->d_enc_rep);
     if (m->d_cidx) cudaFree(m->d_cidx);
     if (m->d_dec) cudaFree(m->d_dec);
+    for (LazyTable *t : {&m->enc_ready, &m->dec_ready, &m->cidx_ready})
+        if (t->built) cudaEventDestroy(t->built);
     delete m;
     return CTR_OK;
 }
@@ -702,9 +751,11 @@ __global__ void expand_checkpoints_kernel(const uint64_t *sym_off, const uint64_
             if (v_index) v_index[v] = stream_index[k];
         }
     }
-    // padding entries [V, V_max] : empty streams at the end of the symbol array
+    // padding entries [V, V_max] : empty streams behind the last real stream (the last chunk ends where that
+    // stream ends, which need not be the end of the symbol array)
+    const uint64_t sym_end = sym_off[K] <= N ? sym_off[K] : N;
     for (uint64_t v = V + k; v <= V_max; v += (uint64_t)gridDim.x * blockDim.x) {
-        v_sym_off[v] = N;
+        v_sym_off[v] = sym_end;
         if (v < V_max) {
             v_begin[v] = 0;
             v_end[v] = 0;
@@ -1242,7 +1293,7 @@ int decode_host(ctr_model_t model, const uint32_t *words, const uint64_t *offset
     L.n_symbols = N;
     L.model_index_mode = index_mode;
     const uint64_t total = offsets[K];
-    if ((rc = d_words.alloc(total * 4, s))) return rc;
+    if ((rc = d_words.alloc(align_up(total * 4, 16), s))) return rc;  // decoders read whole 16-byte blocks
     if (total) CUDA_TRY(cudaMemcpyAsync(d_words.p, words, total * 4, cudaMemcpyHostToDevice, s));
     if ((rc = d_offsets.alloc((K + 1) * 8, s))) return rc;
     CUDA_TRY(cudaMemcpyAsync(d_offsets.p, offsets, (K + 1) * 8, cudaMemcpyHostToDevice, s));

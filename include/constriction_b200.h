@@ -166,6 +166,14 @@ int ctr_ans_encode_reverse(ctr_model_t model, const int32_t *symbols_dev, const 
                            uint64_t *states_out_dev, uint32_t *status_dev, void *stream);
 
 /* Every stream k decodes its symbols (forward order) from words[offsets[k]..offsets[k+1]).
+ *   words_dev        MUST be 16-byte aligned, and the allocation behind it must extend to a multiple of 16 bytes
+ *                    (4 words): the decoders (ANS and range) stage each stream with aligned 16-byte asynchronous
+ *                    copies, so the block that holds a stream's last word is read whole -- up to 12 bytes past
+ *                    offsets[K] words, never before words_dev.  A misaligned base returns CTR_ERR_BAD_ARGUMENT;
+ *                    the padding cannot be checked by the library (cudaMalloc / cudaMallocAsync / framework
+ *                    allocators round sizes up to >= 256 bytes, so whole allocations always qualify; a tightly
+ *                    sized sub-buffer carved out of a larger one qualifies as long as the bytes behind it are
+ *                    mapped).  The padding is never interpreted.
  *   states_in_dev    u64[K]; required with CTR_FLAG_RAW (all words are bulk), else NULL
  *   states_out_dev   u64[K] or NULL
  *   words_left_dev   u64[K] or NULL; bulk words not consumed (Pos::pos().0, stack.rs:1107-1115)
