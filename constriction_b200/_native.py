@@ -84,11 +84,27 @@ SIGNATURES = {
     "ctr_range_encode_host": (C.c_int, [vp, vp, C.c_uint64, C.c_uint64, vp, vp, C.c_int32, vp, C.c_uint64, vp,
                                         C.POINTER(C.c_int), u64p]),
     "ctr_range_decode_host": (C.c_int, [vp, vp, vp, C.c_uint64, C.c_uint64, vp, vp, C.c_int32, vp, C.POINTER(C.c_int), u64p]),
+    "ctr_ans_encode_reverse_host_async": (C.c_int, [vp, vp, C.c_uint64, C.c_uint64, vp, vp, C.c_int32, vp, C.c_uint64, vp,
+                                                    C.POINTER(C.c_int), u64p, C.POINTER(vp)]),
+    "ctr_ans_decode_host_async": (C.c_int, [vp, vp, vp, C.c_uint64, C.c_uint64, vp, vp, C.c_int32, vp, C.POINTER(C.c_int), u64p,
+                                            C.POINTER(vp)]),
+    "ctr_range_encode_host_async": (C.c_int, [vp, vp, C.c_uint64, C.c_uint64, vp, vp, C.c_int32, vp, C.c_uint64, vp,
+                                              C.POINTER(C.c_int), u64p, C.POINTER(vp)]),
+    "ctr_range_decode_host_async": (C.c_int, [vp, vp, vp, C.c_uint64, C.c_uint64, vp, vp, C.c_int32, vp, C.POINTER(C.c_int), u64p,
+                                              C.POINTER(vp)]),
+    "ctr_host_job_wait": (C.c_int, [vp]),
     "ctr_stream_write_value32": (C.c_int, [vp, C.c_uint32, vp]),
     "ctr_stream_wait_value32": (C.c_int, [vp, C.c_uint32, vp]),
-    "ctr_stream_write_value32_many": (C.c_int, [vp, C.c_uint32, C.c_uint32, C.c_uint32, vp]),
-    "ctr_stream_wait_value32_many": (C.c_int, [vp, C.c_uint32, C.c_uint32, vp]),
-    "ctr_peer_push": (C.c_int, [vp, C.c_uint32, C.c_uint32, C.c_uint64, vp, C.c_uint64, vp]),
+    "ctr_gather_create": (C.c_int, [C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint64, vp, vp, vp, C.POINTER(vp)]),
+    "ctr_gather_destroy": (C.c_int, [vp]),
+    "ctr_gather_begin_turn": (C.c_int, [vp, u32p, C.POINTER(vp), u64p, C.POINTER(vp)]),
+    "ctr_gather_slot": (C.c_int, [vp, C.c_uint32, C.c_uint32, C.POINTER(vp), C.POINTER(vp)]),
+    "ctr_gather_push": (C.c_int, [vp, C.c_uint32, C.c_uint64, vp]),
+    "ctr_gather_wait": (C.c_int, [vp, C.c_uint32, vp]),
+    "ctr_gather_release": (C.c_int, [vp, C.c_uint32, vp]),
+    "ctr_gather_sync": (C.c_int, [vp]),
+    "ctr_gather_compressed_nccl": (C.c_int, [vp, C.c_uint32, C.c_uint32, vp, vp, C.c_uint64, C.c_uint64, C.c_uint64, vp, vp,
+                                             vp, vp, vp]),
     "ctr_kernel_launch_count": (C.c_uint64, []),
     "ctr_profile_enable": (None, [C.c_int]),
     "ctr_profile_read": (C.c_int, [C.c_int, C.POINTER(C.c_double), u64p]),
@@ -120,7 +136,7 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)  # AttributeError here = header and library out of sync
         fn.restype = res
         fn.argtypes = args
-    if lib.ctr_abi_version() != 2:
+    if lib.ctr_abi_version() != 3:
         raise RuntimeError("libconstriction_b200.so: ABI version mismatch")
     _LIB = lib
     return lib

@@ -281,8 +281,11 @@ class BatchCoder:
         ws_bytes = lib.ctr_ans_encode_workspace_bytes(C.byref(L))
         cap = lib.ctr_ans_max_compressed_words(C.byref(L))
         ws = self._workspace(ws_bytes)
-        if out is not None and out.words.numel() >= cap and out.offsets.numel() == n_streams + 1:
+        if out is not None and out.offsets.numel() == n_streams + 1:
+            # the caller's container (e.g. a slot of a multi-GPU receive buffer); it may hold fewer words than the
+            # worst case: a batch that does not fit is reported as MemoryError by check()
             words, offsets = out.words, out.offsets
+            cap = words.numel()
         else:
             words = torch.empty(cap, dtype=torch.int32, device=self.device)
             offsets = torch.empty(n_streams + 1, dtype=torch.int64, device=self.device)

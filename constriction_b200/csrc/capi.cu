@@ -15,6 +15,7 @@
 #include <vector>
 
 #include "../../include/constriction_b200.h"
+#include "host_common.h"
 #include "ans_kernels.cuh"
 #include "compact.cuh"
 #include "gauss_kernels.cuh"
@@ -66,6 +67,25 @@ int cuda_fail(cudaError_t e, const char *what) {
     g_last_cuda_error = std::string(what) + ": " + cudaGetErrorString(e);
     return CTR_ERR_CUDA;
 }
+}  // namespace
+
+// shared with the other host translation units (host_common.h)
+namespace ctr {
+int host_cuda_fail(cudaError_t e, const char *what) { return cuda_fail(e, what); }
+int host_fail(const std::string &what) {
+    g_last_cuda_error = what;
+    return CTR_ERR_CUDA;
+}
+void host_count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+}  // namespace ctr
+namespace {
+void keep_pool_memory();
+}
+namespace ctr {
+void host_keep_pool_memory() { keep_pool_memory(); }
+}  // namespace ctr
+
+namespace {
 
 #define CUDA_TRY(expr)                                       \
     do {                                                     \
@@ -1008,34 +1028,6 @@ extern "C" int ctr_stream_wait_value32(void *addr, uint32_t value, void *stream)
     return CTR_OK;
 }
 
-// One call for a whole phase of the exchange (the Python side would otherwise spend more time issuing the
-// copies and flags one by one than the GPUs spend executing them).
-extern "C" int ctr_peer_push(void *const *dst_bases, uint32_t n_dst, uint32_t first, uint64_t dst_offset_bytes,
-                             const void *src, uint64_t bytes, void *stream) {
-    if (!dst_bases || n_dst == 0 || (!src && bytes)) return CTR_ERR_BAD_ARGUMENT;
-    for (uint32_t i = 0; i < n_dst && bytes; ++i) {
-        char *dst = static_cast<char *>(dst_bases[(first + i) % n_dst]) + dst_offset_bytes;
-        CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
-    }
-    return CTR_OK;
-}
-
-extern "C" int ctr_stream_write_value32_many(void *const *addrs, uint32_t n, uint32_t first, uint32_t value, void *stream) {
-    for (uint32_t i = 0; i < n; ++i) {
-        const int rc = ctr_stream_write_value32(addrs[(first + i) % n], value, stream);
-        if (rc) return rc;
-    }
-    return CTR_OK;
-}
-
-extern "C" int ctr_stream_wait_value32_many(void *const *addrs, uint32_t n, uint32_t value, void *stream) {
-    for (uint32_t i = 0; i < n; ++i) {
-        const int rc = ctr_stream_wait_value32(addrs[i], value, stream);
-        if (rc) return rc;
-    }
-    return CTR_OK;
-}
-
 // =====================================================================================================
 // checkpoints
 // =====================================================================================================
@@ -1185,173 +1177,3 @@ extern "C" int ctr_range_decode_gaussian(int32_t min_symbol, int32_t max_symbol,
                                                 status_dev, stream);
 }
 
-// =====================================================================================================
-// host-buffer convenience
-// =====================================================================================================
-namespace {
-
-struct DeviceBuf {
-    void *p = nullptr;
-    cudaStream_t s = nullptr;
-    int alloc(size_t bytes, cudaStream_t stream) {
-        s = stream;
-        CUDA_TRY(cudaMallocAsync(&p, bytes ? bytes : 16, stream));
-        return CTR_OK;
-    }
-    template <typename T>
-    T *as() {
-        return static_cast<T *>(p);
-    }
-    ~DeviceBuf() {
-        if (p) cudaFreeAsync(p, s);
-    }
-};
-
-cudaStream_t host_stream() {
-    static thread_local cudaStream_t s = nullptr;
-    if (!s) {
-        cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking);
-        keep_pool_memory();
-    }
-    return s;
-}
-
-uint64_t index_count(int mode, uint64_t N, uint64_t K) { return mode == 1 ? N : (mode == 2 ? K : 0); }
-
-int read_status(uint32_t *d_status, cudaStream_t s, int *data_status, uint64_t *failing_stream) {
-    uint32_t h[4];
-    CUDA_TRY(cudaMemcpyAsync(h, d_status, 16, cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(cudaStreamSynchronize(s));
-    if (data_status) *data_status = (int)h[0];
-    if (failing_stream) *failing_stream = ((uint64_t)h[3] << 32) | h[2];
-    return CTR_OK;
-}
-
-template <bool RANGE>
-int encode_host(ctr_model_t model, const int32_t *symbols, uint64_t N, uint64_t K, const uint64_t *sym_off,
-                const uint32_t *model_index, int32_t index_mode, uint32_t *words_out, uint64_t words_capacity,
-                uint64_t *offsets_out, int *data_status, uint64_t *failing_stream) {
-    if (!model || !words_out || !offsets_out || (!symbols && N)) return CTR_ERR_BAD_ARGUMENT;
-    if (ctr_device_count() == 0) return cuda_fail(cudaErrorNoDevice, "no CUDA device");
-    cudaStream_t s = host_stream();
-    DeviceBuf d_sym, d_off, d_idx, d_ws, d_words, d_offsets, d_status;
-    int rc;
-    ctr_layout L;
-    memset(&L, 0, sizeof L);
-    L.n_streams = K;
-    L.n_symbols = N;
-    L.model_index_mode = index_mode;
-    if ((rc = d_sym.alloc(N * 4, s))) return rc;
-    CUDA_TRY(cudaMemcpyAsync(d_sym.p, symbols, N * 4, cudaMemcpyHostToDevice, s));
-    if (sym_off) {
-        if ((rc = d_off.alloc((K + 1) * 8, s))) return rc;
-        CUDA_TRY(cudaMemcpyAsync(d_off.p, sym_off, (K + 1) * 8, cudaMemcpyHostToDevice, s));
-        L.sym_offsets_dev = d_off.as<uint64_t>();
-    }
-    const uint64_t n_idx = index_count(index_mode, N, K);
-    if (n_idx) {
-        if (!model_index) return CTR_ERR_BAD_ARGUMENT;
-        if ((rc = d_idx.alloc(n_idx * 4, s))) return rc;
-        CUDA_TRY(cudaMemcpyAsync(d_idx.p, model_index, n_idx * 4, cudaMemcpyHostToDevice, s));
-        L.model_index_dev = d_idx.as<uint32_t>();
-    }
-    const size_t ws_bytes = ctr_ans_encode_workspace_bytes(&L);
-    const uint64_t cap = ctr_ans_max_compressed_words(&L);
-    if ((rc = d_ws.alloc(ws_bytes, s))) return rc;
-    if ((rc = d_words.alloc(cap * 4, s))) return rc;
-    if ((rc = d_offsets.alloc((K + 1) * 8, s))) return rc;
-    if ((rc = d_status.alloc(16, s))) return rc;
-    CUDA_TRY(cudaMemsetAsync(d_status.p, 0, 16, s));
-    if (RANGE)
-        rc = ctr_range_encode(model, d_sym.as<int32_t>(), &L, nullptr, d_ws.p, ws_bytes, d_words.as<uint32_t>(), cap,
-                              d_offsets.as<uint64_t>(), nullptr, d_status.as<uint32_t>(), s);
-    else
-        rc = ctr_ans_encode_reverse(model, d_sym.as<int32_t>(), &L, nullptr, d_ws.p, ws_bytes, d_words.as<uint32_t>(),
-                                    cap, d_offsets.as<uint64_t>(), nullptr, d_status.as<uint32_t>(), s);
-    if (rc) return rc;
-    CUDA_TRY(cudaMemcpyAsync(offsets_out, d_offsets.p, (K + 1) * 8, cudaMemcpyDeviceToHost, s));
-    if ((rc = read_status(d_status.as<uint32_t>(), s, data_status, failing_stream))) return rc;
-    const uint64_t total = offsets_out[K];
-    if (total > words_capacity) return CTR_ERR_OUT_OF_SPACE;
-    if (total) CUDA_TRY(cudaMemcpyAsync(words_out, d_words.p, total * 4, cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(cudaStreamSynchronize(s));
-    return CTR_OK;
-}
-
-template <bool RANGE>
-int decode_host(ctr_model_t model, const uint32_t *words, const uint64_t *offsets, uint64_t N, uint64_t K,
-                const uint64_t *sym_off, const uint32_t *model_index, int32_t index_mode, int32_t *symbols_out,
-                int *data_status, uint64_t *failing_stream) {
-    if (!model || !offsets || (!symbols_out && N)) return CTR_ERR_BAD_ARGUMENT;
-    if (ctr_device_count() == 0) return cuda_fail(cudaErrorNoDevice, "no CUDA device");
-    cudaStream_t s = host_stream();
-    DeviceBuf d_sym, d_off, d_idx, d_words, d_offsets, d_status;
-    int rc;
-    ctr_layout L;
-    memset(&L, 0, sizeof L);
-    L.n_streams = K;
-    L.n_symbols = N;
-    L.model_index_mode = index_mode;
-    const uint64_t total = offsets[K];
-    if ((rc = d_words.alloc(align_up(total * 4, 16), s))) return rc;  // decoders read whole 16-byte blocks
-    if (total) CUDA_TRY(cudaMemcpyAsync(d_words.p, words, total * 4, cudaMemcpyHostToDevice, s));
-    if ((rc = d_offsets.alloc((K + 1) * 8, s))) return rc;
-    CUDA_TRY(cudaMemcpyAsync(d_offsets.p, offsets, (K + 1) * 8, cudaMemcpyHostToDevice, s));
-    if (sym_off) {
-        if ((rc = d_off.alloc((K + 1) * 8, s))) return rc;
-        CUDA_TRY(cudaMemcpyAsync(d_off.p, sym_off, (K + 1) * 8, cudaMemcpyHostToDevice, s));
-        L.sym_offsets_dev = d_off.as<uint64_t>();
-    }
-    const uint64_t n_idx = index_count(index_mode, N, K);
-    if (n_idx) {
-        if (!model_index) return CTR_ERR_BAD_ARGUMENT;
-        if ((rc = d_idx.alloc(n_idx * 4, s))) return rc;
-        CUDA_TRY(cudaMemcpyAsync(d_idx.p, model_index, n_idx * 4, cudaMemcpyHostToDevice, s));
-        L.model_index_dev = d_idx.as<uint32_t>();
-    }
-    if ((rc = d_sym.alloc(N * 4, s))) return rc;
-    if ((rc = d_status.alloc(16, s))) return rc;
-    CUDA_TRY(cudaMemsetAsync(d_status.p, 0, 16, s));
-    if (RANGE)
-        rc = ctr_range_decode(model, d_words.as<uint32_t>(), d_offsets.as<uint64_t>(), &L, nullptr,
-                              d_sym.as<int32_t>(), nullptr, nullptr, d_status.as<uint32_t>(), s);
-    else
-        rc = ctr_ans_decode(model, d_words.as<uint32_t>(), d_offsets.as<uint64_t>(), &L, nullptr, d_sym.as<int32_t>(),
-                            nullptr, nullptr, d_status.as<uint32_t>(), s);
-    if (rc) return rc;
-    if (N) CUDA_TRY(cudaMemcpyAsync(symbols_out, d_sym.p, N * 4, cudaMemcpyDeviceToHost, s));
-    return read_status(d_status.as<uint32_t>(), s, data_status, failing_stream);
-}
-
-}  // namespace
-
-extern "C" int ctr_ans_encode_reverse_host(ctr_model_t model, const int32_t *symbols_host, uint64_t n_symbols,
-    uint64_t n_streams, const uint64_t *sym_offsets_host, const uint32_t *model_index_host, int32_t model_index_mode,
-    uint32_t *words_out_host, uint64_t words_capacity, uint64_t *offsets_out_host, int *data_status,
-    uint64_t *failing_stream) {
-    return encode_host<false>(model, symbols_host, n_symbols, n_streams, sym_offsets_host, model_index_host,
-                              model_index_mode, words_out_host, words_capacity, offsets_out_host, data_status,
-                              failing_stream);
-}
-extern "C" int ctr_range_encode_host(ctr_model_t model, const int32_t *symbols_host, uint64_t n_symbols,
-    uint64_t n_streams, const uint64_t *sym_offsets_host, const uint32_t *model_index_host, int32_t model_index_mode,
-    uint32_t *words_out_host, uint64_t words_capacity, uint64_t *offsets_out_host, int *data_status,
-    uint64_t *failing_stream) {
-    return encode_host<true>(model, symbols_host, n_symbols, n_streams, sym_offsets_host, model_index_host,
-                              model_index_mode, words_out_host, words_capacity, offsets_out_host, data_status,
-                              failing_stream);
-}
-extern "C" int ctr_ans_decode_host(ctr_model_t model, const uint32_t *words_host, const uint64_t *offsets_host,
-                                   uint64_t n_symbols, uint64_t n_streams, const uint64_t *sym_offsets_host,
-                                   const uint32_t *model_index_host, int32_t model_index_mode,
-                                   int32_t *symbols_out_host, int *data_status, uint64_t *failing_stream) {
-    return decode_host<false>(model, words_host, offsets_host, n_symbols, n_streams, sym_offsets_host,
-                              model_index_host, model_index_mode, symbols_out_host, data_status, failing_stream);
-}
-extern "C" int ctr_range_decode_host(ctr_model_t model, const uint32_t *words_host, const uint64_t *offsets_host,
-                                     uint64_t n_symbols, uint64_t n_streams, const uint64_t *sym_offsets_host,
-                                     const uint32_t *model_index_host, int32_t model_index_mode,
-                                     int32_t *symbols_out_host, int *data_status, uint64_t *failing_stream) {
-    return decode_host<true>(model, words_host, offsets_host, n_symbols, n_streams, sym_offsets_host,
-                             model_index_host, model_index_mode, symbols_out_host, data_status, failing_stream);
-}

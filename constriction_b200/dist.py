@@ -141,149 +141,175 @@ def all_gather_compressed(words: torch.Tensor, offsets: torch.Tensor, group: Opt
     return all_gather_compressed_end(all_gather_compressed_begin(words, offsets, group, stream_counts))
 
 
-class PeerGather:
-    """The same exchange without any SM: every rank *pushes* its words and offsets straight into every peer's
-    dense container with copy-engine transfers over NVLink, ordered by stream memory operations
-    (cuStreamWriteValue32 / cuStreamWaitValue32 on flags in peer memory), so the gather runs concurrently with
-    coder kernels that occupy every SM of the GPU.  (Any kernel-based collective -- an NCCL all-gather, even an
-    8-byte one -- has to wait for a free SM, and the ANS encode kernel holds all registers of all SMs for its
-    whole run: with NCCL the exchange and the coders serialise.)  The receive buffers are symmetric memory
-    (`torch.distributed._symmetric_memory`: every rank's buffer is mapped into every rank's address space).
+class SlotGather:
+    """The exchange without any SM and without a cross-rank host wait (C ABI: ctr_gather_*, csrc/gather.cu).
 
-    Protocol of one gather (sequence number q, all on the caller's side stream, no kernel launches):
-      begin:  my total -> meta[me] of every rank (8-byte copies); flag A[me] := q on every rank;
-              wait until A[r] >= q for all r; meta -> pinned host memory; event
-      end:    (host waits for the event: it needs the sizes to issue copies)  my words -> words[base_me ..] and my
-              offsets -> offsets[K_me ..] of every rank; flag B[me] := q on every rank; wait until B[r] >= q for all r
-      finish: (on the consumer's stream, after the gather's event) offsets of rank r += base_r   (one small kernel)
+    Every rank owns receive buffers in symmetric memory (`torch.distributed._symmetric_memory`: mapped into every
+    rank's address space over NVLink), divided into fixed slots, one per source rank: slot (turn mod n_buffers, r)
+    holds rank r's container of that turn exactly as its encoder wrote it.  A rank encodes straight into its own
+    slot; a worker thread of the library waits for that encode and pushes the used part of the slot into every
+    peer's buffer with copy-engine transfers, ordered by stream memory operations on flags in peer memory
+    (cuStreamWriteValue32 / cuStreamWaitValue32), so the gather runs while coder kernels occupy every SM and no
+    Python thread ever blocks on another rank.  One node, one process per GPU.
 
-    One node, one process per GPU.  Receive buffers are allocated and exchanged once (`capacity_words` per rank
-    and buffer); `n_buffers` of them are used round-robin, so that a container gathered in step i stays valid
-    while step i+1 is being gathered."""
+        turn = sg.begin_turn()                                  # my slot of this turn
+        comp = bc.ans_encode(syms, model, ..., out=turn.out)    # encode straight into it
+        sg.push(turn, comp.n_streams)                           # returns at once
+        ...
+        sg.wait(turn)                                           # current stream: all peers' slots have arrived
+        other = sg.shard(turn, r, n_streams, n_symbols, "ans")  # rank r's container (views, no copy)
+        bc.ans_decode(other, model)
+        sg.release(turn)                                        # peers may overwrite this buffer (turn + n_buffers)
+    """
 
-    def __init__(self, capacity_words: int, stream_counts: Sequence[int], group: Optional[dist.ProcessGroup] = None,
-                 n_buffers: int = 2, dtype=torch.int32):
+    @dataclass
+    class Turn:
+        number: int
+        out: "object"  # batch.Compressed whose words / offsets are my slot (pass as `out=` to the encoders)
+
+    def __init__(self, slot_words: int, slot_streams: int, group: Optional[dist.ProcessGroup] = None, n_buffers: int = 2):
         import torch.distributed._symmetric_memory as symm_mem
 
         from . import _native as N
+        self._N = N
         self._lib = N.load()
         self.group = group
         pg = group if group is not None else dist.group.WORLD
         self.world = world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
-        self.ks = [int(x) for x in stream_counts]
-        self.stream_base = [0]
-        for kk in self.ks:
-            self.stream_base.append(self.stream_base[-1] + kk)
         dev = torch.device("cuda", torch.cuda.current_device())
         self.dev = dev
-        cap = torch.tensor([int(capacity_words)], dtype=torch.int64, device=dev)
-        dist.all_reduce(cap, op=dist.ReduceOp.MAX, group=group)  # symmetric buffers: same size on every rank
-        self.cap = int(cap.item())
+        sizes = torch.tensor([int(slot_words), int(slot_streams)], dtype=torch.int64, device=dev)
+        dist.all_reduce(sizes, op=dist.ReduceOp.MAX, group=group)  # symmetric buffers: same geometry on every rank
+        self.slot_words = (int(sizes[0].item()) + 63) // 64 * 64
+        self.slot_streams = int(sizes[1].item())
         self.n_buffers = n_buffers
-        n_words, n_off = world * self.cap, self.stream_base[-1] + 1
-        self.dense, self.g_off, self._handles = [], [], []
-        self._dense_ptrs, self._off_ptrs = [], []
-        self.peer_dense = [[None] * n_buffers for _ in range(world)]
-        self.peer_off = [[None] * n_buffers for _ in range(world)]
-        for b in range(n_buffers):
-            d = symm_mem.empty(n_words, dtype=dtype, device=dev)
-            o = symm_mem.empty(n_off, dtype=torch.int64, device=dev)
-            hd, ho = symm_mem.rendezvous(d, pg), symm_mem.rendezvous(o, pg)
-            self._handles += [hd, ho]
-            self.dense.append(d)
-            self.g_off.append(o)
-            for r in range(world):
-                self.peer_dense[r][b] = d if r == self.rank else hd.get_buffer(r, (n_words,), dtype, 0)
-                self.peer_off[r][b] = o if r == self.rank else ho.get_buffer(r, (n_off,), torch.int64, 0)
-            self._dense_ptrs.append((ctypes.c_void_p * world)(*[int(x) for x in hd.buffer_ptrs]))
-            self._off_ptrs.append((ctypes.c_void_p * world)(*[int(x) for x in ho.buffer_ptrs]))
-        # sizes and flags: meta int64[world]; flags int32[2 * world] (A then B), zero-initialised
-        self.meta = symm_mem.empty(world, dtype=torch.int64, device=dev)
-        self.flags = symm_mem.empty(2 * world, dtype=torch.int32, device=dev)
-        self.meta.zero_()
+        n_words = n_buffers * world * self.slot_words
+        n_off = n_buffers * world * (self.slot_streams + 1)
+        self.words = symm_mem.empty(n_words, dtype=torch.int32, device=dev)
+        self.offsets = symm_mem.empty(n_off, dtype=torch.int64, device=dev)
+        self.flags = symm_mem.empty(2 * n_buffers * world, dtype=torch.int32, device=dev)
         self.flags.zero_()
         torch.cuda.synchronize()
-        hm, hf = symm_mem.rendezvous(self.meta, pg), symm_mem.rendezvous(self.flags, pg)
-        self._handles += [hm, hf]
-        self.peer_meta = [self.meta if r == self.rank else hm.get_buffer(r, (world,), torch.int64, 0) for r in range(world)]
-        self.flag_ptrs = [int(x) for x in hf.buffer_ptrs]  # flags of rank r, mapped here
-        self._meta_ptrs = (ctypes.c_void_p * world)(*[int(x) for x in hm.buffer_ptrs])
-        # flag (slot, me) in every rank's array; flags (slot, r) in mine
-        self._signal_ptrs = [(ctypes.c_void_p * world)(*[self.flag_ptrs[d] + 4 * (slot * world + self.rank) for d in range(world)])
-                             for slot in range(2)]
-        self._wait_ptrs = [(ctypes.c_void_p * world)(*[self.flag_ptrs[self.rank] + 4 * (slot * world + r) for r in range(world)])
-                           for slot in range(2)]
-        self.meta_host = torch.empty(world, dtype=torch.int64).pin_memory()
-        counts = torch.tensor(self.ks, dtype=torch.int64)
-        counts[-1] += 1  # the final entry of the table belongs to the last rank
-        self._owner = torch.repeat_interleave(torch.arange(world), counts).to(dev)  # rank that supplies each entry
-        self._seq = 0
-        self._turn = 0
-        # self-test of the stream memory operations on peer memory (value 0: leaves the protocol untouched); raises
-        # here, where callers can still fall back to the NCCL path, rather than in the first gather
-        self._signal_all(0, 0)
-        self._wait_all(0, 0)
-        torch.cuda.synchronize()
-        dist.barrier(group=group)
-        torch.cuda.synchronize()
+        self._handles = [symm_mem.rendezvous(t, pg) for t in (self.words, self.offsets, self.flags)]
+        arr = lambda h: (ctypes.c_void_p * world)(*[int(x) for x in h.buffer_ptrs])
+        self._h = ctypes.c_void_p()
+        dist.barrier(group=group)  # every rank has zeroed its flags
+        N.raise_for(self._lib.ctr_gather_create(world, self.rank, n_buffers, self.slot_words, self.slot_streams,
+                                                arr(self._handles[0]), arr(self._handles[1]), arr(self._handles[2]),
+                                                ctypes.byref(self._h)))
 
-    # -- stream memory operations on the current stream ------------------------------------------------
-    def _check(self, rc: int) -> None:
+    def close(self) -> None:
+        if self._h:
+            self._lib.ctr_gather_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _slot_views(self, turn: int, src: int):
+        b = turn % self.n_buffers
+        w0 = (b * self.world + src) * self.slot_words
+        o0 = (b * self.world + src) * (self.slot_streams + 1)
+        return self.words[w0:w0 + self.slot_words], self.offsets[o0:o0 + self.slot_streams + 1]
+
+    def begin_turn(self, n_streams: int, n_symbols: int = 0, coder: str = "ans") -> "SlotGather.Turn":
+        from .batch import Compressed
+        q = ctypes.c_uint32()
+        self._N.raise_for(self._lib.ctr_gather_begin_turn(self._h, ctypes.byref(q), None, None, None))
+        w, o = self._slot_views(q.value, self.rank)
+        return SlotGather.Turn(q.value, Compressed(w, o[:n_streams + 1], n_streams, n_symbols, coder))
+
+    def push(self, turn: "SlotGather.Turn", n_streams: int) -> None:
+        """Behind the encode on the current stream; returns at once."""
+        self._N.raise_for(self._lib.ctr_gather_push(self._h, turn.number, n_streams, torch.cuda.current_stream().cuda_stream))
+
+    def wait(self, turn: "SlotGather.Turn") -> None:
+        self._N.raise_for(self._lib.ctr_gather_wait(self._h, turn.number, torch.cuda.current_stream().cuda_stream))
+
+    def release(self, turn: "SlotGather.Turn") -> None:
+        self._N.raise_for(self._lib.ctr_gather_release(self._h, turn.number, torch.cuda.current_stream().cuda_stream))
+
+    def sync(self) -> None:
+        self._N.raise_for(self._lib.ctr_gather_sync(self._h))
+
+    def shard(self, turn: "SlotGather.Turn", src_rank: int, n_streams: int, n_symbols: int, coder: str = "ans", sym_offsets=None):
+        """Rank `src_rank`'s container of this turn as a batch.Compressed (views into my receive buffer)."""
+        from .batch import Compressed
+        w, o = self._slot_views(turn.number, src_rank)
+        return Compressed(w, o[:n_streams + 1], n_streams, n_symbols, coder, sym_offsets)
+
+
+class NcclComm:
+    """A raw NCCL communicator over the ranks of a torch.distributed group (ctypes on the NCCL library PyTorch
+    ships), for the C ABI's ctr_gather_compressed_nccl: what a Rust / C host passes as its own ncclComm_t."""
+
+    def __init__(self, group: Optional[dist.ProcessGroup] = None):
+        import glob
+        import os
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        lib = None
+        cands = []
+        try:
+            import nvidia.nccl
+            for base in nvidia.nccl.__path__:  # namespace package
+                cands += glob.glob(os.path.join(base, "lib", "libnccl.so*"))
+        except Exception:
+            pass
+        for path in cands + ["libnccl.so.2"]:
+            try:
+                lib = ctypes.CDLL(path, mode=ctypes.RTLD_GLOBAL)
+                os.environ.setdefault("CTR_NCCL_LIB", path)
+                break
+            except OSError:
+                continue
+        if lib is None:
+            raise RuntimeError("libnccl not found")
+        self._nccl = lib
+        uid = (ctypes.c_byte * 128)()
+        if self.rank == 0:
+            rc = lib.ncclGetUniqueId(ctypes.byref(uid))
+            if rc:
+                raise RuntimeError(f"ncclGetUniqueId failed ({rc})")
+        box = [bytes(uid)]
+        dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        uid = (ctypes.c_byte * 128).from_buffer_copy(box[0])
+
+        class _Uid(ctypes.Structure):
+            _fields_ = [("internal", ctypes.c_byte * 128)]
+
+        u = _Uid()
+        ctypes.memmove(ctypes.byref(u), uid, 128)
+        self.comm = ctypes.c_void_p()
+        lib.ncclCommInitRank.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int, _Uid, ctypes.c_int]
+        rc = lib.ncclCommInitRank(ctypes.byref(self.comm), self.world, u, self.rank)
         if rc:
-            raise RuntimeError("PeerGather: " + self._lib.ctr_status_string(rc).decode() + " " + self._lib.ctr_last_cuda_error().decode())
+            raise RuntimeError(f"ncclCommInitRank failed ({rc})")
 
-    def _signal_all(self, slot: int, value: int) -> None:
-        self._check(self._lib.ctr_stream_write_value32_many(self._signal_ptrs[slot], self.world, (self.rank + 1) % self.world, value,
-                                                           torch.cuda.current_stream().cuda_stream))
+    def close(self):
+        if self.comm:
+            self._nccl.ncclCommDestroy.argtypes = [ctypes.c_void_p]
+            self._nccl.ncclCommDestroy(self.comm)
+            self.comm = None
 
-    def _wait_all(self, slot: int, value: int) -> None:
-        self._check(self._lib.ctr_stream_wait_value32_many(self._wait_ptrs[slot], self.world, value,
-                                                          torch.cuda.current_stream().cuda_stream))
 
-    def gather_begin(self, words: torch.Tensor, offsets: torch.Tensor) -> PendingGather:
-        self._seq += 1
-        q = self._seq
-        self._check(self._lib.ctr_peer_push(self._meta_ptrs, self.world, (self.rank + 1) % self.world, 8 * self.rank,
-                                            offsets[-1:].data_ptr(), 8, torch.cuda.current_stream().cuda_stream))
-        self._signal_all(0, q)
-        self._wait_all(0, q)
-        self.meta_host.copy_(self.meta, non_blocking=True)
-        ready = torch.cuda.Event()
-        ready.record()
-        return PendingGather(words, offsets, self.group, self.meta, self.meta_host, ready, self.ks)
-
-    def gather_end(self, p: PendingGather) -> GatheredContainer:
-        world, rank = self.world, self.rank
-        p.ready.synchronize()
-        lens = [int(x) for x in p.metas_host]
-        if max(lens) > self.cap:
-            raise MemoryError("PeerGather: a rank's container exceeds the receive capacity")
-        word_base = [0]
-        for n in lens:
-            word_base.append(word_base[-1] + n)
-        b = self._turn
-        self._turn = (self._turn + 1) % self.n_buffers
-        wb, n = word_base[rank], lens[rank]
-        sb, k = self.stream_base[rank], self.ks[rank]
-        n_off = k + 1 if rank == world - 1 else k  # the last rank also supplies the final entry
-        stream = torch.cuda.current_stream().cuda_stream
-        first = (rank + 1) % world  # start with my right neighbour: in every round the destinations form a permutation
-        self._check(self._lib.ctr_peer_push(self._dense_ptrs[b], world, first, 4 * wb, p.words.data_ptr(), 4 * n, stream))
-        self._check(self._lib.ctr_peer_push(self._off_ptrs[b], world, first, 8 * sb, p.offsets.data_ptr(), 8 * n_off, stream))
-        self._signal_all(1, self._seq)
-        self._wait_all(1, self._seq)
-        total = word_base[-1]
-        gc = GatheredContainer(self.dense[b][:max(total, 1)], self.g_off[b], self.stream_base[:-1], word_base[:-1])
-        gc._rebase = torch.tensor(word_base[:world], dtype=torch.int64)
-        return gc
-
-    def finish(self, gc: GatheredContainer) -> GatheredContainer:
-        """Rebases the gathered offset table (rank r's entries += first word of rank r) on the current stream; call
-        it once, after waiting for the event recorded behind `gather_end`.  Until then `gc.offsets` holds the
-        ranks' local offsets."""
-        base = getattr(gc, "_rebase", None)
-        if base is not None:
-            gc.offsets += base.pin_memory().to(gc.offsets.device, non_blocking=True)[self._owner]
-            gc._rebase = None
-        return gc
+def gather_compressed_nccl(comm: NcclComm, words: torch.Tensor, offsets: torch.Tensor, slot_words: int, slot_streams: int):
+    """ctr_gather_compressed_nccl on the current stream: returns (words int32[world][slot_words],
+    offsets int64[world][slot_streams + 1], meta int64[world][2] on the host = {total words, streams} per rank)."""
+    from . import _native as N
+    lib = N.load()
+    dev = words.device
+    world = comm.world
+    k = offsets.numel() - 1
+    w_out = torch.empty((world, slot_words), dtype=torch.int32, device=dev)
+    o_out = torch.zeros((world, slot_streams + 1), dtype=torch.int64, device=dev)
+    meta_dev = torch.empty(2 * world + 2, dtype=torch.int64, device=dev)
+    meta_host = torch.empty((world, 2), dtype=torch.int64).pin_memory()
+    N.raise_for(lib.ctr_gather_compressed_nccl(comm.comm, world, comm.rank, words.data_ptr(), offsets.data_ptr(), k, slot_words,
+                                               slot_streams, w_out.data_ptr(), o_out.data_ptr(), meta_dev.data_ptr(),
+                                               meta_host.data_ptr(), torch.cuda.current_stream().cuda_stream))
+    return w_out, o_out, meta_host

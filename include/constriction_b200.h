@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define CTR_ABI_VERSION 2
+#define CTR_ABI_VERSION 3
 
 /* call-level and data-level status codes */
 #define CTR_OK 0
@@ -244,14 +244,16 @@ int ctr_range_decode_gaussian(int32_t min_symbol, int32_t max_symbol, const doub
                               uint64_t *words_read_dev, uint32_t *status_dev, void *stream);
 
 /* ---- host-buffer entry points (the reference-facing call: host in, host out) ------------------
- * Same semantics with HOST buffers (pinned memory makes the copies asynchronous DMA): device memory
- * comes from the stream-ordered CUDA memory pool, inputs are copied in, the kernels run, results are
- * copied back and the call synchronises before returning.  The caller owns all buffers:
- * `words_out_host` needs room for `words_capacity` words (ctr_ans_max_compressed_words gives a safe
- * bound; CTR_ERR_OUT_OF_SPACE if the batch needs more).  `*data_status` / `*failing_stream` receive
- * the data-level status.  These are what a pyo3 / Rust binding for
- * `AnsCoder::encode_iid_symbols_reverse` / `decode_iid_symbols` over many coders would call;
- * bench.py's `e2e` number times them. */
+ * Same semantics with HOST buffers: what a pyo3 / Rust binding for `AnsCoder::encode_iid_symbols_reverse` /
+ * `decode_iid_symbols` (stack.rs:835-849, stream/mod.rs:1016-1031) over many coders calls; bench.py's `e2e` number
+ * times them.  A call is PCIe-bound, so the library pipelines it: the batch is cut into chunks of consecutive
+ * streams (each a complete batch of its own) that flow through upload -> coder kernel -> download on three CUDA
+ * streams, device buffers from the stream-ordered memory pool.  Pinned host buffers (cudaHostAlloc /
+ * cudaHostRegister) make every copy an asynchronous DMA; pageable buffers work but serialise the pipeline.
+ * The caller owns all buffers: `words_out_host` needs room for `words_capacity` words
+ * (ctr_ans_max_compressed_words gives a safe bound; CTR_ERR_OUT_OF_SPACE if the batch needs more), offsets_out_host
+ * u64[K+1].  `*data_status` / `*failing_stream` receive the data-level status.  sym_offsets_host that do not
+ * describe slices of the symbol array return CTR_ERR_BAD_ARGUMENT. */
 int ctr_ans_encode_reverse_host(ctr_model_t model, const int32_t *symbols_host, uint64_t n_symbols,
                                 uint64_t n_streams, const uint64_t *sym_offsets_host,
                                 const uint32_t *model_index_host, int32_t model_index_mode,
@@ -270,18 +272,85 @@ int ctr_range_decode_host(ctr_model_t model, const uint32_t *words_host, const u
                           const uint32_t *model_index_host, int32_t model_index_mode, int32_t *symbols_out_host,
                           int *data_status, uint64_t *failing_stream);
 
-/* ---- stream-ordered signalling without any SM (multi-GPU exchange, constriction_b200/dist.py) ----
+/* Asynchronous forms: the same pipeline runs on a thread of the library; the call returns at once with a job handle
+ * and every buffer (inputs, outputs, data_status, failing_stream) must stay valid until ctr_host_job_wait, which
+ * returns the call's status and frees the handle.  One host thread can so keep both directions of the bus busy:
+ * start the encode of batch i+1 (upload-bound) and the decode of batch i (download-bound), then wait for both. */
+typedef struct ctr_host_job_s *ctr_host_job_t;
+int ctr_ans_encode_reverse_host_async(ctr_model_t model, const int32_t *symbols_host, uint64_t n_symbols,
+                                      uint64_t n_streams, const uint64_t *sym_offsets_host,
+                                      const uint32_t *model_index_host, int32_t model_index_mode,
+                                      uint32_t *words_out_host, uint64_t words_capacity, uint64_t *offsets_out_host,
+                                      int *data_status, uint64_t *failing_stream, ctr_host_job_t *job);
+int ctr_ans_decode_host_async(ctr_model_t model, const uint32_t *words_host, const uint64_t *offsets_host,
+                              uint64_t n_symbols, uint64_t n_streams, const uint64_t *sym_offsets_host,
+                              const uint32_t *model_index_host, int32_t model_index_mode, int32_t *symbols_out_host,
+                              int *data_status, uint64_t *failing_stream, ctr_host_job_t *job);
+int ctr_range_encode_host_async(ctr_model_t model, const int32_t *symbols_host, uint64_t n_symbols, uint64_t n_streams,
+                                const uint64_t *sym_offsets_host, const uint32_t *model_index_host,
+                                int32_t model_index_mode, uint32_t *words_out_host, uint64_t words_capacity,
+                                uint64_t *offsets_out_host, int *data_status, uint64_t *failing_stream,
+                                ctr_host_job_t *job);
+int ctr_range_decode_host_async(ctr_model_t model, const uint32_t *words_host, const uint64_t *offsets_host,
+                                uint64_t n_symbols, uint64_t n_streams, const uint64_t *sym_offsets_host,
+                                const uint32_t *model_index_host, int32_t model_index_mode, int32_t *symbols_out_host,
+                                int *data_status, uint64_t *failing_stream, ctr_host_job_t *job);
+int ctr_host_job_wait(ctr_host_job_t job);
+
+/* ---- multi-GPU exchange of compressed containers (ctr_gather_compressed) ----------------------
+ * Streams are independent coders, so encode and decode shard over the GPUs of a node with no communication; the one
+ * exchange step is an all-gather of the per-rank containers (what a host does with the per-shard Vec<u32>s that
+ * `into_compressed()` returns, stack.rs:891-895 / queue.rs:349-355, cf. tests/issue52.rs:38-53).  The gathered
+ * container is SLOTTED: words u32[n_buffers][world][slot_words], offsets u64[n_buffers][world][slot_streams + 1];
+ * slot (turn mod n_buffers, r) holds rank r's container of that turn exactly as its encoder wrote it (offsets relative
+ * to the slot), so ctr_*_decode(model, slot words, slot offsets, ...) decodes rank r's streams on any rank.
+ *
+ * Peer-memory implementation (one process per GPU, one node): `words_bases[r]`, `offsets_bases[r]`, `flags_bases[r]`
+ * are rank r's receive buffers mapped into THIS process (symmetric memory over NVLink; allocation and exchange of the
+ * mappings is the host's business: torch.distributed._symmetric_memory, or cuMemCreate + cuMemExportToShareableHandle).
+ * `flags` is u32[2][n_buffers][world], zeroed before the first turn; slot_words a multiple of 4.  Per turn:
+ *   ctr_gather_begin_turn   -> turn number q and MY slot in MY buffers: encode straight into it
+ *   (the caller enqueues ctr_*_encode with words_out = slot, offsets_out = slot offsets on `encode_stream`)
+ *   ctr_gather_push         enqueues an 8-byte size read-back behind the encode and returns at once; a worker thread of
+ *                           the library waits for THIS rank's encode, then pushes the used part of the slot to every
+ *                           peer with copy-engine transfers (no SM, no kernel) and raises `arrived` flags in the
+ *                           peers' memory with cuStreamWriteValue32 -- no cross-rank host wait, no size exchange
+ *   ctr_gather_wait         `consumer_stream` waits (cuStreamWaitValue32) until every peer's slot of turn q has arrived
+ *   ctr_gather_release      `consumer_stream` tells every peer that this rank is done reading turn q (a peer's push
+ *                           of turn q + n_buffers waits for it); also required before THIS rank encodes turn
+ *                           q + n_buffers into the same buffer (stream order on the caller's side)
+ *   ctr_gather_sync         host waits until all pushes issued so far have completed; returns a data-level error of
+ *                           the worker (CTR_ERR_OUT_OF_SPACE if a container exceeded slot_words)                     */
+typedef struct ctr_gather_s *ctr_gather_t;
+int ctr_gather_create(uint32_t world, uint32_t rank, uint32_t n_buffers, uint64_t slot_words, uint64_t slot_streams,
+                      void *const *words_bases, void *const *offsets_bases, void *const *flags_bases, ctr_gather_t *out);
+int ctr_gather_destroy(ctr_gather_t g);
+int ctr_gather_begin_turn(ctr_gather_t g, uint32_t *turn, uint32_t **words_slot_dev, uint64_t *words_capacity,
+                          uint64_t **offsets_slot_dev);
+int ctr_gather_slot(ctr_gather_t g, uint32_t turn, uint32_t src_rank, const uint32_t **words_slot_dev,
+                    const uint64_t **offsets_slot_dev);
+int ctr_gather_push(ctr_gather_t g, uint32_t turn, uint64_t n_streams, void *encode_stream);
+int ctr_gather_wait(ctr_gather_t g, uint32_t turn, void *consumer_stream);
+int ctr_gather_release(ctr_gather_t g, uint32_t turn, void *consumer_stream);
+int ctr_gather_sync(ctr_gather_t g);
+
+/* NCCL implementation of the same exchange on a caller-supplied communicator (`nccl_comm` is an ncclComm_t; NCCL is
+ * resolved at run time with dlsym, CTR_NCCL_LIB names the library if the host has not loaded it).  One buffer:
+ * words_out_dev u32[world][slot_words], offsets_out_dev u64[world][slot_streams + 1].  meta_dev is u64[2 * world + 2]
+ * of device scratch, meta_host u64[2 * world] receives {total words, streams} of every rank.  Enqueues an
+ * ncclAllGather of the sizes, WAITS on the host for them (the one synchronisation), then enqueues grouped
+ * ncclBroadcasts that write every rank's words and offset table straight into its slot.  Returns
+ * CTR_ERR_OUT_OF_SPACE if a rank's container does not fit its slot. */
+int ctr_gather_compressed_nccl(void *nccl_comm, uint32_t world, uint32_t rank, const uint32_t *words_dev,
+                               const uint64_t *offsets_dev, uint64_t n_streams, uint64_t slot_words,
+                               uint64_t slot_streams, uint32_t *words_out_dev, uint64_t *offsets_out_dev,
+                               uint64_t *meta_dev, uint64_t *meta_host, void *stream);
+
+/* ---- stream-ordered signalling without any SM (building blocks of the exchange above) ----
  * cuStreamWriteValue32 / cuStreamWaitValue32 (>=) on `stream`: `addr` is a 4-byte aligned device address, which may
- * be a peer GPU's memory mapped into this process (symmetric memory).  Used to order copy-engine pushes between
- * the GPUs of a node while coder kernels occupy every SM (an NCCL barrier kernel would have to wait for them). */
+ * be a peer GPU's memory mapped into this process (symmetric memory). */
 int ctr_stream_write_value32(void *addr, uint32_t value, void *stream);
 int ctr_stream_wait_value32(void *addr, uint32_t value, void *stream);
-/* the same for a list of addresses (written in the order first, first+1, ... mod n), and a copy-engine push of one
- * device buffer to the same offset of n_dst (peer-mapped) destination buffers, starting with destination `first` */
-int ctr_stream_write_value32_many(void *const *addrs, uint32_t n, uint32_t first, uint32_t value, void *stream);
-int ctr_stream_wait_value32_many(void *const *addrs, uint32_t n, uint32_t value, void *stream);
-int ctr_peer_push(void *const *dst_bases, uint32_t n_dst, uint32_t first, uint64_t dst_offset_bytes, const void *src,
-                  uint64_t bytes, void *stream);
 
 /* ---- launch accounting and kernel timing (bench.py's `gpu_launches` and `roofline`) ----------
  * With profiling enabled the library brackets every main coder kernel (not the compaction helpers)

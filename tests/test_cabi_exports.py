@@ -21,7 +21,7 @@ def test_library_exports_every_declared_symbol():
     for name in names:
         assert hasattr(lib, name), f"{name} declared in the header but not exported"
     assert set(names) == set(N.SIGNATURES), set(names) ^ set(N.SIGNATURES)
-    assert lib.ctr_abi_version() == 2
+    assert lib.ctr_abi_version() == 3
     assert lib.ctr_status_string(1).decode().startswith("Tried to encode symbol")
 
 
@@ -96,4 +96,9 @@ def test_call_level_argument_checks():
     assert lib.ctr_range_encode_gaussian(-5, 5, *g_enc, C.byref(big), *enc_args) == N.ERR_BAD_ARGUMENT
     # stream memory operations: null address
     assert lib.ctr_stream_write_value32(None, 1, None) == N.ERR_BAD_ARGUMENT
-    assert lib.ctr_peer_push(None, 0, 0, 0, None, 0, None) == N.ERR_BAD_ARGUMENT
+    # gather: null / inconsistent arguments
+    out = C.c_void_p()
+    assert lib.ctr_gather_create(0, 0, 2, 64, 4, one, one, one, C.byref(out)) == N.ERR_BAD_ARGUMENT
+    assert lib.ctr_gather_create(2, 2, 2, 64, 4, one, one, one, C.byref(out)) == N.ERR_BAD_ARGUMENT
+    assert lib.ctr_gather_push(None, 1, 1, None) == N.ERR_BAD_ARGUMENT
+    assert lib.ctr_gather_compressed_nccl(None, 2, 0, one, one, 1, 64, 4, one, one, one, one, None) == N.ERR_BAD_ARGUMENT
