@@ -7,7 +7,10 @@ shared memory.  A "step" is one pass of the hot path over the batch: ANS encode 
 (coder kernel + compaction into the dense container), [N>1: NCCL all-gather of the compressed
 containers], ANS decode of all streams.  `value` is measured with inputs resident in HBM; `e2e` is
 the same step through the host-buffer C ABI (pinned host buffers, H2D/D2H copies inside the timed
-region).  Weak scaling: every GPU gets its own 1e8-symbol shard.
+region).  Weak scaling: every GPU gets its own 1e8-symbol shard.  The line also carries `extra_configs`:
+BASELINE.json configs[3] (1e9 symbols in 8192 RangeEncoder streams, sharded over the N ranks, gathered),
+configs[4] (64x192x32x32 latents, sharded by image) and the north star's 1e9-symbol size, each with its
+own timings and parity bit.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
     torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
@@ -47,6 +50,7 @@ def parse_args():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cpu-sample", type=int, default=50_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra-configs", action="store_true")
     return ap.parse_args()
 
 
@@ -179,15 +183,56 @@ def cpu_round_trip(oracle, syms, k, cdf, threads):
     return t1 - t0, t2 - t1
 
 
-def cpu_baseline(n_sample, k, threads):
+def cpu_model_string():
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.lower().startswith("model name"):
+                    return line.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
+
+
+def cpu_baseline(n_sample, k, threads, small=False):
+    """SURVEY 8(d)'s three rows of the restated reference on this box's host cores:
+    (i) one thread, lazily evaluated QuantizedGaussian (what stock constriction computes for this model: 2 erf per
+    encoded symbol, inverse + ~3 erf per decoded symbol); (ii) one thread, tabulated model; (iii) all cores, tabulated.
+    `value` is row (iii), the fastest, so that every reported ratio is conservative."""
     from oracle import refapi as O
     cdf = O.qgauss_cdf(*MODEL)
     syms = synth_symbols_numpy(n_sample, 2)
     cpu_round_trip(O, syms[: n_sample // 10], k, cdf, threads)  # warm the threads / caches
     te, td = min((cpu_round_trip(O, syms, k, cdf, threads) for _ in range(2)), key=sum)
-    return {"value": n_sample / (te + td) / 1e6, "unit": "Msymbols/s", "cores": threads, "kind": "port",
+    rows = {"table_all_cores": {"value": n_sample / (te + td) / 1e6, "cores": threads, "sample": n_sample,
+                                "encode_s": te, "decode_s": td}}
+    n1 = min(n_sample, 4_000_000 if small else 20_000_000)
+    one = syms[:n1]
+    t0 = time.perf_counter()
+    w = O.ans_encode_iid(one, cdf, MODEL[0])
+    t1 = time.perf_counter()
+    out = O.ans_decode_iid(w, n1, cdf, MODEL[0])
+    t2 = time.perf_counter()
+    assert np.array_equal(out, one)
+    rows["table_1thread"] = {"value": n1 / (t2 - t0) / 1e6, "cores": 1, "sample": n1, "ns_per_symbol_encode": (t1 - t0) / n1 * 1e9,
+                             "ns_per_symbol_decode": (t2 - t1) / n1 * 1e9}
+    n2 = min(n_sample, 1_000_000 if small else 4_000_000)
+    lazy = syms[:n2]
+    t0 = time.perf_counter()
+    w2 = O.ans_encode_qgauss_lazy(lazy, *MODEL)
+    t1 = time.perf_counter()
+    out = O.ans_decode_qgauss_lazy(w2, n2, *MODEL)
+    t2 = time.perf_counter()
+    assert np.array_equal(out, lazy) and np.array_equal(w2, O.ans_encode_iid(lazy, cdf, MODEL[0]))
+    rows["lazy_erf_1thread"] = {"value": n2 / (t2 - t0) / 1e6, "cores": 1, "sample": n2, "ns_per_symbol_encode": (t1 - t0) / n2 * 1e9,
+                                "ns_per_symbol_decode": (t2 - t1) / n2 * 1e9,
+                                "note": "the work stock constriction does for QuantizedGaussian (quantize.rs:525-568,580-779)"}
+    return {"value": rows["table_all_cores"]["value"], "unit": "Msymbols/s", "cores": threads, "kind": "port",
+            "cpu_model": cpu_model_string(), "rows": rows,
+            "reference_published": "README.md:202-206 (i7-7500U, Rust, table models): ANS 24.2 ns encode / 6.1 ns decode per symbol",
             "sample": f"{n_sample} symbols of the same workload in {k} streams, tabulated model, C restatement "
-                      f"(oracle/) of stack.rs encode/decode, {threads} threads; encode {te:.3f}s decode {td:.3f}s"}
+                      f"(oracle/) of stack.rs encode/decode, {threads} threads; encode {te:.3f}s decode {td:.3f}s; "
+                      f"rows (i)/(ii) on one thread over {n2}/{n1} symbols"}
 
 
 def run_reference(args):
@@ -215,8 +260,9 @@ def run_reference(args):
         "config": {"workload": "configs[1]: 1e8 i.i.d. symbols, QuantizedGaussian(-50,50,3.2,9.6), ANS encode+decode",
                    "symbols_per_step": n_sample, "streams": k,
                    "note": "reference = CPU restatement of constriction's stack.rs loops (Rust toolchain absent); "
-                           "each step is a bounded sample of the workload"},
-        "cpu_baseline": {"value": value, "unit": "Msymbols/s", "cores": threads, "kind": "port",
+                           "each step is a bounded sample of the workload; tabulated model on all cores, i.e. faster "
+                           "than stock constriction's lazily evaluated QuantizedGaussian"},
+        "cpu_baseline": {"value": value, "unit": "Msymbols/s", "cores": threads, "kind": "port", "cpu_model": cpu_model_string(),
                          "sample": f"{n_sample} symbols per step, {k} streams, tabulated model, {threads} threads"},
         "e2e": {"value": value, "unit": "Msymbols/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -226,6 +272,31 @@ def run_reference(args):
 # ----------------------------------------------------------------------------------------------------
 # GPU arm
 # ----------------------------------------------------------------------------------------------------
+def pin_to_gpu_numa_node(local_rank):
+    """Run this process (and the pinned buffers it allocates from now on) on the CPUs next to its GPU.  Returns the
+    previous affinity mask so that the CPU baseline can have all cores back."""
+    try:
+        before = os.sched_getaffinity(0)
+        import pynvml as nv
+        nv.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = local_rank
+        if vis:
+            ids = [v.strip() for v in vis.split(",") if v.strip()]
+            if local_rank < len(ids) and ids[local_rank].isdigit():
+                phys = int(ids[local_rank])
+        h = nv.nvmlDeviceGetHandleByIndex(phys)
+        n_words = (os.cpu_count() + 63) // 64
+        mask = nv.nvmlDeviceGetCpuAffinity(h, n_words)
+        cpus = {64 * i + b for i, w in enumerate(mask) for b in range(64) if (int(w) >> b) & 1} & before
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return before, len(cpus)
+        return before, len(before)
+    except Exception:
+        return None, None
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -240,6 +311,7 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py --impl ours needs a CUDA device (no CPU fallback)")
     torch.cuda.set_device(local_rank)
+    all_cpus, numa_cpus = pin_to_gpu_numa_node(local_rank)
     if world > 1:
         # NCCL prints its version banner to stdout when the first communicator is created; stdout must carry
         # exactly one JSON line, so file descriptor 1 points to stderr until the warm-up is over
@@ -250,74 +322,73 @@ def run_ours(args):
     lib = N.load()
     n, k = args.symbols, args.streams
 
-    # synthetic shard, generated on the device (seed differs per rank), resident in HBM
-    g = torch.Generator(device="cuda")
-    g.manual_seed(2 + rank)
-    syms = torch.clamp(torch.round(torch.randn(n, device="cuda", generator=g) * MODEL[3] + MODEL[2]), MODEL[0],
-                       MODEL[1]).to(torch.int32)
+    def synth(seed_rank):  # synthetic shard, generated on the device (seed differs per rank), resident in HBM
+        g = torch.Generator(device="cuda")
+        g.manual_seed(2 + seed_rank)
+        return torch.clamp(torch.round(torch.randn(n, device="cuda", generator=g) * MODEL[3] + MODEL[2]), MODEL[0],
+                           MODEL[1]).to(torch.int32)
+
+    syms = synth(rank)
     model = B.ModelTable.quantized_gaussian(MODEL[0], MODEL[1], [MODEL[2]], [MODEL[3]])
     bc = B.BatchCoder()
     out = torch.empty_like(syms)
-    comp = None
+    L0 = N.Layout()
+    L0.n_streams, L0.n_symbols = k, n
+    cap_words = int(lib.ctr_ans_max_compressed_words(C.byref(L0)))
+    state = {"comp": None, "prev": None, "sg": None}
+    neighbour = (rank + 1) % world
 
-    side = torch.cuda.Stream() if world > 1 else None
-    gathered = {}
-    comps = [None, None]       # N > 1: two containers, so that step i+1 can encode while step i's container is gathered
-    pipe = {"i": 0, "prev": None}
-
-    def step():
-        # N == 1: encode -> decode.
-        # N > 1: encode -> decode of the own shard on the main stream; on a side stream the all-gather of the
-        # containers: sizes first (16 bytes per rank, the host waits for them while the decode runs), then the
-        # words and offset tables.  The gather of step i is joined at the end of step i+1 (it only has to be done
-        # before its source container is overwritten by the encode of step i+2), so in steady state a step costs
-        # max(encode + decode, gather); drain() joins the last one inside the timed region.
-        nonlocal comp
-        if world == 1:
-            comp = bc.ans_encode(syms, model, n_streams=k, out=comp)
-            bc.ans_decode(comp, model, out=out)
-            return
-        buf = pipe["i"] & 1
-        pipe["i"] += 1
-        comp = comps[buf] = bc.ans_encode(syms, model, n_streams=k, out=comps[buf])
-        encoded = torch.cuda.Event()
-        encoded.record()
-        if pipe.get("pg") is None and os.environ.get("CTR_GATHER", "peer") == "peer":
-            torch.cuda.synchronize()  # (set-up, first warm-up step only)
+    gather_kind = None
+    if world > 1:
+        if os.environ.get("CTR_GATHER", "peer") == "peer":
             try:
-                pipe["pg"] = D.PeerGather(comp.words.numel(), [k] * world)
+                state["sg"] = D.SlotGather(cap_words, k)
                 ok = 1
             except Exception as exc:  # no symmetric memory / stream memory operations here: NCCL all-gather instead
-                sys.stderr.write(f"rank {rank}: PeerGather unavailable ({exc}); using the NCCL all-gather\n")
+                sys.stderr.write(f"rank {rank}: SlotGather unavailable ({exc}); using the NCCL all-gather\n")
                 ok = 0
             flag = torch.tensor([ok], device="cuda")
             dist.all_reduce(flag, op=dist.ReduceOp.MIN)  # all ranks take the same path
             if int(flag.item()) == 0:
-                pipe["pg"] = None
-                os.environ["CTR_GATHER"] = "nccl"
-        pg = pipe.get("pg")
-        with torch.cuda.stream(side):
-            side.wait_event(encoded)
-            pending = (pg.gather_begin(comp.words, comp.offsets) if pg else
-                       D.all_gather_compressed_begin(comp.words, comp.offsets, stream_counts=[k] * world))
-        bc.ans_decode(comp, model, out=out)
-        with torch.cuda.stream(side):
-            gathered["gc"] = pg.gather_end(pending) if pg else D.all_gather_compressed_end(pending)
-            done = torch.cuda.Event()
-            done.record()
-        join()
-        pipe["prev"] = (done, gathered["gc"])
+                state["sg"] = None
+        gather_kind = ("ctr_gather_*: every rank encodes into its slot of a symmetric-memory container and a library thread pushes "
+                       "it to all peers with copy-engine transfers over NVLink, ordered by stream memory operations (no kernel, "
+                       "no cross-rank host wait)") if state["sg"] else "NCCL all-gather (torch.distributed), one host wait for the sizes"
+    sg = state["sg"]
 
-    def join():  # the previous step's gather: wait for it on the main stream and finalise its offset table
-        if pipe["prev"] is not None:
-            done, gc = pipe["prev"]
-            torch.cuda.current_stream().wait_event(done)
-            if pipe.get("pg") is not None:
-                pipe["pg"].finish(gc)
-            pipe["prev"] = None
+    def step():
+        # N == 1: encode -> decode.
+        # N > 1: encode my shard straight into my slot of the gathered container; push it to all peers (asynchronously,
+        # no SM); wait for the PREVIOUS turn's container to be complete and decode my right neighbour's shard out of
+        # it (so every decode reads words that crossed NVLink); release that turn.  In steady state a step costs
+        # max(encode + decode, gather); drain() joins the last gather inside the timed region.
+        if world == 1:
+            state["comp"] = bc.ans_encode(syms, model, n_streams=k, out=state["comp"])
+            bc.ans_decode(state["comp"], model, out=out)
+            return
+        if sg is None:
+            state["comp"] = bc.ans_encode(syms, model, n_streams=k, out=state["comp"])
+            gc = D.all_gather_compressed(state["comp"].words, state["comp"].offsets, stream_counts=[k] * world)
+            state["gc"] = gc
+            bc.ans_decode(state["comp"], model, out=out)
+            return
+        turn = sg.begin_turn(k, n, "ans")
+        state["comp"] = bc.ans_encode(syms, model, n_streams=k, out=turn.out)
+        sg.push(turn, k)
+        prev = state["prev"]
+        if prev is None:
+            bc.ans_decode(state["comp"], model, out=out)
+        else:
+            sg.wait(prev)
+            bc.ans_decode(sg.shard(prev, neighbour, k, n, "ans"), model, out=out)
+            sg.release(prev)
+        state["prev"] = turn
 
-    def drain():
-        join()
+    def drain():  # the last turn's gather completes inside the timed region
+        if sg is not None and state["prev"] is not None:
+            sg.wait(state["prev"])
+            sg.release(state["prev"])
+            state["prev"] = None
 
     def sync_all():
         torch.cuda.synchronize()
@@ -328,24 +399,26 @@ def run_ours(args):
     sampler = ClockSampler(local_rank)  # started before the warm-up so that the GPU is not idle right before the timed steps
     for _ in range(max(args.warmup, 3)):
         step()
-    drain()
     torch.cuda.synchronize()
     if world > 1:
         sys.stdout.flush()
         os.dup2(saved_stdout, 1)
         os.close(saved_stdout)
     bc.check()
-    assert torch.equal(out, syms), "decode(encode(x)) != x"
-    total_words = comp.total_words()
-    if world > 1:  # the gathered container holds my shard at its place, and decoding from it gives my symbols
-        gc = gathered["gc"]
-        lo = gc.stream_base[rank]
-        assert torch.equal(gc.words[gc.word_base[rank]:gc.word_base[rank] + total_words], comp.words[:total_words])
-        mine = B.Compressed(gc.words, gc.offsets[lo:lo + k + 1].contiguous(), k, n, "ans")
-        check = bc.ans_decode(mine, model)
+    total_words = state["comp"].total_words()
+    if sg is not None:  # `out` = my neighbour's shard, decoded from the container that was gathered one step ago
+        want = synth(neighbour)
+        assert torch.equal(out, want), "decode of the neighbour's shard from the gathered container != its symbols"
+        del want
+        last = state["prev"]
+        drain()
         torch.cuda.synchronize()
-        assert torch.equal(check, syms), "decode from the gathered container != x"
-        del check, mine
+        for r in range(world):  # every slot of the last turn: offsets sane, and my own slot equals what I encoded
+            sh = sg.shard(last, r, k, n, "ans")
+            assert int(sh.offsets[0].item()) == 0 and int(sh.offsets[-1].item()) > 0
+        sg.sync()
+    else:
+        assert torch.equal(out, syms), "decode(encode(x)) != x"
 
     # ---- timed region: device-resident inputs --------------------------------------------------------
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
@@ -368,6 +441,8 @@ def run_ours(args):
         sync_all()
     launches = B.kernel_launch_count() - launches0
     lib.ctr_profile_enable(0)
+    if sg is not None:
+        sg.sync()
     total_ms = ev[0].elapsed_time(ev[-1])
     t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -389,116 +464,140 @@ def run_ours(args):
     bytes_per_launch = 4.0 * n + 4.0 * total_words  # symbols in/out + compressed words out/in (same for both kernels)
     dom_name, dom_ms = ("ans_encode_kernel", enc_kernel_ms) if enc_kernel_ms >= dec_kernel_ms else ("ans_decode_kernel", dec_kernel_ms)
     achieved = bytes_per_launch / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
-    traffic = None  # DRAM bytes per launch of that kernel from the committed ncu capture (same workload only)
+    traffic, traffic_src = None, None  # DRAM bytes per launch of that kernel from the committed ncu capture (same workload only)
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
             tj = json.load(f)
         if tj["symbols"] == n and tj["streams"] == k:
             traffic = tj["dram_bytes_per_launch"].get(dom_name)
+            traffic_src = "committed ncu --set full capture (profiles/traffic.json: %s), not measured in this run" % tj.get("source", "")
     except Exception:
         pass
     roofline = {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": bytes_per_launch,
                 "kernel_ms": {"ans_encode_kernel": enc_kernel_ms, "ans_decode_kernel": dec_kernel_ms},
+                "frac_by_kernel": {"ans_encode_kernel": bytes_per_launch / (enc_kernel_ms * 1e-3) / 1e9 / peak if enc_kernel_ms else None,
+                                   "ans_decode_kernel": bytes_per_launch / (dec_kernel_ms * 1e-3) / 1e9 / peak if dec_kernel_ms else None},
                 "frac_of_step": {"ans_encode_kernel": enc_kernel_ms / ms_per_step, "ans_decode_kernel": dec_kernel_ms / ms_per_step}}
 
-    # ---- e2e: host buffers through the C ABI, copies inside the timed region ---------------------------
-    # The batch goes through the host-buffer entry points as two halves (k/2 streams, n/2 symbols each), each half
-    # on its own host thread: encode_host(half) -> decode_host(half), every step.  The calls are synchronous and
-    # PCIe-bound in one direction at a time (encode: 4 bytes per symbol host->device, decode: 4 bytes per symbol
-    # device->host), so the second thread starts when the first has finished its first encode and from then on
-    # one half uploads while the other downloads: both directions of the bus are busy.  `serial_ms_per_step` is
-    # the same work issued from one thread, one call after the other.
-    halves = []
-    for h in range(2):
-        k_h = k // 2 if h == 0 else k - k // 2
-        n_h = n // 2 if h == 0 else n - n // 2
-        hs = torch.empty(n_h, dtype=torch.int32).pin_memory()
-        hs.copy_(syms[:n_h] if h == 0 else syms[n // 2:])
-        Lh = N.Layout()
-        Lh.n_streams, Lh.n_symbols = k_h, n_h
-        cap_h = int(lib.ctr_ans_max_compressed_words(C.byref(Lh)))
-        halves.append(dict(k=k_h, n=n_h, syms=hs, cap=cap_h, words=torch.empty(cap_h, dtype=torch.int32).pin_memory(),
-                           off=torch.empty(k_h + 1, dtype=torch.int64).pin_memory(),
-                           out=torch.empty(n_h, dtype=torch.int32).pin_memory(), status=C.c_int(), bad=C.c_uint64()))
-
-    def enc_half(H):
-        rc = lib.ctr_ans_encode_reverse_host(model.handle, H["syms"].data_ptr(), H["n"], H["k"], None, None, 0,
-                                             H["words"].data_ptr(), H["cap"], H["off"].data_ptr(), C.byref(H["status"]),
-                                             C.byref(H["bad"]))
-        assert rc == 0 and H["status"].value == 0, (rc, H["status"].value)
-
-    def dec_half(H):
-        rc = lib.ctr_ans_decode_host(model.handle, H["words"].data_ptr(), H["off"].data_ptr(), H["n"], H["k"], None, None, 0,
-                                     H["out"].data_ptr(), C.byref(H["status"]), C.byref(H["bad"]))
-        assert rc == 0 and H["status"].value == 0, (rc, H["status"].value)
-
-    def e2e_serial_step():
-        for H in halves:
-            enc_half(H)
-            dec_half(H)
-
-    def e2e_pipelined(steps):
-        first_encoded = threading.Event()
-        errors = []
-
-        def worker(H, lead):
+    # ---- other BASELINE configs, each with its own timing and parity bit ----------------------------------
+    extra = None
+    if not args.no_extra_configs:
+        import bench_configs as BC
+        del out
+        state["comp"] = None
+        torch.cuda.empty_cache()
+        extra = {}
+        for name, fn in (("configs[3]", BC.baseline_config3_sharded), ("configs[4]", BC.baseline_config4_sharded),
+                         ("north_star_1e9", BC.north_star_1e9)):
             try:
-                torch.cuda.set_device(local_rank)
-                if not lead:
-                    first_encoded.wait()
-                for i in range(steps):
-                    enc_half(H)
-                    if lead and i == 0:
-                        first_encoded.set()
-                    dec_half(H)
-            except BaseException as exc:  # noqa: BLE001
-                errors.append(exc)
-                first_encoded.set()
+                sync_all()
+                extra[name] = fn(world, rank)
+            except Exception as exc:  # noqa: BLE001 -- an extra config must never take the contract line down
+                extra[name] = {"error": f"{type(exc).__name__}: {exc}"}
+            torch.cuda.empty_cache()
+        out = torch.empty_like(syms)
 
-        threads = [threading.Thread(target=worker, args=(halves[0], True)), threading.Thread(target=worker, args=(halves[1], False))]
+    # ---- e2e: host buffers through the C ABI, copies inside the timed region ---------------------------
+    # One host thread, the library's own pipeline (csrc/host_pipeline.cu): every step starts the encode of the batch
+    # (ctr_ans_encode_reverse_host_async: upload-bound) and the decode of the container the previous step produced
+    # (ctr_ans_decode_host_async: download-bound) and waits for both, so both directions of the bus are busy.  Every
+    # step moves the whole batch up and down: 1e8 symbols encoded and 1e8 symbols decoded per step.
+    # `serial_ms_per_step` is the same work with the synchronous calls, one after the other.
+    def pinned(nel, dtype):
+        return torch.empty(nel, dtype=dtype).pin_memory()
+
+    h_syms = pinned(n, torch.int32)
+    h_syms.copy_(syms)
+    h_out = pinned(n, torch.int32)
+    words_cap = min(cap_words, int(total_words * 1.25) + 4 * k + 1024)
+    conts = [dict(words=pinned(words_cap, torch.int32), off=pinned(k + 1, torch.int64), status=C.c_int(), bad=C.c_uint64())
+             for _ in range(2)]
+    dstatus, dbad = C.c_int(), C.c_uint64()
+
+    def enc_args(ct):
+        return (model.handle, h_syms.data_ptr(), n, k, None, None, 0, ct["words"].data_ptr(), words_cap, ct["off"].data_ptr(),
+                C.byref(ct["status"]), C.byref(ct["bad"]))
+
+    def dec_args(ct):
+        return (model.handle, ct["words"].data_ptr(), ct["off"].data_ptr(), n, k, None, None, 0, h_out.data_ptr(),
+                C.byref(dstatus), C.byref(dbad))
+
+    def e2e_serial_step(ct):
+        rc = lib.ctr_ans_encode_reverse_host(*enc_args(ct))
+        assert rc == 0 and ct["status"].value == 0, (rc, ct["status"].value)
+        rc = lib.ctr_ans_decode_host(*dec_args(ct))
+        assert rc == 0 and dstatus.value == 0, (rc, dstatus.value)
+
+    def e2e_overlapped_step(i):
+        j_enc, j_dec = C.c_void_p(), C.c_void_p()
+        assert lib.ctr_ans_encode_reverse_host_async(*enc_args(conts[(i + 1) & 1]), C.byref(j_enc)) == 0
+        assert lib.ctr_ans_decode_host_async(*dec_args(conts[i & 1]), C.byref(j_dec)) == 0
+        rc_e, rc_d = lib.ctr_host_job_wait(j_enc), lib.ctr_host_job_wait(j_dec)
+        assert rc_e == 0 and rc_d == 0 and conts[(i + 1) & 1]["status"].value == 0 and dstatus.value == 0, (rc_e, rc_d)
+
+    e2e = None
+    if args.e2e_steps:
+        e2e_serial_step(conts[0])
+        assert torch.equal(h_out, h_syms)
+        e2e_overlapped_step(0)
+        h_out.zero_()
+        sync_all()
         t0 = time.perf_counter()
-        for th in threads:
-            th.start()
-        for th in threads:
-            th.join()
-        dt = time.perf_counter() - t0
-        if errors:
-            raise errors[0]
-        return dt
+        for _ in range(args.e2e_steps):
+            e2e_serial_step(conts[0])
+        serial_s = (time.perf_counter() - t0) / args.e2e_steps
+        assert torch.equal(h_out, h_syms)
+        h_out.zero_()
+        e2e_serial_step(conts[0])  # container 0 is what the first overlapped step decodes
+        sync_all()
+        t0 = time.perf_counter()
+        for i in range(args.e2e_steps):
+            e2e_overlapped_step(i)
+        e2e_s = (time.perf_counter() - t0) / args.e2e_steps
+        assert torch.equal(h_out, h_syms)
+        assert torch.equal(conts[0]["off"], conts[1]["off"])
+        # what the bus allows: both directions at once, pinned, 4 bytes per symbol + the words each way
+        d_a, d_b = torch.empty(n, dtype=torch.int32, device="cuda"), syms
+        s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        with torch.cuda.stream(s1):
+            d_a.copy_(h_syms, non_blocking=True)
+        with torch.cuda.stream(s2):
+            h_out.copy_(d_b, non_blocking=True)
+        torch.cuda.synchronize()
+        duplex_s = time.perf_counter() - t0
+        t = torch.tensor([e2e_s, serial_s, duplex_s], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s, serial_s, duplex_s = (float(x) for x in t.tolist())
+        words_bytes = 4 * int(conts[0]["off"][-1].item())
+        h2d, d2h = 4 * n + words_bytes + 8 * (k + 1), words_bytes + 8 * (k + 1) + 4 * n + 64
+        pcie_gbs = 4e-9 * n / duplex_s  # per direction, both directions busy
+        bound_s = max(h2d, d2h) / (pcie_gbs * 1e9)
+        e2e = {"value": world * n / e2e_s / 1e6, "unit": "Msymbols/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "ms_per_step": e2e_s * 1e3, "steps": args.e2e_steps, "serial_ms_per_step": serial_s * 1e3,
+               "serial_value": world * n / serial_s / 1e6,
+               "pcie_roofline": {"gbs_per_direction_full_duplex": pcie_gbs, "ms_per_step": bound_s * 1e3,
+                                 "value": world * n / bound_s / 1e6, "frac": bound_s / e2e_s,
+                                 "how": "one pinned 4n-byte copy per direction at the same time, timed in this run"},
+               "numa": {"cpus_near_gpu": numa_cpus},
+               "api": "one host thread: ctr_ans_encode_reverse_host_async(batch) + ctr_ans_decode_host_async(previous step's "
+                      "container), then ctr_host_job_wait on both (pinned host buffers; the library pipelines every call as "
+                      "chunks of streams over 3 CUDA streams); serial_* = the synchronous calls one after the other"}
 
-    e2e_serial_step()
-    e2e_pipelined(1)
-    for H in halves:
-        assert torch.equal(H["out"], H["syms"])
-        H["out"].zero_()
-    sync_all()
-    t0 = time.perf_counter()
-    for _ in range(args.e2e_steps):
-        e2e_serial_step()
-    serial_s = (time.perf_counter() - t0) / max(args.e2e_steps, 1)
-    sync_all()
-    e2e_s = e2e_pipelined(args.e2e_steps) / max(args.e2e_steps, 1) if args.e2e_steps else 0.0
-    for H in halves:
-        assert torch.equal(H["out"], H["syms"])
-    t = torch.tensor([e2e_s, serial_s], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_s, serial_s = float(t[0].item()), float(t[1].item())
-    words_bytes = 4 * sum(int(H["off"][-1].item()) for H in halves)
-    e2e = {"value": world * n / e2e_s / 1e6 if args.e2e_steps else None, "unit": "Msymbols/s",
-           "h2d_bytes_per_step": 4 * n + words_bytes + 8 * (k + 2),
-           "d2h_bytes_per_step": words_bytes + 8 * (k + 2) + 4 * n + 64,
-           "ms_per_step": e2e_s * 1e3, "steps": args.e2e_steps, "serial_ms_per_step": serial_s * 1e3,
-           "api": "ctr_ans_encode_reverse_host + ctr_ans_decode_host (pinned host buffers); the batch as two halves of "
-                  "k/2 streams on two host threads, one uploading while the other downloads (PCIe full duplex)"}
-
-    gather_kind = None if world == 1 else ("copy-engine pushes into peer-mapped containers over NVLink, ordered by stream memory operations (no kernel)" if pipe.get("pg") else "NCCL all-gather")
     if rank == 0:
         cpu = None
-        if world == 1 and not args.no_cpu_baseline:
-            cpu = cpu_baseline(min(n, args.cpu_sample), k, os.cpu_count() or 1)
+        if not args.no_cpu_baseline:
+            if all_cpus:
+                try:
+                    os.sched_setaffinity(0, all_cpus)
+                except Exception:
+                    pass
+            small = world > 1
+            cpu = cpu_baseline(min(n, args.cpu_sample // (5 if small else 1)), k, os.cpu_count() or 1, small=small)
         line = {
             "metric": METRIC, "value": value, "unit": "Msymbols/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
@@ -508,14 +607,20 @@ def run_ours(args):
                        "symbols_per_gpu": n, "streams_per_gpu": k, "compressed_words_per_gpu": total_words,
                        "bits_per_symbol": 32.0 * total_words / n,
                        "l2": "inputs (400 MB symbols) larger than the 126 MB L2; no flush between steps",
-                       "step": "ANS encode (kernel with fused compaction) -> ANS decode; N>1: the NCCL all-gather of the "
-                               "containers runs on a side stream, overlapped with the decode and the next step's encode "
-                               "(double-buffered containers), every gather joined inside the timed region",
-                       "gather": gather_kind},
+                       "step": ("ANS encode (kernel with fused compaction) -> ANS decode" if world == 1 else
+                                "ANS encode of the own shard into the own slot of the gathered container -> push to all peers "
+                                "(side streams, overlapped with the following kernels) -> ANS decode of the right neighbour's "
+                                "shard of the previous turn out of the gathered container; every gather joined inside the timed region"),
+                       "gather": gather_kind,
+                       "parity_note": "erf/exp restate FreeBSD msun (what Rust libm 0.2.16 implements); equality with a real "
+                                      "Rust build is pinned by the reference's golden vectors G1-G8 only (SURVEY 8c)"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
-            "clocks": clocks.summary(),
+            "clocks": clocks.summary(), "extra_configs": extra,
         }
         print(json.dumps(line))
+    if sg is not None:
+        sync_all()
+        sg.close()
     if world > 1:
         dist.destroy_process_group()
 

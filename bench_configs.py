@@ -283,6 +283,252 @@ def config6(images=64, coder="ans"):
             "bits_per_symbol": 32.0 * comp.total_words() / n}
 
 
+# ----------------------------------------------------------------------------------------------------
+# The multi-GPU configs of BASELINE.json, callable under torch.distributed from bench.py (`extra_configs`)
+# ----------------------------------------------------------------------------------------------------
+def _max_over_ranks(values, world):
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor(list(values), dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return [float(x) for x in t.tolist()]
+
+
+def _all_ranks_ok(ok, world):
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([1 if ok else 0], device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    return bool(int(t.item()))
+
+
+def _exchange(sg, bc, world, rank, encode_into, k_of, n_of, coder, decode_neighbour, steps=4):
+    """Times `encode -> push -> wait for every peer's slot -> release` (the whole exchange exposed, nothing overlapped)
+    and checks that the right neighbour's shard decodes out of the gathered container."""
+    import torch
+    if world == 1:
+        return None, True
+    nb = (rank + 1) % world
+    turns = []
+
+    def one():
+        turn = sg.begin_turn(k_of(rank), n_of(rank), coder)
+        encode_into(turn.out)
+        sg.push(turn, k_of(rank))
+        sg.wait(turn)
+        turns.append(turn)
+        if len(turns) > 1:
+            sg.release(turns.pop(0))
+
+    ms = timed(one, warmup=2, steps=steps)
+    ok = decode_neighbour(sg.shard(turns[-1], nb, k_of(nb), n_of(nb), coder), nb)
+    bc.check()
+    torch.cuda.synchronize()
+    sg.release(turns.pop())
+    sg.sync()
+    return ms, ok
+
+
+def baseline_config3_sharded(world=1, rank=0, total_streams=8192, total_symbols=1_000_000_000):
+    """BASELINE configs[3]: 1e9 symbols as 8192 independent RangeEncoder streams (122,070 symbols each + remainder),
+    sharded over the ranks by blocks of streams (strong scaling: 8192 / N streams per GPU), containers gathered."""
+    import torch
+    from constriction_b200 import batch as B
+    from constriction_b200 import dist as D
+    from oracle import refapi as O
+    base, extra = divmod(total_symbols, total_streams)
+
+    def shard(r):
+        lo, hi = D.shard_bounds(total_streams, world, r)
+        lens = torch.full((hi - lo,), base, dtype=torch.int64)
+        lens[: max(0, min(hi, extra) - lo)] += 1  # the first `extra` streams of the job carry one more symbol
+        off = torch.cat([torch.zeros(1, dtype=torch.int64), torch.cumsum(lens, 0)])
+        return hi - lo, int(off[-1]), off
+
+    def symbols(r, n):
+        g = torch.Generator(device="cuda")
+        g.manual_seed(4 + r)
+        return torch.clamp(torch.round(torch.randn(n, device="cuda", generator=g) * 9.6 + 3.2), -50, 50).to(torch.int32)
+
+    k, n, off_h = shard(rank)
+    off = off_h.cuda()
+    syms = symbols(rank, n)
+    model = B.ModelTable.quantized_gaussian(-50, 50, [3.2], [9.6])
+    bc = B.BatchCoder()
+    st = {}
+
+    def enc():
+        st["c"] = bc.range_encode(syms, model, sym_offsets=off, out=st.get("c"))
+
+    ms_enc = timed(enc, warmup=2, steps=4)
+    comp = st["c"]
+    out = torch.empty_like(syms)
+    ms_dec = timed(lambda: bc.range_decode(comp, model, out=out), warmup=1, steps=3)
+    bc.check()
+    ok = bool(torch.equal(out, syms))
+    cdf = model.cdf()[0]
+    for s_ in (0, k - 1):
+        a, b = int(off_h[s_]), int(off_h[s_ + 1])
+        ok &= bool(np.array_equal(comp.stream_words(s_), O.range_encode_iid(syms[a:b].cpu().numpy(), cdf, -50)))
+    total_words = comp.total_words()
+    # checkpoints every 1024 symbols: identical words, every chunk decodes on its own lane
+    ck = bc.range_encode(syms, model, sym_offsets=off, checkpoint_every=1024)
+    ok &= bool(torch.equal(ck.words[:ck.total_words()], comp.words[:total_words]))
+    out.zero_()
+    ms_dec_ck = timed(lambda: bc.range_decode(ck, model, out=out), warmup=2, steps=4)
+    bc.check()
+    ok &= bool(torch.equal(out, syms))
+    del ck
+    ms_x, sg = None, None
+    if world > 1:
+        sizes = [shard(r) for r in range(world)]
+        sg = D.SlotGather(int(total_words * 1.1) + 4096, max(x[0] for x in sizes))
+
+        def dec_nb(sh, nb):
+            knb, nnb, offnb = sizes[nb]
+            sh.sym_offsets = offnb.cuda()
+            got = bc.range_decode(sh, model)
+            return bool(torch.equal(got, symbols(nb, nnb)))
+
+        ms_x, ok_x = _exchange(sg, bc, world, rank, lambda o: bc.range_encode(syms, model, sym_offsets=off, out=o),
+                               lambda r: sizes[r][0], lambda r: sizes[r][1], "range", dec_nb)
+        ok &= ok_x
+        sg.close()
+    ms_enc, ms_dec, ms_dec_ck, ms_xm = _max_over_ranks([ms_enc, ms_dec, ms_dec_ck, ms_x or 0.0], world)
+    ok = _all_ranks_ok(ok, world)
+    N = total_symbols
+    return {"workload": f"{N} symbols as {total_streams} RangeEncoder streams (contiguous), QG(-50,50,3.2,9.6), "
+                        f"{total_streams // world} streams per GPU on {world} GPU(s)",
+            "ms_encode": ms_enc, "ms_decode": ms_dec, "ms_decode_with_checkpoints_every_1024": ms_dec_ck,
+            "ms_encode_plus_gather_exposed": ms_xm if world > 1 else None,
+            "Msymbols_per_s_encode": N / ms_enc / 1e3, "Msymbols_per_s_decode": N / ms_dec / 1e3,
+            "Msymbols_per_s_round_trip": N / (ms_enc + ms_dec) / 1e3,
+            "Msymbols_per_s_round_trip_checkpointed": N / (ms_enc + ms_dec_ck) / 1e3,
+            "compressed_MB_per_gpu": total_words * 4 / 1e6, "parity": ok,
+            "note": "times are the max over ranks; one dependent chain per stream: latency-bound, not HBM-bound"}
+
+
+def baseline_config4_sharded(world=1, rank=0, images=64):
+    """BASELINE configs[4]: int32[64,192,32,32] latents, 192 per-channel QuantizedGaussian models, one ANS stream per
+    (image, channel); sharded by image (64 / N images per GPU), containers gathered."""
+    import torch
+    from constriction_b200 import batch as B
+    from constriction_b200 import dist as D
+    from oracle import refapi as O
+    rng = np.random.default_rng(5)
+    C_, HW = 192, 32 * 32
+    mu = rng.normal(0, 2, C_)
+    sigma = np.exp(rng.uniform(np.log(0.3), np.log(12), C_))
+    model = B.ModelTable.quantized_gaussian(-64, 64, mu, sigma)
+    t_mu = torch.from_numpy(mu).cuda().float()[None, :, None]
+    t_sg = torch.from_numpy(sigma).cuda().float()[None, :, None]
+
+    def images_of(r):
+        lo, hi = D.shard_bounds(images, world, r)
+        return hi - lo
+
+    def symbols(r):
+        g = torch.Generator(device="cuda")
+        g.manual_seed(50 + r)
+        lat = torch.clamp(torch.round(torch.randn(images_of(r), C_, HW, device="cuda", generator=g) * t_sg + t_mu), -64, 64)
+        return lat.to(torch.int32).reshape(-1).contiguous()
+
+    im = images_of(rank)
+    syms = symbols(rank)
+    k, n = im * C_, im * C_ * HW
+    off = torch.arange(k + 1, device="cuda", dtype=torch.int64) * HW
+    sidx = torch.arange(C_, device="cuda", dtype=torch.int32).repeat(im)
+    bc = B.BatchCoder()
+    st = {}
+
+    def enc():
+        st["c"] = bc.ans_encode(syms, model, sym_offsets=off, model_index=sidx, index_mode=2, out=st.get("c"))
+
+    ms_enc = timed(enc, warmup=3, steps=10)
+    comp = st["c"]
+    out = torch.empty_like(syms)
+    ms_dec = timed(lambda: bc.ans_decode(comp, model, model_index=sidx, index_mode=2, out=out), warmup=3, steps=10)
+    bc.check()
+    ok = bool(torch.equal(out, syms))
+    cdfs = model.cdf()
+    for s_ in (0, 191, k - 1):
+        want = O.ans_encode_iid(syms[s_ * HW:(s_ + 1) * HW].cpu().numpy(), cdfs[s_ % C_], -64)
+        ok &= bool(np.array_equal(comp.stream_words(s_), want))
+    total_words = comp.total_words()
+    ck = bc.ans_encode(syms, model, sym_offsets=off, model_index=sidx, index_mode=2, checkpoint_every=128)
+    ok &= bool(torch.equal(ck.words[:ck.total_words()], comp.words[:total_words]))
+    out.zero_()
+    ms_dec_ck = timed(lambda: bc.ans_decode(ck, model, model_index=sidx, index_mode=2, out=out), warmup=3, steps=10)
+    bc.check()
+    ok &= bool(torch.equal(out, syms))
+    ms_x = None
+    if world > 1:
+        ks = [images_of(r) * C_ for r in range(world)]
+        sg = D.SlotGather(int(total_words * 1.2) + 4096, max(ks))
+
+        def dec_nb(sh, nb):
+            sh.sym_offsets = torch.arange(ks[nb] + 1, device="cuda", dtype=torch.int64) * HW
+            idx = torch.arange(C_, device="cuda", dtype=torch.int32).repeat(images_of(nb))
+            got = bc.ans_decode(sh, model, model_index=idx, index_mode=2)
+            return bool(torch.equal(got, symbols(nb)))
+
+        ms_x, ok_x = _exchange(sg, bc, world, rank,
+                               lambda o: bc.ans_encode(syms, model, sym_offsets=off, model_index=sidx, index_mode=2, out=o),
+                               lambda r: ks[r], lambda r: ks[r] * HW, "ans", dec_nb, steps=10)
+        ok &= ok_x
+        sg.close()
+    ms_enc, ms_dec, ms_dec_ck, ms_xm = _max_over_ranks([ms_enc, ms_dec, ms_dec_ck, ms_x or 0.0], world)
+    ok = _all_ranks_ok(ok, world)
+    N = images * C_ * HW
+    return {"workload": f"latents int32[{images},192,32,32], 192 per-channel QuantizedGaussian(-64,64), {images * C_} ANS streams "
+                        f"x {HW} symbols, {images // world} images per GPU on {world} GPU(s)",
+            "us_encode": ms_enc * 1e3, "us_decode": ms_dec * 1e3, "us_decode_with_checkpoints_every_128": ms_dec_ck * 1e3,
+            "us_encode_plus_gather_exposed": ms_xm * 1e3 if world > 1 else None,
+            "Msymbols_per_s_round_trip": N / (ms_enc + ms_dec) / 1e3,
+            "Msymbols_per_s_round_trip_checkpointed": N / (ms_enc + ms_dec_ck) / 1e3,
+            "bits_per_symbol": 32.0 * total_words / n, "parity": ok,
+            "note": "times are the max over ranks; a 50 MB problem: launch- and latency-bound"}
+
+
+def north_star_1e9(world=1, rank=0, n=1_000_000_000, k=148 * 1024):
+    """The north star's size: 1e9 i.i.d. symbols per GPU, ANS encode + decode (configs[1]'s model and layout)."""
+    import torch
+    from constriction_b200 import batch as B
+    from oracle import refapi as O
+    g = torch.Generator(device="cuda")
+    g.manual_seed(9 + rank)
+    syms = torch.empty(n, dtype=torch.int32, device="cuda")
+    for i in range(0, n, 1 << 27):  # generated in pieces: the float temporaries of one shot would need 12 GB
+        m = min(1 << 27, n - i)
+        syms[i:i + m] = torch.clamp(torch.round(torch.randn(m, device="cuda", generator=g) * 9.6 + 3.2), -50, 50).to(torch.int32)
+    model = B.ModelTable.quantized_gaussian(-50, 50, [3.2], [9.6])
+    bc = B.BatchCoder()
+    st = {}
+
+    def enc():
+        st["c"] = bc.ans_encode(syms, model, n_streams=k, out=st.get("c"))
+
+    ms_enc = timed(enc, warmup=2, steps=4)
+    comp = st["c"]
+    out = torch.empty_like(syms)
+    ms_dec = timed(lambda: bc.ans_decode(comp, model, out=out), warmup=2, steps=4)
+    bc.check()
+    ok = bool(torch.equal(out, syms))
+    cdf = model.cdf()[0]
+    for s_ in (0, 4097, k - 1):
+        ok &= bool(np.array_equal(comp.stream_words(s_), O.ans_encode_iid(syms[s_::k].cpu().numpy(), cdf, -50)))
+    total_words = comp.total_words()
+    ms_enc, ms_dec = _max_over_ranks([ms_enc, ms_dec], world)
+    ok = _all_ranks_ok(ok, world)
+    return {"workload": f"{n} i.i.d. symbols per GPU, QG(-50,50,3.2,9.6), {k} ANS streams (interleaved), {world} GPU(s)",
+            "ms_encode": ms_enc, "ms_decode": ms_dec, "Msymbols_per_s_round_trip": world * n / (ms_enc + ms_dec) / 1e3,
+            "hbm_frac_encode": (4.0 * n + 4.0 * total_words) / (ms_enc * 1e-3) / 1e9 / 6546.9,
+            "hbm_frac_decode": (4.0 * n + 4.0 * total_words) / (ms_dec * 1e-3) / 1e9 / 6546.9,
+            "bits_per_symbol": 32.0 * total_words / n, "parity": ok}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--configs", default="3,4,5")

@@ -644,6 +644,130 @@ int orc_ans_encode_qgauss_lazy_reverse(orc_ans *c, const int32_t *symbols, size_
     return ORC_OK;
 }
 
+/* Inverse of the standard normal CDF for the STARTING GUESS of the guided search below.  The reference calls
+ * probability-0.20.3 `Gaussian::inverse` (algorithm AS241, source not available here); the guess never influences
+ * the result (see orc_qgauss_quantile), only the number of search steps, so a rational approximation of comparable
+ * cost and 1e-9 relative accuracy (P. J. Acklam's) stands in for it in the "reference-shaped" CPU baseline. */
+static double inv_std_normal_cdf(double p) {
+    static const double a[6] = {-3.969683028665376e+01, 2.209460984245205e+02, -2.759285104469687e+02,
+                                1.383577518672690e+02,  -3.066479806614716e+01, 2.506628277459239e+00};
+    static const double b[5] = {-5.447609879822406e+01, 1.615858368580409e+02, -1.556989798598866e+02,
+                                6.680131188771972e+01, -1.328068155288572e+01};
+    static const double c[6] = {-7.784894002430293e-03, -3.223964580411365e-01, -2.400758277161838e+00,
+                                -2.549732539343734e+00, 4.374664141464968e+00,  2.938163982698783e+00};
+    static const double d[4] = {7.784695709041462e-03, 3.224671290700398e-01, 2.445134137142996e+00,
+                                3.754408661907416e+00};
+    if (p < 0.02425) {
+        double q = sqrt(-2.0 * log(p));
+        return (((((c[0] * q + c[1]) * q + c[2]) * q + c[3]) * q + c[4]) * q + c[5]) /
+               ((((d[0] * q + d[1]) * q + d[2]) * q + d[3]) * q + 1.0);
+    }
+    if (p > 1.0 - 0.02425) {
+        double q = sqrt(-2.0 * log(1.0 - p));
+        return -(((((c[0] * q + c[1]) * q + c[2]) * q + c[3]) * q + c[4]) * q + c[5]) /
+               ((((d[0] * q + d[1]) * q + d[2]) * q + d[3]) * q + 1.0);
+    }
+    double q = p - 0.5, r = q * q;
+    return (((((a[0] * r + a[1]) * r + a[2]) * r + a[3]) * r + a[4]) * r + a[5]) * q /
+           (((((b[0] * r + b[1]) * r + b[2]) * r + b[3]) * r + b[4]) * r + 1.0);
+}
+
+/* quantize.rs:580-779 in the reference's own shape: guess from the inverse CDF (:596-599), clamp to the support
+ * (:601-615), then search downwards (:620-688) or upwards (:689-767) with a doubling step followed by bisection,
+ * evaluating one Gaussian CDF per probe.  Same result as orc_qgauss_quantile (tests/test_oracle_golden.py); this
+ * variant exists so that the single-thread "lazy model" CPU baseline does the reference's amount of work. */
+int orc_qgauss_quantile_guided(int32_t min_sym, int32_t max_sym, double mean, double std, uint32_t quantile,
+                               int32_t *symbol_out, uint32_t *left_out, uint32_t *prob_out) {
+    double fw;
+    int rc = qgauss_free_weight(min_sym, max_sym, &fw);
+    if (rc) return rc;
+    if (!(std > 0.0)) return ORC_ERR_BAD_MODEL;
+    if (quantile >= ORC_TOTAL) return ORC_ERR_INVALID_DATA;
+    const double guess = mean + std * inv_std_normal_cdf(((double)quantile + 0.5) * (1.0 / (double)ORC_TOTAL));
+    int64_t symbol = guess >= 2147483647.0 ? 2147483647 : (guess <= -2147483648.0 ? -2147483648ll : (int64_t)guess); /* `as i32` */
+    uint32_t left, right;
+    if (symbol <= min_sym) {
+        symbol = min_sym;
+        left = 0;
+    } else {
+        if (symbol > max_sym) symbol = max_sym;
+        left = qgauss_left(fw, min_sym, mean, std, (int32_t)symbol);
+    }
+    int64_t step = 1;
+    if (left > quantile) { /* guess too high: :620-688 */
+        symbol -= step;
+        int found_lower = 0;
+        for (;;) {
+            const uint32_t old_left = left;
+            left = qgauss_left(fw, min_sym, mean, std, (int32_t)symbol);
+            if (symbol == min_sym && step <= 1) {
+                right = old_left;
+                break;
+            }
+            if (left <= quantile) {
+                found_lower = 1;
+                if (step <= 1) {
+                    right = qgauss_right(fw, min_sym, max_sym, mean, std, (int32_t)symbol);
+                    break;
+                }
+                step >>= 1;
+                symbol += step;
+            } else if (found_lower) {
+                if (step > 1) step >>= 1;
+                symbol -= step;
+            } else {
+                step <<= 1;
+                while (symbol - step < min_sym) step >>= 1;
+                symbol -= step;
+            }
+        }
+    } else { /* guess right or too low: :689-767 */
+        int found_upper = 0;
+        for (;;) {
+            right = qgauss_right(fw, min_sym, max_sym, mean, std, (int32_t)symbol);
+            if (symbol == max_sym && step <= 1) {
+                left = qgauss_left(fw, min_sym, mean, std, (int32_t)symbol);
+                break;
+            }
+            if (right > quantile) {
+                found_upper = 1;
+                if (step <= 1) {
+                    left = qgauss_left(fw, min_sym, mean, std, (int32_t)symbol); /* re-evaluated, :728-735 */
+                    if (left <= quantile || symbol == min_sym) break;
+                } else {
+                    step >>= 1;
+                }
+                symbol -= step;
+            } else if (found_upper) {
+                if (step > 1) step >>= 1;
+                symbol += step;
+            } else {
+                step <<= 1;
+                while (symbol + step > max_sym) step >>= 1;
+                symbol += step;
+            }
+        }
+    }
+    *symbol_out = (int32_t)symbol;
+    *left_out = left;
+    *prob_out = right - left;
+    return ORC_OK;
+}
+
+/* decode_iid_symbols / decode_symbols with lazily evaluated Gaussians (stack.rs:1070-1100 + quantize.rs:580-779) */
+int orc_ans_decode_qgauss_lazy(orc_ans *c, int32_t *symbols, size_t n, int32_t min_sym, int32_t max_sym,
+                               const double *means, const double *stds, int per_symbol_params) {
+    for (size_t i = 0; i < n; i++) {
+        uint32_t left, prob;
+        double m = per_symbol_params ? means[i] : means[0];
+        double s = per_symbol_params ? stds[i] : stds[0];
+        int rc = orc_qgauss_quantile_guided(min_sym, max_sym, m, s, orc_ans_peek_quantile(c), &symbols[i], &left, &prob);
+        if (rc) return rc;
+        orc_ans_decode_advance(c, left, prob);
+    }
+    return ORC_OK;
+}
+
 /* ------------------------------------------------------------------ */
 /* Range coder                                                          */
 /* ------------------------------------------------------------------ */

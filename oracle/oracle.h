@@ -105,6 +105,13 @@ int orc_ans_encode_qgauss_lazy_reverse(orc_ans *c, const int32_t *symbols, size_
                                        int32_t max_sym, const double *means, const double *stds,
                                        int per_symbol_params);
 
+/* quantize.rs:580-779 with the reference's control flow (inverse-CDF guess, doubling steps, bisection) and the
+ * lazily evaluated decode loop on top of it: the work stock constriction does per decoded QuantizedGaussian symbol */
+int orc_qgauss_quantile_guided(int32_t min_sym, int32_t max_sym, double mean, double std, uint32_t quantile,
+                               int32_t *symbol, uint32_t *left, uint32_t *prob);
+int orc_ans_decode_qgauss_lazy(orc_ans *c, int32_t *symbols, size_t n, int32_t min_sym, int32_t max_sym,
+                               const double *means, const double *stds, int per_symbol_params);
+
 /* ---------- Range coder (queue.rs) ---------- */
 typedef struct {
     uint32_t *bulk;

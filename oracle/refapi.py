@@ -107,6 +107,8 @@ def lib():
         L.orc_ans_decode_indexed.argtypes = [ap, i32p, u32p, C.c_size_t, u32p, C.c_size_t, C.c_int32, C.c_size_t]
         L.orc_ans_decode_indexed.restype = None
         L.orc_ans_encode_qgauss_lazy_reverse.argtypes = [ap, i32p, C.c_size_t, C.c_int32, C.c_int32, f64p, f64p, C.c_int]
+        L.orc_ans_decode_qgauss_lazy.argtypes = [ap, i32p, C.c_size_t, C.c_int32, C.c_int32, f64p, f64p, C.c_int]
+        L.orc_qgauss_quantile_guided.argtypes = [C.c_int32, C.c_int32, C.c_double, C.c_double, C.c_uint32, i32p, u32p, u32p]
         ep = C.POINTER(_REnc)
         for name in ("orc_renc_init", "orc_renc_free", "orc_renc_clear"):
             getattr(L, name).argtypes = [ep]
@@ -207,6 +209,45 @@ def ans_encode_iid(symbols: np.ndarray, cdf: np.ndarray, min_sym: int) -> np.nda
         return out[:n].copy()
     finally:
         L.orc_ans_free(C.byref(c))
+
+
+def ans_encode_qgauss_lazy(symbols: np.ndarray, lo: int, hi: int, mean: float, std: float) -> np.ndarray:
+    """One DefaultAnsCoder fed a lazily evaluated QuantizedGaussian: two Gaussian CDFs per symbol, exactly the work
+    `encode_iid_symbols_reverse(symbols, &quantizer.quantize(Gaussian))` does in the reference."""
+    L = lib()
+    c = _Ans()
+    L.orc_ans_init(C.byref(c))
+    symbols = np.ascontiguousarray(symbols, dtype=np.int32)
+    m, s = (C.c_double * 1)(mean), (C.c_double * 1)(std)
+    try:
+        _raise(L.orc_ans_encode_qgauss_lazy_reverse(C.byref(c), _p(symbols, i32p), symbols.size, lo, hi, m, s, 0))
+        out = np.empty(c.len + 2, dtype=np.uint32)
+        n = L.orc_ans_get_compressed(C.byref(c), _p(out, u32p))
+        return out[:n].copy()
+    finally:
+        L.orc_ans_free(C.byref(c))
+
+
+def ans_decode_qgauss_lazy(words: np.ndarray, n: int, lo: int, hi: int, mean: float, std: float) -> np.ndarray:
+    """The matching decode: `quantile_function` of the lazily evaluated model per symbol (quantize.rs:580-779)."""
+    L = lib()
+    c = _Ans()
+    L.orc_ans_init(C.byref(c))
+    words = np.ascontiguousarray(words, dtype=np.uint32)
+    m, s = (C.c_double * 1)(mean), (C.c_double * 1)(std)
+    try:
+        _raise(L.orc_ans_from_compressed(C.byref(c), _p(words, u32p), words.size))
+        out = np.empty(n, dtype=np.int32)
+        _raise(L.orc_ans_decode_qgauss_lazy(C.byref(c), _p(out, i32p), n, lo, hi, m, s, 0))
+        return out
+    finally:
+        L.orc_ans_free(C.byref(c))
+
+
+def qgauss_quantile_guided(lo: int, hi: int, mean: float, std: float, q: int):
+    sym, left, prob = C.c_int32(), C.c_uint32(), C.c_uint32()
+    _raise(lib().orc_qgauss_quantile_guided(lo, hi, mean, std, q, C.byref(sym), C.byref(left), C.byref(prob)))
+    return sym.value, left.value, prob.value
 
 
 def ans_decode_iid(words: np.ndarray, n: int, cdf: np.ndarray, min_sym: int) -> np.ndarray:
