@@ -532,8 +532,8 @@ def run_ours(args):
 
     def e2e_overlapped_step(i):
         j_enc, j_dec = C.c_void_p(), C.c_void_p()
+        assert lib.ctr_ans_decode_host_async(*dec_args(conts[i & 1]), C.byref(j_dec)) == 0  # (its small word uploads go first)
         assert lib.ctr_ans_encode_reverse_host_async(*enc_args(conts[(i + 1) & 1]), C.byref(j_enc)) == 0
-        assert lib.ctr_ans_decode_host_async(*dec_args(conts[i & 1]), C.byref(j_dec)) == 0
         rc_e, rc_d = lib.ctr_host_job_wait(j_enc), lib.ctr_host_job_wait(j_dec)
         assert rc_e == 0 and rc_d == 0 and conts[(i + 1) & 1]["status"].value == 0 and dstatus.value == 0, (rc_e, rc_d)
 

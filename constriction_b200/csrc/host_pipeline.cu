@@ -11,16 +11,20 @@
 //   * contiguous layout -- the chunk's symbols are one contiguous range; its offsets are rebased on the device.
 // The only host waits inside an encode call are for the size of a finished chunk (its words are copied back to
 // the place where the previous chunk's words end), taken while later chunks are already in flight; a decode call
-// has none.  Device buffers come from the stream-ordered memory pool, once per call and pipeline slot.
+// has none.  Every pipeline slot keeps one grow-only block of device memory between calls.
 //
 // `_async` variants run the same pipeline on a thread of the library and return a job handle, so that one host
 // thread can keep both directions of the bus busy (upload of the batch being encoded, download of the batch
 // being decoded).
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 
+#include <stdio.h>
+
 #include <algorithm>
+#include <chrono>
 #include <mutex>
 #include <thread>
 #include <vector>
@@ -37,20 +41,117 @@ constexpr int kMaxChunks = 16;
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+// CTR_HOST_TRACE=1: host-side timeline of the pipeline on stderr (diagnostics)
+bool trace_on() {
+    static const bool on = getenv("CTR_HOST_TRACE") != nullptr;
+    return on;
+}
+double now_ms() {
+    static const auto t0 = std::chrono::steady_clock::now();
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+}
+#define CTR_TRACE(...)                                  \
+    do {                                                \
+        if (trace_on()) {                               \
+            fprintf(stderr, "[%9.3f] ", now_ms());      \
+            fprintf(stderr, __VA_ARGS__);               \
+            fputc('\n', stderr);                        \
+        }                                               \
+    } while (0)
+
 // out[i] = in[i] - in[0]
 __global__ void rebase_offsets_kernel(const uint64_t *in, uint64_t *out, uint64_t n) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = in[i] - in[0];
 }
 
+// ---- encode results straight into pinned host memory ---------------------------------------------------------------
+// When the caller's output buffers are pinned (device-accessible under unified addressing), a chunk's results leave
+// through SM stores instead of copy-engine transfers: one small kernel per chunk writes the chunk's words to the place
+// where the previous chunk's words end, its offsets rebased by that amount, and hands the running total (and the
+// merged data status) to the next chunk through device memory.  The host then never needs a chunk's size -- an
+// encode call has no host wait besides slot reuse -- and the small downloads do not queue behind a concurrent decode
+// job's symbol downloads on the copy engine.
+struct EmitChain {  // device memory, one entry per chunk + 1
+    uint64_t base;       // words of all earlier chunks
+    uint32_t status[4];  // merged data status so far {code, overflow flag, failing stream lo, hi}
+};
+
+__global__ void emit_chunk_kernel(const uint32_t *__restrict__ words, const uint64_t *__restrict__ offsets, uint64_t kc, uint64_t k0,
+                                  uint64_t chunk_capacity, const uint32_t *__restrict__ chunk_status, const EmitChain *in,
+                                  EmitChain *out, uint32_t *host_words, uint64_t capacity, uint64_t *host_offsets,
+                                  uint64_t *host_final /* {total, status lo/hi words} or null unless last chunk */) {
+    const uint64_t base = in->base;
+    const uint64_t total = offsets[kc];
+    const bool fits = total <= chunk_capacity && base + total <= capacity;
+    const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, nthreads = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t k = tid; k < kc; k += nthreads) host_offsets[k0 + k] = offsets[k] + base;
+    if (fits) {
+        // 16-byte stores once the destination is 16-byte aligned (the source then is not, in general: 4 scalar loads)
+        uint32_t *dst = host_words + base;
+        const uint64_t head = min(total, (uint64_t)((16 - ((uintptr_t)dst & 15)) & 15) / 4);
+        if (tid < head) dst[tid] = words[tid];
+        const uint64_t vecs = (total - head) / 4;
+        uint4 *dst4 = reinterpret_cast<uint4 *>(dst + head);
+        const uint32_t *src = words + head;
+        for (uint64_t v = tid; v < vecs; v += nthreads) {
+            const uint32_t *p = src + 4 * v;
+            dst4[v] = make_uint4(p[0], p[1], p[2], p[3]);
+        }
+        for (uint64_t j = head + 4 * vecs + tid; j < total; j += nthreads) dst[j] = words[j];
+    }
+    if (tid == 0) {
+        EmitChain o = *in;
+        o.base = base + (fits ? total : 0);
+        if (!fits) o.status[1] = 1u;
+        if (chunk_status[0] > o.status[0]) {
+            const uint64_t bad = k0 + (((uint64_t)chunk_status[3] << 32) | chunk_status[2]);
+            o.status[0] = chunk_status[0];
+            o.status[2] = (uint32_t)bad;
+            o.status[3] = (uint32_t)(bad >> 32);
+        }
+        *out = o;
+        if (host_final) {
+            host_offsets[k0 + kc] = o.base;
+            host_final[0] = o.base;
+            host_final[1] = ((uint64_t)o.status[1] << 32) | o.status[0];
+            host_final[2] = ((uint64_t)o.status[3] << 32) | o.status[2];
+        }
+    }
+}
+
+// device-accessible host memory (cudaHostAlloc / cudaHostRegister)?
+bool is_pinned(const void *p) {
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return attr.type == cudaMemoryTypeHost && attr.devicePointer != nullptr;
+}
+
 struct SlotRes {
     cudaStream_t s = nullptr;
     cudaEvent_t ev_size = nullptr, ev_done = nullptr;
     uint64_t *h_meta = nullptr;  // pinned: {total words, status[0..3] as 2 x u64}
+    // device memory of the chunk in this slot: one grow-only block per slot, kept between calls (allocating from
+    // the stream-ordered pool per call made two concurrent pipelines -- an encode and a decode job -- wait for each
+    // other's frees), carved up by a bump pointer
+    char *arena = nullptr;
+    size_t arena_bytes = 0, used = 0;
 };
 struct PipeRes {
     int device = -1;
     SlotRes slot[kSlots];
+    // decode calls: the compressed words of ALL chunks are uploaded on their own stream as soon as the call starts
+    // (they are small next to the symbols that come back), so that no kernel ever waits for an upload that queues
+    // behind a concurrent encode job's symbol copies
+    EmitChain *chain = nullptr;            // device, kMaxChunks + 1 entries (encode calls with pinned outputs)
+    cudaEvent_t emit_ev[kMaxChunks] = {};
+    cudaStream_t up = nullptr;
+    cudaEvent_t up_ev[kMaxChunks] = {};
+    char *up_arena = nullptr;
+    size_t up_bytes = 0;
 };
 
 std::mutex g_pool_mutex;
@@ -78,6 +179,15 @@ PipeRes *acquire_pipe() {
              cudaEventCreateWithFlags(&r->slot[i].ev_done, cudaEventDisableTiming) == cudaSuccess &&
              cudaHostAlloc((void **)&r->slot[i].h_meta, 64, cudaHostAllocDefault) == cudaSuccess;
     }
+    {  // small, latency-critical uploads: highest priority
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        ok = ok && cudaStreamCreateWithPriority(&r->up, cudaStreamNonBlocking, hi) == cudaSuccess;
+    }
+    for (int i = 0; i < kMaxChunks && ok; ++i)
+        ok = cudaEventCreateWithFlags(&r->up_ev[i], cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&r->emit_ev[i], cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaMalloc((void **)&r->chain, sizeof(EmitChain) * (kMaxChunks + 1)) == cudaSuccess;
     if (!ok) {
         cudaGetLastError();
         delete r;  // (leaks what was created; this only happens when the device is unusable)
@@ -90,24 +200,26 @@ void release_pipe(PipeRes *r) {
     g_pool.push_back(r);
 }
 
-struct DevBuf {
-    void *p = nullptr;
-    cudaStream_t s = nullptr;
-    int alloc(size_t bytes, cudaStream_t stream) {
-        s = stream;
-        CTR_HOST_TRY(cudaMallocAsync(&p, bytes ? align_up(bytes, 16) : 16, stream));
-        return CTR_OK;
-    }
-    template <typename T>
-    T *as() const {
-        return static_cast<T *>(p);
-    }
-    void release() {  // stream-ordered: the pool hands the memory to the next allocation on this stream
-        if (p) cudaFreeAsync(p, s);
-        p = nullptr;
-    }
-    ~DevBuf() { release(); }
-};
+// the slot's stream must be idle (its previous chunk has left the device) when a chunk's memory is laid out
+int arena_reserve(SlotRes &S, size_t bytes) {
+    S.used = 0;
+    if (bytes <= S.arena_bytes) return CTR_OK;
+    CTR_HOST_TRY(cudaStreamSynchronize(S.s));
+    if (S.arena) cudaFree(S.arena);
+    S.arena = nullptr;
+    S.arena_bytes = 0;
+    const size_t want = align_up(bytes + bytes / 8, 1 << 20);
+    CTR_HOST_TRY(cudaMalloc((void **)&S.arena, want));
+    S.arena_bytes = want;
+    return CTR_OK;
+}
+inline size_t arena_size(size_t bytes) { return align_up(bytes ? bytes : 16, 256); }
+template <typename T>
+T *arena_take(SlotRes &S, size_t bytes) {
+    T *p = reinterpret_cast<T *>(S.arena + S.used);
+    S.used += arena_size(bytes);
+    return p;
+}
 
 // geometry of the whole batch and of one chunk of streams [k0, k1)
 struct Batch {
@@ -135,6 +247,7 @@ Batch make_batch(uint64_t N, uint64_t K, const uint64_t *sym_off) {
 std::vector<Chunk> plan_chunks(const Batch &b) {
     uint64_t want = b.N / kMinChunkSymbols;
     want = std::max<uint64_t>(1, std::min<uint64_t>(want, kMaxChunks));
+    if (const char *e = getenv("CTR_HOST_CHUNKS")) want = std::max(1, atoi(e));  // experiments
     if (!b.sym_off) want = std::min<uint64_t>(want, std::max<uint64_t>(1, b.K / kMinStripStreams));
     want = std::min<uint64_t>(want, std::max<uint64_t>(1, b.K));
     std::vector<Chunk> out;
@@ -174,6 +287,27 @@ bool offsets_valid(const uint64_t *sym_off, uint64_t K, uint64_t N) {
     return true;
 }
 
+// Big copies are issued in pieces so that the copies of a concurrent job in the same direction (an encode job's
+// symbols and a decode job's words both go up) interleave at piece granularity instead of chunk granularity.
+size_t piece_bytes() {
+    static const size_t v = [] {
+        const char *e = getenv("CTR_HOST_PIECE_MB");
+        const long mb = e ? atol(e) : 16;
+        return mb > 0 ? (size_t)mb << 20 : ~(size_t)0;
+    }();
+    return v;
+}
+
+int copy_1d(char *dst, const char *src, size_t bytes, cudaMemcpyKind kind, cudaStream_t s) {
+    const size_t piece = piece_bytes();
+    for (size_t done = 0; done < bytes;) {
+        const size_t m = std::min(piece, bytes - done);
+        CTR_HOST_TRY(cudaMemcpyAsync(dst + done, src + done, m, kind, s));
+        done += m;
+    }
+    return CTR_OK;
+}
+
 // H2D (to_device) or D2H of one per-symbol array (4-byte elements) of a chunk
 int copy_symbol_array(void *dev, const void *host_base, const Batch &b, const Chunk &c, bool to_device, cudaStream_t s) {
     const cudaMemcpyKind kind = to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost;
@@ -181,17 +315,16 @@ int copy_symbol_array(void *dev, const void *host_base, const Batch &b, const Ch
     char *d = static_cast<char *>(dev);
     if (b.sym_off) {
         if (!c.n) return CTR_OK;
-        if (to_device)
-            CTR_HOST_TRY(cudaMemcpyAsync(d, h + c.s0 * 4, c.n * 4, kind, s));
-        else
-            CTR_HOST_TRY(cudaMemcpyAsync(h + c.s0 * 4, d, c.n * 4, kind, s));
-        return CTR_OK;
+        return to_device ? copy_1d(d, h + c.s0 * 4, c.n * 4, kind, s) : copy_1d(h + c.s0 * 4, d, c.n * 4, kind, s);
     }
-    if (c.rows_full) {
+    const uint64_t rows_per_piece = std::max<uint64_t>(1, piece_bytes() / (c.kc * 4));
+    for (uint64_t r0 = 0; r0 < c.rows_full; r0 += rows_per_piece) {
+        const uint64_t rows = std::min(rows_per_piece, c.rows_full - r0);
+        char *hp = h + (r0 * b.K + c.k0) * 4, *dp = d + r0 * c.kc * 4;
         if (to_device)
-            CTR_HOST_TRY(cudaMemcpy2DAsync(d, c.kc * 4, h + c.k0 * 4, b.K * 4, c.kc * 4, c.rows_full, kind, s));
+            CTR_HOST_TRY(cudaMemcpy2DAsync(dp, c.kc * 4, hp, b.K * 4, c.kc * 4, rows, kind, s));
         else
-            CTR_HOST_TRY(cudaMemcpy2DAsync(h + c.k0 * 4, b.K * 4, d, c.kc * 4, c.kc * 4, c.rows_full, kind, s));
+            CTR_HOST_TRY(cudaMemcpy2DAsync(hp, b.K * 4, dp, c.kc * 4, c.kc * 4, rows, kind, s));
     }
     if (c.tail) {
         char *hp = h + (c.rows_full * b.K + c.k0) * 4, *dp = d + c.rows_full * c.kc * 4;
@@ -203,11 +336,11 @@ int copy_symbol_array(void *dev, const void *host_base, const Batch &b, const Ch
     return CTR_OK;
 }
 
-struct SlotBufs {
-    DevBuf sym, idx, off_raw, off, ws, words, offsets, status;
-    void release() {
-        for (DevBuf *b : {&sym, &idx, &off_raw, &off, &ws, &words, &offsets, &status}) b->release();
-    }
+struct SlotBufs {  // device buffers of one chunk (pointers into its slot's arena)
+    int32_t *sym = nullptr;
+    uint32_t *idx = nullptr, *words = nullptr, *status = nullptr;
+    uint64_t *off_raw = nullptr, *off = nullptr, *offsets = nullptr;
+    void *ws = nullptr;
 };
 
 struct Call {  // arguments of one host call (both directions)
@@ -236,27 +369,37 @@ void note_status(const uint64_t *h_meta, uint64_t k0, int *status, uint64_t *bad
     }
 }
 
-int fill_layout(ctr_layout *L, const Call &a, const Batch &b, const Chunk &c, SlotBufs &B, cudaStream_t s) {
+size_t layout_bytes(const Call &a, const Batch &b, const Chunk &c) {
+    size_t n = 0;
+    if (b.sym_off) n += 2 * arena_size((c.kc + 1) * 8);
+    if (a.index_mode == CTR_INDEX_PER_SYMBOL) n += arena_size(c.n * 4);
+    if (a.index_mode == CTR_INDEX_PER_STREAM) n += arena_size(c.kc * 4);
+    return n;
+}
+
+int fill_layout(ctr_layout *L, const Call &a, const Batch &b, const Chunk &c, SlotBufs &B, SlotRes &S) {
+    cudaStream_t s = S.s;
     memset(L, 0, sizeof *L);
     L->n_streams = c.kc;
     L->n_symbols = c.n;
     L->model_index_mode = a.index_mode;
     int rc;
     if (b.sym_off) {
-        if ((rc = B.off_raw.alloc((c.kc + 1) * 8, s)) || (rc = B.off.alloc((c.kc + 1) * 8, s))) return rc;
-        CTR_HOST_TRY(cudaMemcpyAsync(B.off_raw.p, b.sym_off + c.k0, (c.kc + 1) * 8, cudaMemcpyHostToDevice, s));
-        rebase_offsets_kernel<<<(unsigned)((c.kc + 1 + 255) / 256), 256, 0, s>>>(B.off_raw.as<uint64_t>(), B.off.as<uint64_t>(), c.kc + 1);
+        B.off_raw = arena_take<uint64_t>(S, (c.kc + 1) * 8);
+        B.off = arena_take<uint64_t>(S, (c.kc + 1) * 8);
+        CTR_HOST_TRY(cudaMemcpyAsync(B.off_raw, b.sym_off + c.k0, (c.kc + 1) * 8, cudaMemcpyHostToDevice, s));
+        rebase_offsets_kernel<<<(unsigned)((c.kc + 1 + 255) / 256), 256, 0, s>>>(B.off_raw, B.off, c.kc + 1);
         ctr::host_count_launch();
-        L->sym_offsets_dev = B.off.as<uint64_t>();
+        L->sym_offsets_dev = B.off;
     }
     if (a.index_mode == CTR_INDEX_PER_SYMBOL) {
-        if ((rc = B.idx.alloc(c.n * 4, s))) return rc;
-        if ((rc = copy_symbol_array(B.idx.p, a.model_index, b, c, true, s))) return rc;
-        L->model_index_dev = B.idx.as<uint32_t>();
+        B.idx = arena_take<uint32_t>(S, c.n * 4);
+        if ((rc = copy_symbol_array(B.idx, a.model_index, b, c, true, s))) return rc;
+        L->model_index_dev = B.idx;
     } else if (a.index_mode == CTR_INDEX_PER_STREAM) {
-        if ((rc = B.idx.alloc(c.kc * 4, s))) return rc;
-        CTR_HOST_TRY(cudaMemcpyAsync(B.idx.p, a.model_index + c.k0, c.kc * 4, cudaMemcpyHostToDevice, s));
-        L->model_index_dev = B.idx.as<uint32_t>();
+        B.idx = arena_take<uint32_t>(S, c.kc * 4);
+        CTR_HOST_TRY(cudaMemcpyAsync(B.idx, a.model_index + c.k0, c.kc * 4, cudaMemcpyHostToDevice, s));
+        L->model_index_dev = B.idx;
     }
     return CTR_OK;
 }
@@ -265,12 +408,15 @@ int run_encode(const Call &a, PipeRes *res) {
     const Batch b = make_batch(a.N, a.K, a.sym_off);
     const std::vector<Chunk> chunks = plan_chunks(b);
     const size_t n = chunks.size();
-    std::vector<SlotBufs> bufs(n);  // buffers are released (stream-ordered) when the call returns
+    std::vector<SlotBufs> bufs(n);
     std::vector<uint64_t> cap(n);
     uint64_t base = 0;  // words of the chunks finished so far
     int status = 0, rc = CTR_OK;
     uint64_t bad = 0;
     bool out_of_space = false;
+    // pinned outputs: results leave through SM stores (emit_chunk_kernel), no host wait for sizes
+    const bool direct = n <= (size_t)kMaxChunks && is_pinned(a.words_out) && is_pinned(a.offsets_out) && !getenv("CTR_HOST_NO_DIRECT");
+    if (direct) CTR_HOST_TRY(cudaMemsetAsync(res->chain, 0, sizeof(EmitChain), res->slot[0].s));
 
     auto issue = [&](size_t i) -> int {
         const Chunk &c = chunks[i];
@@ -278,37 +424,58 @@ int run_encode(const Call &a, PipeRes *res) {
         SlotBufs &B = bufs[i];
         int r;
         ctr_layout L;
-        if ((r = B.sym.alloc(c.n * 4, S.s))) return r;
-        if ((r = copy_symbol_array(B.sym.p, a.symbols_in, b, c, true, S.s))) return r;
-        if ((r = fill_layout(&L, a, b, c, B, S.s))) return r;
+        memset(&L, 0, sizeof L);
+        L.n_streams = c.kc;
+        L.n_symbols = c.n;
+        L.sym_offsets_dev = b.sym_off ? reinterpret_cast<const uint64_t *>(16) : nullptr;  // (sizes only)
         const size_t ws_bytes = ctr_ans_encode_workspace_bytes(&L);
         cap[i] = ctr_ans_max_compressed_words(&L);
-        if ((r = B.ws.alloc(ws_bytes, S.s)) || (r = B.words.alloc(cap[i] * 4, S.s)) || (r = B.offsets.alloc((c.kc + 1) * 8, S.s)) ||
-            (r = B.status.alloc(16, S.s)))
+        if ((r = arena_reserve(S, arena_size(c.n * 4) + layout_bytes(a, b, c) + arena_size(ws_bytes) + arena_size(cap[i] * 4) +
+                                      arena_size((c.kc + 1) * 8) + arena_size(16))))
             return r;
-        CTR_HOST_TRY(cudaMemsetAsync(B.status.p, 0, 16, S.s));
-        r = a.range ? ctr_range_encode(a.model, B.sym.as<int32_t>(), &L, nullptr, B.ws.p, ws_bytes, B.words.as<uint32_t>(), cap[i],
-                                       B.offsets.as<uint64_t>(), nullptr, B.status.as<uint32_t>(), S.s)
-                    : ctr_ans_encode_reverse(a.model, B.sym.as<int32_t>(), &L, nullptr, B.ws.p, ws_bytes, B.words.as<uint32_t>(),
-                                             cap[i], B.offsets.as<uint64_t>(), nullptr, B.status.as<uint32_t>(), S.s);
+        B.sym = arena_take<int32_t>(S, c.n * 4);
+        if ((r = copy_symbol_array(B.sym, a.symbols_in, b, c, true, S.s))) return r;
+        if ((r = fill_layout(&L, a, b, c, B, S))) return r;
+        B.ws = arena_take<char>(S, ws_bytes);
+        B.words = arena_take<uint32_t>(S, cap[i] * 4);
+        B.offsets = arena_take<uint64_t>(S, (c.kc + 1) * 8);
+        B.status = arena_take<uint32_t>(S, 16);
+        CTR_HOST_TRY(cudaMemsetAsync(B.status, 0, 16, S.s));
+        r = a.range ? ctr_range_encode(a.model, B.sym, &L, nullptr, B.ws, ws_bytes, B.words, cap[i], B.offsets, nullptr, B.status, S.s)
+                    : ctr_ans_encode_reverse(a.model, B.sym, &L, nullptr, B.ws, ws_bytes, B.words, cap[i], B.offsets, nullptr,
+                                             B.status, S.s);
         if (r) return r;
+        if (direct) {
+            if (i > 0) CTR_HOST_TRY(cudaStreamWaitEvent(S.s, res->emit_ev[i - 1], 0));  // the chain: base and status of chunk i-1
+            const bool last = i + 1 == n;
+            emit_chunk_kernel<<<64, 256, 0, S.s>>>(B.words, B.offsets, c.kc, c.k0, cap[i], B.status, res->chain + i, res->chain + i + 1,
+                                                   a.words_out, a.words_capacity, a.offsets_out, last ? res->slot[0].h_meta : nullptr);
+            ctr::host_count_launch();
+            CTR_HOST_TRY(cudaEventRecord(res->emit_ev[i], S.s));
+            CTR_HOST_TRY(cudaEventRecord(S.ev_done, S.s));
+            CTR_TRACE("enc issue %zu done (direct)", i);
+            return CTR_OK;
+        }
         // chunk-relative offsets go straight to their place; the host rebases them once the chunk's base is known
-        CTR_HOST_TRY(cudaMemcpyAsync(a.offsets_out + c.k0, B.offsets.p, c.kc * 8, cudaMemcpyDeviceToHost, S.s));
-        CTR_HOST_TRY(cudaMemcpyAsync(S.h_meta, B.offsets.as<uint64_t>() + c.kc, 8, cudaMemcpyDeviceToHost, S.s));
-        CTR_HOST_TRY(cudaMemcpyAsync(S.h_meta + 1, B.status.p, 16, cudaMemcpyDeviceToHost, S.s));
+        CTR_HOST_TRY(cudaMemcpyAsync(a.offsets_out + c.k0, B.offsets, c.kc * 8, cudaMemcpyDeviceToHost, S.s));
+        CTR_HOST_TRY(cudaMemcpyAsync(S.h_meta, B.offsets + c.kc, 8, cudaMemcpyDeviceToHost, S.s));
+        CTR_HOST_TRY(cudaMemcpyAsync(S.h_meta + 1, B.status, 16, cudaMemcpyDeviceToHost, S.s));
         CTR_HOST_TRY(cudaEventRecord(S.ev_size, S.s));
+        CTR_TRACE("enc issue %zu done (k %llu..%llu)", i, (unsigned long long)c.k0, (unsigned long long)c.k1);
         return CTR_OK;
     };
     auto finish = [&](size_t i) -> int {
         const Chunk &c = chunks[i];
         SlotRes &S = res->slot[i % kSlots];
+        CTR_TRACE("enc finish %zu wait", i);
         CTR_HOST_TRY(cudaEventSynchronize(S.ev_size));
+        CTR_TRACE("enc finish %zu size known", i);
         const uint64_t total = S.h_meta[0];
         note_status(S.h_meta, c.k0, &status, &bad);
         if (base + total > a.words_capacity || total > cap[i]) {
             out_of_space = true;
         } else if (total) {
-            CTR_HOST_TRY(cudaMemcpyAsync(a.words_out + base, bufs[i].words.p, total * 4, cudaMemcpyDeviceToHost, S.s));
+            CTR_HOST_TRY(cudaMemcpyAsync(a.words_out + base, bufs[i].words, total * 4, cudaMemcpyDeviceToHost, S.s));
         }
         CTR_HOST_TRY(cudaEventRecord(S.ev_done, S.s));
         if (base)
@@ -320,17 +487,22 @@ int run_encode(const Call &a, PipeRes *res) {
     for (size_t i = 0; i < n && !rc; ++i) {
         if (i >= (size_t)kSlots) {  // the chunk that used this slot has left the device: its buffers go back to the pool
             rc = cudaEventSynchronize(res->slot[i % kSlots].ev_done) == cudaSuccess ? CTR_OK : CTR_ERR_CUDA;
-            bufs[i - kSlots].release();
         }
         if (!rc) rc = issue(i);
-        if (!rc && i >= 1) rc = finish(i - 1);
+        if (!rc && i >= 1 && !direct) rc = finish(i - 1);
     }
-    if (!rc && n) rc = finish(n - 1);
+    if (!rc && n && !direct) rc = finish(n - 1);
     for (int i = 0; i < kSlots; ++i) {
         const cudaError_t e = cudaStreamSynchronize(res->slot[i].s);
         if (e != cudaSuccess && !rc) rc = ctr::host_cuda_fail(e, "cudaStreamSynchronize");
     }
     if (rc) return rc;
+    if (direct) {  // the last chunk's kernel wrote offsets[K], the total and the merged status
+        const uint64_t *m = res->slot[0].h_meta;
+        if (a.data_status) *a.data_status = (int)(uint32_t)m[1];
+        if (a.failing_stream) *a.failing_stream = m[2];
+        return (m[1] >> 32) ? CTR_ERR_OUT_OF_SPACE : CTR_OK;
+    }
     a.offsets_out[a.K] = base;
     if (a.data_status) *a.data_status = status;
     if (a.failing_stream) *a.failing_stream = bad;
@@ -345,49 +517,80 @@ int run_decode(const Call &a, PipeRes *res) {
     int status = 0, rc = CTR_OK;
     uint64_t bad = 0;
 
+    // all compressed words and offset tables go up first, chunk by chunk, on the upload stream
+    {
+        size_t need = 0;
+        for (const Chunk &c : chunks) {
+            if (a.offsets_in[c.k1] < a.offsets_in[c.k0]) return CTR_ERR_BAD_ARGUMENT;
+            need += arena_size((a.offsets_in[c.k1] - a.offsets_in[c.k0]) * 4) + arena_size((c.kc + 1) * 8);
+        }
+        if (need > res->up_bytes) {
+            if (res->up_arena) cudaFree(res->up_arena);
+            res->up_arena = nullptr;
+            res->up_bytes = 0;
+            const size_t want = align_up(need + need / 8, 1 << 20);
+            CTR_HOST_TRY(cudaMalloc((void **)&res->up_arena, want));
+            res->up_bytes = want;
+        }
+        size_t at = 0;
+        for (size_t i = 0; i < n; ++i) {
+            const Chunk &c = chunks[i];
+            const uint64_t w0 = a.offsets_in[c.k0], w1 = a.offsets_in[c.k1];
+            bufs[i].words = reinterpret_cast<uint32_t *>(res->up_arena + at);  // (256-byte blocks: the decoders' 16-byte reads stay inside)
+            at += arena_size((w1 - w0) * 4);
+            bufs[i].ws = res->up_arena + at;
+            at += arena_size((c.kc + 1) * 8);
+            int r = copy_1d(reinterpret_cast<char *>(bufs[i].words), reinterpret_cast<const char *>(a.words_in + w0), (w1 - w0) * 4,
+                            cudaMemcpyHostToDevice, res->up);
+            if (r) return r;
+            CTR_HOST_TRY(cudaMemcpyAsync(bufs[i].ws, a.offsets_in + c.k0, (c.kc + 1) * 8, cudaMemcpyHostToDevice, res->up));
+            CTR_HOST_TRY(cudaEventRecord(res->up_ev[i], res->up));
+        }
+    }
+
     auto issue = [&](size_t i) -> int {
         const Chunk &c = chunks[i];
         SlotRes &S = res->slot[i % kSlots];
         SlotBufs &B = bufs[i];
         int r;
         ctr_layout L;
-        const uint64_t w0 = a.offsets_in[c.k0], w1 = a.offsets_in[c.k1];
-        if (w1 < w0) return CTR_ERR_BAD_ARGUMENT;
-        if ((r = B.words.alloc((w1 - w0) * 4, S.s))) return r;
-        if (w1 > w0) CTR_HOST_TRY(cudaMemcpyAsync(B.words.p, a.words_in + w0, (w1 - w0) * 4, cudaMemcpyHostToDevice, S.s));
-        if ((r = B.ws.alloc((c.kc + 1) * 8, S.s)) || (r = B.offsets.alloc((c.kc + 1) * 8, S.s))) return r;
-        CTR_HOST_TRY(cudaMemcpyAsync(B.ws.p, a.offsets_in + c.k0, (c.kc + 1) * 8, cudaMemcpyHostToDevice, S.s));
-        rebase_offsets_kernel<<<(unsigned)((c.kc + 1 + 255) / 256), 256, 0, S.s>>>(B.ws.as<uint64_t>(), B.offsets.as<uint64_t>(), c.kc + 1);
+        if ((r = arena_reserve(S, arena_size((c.kc + 1) * 8) + layout_bytes(a, b, c) + arena_size(c.n * 4) + arena_size(16)))) return r;
+        B.offsets = arena_take<uint64_t>(S, (c.kc + 1) * 8);
+        CTR_HOST_TRY(cudaStreamWaitEvent(S.s, res->up_ev[i], 0));
+        rebase_offsets_kernel<<<(unsigned)((c.kc + 1 + 255) / 256), 256, 0, S.s>>>(static_cast<const uint64_t *>(B.ws), B.offsets, c.kc + 1);
         ctr::host_count_launch();
-        if ((r = fill_layout(&L, a, b, c, B, S.s))) return r;
-        if ((r = B.sym.alloc(c.n * 4, S.s)) || (r = B.status.alloc(16, S.s))) return r;
-        CTR_HOST_TRY(cudaMemsetAsync(B.status.p, 0, 16, S.s));
-        r = a.range ? ctr_range_decode(a.model, B.words.as<uint32_t>(), B.offsets.as<uint64_t>(), &L, nullptr, B.sym.as<int32_t>(),
-                                       nullptr, nullptr, B.status.as<uint32_t>(), S.s)
-                    : ctr_ans_decode(a.model, B.words.as<uint32_t>(), B.offsets.as<uint64_t>(), &L, nullptr, B.sym.as<int32_t>(),
-                                     nullptr, nullptr, B.status.as<uint32_t>(), S.s);
+        if ((r = fill_layout(&L, a, b, c, B, S))) return r;
+        B.sym = arena_take<int32_t>(S, c.n * 4);
+        B.status = arena_take<uint32_t>(S, 16);
+        CTR_HOST_TRY(cudaMemsetAsync(B.status, 0, 16, S.s));
+        r = a.range ? ctr_range_decode(a.model, B.words, B.offsets, &L, nullptr, B.sym, nullptr, nullptr, B.status, S.s)
+                    : ctr_ans_decode(a.model, B.words, B.offsets, &L, nullptr, B.sym, nullptr, nullptr, B.status, S.s);
         if (r) return r;
-        if ((r = copy_symbol_array(B.sym.p, a.symbols_out, b, c, false, S.s))) return r;
-        CTR_HOST_TRY(cudaMemcpyAsync(S.h_meta + 1, B.status.p, 16, cudaMemcpyDeviceToHost, S.s));
+        if ((r = copy_symbol_array(B.sym, a.symbols_out, b, c, false, S.s))) return r;
+        CTR_HOST_TRY(cudaMemcpyAsync(S.h_meta + 1, B.status, 16, cudaMemcpyDeviceToHost, S.s));
         CTR_HOST_TRY(cudaEventRecord(S.ev_done, S.s));
+        CTR_TRACE("dec issue %zu done", i);
         return CTR_OK;
     };
     auto finish = [&](size_t i) -> int {  // slot reuse / end of call: the chunk has left the device
         SlotRes &S = res->slot[i % kSlots];
+        CTR_TRACE("dec finish %zu wait", i);
         CTR_HOST_TRY(cudaEventSynchronize(S.ev_done));
+        CTR_TRACE("dec finish %zu left the device", i);
         note_status(S.h_meta, chunks[i].k0, &status, &bad);
         return CTR_OK;
     };
     for (size_t i = 0; i < n && !rc; ++i) {
-        if (i >= (size_t)kSlots) {
-            rc = finish(i - kSlots);
-            bufs[i - kSlots].release();
-        }
+        if (i >= (size_t)kSlots) rc = finish(i - kSlots);
         if (!rc) rc = issue(i);
     }
     for (size_t i = n >= (size_t)kSlots ? n - kSlots : 0; i < n && !rc; ++i) rc = finish(i);
     for (int i = 0; i < kSlots; ++i) {
         const cudaError_t e = cudaStreamSynchronize(res->slot[i].s);
+        if (e != cudaSuccess && !rc) rc = ctr::host_cuda_fail(e, "cudaStreamSynchronize");
+    }
+    {
+        const cudaError_t e = cudaStreamSynchronize(res->up);
         if (e != cudaSuccess && !rc) rc = ctr::host_cuda_fail(e, "cudaStreamSynchronize");
     }
     if (rc) return rc;
@@ -413,7 +616,9 @@ int run_call(const Call &a) {
     if (a.sym_off && !offsets_valid(a.sym_off, a.K, a.N)) return CTR_ERR_BAD_ARGUMENT;
     PipeRes *res = acquire_pipe();
     if (!res) return ctr::host_fail("host pipeline: cannot create streams / pinned staging");
+    CTR_TRACE("%s call start", a.decode ? "dec" : "enc");
     const int rc = a.decode ? run_decode(a, res) : run_encode(a, res);
+    CTR_TRACE("%s call end", a.decode ? "dec" : "enc");
     release_pipe(res);
     return rc;
 }
