@@ -51,6 +51,8 @@ def parse_args():
     ap.add_argument("--cpu-sample", type=int, default=50_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra-configs", action="store_true")
+    ap.add_argument("--gather-lag", type=int, default=int(os.environ.get("CTR_GATHER_LAG", "1")),
+                    help="N>1: a turn's gathered container is consumed this many steps after it was encoded")
     return ap.parse_args()
 
 
@@ -335,14 +337,14 @@ def run_ours(args):
     L0 = N.Layout()
     L0.n_streams, L0.n_symbols = k, n
     cap_words = int(lib.ctr_ans_max_compressed_words(C.byref(L0)))
-    state = {"comp": None, "prev": None, "sg": None}
+    state = {"comp": None, "prev": [], "sg": None}
     neighbour = (rank + 1) % world
 
     gather_kind = None
     if world > 1:
         if os.environ.get("CTR_GATHER", "peer") == "peer":
             try:
-                state["sg"] = D.SlotGather(cap_words, k)
+                state["sg"] = D.SlotGather(cap_words, k, n_buffers=args.gather_lag + 1)
                 ok = 1
             except Exception as exc:  # no symmetric memory / stream memory operations here: NCCL all-gather instead
                 sys.stderr.write(f"rank {rank}: SlotGather unavailable ({exc}); using the NCCL all-gather\n")
@@ -375,20 +377,21 @@ def run_ours(args):
         turn = sg.begin_turn(k, n, "ans")
         state["comp"] = bc.ans_encode(syms, model, n_streams=k, out=turn.out)
         sg.push(turn, k)
-        prev = state["prev"]
-        if prev is None:
+        pending = state["prev"]
+        if len(pending) < args.gather_lag:
             bc.ans_decode(state["comp"], model, out=out)
         else:
+            prev = pending.pop(0)
             sg.wait(prev)
             bc.ans_decode(sg.shard(prev, neighbour, k, n, "ans"), model, out=out)
             sg.release(prev)
-        state["prev"] = turn
+        pending.append(turn)
 
     def drain():  # the last turn's gather completes inside the timed region
-        if sg is not None and state["prev"] is not None:
-            sg.wait(state["prev"])
-            sg.release(state["prev"])
-            state["prev"] = None
+        while sg is not None and state["prev"]:
+            prev = state["prev"].pop(0)
+            sg.wait(prev)
+            sg.release(prev)
 
     def sync_all():
         torch.cuda.synchronize()
@@ -410,7 +413,7 @@ def run_ours(args):
         want = synth(neighbour)
         assert torch.equal(out, want), "decode of the neighbour's shard from the gathered container != its symbols"
         del want
-        last = state["prev"]
+        last = state["prev"][-1]
         drain()
         torch.cuda.synchronize()
         for r in range(world):  # every slot of the last turn: offsets sane, and my own slot equals what I encoded
@@ -432,18 +435,23 @@ def run_ours(args):
     lib.ctr_profile_read(1, None, None)
     launches0 = B.kernel_launch_count()
     with sampler as clocks:
+        t_host0 = time.perf_counter()
         ev[0].record()
         for i in range(args.steps):
             step()
             if i + 1 == args.steps:
                 drain()
             ev[i + 1].record()
+        host_issue_ms = (time.perf_counter() - t_host0) * 1e3 / args.steps  # time the host needs to ENQUEUE a step
         sync_all()
     launches = B.kernel_launch_count() - launches0
     lib.ctr_profile_enable(0)
     if sg is not None:
         sg.sync()
     total_ms = ev[0].elapsed_time(ev[-1])
+    if os.environ.get("CTR_BENCH_DEBUG"):
+        per = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
+        sys.stderr.write(f"rank {rank}: steps(ms) " + " ".join(f"{x:.3f}" for x in per) + f" host_issue {host_issue_ms:.3f}\n")
     t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -611,9 +619,11 @@ def run_ours(args):
                                 "ANS encode of the own shard into the own slot of the gathered container -> push to all peers "
                                 "(side streams, overlapped with the following kernels) -> ANS decode of the right neighbour's "
                                 "shard of the previous turn out of the gathered container; every gather joined inside the timed region"),
+                       "gather_lag_steps": args.gather_lag if world > 1 else None,
                        "gather": gather_kind,
                        "parity_note": "erf/exp restate FreeBSD msun (what Rust libm 0.2.16 implements); equality with a real "
                                       "Rust build is pinned by the reference's golden vectors G1-G8 only (SURVEY 8c)"},
+            "host_issue_ms_per_step": host_issue_ms,
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
             "clocks": clocks.summary(), "extra_configs": extra,
         }

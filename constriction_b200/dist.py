@@ -188,12 +188,13 @@ class SlotGather:
         n_off = n_buffers * world * (self.slot_streams + 1)
         self.words = symm_mem.empty(n_words, dtype=torch.int32, device=dev)
         self.offsets = symm_mem.empty(n_off, dtype=torch.int64, device=dev)
-        self.flags = symm_mem.empty(2 * n_buffers * world, dtype=torch.int32, device=dev)
+        self.flags = symm_mem.empty(3 * n_buffers * world, dtype=torch.int32, device=dev)
         self.flags.zero_()
         torch.cuda.synchronize()
         self._handles = [symm_mem.rendezvous(t, pg) for t in (self.words, self.offsets, self.flags)]
         arr = lambda h: (ctypes.c_void_p * world)(*[int(x) for x in h.buffer_ptrs])
         self._h = ctypes.c_void_p()
+        self._views = {}
         dist.barrier(group=group)  # every rank has zeroed its flags
         N.raise_for(self._lib.ctr_gather_create(world, self.rank, n_buffers, self.slot_words, self.slot_streams,
                                                 arr(self._handles[0]), arr(self._handles[1]), arr(self._handles[2]),
@@ -212,16 +213,27 @@ class SlotGather:
 
     def _slot_views(self, turn: int, src: int):
         b = turn % self.n_buffers
-        w0 = (b * self.world + src) * self.slot_words
-        o0 = (b * self.world + src) * (self.slot_streams + 1)
-        return self.words[w0:w0 + self.slot_words], self.offsets[o0:o0 + self.slot_streams + 1]
+        key = (b, src)
+        v = self._views.get(key)
+        if v is None:
+            w0 = (b * self.world + src) * self.slot_words
+            o0 = (b * self.world + src) * (self.slot_streams + 1)
+            v = self._views[key] = (self.words[w0:w0 + self.slot_words], self.offsets[o0:o0 + self.slot_streams + 1], {})
+        return v
+
+    def _offsets_view(self, turn: int, src: int, n_streams: int):
+        w, o, cache = self._slot_views(turn, src)
+        ov = cache.get(n_streams)
+        if ov is None:
+            ov = cache[n_streams] = o[:n_streams + 1]
+        return w, ov
 
     def begin_turn(self, n_streams: int, n_symbols: int = 0, coder: str = "ans") -> "SlotGather.Turn":
         from .batch import Compressed
         q = ctypes.c_uint32()
         self._N.raise_for(self._lib.ctr_gather_begin_turn(self._h, ctypes.byref(q), None, None, None))
-        w, o = self._slot_views(q.value, self.rank)
-        return SlotGather.Turn(q.value, Compressed(w, o[:n_streams + 1], n_streams, n_symbols, coder))
+        w, o = self._offsets_view(q.value, self.rank, n_streams)
+        return SlotGather.Turn(q.value, Compressed(w, o, n_streams, n_symbols, coder))
 
     def push(self, turn: "SlotGather.Turn", n_streams: int) -> None:
         """Behind the encode on the current stream; returns at once."""
@@ -239,8 +251,8 @@ class SlotGather:
     def shard(self, turn: "SlotGather.Turn", src_rank: int, n_streams: int, n_symbols: int, coder: str = "ans", sym_offsets=None):
         """Rank `src_rank`'s container of this turn as a batch.Compressed (views into my receive buffer)."""
         from .batch import Compressed
-        w, o = self._slot_views(turn.number, src_rank)
-        return Compressed(w, o[:n_streams + 1], n_streams, n_symbols, coder, sym_offsets)
+        w, o = self._offsets_view(turn.number, src_rank, n_streams)
+        return Compressed(w, o, n_streams, n_symbols, coder, sym_offsets)
 
 
 class NcclComm:

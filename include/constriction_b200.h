@@ -308,7 +308,7 @@ int ctr_host_job_wait(ctr_host_job_t job);
  * Peer-memory implementation (one process per GPU, one node): `words_bases[r]`, `offsets_bases[r]`, `flags_bases[r]`
  * are rank r's receive buffers mapped into THIS process (symmetric memory over NVLink; allocation and exchange of the
  * mappings is the host's business: torch.distributed._symmetric_memory, or cuMemCreate + cuMemExportToShareableHandle).
- * `flags` is u32[2][n_buffers][world], zeroed before the first turn; slot_words a multiple of 4.  Per turn:
+ * `flags` is u32[3][n_buffers][world], zeroed before the first turn; slot_words a multiple of 4.  Per turn:
  *   ctr_gather_begin_turn   -> turn number q and MY slot in MY buffers: encode straight into it
  *   (the caller enqueues ctr_*_encode with words_out = slot, offsets_out = slot offsets on `encode_stream`)
  *   ctr_gather_push         enqueues an 8-byte size read-back behind the encode and returns at once; a worker thread of

@@ -299,6 +299,291 @@ int orc_qgauss_quantile(int32_t min_sym, int32_t max_sym, double mean, double st
 }
 
 /* ------------------------------------------------------------------ */
+/* log1p, atan (libm 0.2.16 <- musl <- FreeBSD msun s_log1p.c, s_atan.c)  */
+/* ------------------------------------------------------------------ */
+static inline uint64_t f64_bits(double x) {
+    uint64_t u;
+    memcpy(&u, &x, 8);
+    return u;
+}
+static inline double f64_from_bits(uint64_t u) {
+    double x;
+    memcpy(&x, &u, 8);
+    return x;
+}
+
+/* call sites: categorical.rs:11,98-126,166-172 */
+double orc_log1p(double x) {
+    static const double ln2_hi = 6.93147180369123816490e-01, ln2_lo = 1.90821492927058770002e-10,
+                        Lg1 = 6.666666666666735130e-01, Lg2 = 3.999999999940941908e-01, Lg3 = 2.857142874366239149e-01,
+                        Lg4 = 2.222219843214978396e-01, Lg5 = 1.818357216161805012e-01, Lg6 = 1.531383769920937332e-01,
+                        Lg7 = 1.479819860511658591e-01;
+    uint64_t ui = f64_bits(x);
+    uint32_t hx = (uint32_t)(ui >> 32);
+    int k = 1;
+    double f = 0.0, c = 0.0;
+    if (hx < 0x3fda827au || (hx >> 31)) { /* 1+x < sqrt(2)+ */
+        if (hx >= 0xbff00000u) {          /* x <= -1.0 */
+            if (x == -1.0) return x / 0.0; /* log1p(-1) = -inf */
+            return (x - x) / 0.0;          /* log1p(x<-1) = NaN */
+        }
+        if ((hx << 1) < (0x3ca00000u << 1)) return x; /* |x| < 2**-53 */
+        if (hx <= 0xbfd2bec4u) {                      /* sqrt(2)/2- <= 1+x < sqrt(2)+ */
+            k = 0;
+            c = 0.0;
+            f = x;
+        }
+    } else if (hx >= 0x7ff00000u) {
+        return x;
+    }
+    if (k) {
+        ui = f64_bits(1.0 + x);
+        uint32_t hu = (uint32_t)(ui >> 32);
+        hu += 0x3ff00000u - 0x3fe6a09eu;
+        k = (int)(hu >> 20) - 0x3ff;
+        /* correction term ~ log(1+x)-log(u), avoid underflow in c/u */
+        if (k < 54) {
+            c = k >= 2 ? 1.0 - (f64_from_bits(ui) - x) : x - (f64_from_bits(ui) - 1.0);
+            c /= f64_from_bits(ui);
+        } else {
+            c = 0.0;
+        }
+        /* reduce u into [sqrt(2)/2, sqrt(2)] */
+        hu = (hu & 0x000fffffu) + 0x3fe6a09eu;
+        ui = ((uint64_t)hu << 32) | (ui & 0xffffffffull);
+        f = f64_from_bits(ui) - 1.0;
+    }
+    double hfsq = 0.5 * f * f;
+    double s = f / (2.0 + f);
+    double z = s * s;
+    double w = z * z;
+    double t1 = w * (Lg2 + w * (Lg4 + w * Lg6));
+    double t2 = z * (Lg1 + w * (Lg3 + w * (Lg5 + w * Lg7)));
+    double R = t2 + t1;
+    double dk = (double)k;
+    return s * (hfsq + R) + (dk * ln2_lo + c) - hfsq + f + dk * ln2_hi;
+}
+
+double orc_atan(double x) {
+    static const double atanhi[4] = {4.63647609000806093515e-01, 7.85398163397448278999e-01, 9.82793723247329054082e-01,
+                                     1.57079632679489655800e+00};
+    static const double atanlo[4] = {2.26987774529616870924e-17, 3.06161699786838301793e-17, 1.39033110312309984516e-17,
+                                     6.12323399573676603587e-17};
+    static const double aT[11] = {3.33333333333329318027e-01,  -1.99999999998764832476e-01, 1.42857142725034663711e-01,
+                                  -1.11111104054623557880e-01, 9.09088713343650656196e-02,  -7.69187620504482999495e-02,
+                                  6.66107313738753120669e-02,  -5.83357013379057348645e-02, 4.97687799461593236017e-02,
+                                  -3.65315727442169155270e-02, 1.62858201153657823623e-02};
+    uint32_t ix = (uint32_t)(f64_bits(x) >> 32);
+    const uint32_t sign = ix >> 31;
+    ix &= 0x7fffffffu;
+    int id;
+    if (ix >= 0x44100000u) { /* |x| >= 2^66 */
+        if (x != x) return x;
+        double z = atanhi[3] + 0x1p-120f;
+        return sign ? -z : z;
+    }
+    if (ix < 0x3fdc0000u) {     /* |x| < 0.4375 */
+        if (ix < 0x3e400000u) return x; /* |x| < 2^-27 */
+        id = -1;
+    } else {
+        x = fabs(x);
+        if (ix < 0x3ff30000u) {     /* |x| < 1.1875 */
+            if (ix < 0x3fe60000u) { /* 7/16 <= |x| < 11/16 */
+                id = 0;
+                x = (2.0 * x - 1.0) / (2.0 + x);
+            } else { /* 11/16 <= |x| < 19/16 */
+                id = 1;
+                x = (x - 1.0) / (x + 1.0);
+            }
+        } else if (ix < 0x40038000u) { /* |x| < 2.4375 */
+            id = 2;
+            x = (x - 1.5) / (1.0 + 1.5 * x);
+        } else { /* 2.4375 <= |x| < 2^66 */
+            id = 3;
+            x = -1.0 / x;
+        }
+    }
+    double z = x * x;
+    double w = z * z;
+    /* break sum from i=0 to 10 aT[i]z**(i+1) into odd and even poly */
+    double s1 = z * (aT[0] + w * (aT[2] + w * (aT[4] + w * (aT[6] + w * (aT[8] + w * aT[10])))));
+    double s2 = w * (aT[1] + w * (aT[3] + w * (aT[5] + w * (aT[7] + w * aT[9]))));
+    if (id < 0) return x - x * (s1 + s2);
+    z = atanhi[id] - (x * (s1 + s2) - atanlo[id] - x);
+    return sign ? -z : z;
+}
+
+/* ------------------------------------------------------------------ */
+/* Other leakily quantised distributions (pybindings/stream/model.rs:740-960).  Their CDFs live in the crate
+ * `probability 0.20.3`, whose source is not available here and for which the reference holds NO golden vectors:
+ * the formulas below are the textbook definitions (PARITY UNPINNED for these three models). */
+/* ------------------------------------------------------------------ */
+double orc_laplace_cdf(double x, double mu, double b) {
+    if (x <= mu) return 0.5 * orc_exp((x - mu) / b);
+    return 1.0 - 0.5 * orc_exp(-(x - mu) / b);
+}
+double orc_cauchy_cdf(double x, double x0, double gamma) {
+    const double frac_1_pi = 0.318309886183790671537767526745028724; /* core::f64::consts::FRAC_1_PI */
+    return frac_1_pi * orc_atan((x - x0) / gamma) + 0.5;
+}
+
+/* LeakyQuantizer table for any CDF of two parameters (quantize.rs:525-568 with D = that distribution) */
+int orc_qdist_cdf(int kind, int32_t min_sym, int32_t max_sym, double p0, double p1, uint32_t *cdf) {
+    double fw;
+    int rc = qgauss_free_weight(min_sym, max_sym, &fw);
+    if (rc) return rc;
+    if (!(p1 > 0.0)) return ORC_ERR_BAD_MODEL;
+    size_t n = (size_t)((int64_t)max_sym - (int64_t)min_sym) + 1;
+    cdf[0] = 0;
+    for (size_t i = 1; i < n; i++) {
+        double x = (double)(int32_t)((int64_t)min_sym + (int64_t)i) - 0.5;
+        double c = kind == 1 ? orc_laplace_cdf(x, p0, p1) : (kind == 2 ? orc_cauchy_cdf(x, p0, p1) : orc_gaussian_cdf(x, p0, p1));
+        cdf[i] = f64_as_u32(fw * c) + (uint32_t)i;
+    }
+    cdf[n] = ORC_TOTAL;
+    return ORC_OK;
+}
+
+/* Binomial(n, p) over {0..n}: CDF(x + 0.5) = sum_{i <= x} pmf(i), pmf by the recurrence
+ * pmf(i+1) = pmf(i) * (n-i)/(i+1) * p/(1-p) started from the mode in log space (PARITY UNPINNED: the
+ * reference evaluates the regularised incomplete beta function of the `special` crate). */
+int orc_binomial_cdf(int32_t n, double p, uint32_t *cdf) {
+    if (n < 1 || !(p >= 0.0) || !(p <= 1.0)) return ORC_ERR_BAD_MODEL;
+    double fw;
+    int rc = qgauss_free_weight(0, n, &fw);
+    if (rc) return rc;
+    double *pmf = (double *)malloc(((size_t)n + 1) * sizeof(double));
+    if (!pmf) return ORC_ERR_BAD_MODEL;
+    const double q = 1.0 - p;
+    int64_t mode = (int64_t)(((double)n + 1.0) * p);
+    if (mode > n) mode = n;
+    pmf[mode] = 1.0;
+    for (int64_t i = mode; i < n; i++) pmf[i + 1] = q > 0.0 ? pmf[i] * ((double)(n - i) / (double)(i + 1)) * (p / q) : 0.0;
+    for (int64_t i = mode; i > 0; i--) pmf[i - 1] = p > 0.0 ? pmf[i] * ((double)i / (double)(n - i + 1)) * (q / p) : 0.0;
+    double norm = 0.0;
+    for (int64_t i = 0; i <= n; i++) norm = norm + pmf[i];
+    double cum = 0.0;
+    cdf[0] = 0;
+    for (int64_t i = 1; i <= n; i++) {
+        cum = cum + pmf[i - 1];
+        cdf[i] = f64_as_u32(fw * (cum / norm)) + (uint32_t)i;
+    }
+    cdf[(size_t)n + 1] = ORC_TOTAL;
+    free(pmf);
+    return ORC_OK;
+}
+
+/* categorical.rs:56-177 perfectly_quantized_probabilities (PRECISION = 24, Probability = u32), computed in f64
+ * whatever the caller's float type (`F: Into<f64>`), followed by contiguous.rs:301-312 (weights -> CDF).
+ * Order-sensitive details that decide ties: `sort_by` is stable (descending win), `max_by` returns the LAST maximum,
+ * `min_by` the FIRST minimum, and the slots stay in sorted order until the final sort by original index. */
+typedef struct {
+    size_t original_index;
+    double prob;
+    uint32_t weight;
+    double win, loss;
+} orc_slot;
+
+static void slots_stable_sort_desc_win(orc_slot *a, orc_slot *tmp, size_t n) {
+    for (size_t width = 1; width < n; width *= 2) {
+        for (size_t lo = 0; lo < n; lo += 2 * width) {
+            size_t mid = lo + width < n ? lo + width : n, hi = lo + 2 * width < n ? lo + 2 * width : n;
+            size_t i = lo, j = mid, k = lo;
+            while (i < mid && j < hi) {
+                /* take from the right run only if it is strictly greater: equal elements keep their order */
+                if (a[j].win > a[i].win)
+                    tmp[k++] = a[j++];
+                else
+                    tmp[k++] = a[i++];
+            }
+            while (i < mid) tmp[k++] = a[i++];
+            while (j < hi) tmp[k++] = a[j++];
+        }
+        memcpy(a, tmp, n * sizeof *a);
+    }
+}
+
+static int cat_perfect_weights(const double *probs, size_t n, uint32_t *weights) {
+    if (n < 2 || n > 0xffffffffull) return ORC_ERR_BAD_MODEL;
+    uint32_t remaining = ORC_TOTAL - (uint32_t)n; /* wrapping_sub in the reference */
+    double norm = 0.0;
+    for (size_t i = 0; i < n; i++) norm = norm + probs[i];
+    if (!isnormal(norm) || signbit(norm)) return ORC_ERR_BAD_MODEL;
+    const double scale = (double)remaining / norm;
+    orc_slot *slots = (orc_slot *)malloc(2 * n * sizeof *slots);
+    if (!slots) return ORC_ERR_BAD_MODEL;
+    orc_slot *tmp = slots + n;
+    for (size_t i = 0; i < n; i++) {
+        const double prob = probs[i];
+        if (prob < 0.0) {
+            free(slots);
+            return ORC_ERR_BAD_MODEL;
+        }
+        const uint32_t current = f64_as_u32(prob * scale);
+        remaining -= current;
+        const uint32_t weight = current + 1u;
+        slots[i].original_index = i;
+        slots[i].prob = prob;
+        slots[i].weight = weight;
+        slots[i].win = prob * orc_log1p(1.0 / (double)weight);
+        slots[i].loss = weight == 1u ? INFINITY : -prob * orc_log1p(-1.0 / (double)weight);
+    }
+    while (remaining != 0u) {
+        slots_stable_sort_desc_win(slots, tmp, n);
+        const size_t batch = remaining < n ? remaining : n;
+        for (size_t i = 0; i < batch; i++) {
+            slots[i].weight += 1u;
+            slots[i].win = slots[i].prob * orc_log1p(1.0 / (double)slots[i].weight);
+            slots[i].loss = -slots[i].prob * orc_log1p(-1.0 / (double)slots[i].weight);
+        }
+        remaining -= (uint32_t)batch;
+    }
+    for (;;) {
+        size_t buyer = 0, seller = 0;
+        for (size_t i = 1; i < n; i++) {
+            if (slots[i].win >= slots[buyer].win) buyer = i;   /* max_by: last maximum */
+            if (slots[i].loss < slots[seller].loss) seller = i; /* min_by: first minimum */
+        }
+        if (buyer == seller) break;
+        if (slots[buyer].win <= slots[seller].loss) break;
+        slots[seller].weight -= 1u;
+        slots[seller].win = -INFINITY;
+        slots[seller].loss = slots[seller].weight == 1u ? INFINITY : -slots[seller].prob * orc_log1p(-1.0 / (double)slots[seller].weight);
+        slots[buyer].weight += 1u;
+        slots[buyer].loss = INFINITY;
+        slots[buyer].win = slots[buyer].prob * orc_log1p(1.0 / (double)slots[buyer].weight);
+    }
+    for (size_t i = 0; i < n; i++) weights[slots[i].original_index] = slots[i].weight;
+    free(slots);
+    return ORC_OK;
+}
+
+int orc_cat_perfect_cdf_f64(const double *pmf, size_t n, uint32_t *cdf) {
+    uint32_t *w = (uint32_t *)malloc((n ? n : 1) * sizeof *w);
+    if (!w) return ORC_ERR_BAD_MODEL;
+    int rc = cat_perfect_weights(pmf, n, w);
+    if (!rc) { /* contiguous.rs:471-497 from_nonzero_fixed_point_probabilities */
+        uint32_t acc = 0;
+        for (size_t i = 0; i < n; i++) {
+            cdf[i] = acc;
+            acc += w[i];
+        }
+        cdf[n] = ORC_TOTAL;
+        if (acc != ORC_TOTAL) rc = ORC_ERR_BAD_MODEL;
+    }
+    free(w);
+    return rc;
+}
+int orc_cat_perfect_cdf_f32(const float *pmf, size_t n, uint32_t *cdf) {
+    double *d = (double *)malloc((n ? n : 1) * sizeof *d);
+    if (!d) return ORC_ERR_BAD_MODEL;
+    for (size_t i = 0; i < n; i++) d[i] = (double)pmf[i]; /* `prob.into()` */
+    int rc = orc_cat_perfect_cdf_f64(d, n, cdf);
+    free(d);
+    return rc;
+}
+
+/* ------------------------------------------------------------------ */
 /* Categorical                                                          */
 /* ------------------------------------------------------------------ */
 

@@ -42,7 +42,21 @@ double orc_erf(double x);
 /* probability-0.20.3 Gaussian::distribution: (1 + erf((x-mu)/(sigma*sqrt2)))/2 */
 double orc_gaussian_cdf(double x, double mean, double std);
 
+double orc_log1p(double x); /* libm log1p (categorical.rs:11) */
+double orc_atan(double x);
+double orc_laplace_cdf(double x, double mu, double b);
+double orc_cauchy_cdf(double x, double x0, double gamma);
+
 /* ---------- entropy models ---------- */
+/* LeakyQuantizer tables of the other closed-form models of the Python API (pybindings/stream/model.rs:740-960):
+ * kind 0 Gaussian(mean, std), 1 Laplace(mean, scale), 2 Cauchy(loc, scale); Binomial(n, p) over {0..n}.
+ * PARITY UNPINNED for Laplace / Cauchy / Binomial: their CDFs come from the crate `probability`, absent here, and the
+ * reference holds no golden vectors for them. */
+int orc_qdist_cdf(int kind, int32_t min_sym, int32_t max_sym, double p0, double p1, uint32_t *cdf);
+int orc_binomial_cdf(int32_t n, double p, uint32_t *cdf);
+/* categorical.rs:56-177 + contiguous.rs:301-312: `Categorical(p)` / `Bernoulli(p)` with perfect=True (the Python default) */
+int orc_cat_perfect_cdf_f32(const float *pmf, size_t n, uint32_t *cdf);
+int orc_cat_perfect_cdf_f64(const double *pmf, size_t n, uint32_t *cdf);
 /* quantize.rs:525-568 LeakilyQuantizedDistribution::left_cumulative_and_probability */
 int orc_qgauss_left_prob(int32_t min_sym, int32_t max_sym, double mean, double std, int32_t symbol,
                          uint32_t *left, uint32_t *prob);
