@@ -56,6 +56,10 @@ SIGNATURES = {
     "ctr_model_quantized_gaussian": (C.c_int, [C.c_int32, C.c_int32, vp, vp, C.c_uint32, vp, C.POINTER(vp)]),
     "ctr_model_categorical_f32": (C.c_int, [vp, C.c_int, C.c_uint32, C.c_uint32, vp, C.POINTER(vp)]),
     "ctr_model_categorical_f64": (C.c_int, [vp, C.c_int, C.c_uint32, C.c_uint32, vp, C.POINTER(vp)]),
+    "ctr_model_categorical_perfect_f32": (C.c_int, [vp, C.c_int, C.c_uint32, C.c_uint32, vp, C.POINTER(vp)]),
+    "ctr_model_categorical_perfect_f64": (C.c_int, [vp, C.c_int, C.c_uint32, C.c_uint32, vp, C.POINTER(vp)]),
+    "ctr_model_quantized": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, vp, vp, C.c_uint32, vp, C.POINTER(vp)]),
+    "ctr_model_binomial": (C.c_int, [vp, vp, C.c_uint32, vp, C.POINTER(vp)]),
     "ctr_model_from_cdf": (C.c_int, [vp, C.c_int, C.c_uint32, C.c_uint32, C.c_int32, vp, C.POINTER(vp)]),
     "ctr_model_uniform": (C.c_int, [C.c_uint32, vp, C.POINTER(vp)]),
     "ctr_model_destroy": (C.c_int, [vp]),

@@ -115,6 +115,57 @@ class ModelTable:
         return cls(out.value, dev)
 
     @classmethod
+    def categorical_perfect(cls, pmf, device=None) -> "ModelTable":
+        """M categorical models with the reference's `perfect` quantisation (categorical.rs:56-177), the default of the
+        Python `Categorical(p)` / `Bernoulli(p)`.  `pmf`: numpy float32 / float64, shape (alphabet,) or (M, alphabet)."""
+        dev = cls._device(device)
+        a = np.asarray(pmf)
+        if a.ndim == 1:
+            a = a[None, :]
+        if a.dtype not in (np.float32, np.float64) or a.ndim != 2:
+            raise TypeError("pmf must be a float32/float64 array of rank 1 or 2")
+        a = np.ascontiguousarray(a)
+        lib = N.load()
+        fn = lib.ctr_model_categorical_perfect_f32 if a.dtype == np.float32 else lib.ctr_model_categorical_perfect_f64
+        out = C.c_void_p()
+        with torch.cuda.device(dev):
+            rc = fn(a.ctypes.data, 0, a.shape[0], a.shape[1], _stream_ptr(), C.byref(out))
+        N.raise_for(rc)
+        return cls(out.value, dev)
+
+    KINDS = {"gaussian": 0, "laplace": 1, "cauchy": 2}
+
+    @classmethod
+    def quantized(cls, kind: str, min_symbol: int, max_symbol: int, p0, p1, device=None) -> "ModelTable":
+        """M leakily quantised two-parameter distributions: kind "gaussian" (mean, std), "laplace" (mean, scale),
+        "cauchy" (location, scale); quantize.rs:284-308,525-568."""
+        dev = cls._device(device)
+        p0 = np.ascontiguousarray(np.atleast_1d(np.asarray(p0, dtype=np.float64)))
+        p1 = np.ascontiguousarray(np.atleast_1d(np.asarray(p1, dtype=np.float64)))
+        if p0.shape != p1.shape or p0.ndim != 1:
+            raise ValueError("parameters must be 1-D arrays of equal length")
+        out = C.c_void_p()
+        with torch.cuda.device(dev):
+            rc = N.load().ctr_model_quantized(cls.KINDS[kind], int(min_symbol), int(max_symbol), p0.ctypes.data, p1.ctypes.data,
+                                              p0.size, _stream_ptr(), C.byref(out))
+        N.raise_for(rc)
+        return cls(out.value, dev)
+
+    @classmethod
+    def binomial(cls, ns, ps, device=None) -> "ModelTable":
+        """M Binomial(n, p) models over {0..n}, rows padded to the widest (pybindings/stream/model.rs:925-960)."""
+        dev = cls._device(device)
+        ns = np.ascontiguousarray(np.atleast_1d(np.asarray(ns, dtype=np.int32)))
+        ps = np.ascontiguousarray(np.atleast_1d(np.asarray(ps, dtype=np.float64)))
+        if ns.shape != ps.shape or ns.ndim != 1:
+            raise ValueError("parameters must be 1-D arrays of equal length")
+        out = C.c_void_p()
+        with torch.cuda.device(dev):
+            rc = N.load().ctr_model_binomial(ns.ctypes.data, ps.ctypes.data, ns.size, _stream_ptr(), C.byref(out))
+        N.raise_for(rc)
+        return cls(out.value, dev)
+
+    @classmethod
     def from_cdf(cls, cdf, min_symbol: int = 0, device=None) -> "ModelTable":
         """M models from fixed-point CDF rows u32[M][alphabet+1] (cdf[0]=0, cdf[-1]=2^24)."""
         dev = cls._device(device)

@@ -472,6 +472,129 @@ extern "C" int ctr_model_categorical_f64(const double *pmf, int is_device, uint3
     return model_categorical<double>(pmf, is_device, n_models, alphabet, stream, out);
 }
 
+// two-parameter leaky quantisers: kind 0 Gaussian, 1 Laplace, 2 Cauchy
+extern "C" int ctr_model_quantized(int32_t kind, int32_t min_symbol, int32_t max_symbol, const double *p0_host,
+                                   const double *p1_host, uint32_t n_models, void *stream, ctr_model_t *out) {
+    if (kind == 0) return ctr_model_quantized_gaussian(min_symbol, max_symbol, p0_host, p1_host, n_models, stream, out);
+    if (!out || !p0_host || !p1_host || n_models == 0 || kind < 0 || kind > 2) return CTR_ERR_BAD_ARGUMENT;
+    if (!(max_symbol > min_symbol)) return CTR_ERR_BAD_MODEL;
+    const uint64_t support = (uint64_t)((int64_t)max_symbol - (int64_t)min_symbol) + 1;
+    if (support > kTotal) return CTR_ERR_BAD_MODEL;
+    for (uint32_t i = 0; i < n_models; ++i)
+        if (!(p1_host[i] > 0.0) || !(p0_host[i] == p0_host[i])) return CTR_ERR_BAD_MODEL;
+    cudaStream_t s = (cudaStream_t)stream;
+    ctr_model_s *m = nullptr;
+    int rc = model_alloc(n_models, (uint32_t)support, min_symbol, &m);
+    if (rc) return rc;
+    double *d_params = nullptr;
+    ErrWord err;
+    auto cleanup = [&](int code) {
+        if (d_params) cudaFree(d_params);
+        if (code) ctr_model_destroy(m);
+        return code;
+    };
+    if ((rc = err.init(s))) return cleanup(rc);
+    if (cudaMalloc(&d_params, (size_t)n_models * 16) != cudaSuccess) return cleanup(cuda_fail(cudaGetLastError(), "cudaMalloc(params)"));
+    if (cudaMemcpyAsync(d_params, p0_host, (size_t)n_models * 8, cudaMemcpyHostToDevice, s) != cudaSuccess ||
+        cudaMemcpyAsync(d_params + n_models, p1_host, (size_t)n_models * 8, cudaMemcpyHostToDevice, s) != cudaSuccess)
+        return cleanup(cuda_fail(cudaGetLastError(), "cudaMemcpyAsync(params)"));
+    const uint64_t entries = (uint64_t)n_models * (support + 1);
+    qdist_cdf_kernel<<<grid_for(entries, 128), 128, 0, s>>>(kind, min_symbol, max_symbol, d_params, d_params + n_models, n_models,
+                                                            (uint32_t)support, m->d_cdf, err.d);
+    g_launches.fetch_add(1);
+    if (cudaGetLastError() != cudaSuccess) return cleanup(cuda_fail(cudaGetLastError(), "qdist_cdf_kernel"));
+    rc = model_finish(m, err.d, /*strict=*/1, s);
+    if (rc) return cleanup(rc);
+    *out = m;
+    return cleanup(CTR_OK);
+}
+
+extern "C" int ctr_model_binomial(const int32_t *n_host, const double *p_host, uint32_t n_models, void *stream, ctr_model_t *out) {
+    if (!out || !n_host || !p_host || n_models == 0) return CTR_ERR_BAD_ARGUMENT;
+    int32_t n_max = 0;
+    for (uint32_t i = 0; i < n_models; ++i) {
+        if (n_host[i] < 1 || !(p_host[i] >= 0.0) || !(p_host[i] <= 1.0)) return CTR_ERR_BAD_MODEL;
+        n_max = std::max(n_max, n_host[i]);
+    }
+    if ((uint64_t)n_max + 1 > kTotal) return CTR_ERR_BAD_MODEL;
+    const uint32_t alphabet = (uint32_t)n_max + 1;
+    cudaStream_t s = (cudaStream_t)stream;
+    ctr_model_s *m = nullptr;
+    int rc = model_alloc(n_models, alphabet, 0, &m);
+    if (rc) return rc;
+    char *d_buf = nullptr;
+    ErrWord err;
+    auto cleanup = [&](int code) {
+        if (d_buf) cudaFree(d_buf);
+        if (code) ctr_model_destroy(m);
+        return code;
+    };
+    if ((rc = err.init(s))) return cleanup(rc);
+    const size_t scratch_bytes = (size_t)n_models * alphabet * 8, p_off = align_up(scratch_bytes, 16), n_off = p_off + (size_t)n_models * 8;
+    if (cudaMalloc(&d_buf, n_off + (size_t)n_models * 4) != cudaSuccess) return cleanup(cuda_fail(cudaGetLastError(), "cudaMalloc(binomial)"));
+    if (cudaMemcpyAsync(d_buf + p_off, p_host, (size_t)n_models * 8, cudaMemcpyHostToDevice, s) != cudaSuccess ||
+        cudaMemcpyAsync(d_buf + n_off, n_host, (size_t)n_models * 4, cudaMemcpyHostToDevice, s) != cudaSuccess)
+        return cleanup(cuda_fail(cudaGetLastError(), "cudaMemcpyAsync(binomial)"));
+    binomial_cdf_kernel<<<grid_for(n_models, 64), 64, 0, s>>>(reinterpret_cast<const int32_t *>(d_buf + n_off),
+                                                             reinterpret_cast<const double *>(d_buf + p_off), n_models, alphabet,
+                                                             reinterpret_cast<double *>(d_buf), m->d_cdf, err.d);
+    g_launches.fetch_add(1);
+    if (cudaGetLastError() != cudaSuccess) return cleanup(cuda_fail(cudaGetLastError(), "binomial_cdf_kernel"));
+    rc = model_finish(m, err.d, /*strict=*/0, s);  // rows of narrower models end in impossible symbols
+    if (rc) return cleanup(rc);
+    *out = m;
+    return cleanup(CTR_OK);
+}
+
+namespace {
+template <typename F>
+int model_categorical_perfect(const F *pmf, int is_device, uint32_t n_models, uint32_t alphabet, void *stream, ctr_model_t *out) {
+    if (!out || !pmf || n_models == 0) return CTR_ERR_BAD_ARGUMENT;
+    if (alphabet < 2 || alphabet > kTotal) return CTR_ERR_BAD_MODEL;  // categorical.rs:72-74, and 2^24 units for n symbols
+    cudaStream_t s = (cudaStream_t)stream;
+    ctr_model_s *m = nullptr;
+    int rc = model_alloc(n_models, alphabet, 0, &m);
+    if (rc) return rc;
+    F *d_pmf = nullptr;
+    char *d_scratch = nullptr;
+    ErrWord err;
+    auto cleanup = [&](int code) {
+        if (d_pmf) cudaFree(d_pmf);
+        if (d_scratch) cudaFree(d_scratch);
+        if (code) ctr_model_destroy(m);
+        return code;
+    };
+    if ((rc = err.init(s))) return cleanup(rc);
+    const F *src = pmf;
+    if (!is_device) {
+        const size_t bytes = (size_t)n_models * alphabet * sizeof(F);
+        if (cudaMalloc(&d_pmf, bytes) != cudaSuccess) return cleanup(cuda_fail(cudaGetLastError(), "cudaMalloc(pmf)"));
+        if (cudaMemcpyAsync(d_pmf, pmf, bytes, cudaMemcpyHostToDevice, s) != cudaSuccess)
+            return cleanup(cuda_fail(cudaGetLastError(), "cudaMemcpyAsync(pmf)"));
+        src = d_pmf;
+    }
+    const uint64_t n8 = ((uint64_t)alphabet + 1) / 2 * 2;
+    if (cudaMalloc(&d_scratch, (size_t)n_models * n8 * (3 * 8 + 3 * 4)) != cudaSuccess)
+        return cleanup(cuda_fail(cudaGetLastError(), "cudaMalloc(perfect scratch)"));
+    categorical_perfect_kernel<F><<<grid_for(n_models, 32), 32, 0, s>>>(src, n_models, alphabet, d_scratch, m->d_cdf, err.d);
+    g_launches.fetch_add(1);
+    if (cudaGetLastError() != cudaSuccess) return cleanup(cuda_fail(cudaGetLastError(), "categorical_perfect_kernel"));
+    rc = model_finish(m, err.d, /*strict=*/1, s);
+    if (rc) return cleanup(rc);
+    *out = m;
+    return cleanup(CTR_OK);
+}
+}  // namespace
+
+extern "C" int ctr_model_categorical_perfect_f32(const float *pmf, int is_device, uint32_t n_models, uint32_t alphabet,
+                                                 void *stream, ctr_model_t *out) {
+    return model_categorical_perfect<float>(pmf, is_device, n_models, alphabet, stream, out);
+}
+extern "C" int ctr_model_categorical_perfect_f64(const double *pmf, int is_device, uint32_t n_models, uint32_t alphabet,
+                                                 void *stream, ctr_model_t *out) {
+    return model_categorical_perfect<double>(pmf, is_device, n_models, alphabet, stream, out);
+}
+
 extern "C" int ctr_model_from_cdf(const uint32_t *cdf, int is_device, uint32_t n_models, uint32_t alphabet,
                                   int32_t min_symbol, void *stream, ctr_model_t *out) {
     if (!out || !cdf || n_models == 0) return CTR_ERR_BAD_ARGUMENT;

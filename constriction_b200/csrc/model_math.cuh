@@ -216,6 +216,127 @@ CTR_HD double gaussian_cdf(double x, double mean, double std) {
     return (1.0 + erf_msun((x - mean) / (std * sqrt2))) / 2.0;
 }
 
+CTR_HD uint64_t to_bits(double x) {
+#if defined(__CUDA_ARCH__)
+    return (uint64_t)__double_as_longlong(x);
+#else
+    uint64_t b;
+    memcpy(&b, &x, 8);
+    return b;
+#endif
+}
+
+// msun s_log1p.c (what libm 0.2.16's log1p implements; reference call sites: categorical.rs:11,98-126,166-172)
+CTR_HD double log1p_msun(double x) {
+    const double ln2_hi = 6.93147180369123816490e-01, ln2_lo = 1.90821492927058770002e-10;
+    const double Lg[7] = {6.666666666666735130e-01, 3.999999999940941908e-01, 2.857142874366239149e-01, 2.222219843214978396e-01,
+                          1.818357216161805012e-01, 1.531383769920937332e-01, 1.479819860511658591e-01};
+    uint64_t ui = to_bits(x);
+    const uint32_t hx = (uint32_t)(ui >> 32);
+    int k = 1;
+    double f = 0.0, c = 0.0;
+    if (hx < 0x3fda827au || (hx >> 31)) {  // 1 + x < sqrt(2)+
+        if (hx >= 0xbff00000u) {           // x <= -1
+            const double zero = 0.0;
+            return x == -1.0 ? x / zero : (x - x) / zero;
+        }
+        if ((hx << 1) < (0x3ca00000u << 1)) return x;  // |x| < 2^-53
+        if (hx <= 0xbfd2bec4u) {                       // sqrt(2)/2- <= 1 + x < sqrt(2)+
+            k = 0;
+            f = x;
+        }
+    } else if (hx >= 0x7ff00000u) {
+        return x;
+    }
+    if (k) {
+        const double u = 1.0 + x;
+        ui = to_bits(u);
+        uint32_t hu = (uint32_t)(ui >> 32);
+        hu += 0x3ff00000u - 0x3fe6a09eu;
+        k = (int)(hu >> 20) - 0x3ff;
+        if (k < 54) {  // correction term ~ log(1 + x) - log(u)
+            c = k >= 2 ? 1.0 - (u - x) : x - (u - 1.0);
+            c /= u;
+        }
+        hu = (hu & 0x000fffffu) + 0x3fe6a09eu;  // reduce u into [sqrt(2)/2, sqrt(2)]
+        f = from_bits(((uint64_t)hu << 32) | (ui & 0xffffffffull)) - 1.0;
+    }
+    const double hfsq = 0.5 * f * f;
+    const double s = f / (2.0 + f);
+    const double z = s * s;
+    const double w = z * z;
+    const double t1 = w * (Lg[1] + w * (Lg[3] + w * Lg[5]));
+    const double t2 = z * (Lg[0] + w * (Lg[2] + w * (Lg[4] + w * Lg[6])));
+    const double r = t2 + t1;
+    const double dk = (double)k;
+    return s * (hfsq + r) + (dk * ln2_lo + c) - hfsq + f + dk * ln2_hi;
+}
+
+// msun s_atan.c
+CTR_HD double atan_msun(double x) {
+    const double hi[4] = {4.63647609000806093515e-01, 7.85398163397448278999e-01, 9.82793723247329054082e-01,
+                          1.57079632679489655800e+00};
+    const double lo[4] = {2.26987774529616870924e-17, 3.06161699786838301793e-17, 1.39033110312309984516e-17,
+                          6.12323399573676603587e-17};
+    const double aT[11] = {3.33333333333329318027e-01,  -1.99999999998764832476e-01, 1.42857142725034663711e-01,
+                           -1.11111104054623557880e-01, 9.09088713343650656196e-02,  -7.69187620504482999495e-02,
+                           6.66107313738753120669e-02,  -5.83357013379057348645e-02, 4.97687799461593236017e-02,
+                           -3.65315727442169155270e-02, 1.62858201153657823623e-02};
+    uint32_t ix = high_word(x);
+    const bool negative = (ix >> 31) != 0;
+    ix &= 0x7fffffffu;
+    int id;
+    if (ix >= 0x44100000u) {  // |x| >= 2^66
+        if (x != x) return x;
+        const double z = hi[3] + 7.52316384526264005e-37;  // + 2^-120
+        return negative ? -z : z;
+    }
+    if (ix < 0x3fdc0000u) {  // |x| < 0.4375
+        if (ix < 0x3e400000u) return x;
+        id = -1;
+    } else {
+        x = absd(x);
+        if (ix < 0x3ff30000u) {
+            if (ix < 0x3fe60000u) {
+                id = 0;
+                x = (2.0 * x - 1.0) / (2.0 + x);
+            } else {
+                id = 1;
+                x = (x - 1.0) / (x + 1.0);
+            }
+        } else if (ix < 0x40038000u) {
+            id = 2;
+            x = (x - 1.5) / (1.0 + 1.5 * x);
+        } else {
+            id = 3;
+            x = -1.0 / x;
+        }
+    }
+    const double z = x * x;
+    const double w = z * z;
+    const double s1 = z * (aT[0] + w * (aT[2] + w * (aT[4] + w * (aT[6] + w * (aT[8] + w * aT[10])))));
+    const double s2 = w * (aT[1] + w * (aT[3] + w * (aT[5] + w * (aT[7] + w * aT[9]))));
+    if (id < 0) return x - x * (s1 + s2);
+    const double r = hi[id] - (x * (s1 + s2) - lo[id] - x);
+    return negative ? -r : r;
+}
+
+// CDFs of the other closed-form models of the Python API (pybindings/stream/model.rs:740-900).  They live in the
+// crate `probability` 0.20.3, whose source is not part of the reference tree and for which the reference holds no
+// golden vectors: textbook definitions, parity with a Rust build UNPINNED.
+CTR_HD double laplace_cdf(double x, double mu, double b) {
+    if (x <= mu) return 0.5 * exp_msun((x - mu) / b);
+    return 1.0 - 0.5 * exp_msun(-(x - mu) / b);
+}
+CTR_HD double cauchy_cdf(double x, double x0, double gamma) {
+    const double frac_1_pi = 0.318309886183790671537767526745028724;
+    return frac_1_pi * atan_msun((x - x0) / gamma) + 0.5;
+}
+// kind: 0 Gaussian(mean, std), 1 Laplace(mean, scale), 2 Cauchy(location, scale)
+CTR_HD double two_parameter_cdf(int kind, double x, double p0, double p1) {
+    return kind == 1 ? laplace_cdf(x, p0, p1) : (kind == 2 ? cauchy_cdf(x, p0, p1) : gaussian_cdf(x, p0, p1));
+}
+
 // Rust `as u32` from a float: truncate toward zero, saturate, NaN -> 0.
 CTR_HD uint32_t f64_to_u32_sat(double v) {
     if (!(v > 0.0)) return 0u;

@@ -79,8 +79,9 @@ class QuantizedGaussian(Model):
 
 
 class Categorical(Model):
-    """pybindings/stream/model.rs:455-560 (fast / lazy quantisation: categorical.rs:16-54,
-    lazy_contiguous.rs:131-167,228-330; both give the same table)."""
+    """pybindings/stream/model.rs:455-560.  perfect=False: fast / lazy quantisation (categorical.rs:16-54,
+    lazy_contiguous.rs:131-167,228-330; both give the same table); perfect=True -- the reference's default when
+    neither flag is given -- the optimal quantisation of categorical.rs:56-177."""
 
     def __init__(self, probabilities=None, lazy=None, perfect=None):
         if lazy is None and perfect is None:
@@ -89,9 +90,7 @@ class Categorical(Model):
             raise ValueError("Both arguments `lazy` and `perfect` cannot be set to `True` at the same time.")
         else:
             lazy, perfect = bool(lazy), bool(perfect)
-        if perfect:
-            raise NotImplementedError(
-                "Categorical(perfect=True) is outside the accelerated path (SURVEY.md 8f rank 4); use perfect=False")
+        self._perfect = perfect
         self._probs = None
         if probabilities is not None:
             p = np.asarray(probabilities)
@@ -100,10 +99,10 @@ class Categorical(Model):
             self._probs = np.ascontiguousarray(p)
             self._table = self._make(self._probs)
 
-    @staticmethod
-    def _make(p):
+    def _make(self, p):
         try:
-            return B.ModelTable.categorical(p)
+            # perfect=True (the reference's default): categorical.rs:56-177; else fast_quantized_cdf
+            return B.ModelTable.categorical_perfect(p) if self._perfect else B.ModelTable.categorical(p)
         except ValueError:
             raise ValueError("Probability distribution not normalizable (the array of probabilities\n"
                              "might be empty, contain negative values or NaNs, or sum to infinity).") from None
@@ -176,22 +175,20 @@ class Uniform(Model):
 
 
 class Bernoulli(Model):
-    """pybindings/stream/model.rs:985-1060 with perfect=False: a two-symbol categorical model over [1 - p, p]
-    quantised by `fast_quantized_cdf` in f64 (categorical.rs:16-54); `p` fixed, or one `p` per symbol."""
+    """pybindings/stream/model.rs:985-1060: a two-symbol categorical model over [1 - p, p] in f64, quantised by
+    `fast_quantized_cdf` (perfect=False, categorical.rs:16-54) or -- the reference's default -- perfectly
+    (categorical.rs:56-177); `p` fixed, or one `p` per symbol."""
 
     def __init__(self, p=None, perfect=None):
-        if perfect is None or perfect:
-            raise NotImplementedError(
-                "Bernoulli(perfect=True) is outside the accelerated path (SURVEY.md 8f rank 4); use perfect=False")
+        self._perfect = True if perfect is None else bool(perfect)
         self._p = None if p is None else float(p)
         self._nparams = 1 if p is None else 0
         if self._p is not None:
             self._table = self._make(np.array([[1.0 - self._p, self._p]], dtype=np.float64))
 
-    @staticmethod
-    def _make(pmf):
+    def _make(self, pmf):
         try:
-            return B.ModelTable.categorical(pmf)
+            return B.ModelTable.categorical_perfect(pmf) if self._perfect else B.ModelTable.categorical(pmf)
         except ValueError:
             raise ValueError("`p` must be >= 0.0 and <= 1.0.") from None
 
@@ -215,16 +212,162 @@ class Bernoulli(Model):
         return self._make(np.ascontiguousarray(np.stack([1.0 - p, p], axis=1)))
 
 
-def _unsupported(name):
-    def ctor(*_a, **_k):
-        raise NotImplementedError(f"{name} is outside the accelerated path (SURVEY.md 8f); "
-                                  "QuantizedGaussian, Categorical(perfect=False), Bernoulli(perfect=False) and Uniform are provided")
-    ctor.__name__ = name
-    return ctor
+class _TwoParameterQuantized(Model):
+    """Leaky quantisation of a two-parameter distribution, any subset of the parameters deferred to per-symbol arrays."""
+    _kind = None
+    _second = "scale"
+
+    def __init__(self, min_symbol_inclusive, max_symbol_inclusive, first=None, second=None):
+        self._lo, self._hi = int(min_symbol_inclusive), int(max_symbol_inclusive)
+        self._p0, self._p1 = first, second
+        self._nparams = (first is None) + (second is None)
+        if second is not None and not float(second) > 0.0:
+            raise ValueError(f"Invalid model parameter: `{self._second}` must be positive.")
+
+    def _concrete_table(self):
+        if self._nparams:
+            raise ValueError("No model parameters specified.")
+        if self._table is None:
+            self._table = B.ModelTable.quantized(self._kind, self._lo, self._hi, [float(self._p0)], [float(self._p1)])
+        return self._table
+
+    def _split(self, params):
+        if self._nparams == 0:
+            raise ValueError("Model parameters were specified but the model is already fully parameterized.")
+        if len(params) != self._nparams:
+            raise ValueError(f"Wrong number of model parameters: expected {self._nparams}, got {len(params)}.")
+        cols = [_float_param(p) for p in params]
+        n = cols[0].size
+        if any(c.size != n for c in cols):
+            raise ValueError("Model parameters have unequal shape")
+        it = iter(cols)
+        p0 = next(it) if self._p0 is None else np.full(n, float(self._p0))
+        p1 = next(it) if self._p1 is None else np.full(n, float(self._p1))
+        return p0, p1
+
+    def _family_len(self, params):
+        return self._split(params)[0].size
+
+    def _family_table(self, params):
+        p0, p1 = self._split(params)
+        if not np.all(p1 > 0.0):
+            raise ValueError(f"Invalid model parameter: `{self._second}` must be positive.")
+        return B.ModelTable.quantized(self._kind, self._lo, self._hi, p0, p1)  # one CDF row per symbol
 
 
-QuantizedLaplace = _unsupported("QuantizedLaplace")
-QuantizedCauchy = _unsupported("QuantizedCauchy")
-Binomial = _unsupported("Binomial")
-CustomModel = _unsupported("CustomModel")
-ScipyModel = _unsupported("ScipyModel")
+class QuantizedLaplace(_TwoParameterQuantized):
+    """pybindings/stream/model.rs:740-830: QuantizedLaplace(min, max, mean=None, scale=None)."""
+    _kind = "laplace"
+
+    def __init__(self, min_symbol_inclusive, max_symbol_inclusive, mean=None, scale=None):
+        super().__init__(min_symbol_inclusive, max_symbol_inclusive, mean, scale)
+
+
+class QuantizedCauchy(_TwoParameterQuantized):
+    """pybindings/stream/model.rs:840-920: QuantizedCauchy(min, max, loc=None, scale=None)."""
+    _kind = "cauchy"
+
+    def __init__(self, min_symbol_inclusive, max_symbol_inclusive, loc=None, scale=None):
+        super().__init__(min_symbol_inclusive, max_symbol_inclusive, loc, scale)
+
+
+class Binomial(Model):
+    """pybindings/stream/model.rs:925-960: Binomial(n=None, p=None) over {0..n}; missing parameters come per symbol
+    (`n` as int32, `p` as float arrays, in this order)."""
+
+    def __init__(self, n=None, p=None):
+        self._n = None if n is None else int(n)
+        self._p = None if p is None else float(p)
+        self._nparams = (n is None) + (p is None)
+
+    def _concrete_table(self):
+        if self._nparams:
+            raise ValueError("No model parameters specified.")
+        if self._table is None:
+            self._table = B.ModelTable.binomial([self._n], [self._p])
+        return self._table
+
+    def _split(self, params):
+        if self._nparams == 0:
+            raise ValueError("Model parameters were specified but the model is already fully parameterized.")
+        if len(params) != self._nparams:
+            raise ValueError(f"Wrong number of model parameters: expected {self._nparams}, got {len(params)}.")
+        it = iter(params)
+        ns = ps = None
+        if self._n is None:
+            ns = np.asarray(next(it))
+            if ns.ndim != 1 or ns.dtype != np.int32:
+                raise TypeError("n must be a rank-1 numpy array with dtype int32")
+        if self._p is None:
+            ps = _float_param(next(it))
+        size = ns.size if ns is not None else ps.size
+        if ns is None:
+            ns = np.full(size, self._n, dtype=np.int32)
+        if ps is None:
+            ps = np.full(size, self._p)
+        if ns.size != ps.size:
+            raise ValueError("Model parameters have unequal shape")
+        return ns, ps
+
+    def _family_len(self, params):
+        return self._split(params)[0].size
+
+    def _family_table(self, params):
+        ns, ps = self._split(params)
+        return B.ModelTable.binomial(ns, ps)
+
+
+class CustomModel(Model):
+    """pybindings/stream/model.rs:150-260 + model/internals.rs:255-420: a model defined by a Python `cdf(x, *params)`
+    callback (`approximate_inverse_cdf` only seeds the reference's search and never changes a result, quantize.rs:580-779).
+    The callback is the user's Python code either way; here it is evaluated once per table entry at the half-integers,
+    pushed through the leaky quantiser's arithmetic (quantize.rs:525-568: trunc(free_weight * cdf(s - 0.5)) + slack) and
+    the resulting CDF rows are uploaded (one row per model, or per symbol for a family)."""
+
+    def __init__(self, cdf, approximate_inverse_cdf, min_symbol_inclusive, max_symbol_inclusive):
+        self._cdf = cdf
+        self._ppf = approximate_inverse_cdf
+        self._lo, self._hi = int(min_symbol_inclusive), int(max_symbol_inclusive)
+        if not self._hi > self._lo:
+            raise ValueError("max_symbol_inclusive must be greater than min_symbol_inclusive")
+        if self._hi - self._lo >= (1 << 24):
+            raise ValueError("support too large for 24-bit probabilities")
+        self._nparams = None  # any number of per-symbol parameter arrays
+
+    def _row(self, args) -> np.ndarray:
+        n = self._hi - self._lo + 1
+        free_weight = float((1 << 24) - 1 - (self._hi - self._lo))
+        row = np.empty(n + 1, dtype=np.uint32)
+        row[0], row[n] = 0, 1 << 24
+        for i in range(1, n):
+            v = free_weight * float(self._cdf(float(self._lo + i) - 0.5, *args))
+            q = 0 if not v > 0.0 else (0xFFFFFFFF if v >= 4294967295.0 else int(v))  # Rust `f64 as u32`
+            row[i] = (q + i) & 0xFFFFFFFF
+        return row
+
+    def _concrete_table(self):
+        if self._table is None:
+            self._table = B.ModelTable.from_cdf(self._row(())[None, :], self._lo)
+        return self._table
+
+    def _columns(self, params):
+        cols = [_float_param(p) for p in params]
+        if any(c.size != cols[0].size for c in cols):
+            raise ValueError("Model parameters have unequal lengths.")
+        return cols
+
+    def _family_len(self, params):
+        return self._columns(params)[0].size
+
+    def _family_table(self, params):
+        cols = self._columns(params)
+        rows = np.stack([self._row(tuple(float(c[i]) for c in cols)) for i in range(cols[0].size)]) if cols[0].size else \
+            self._row(())[None, :]
+        return B.ModelTable.from_cdf(rows, self._lo)
+
+
+class ScipyModel(CustomModel):
+    """pybindings/stream/model.rs:262-345: wraps a `scipy.stats` distribution (or frozen distribution)."""
+
+    def __init__(self, scipy_model, min_symbol_inclusive, max_symbol_inclusive):
+        super().__init__(scipy_model.cdf, scipy_model.ppf, min_symbol_inclusive, max_symbol_inclusive)

@@ -124,6 +124,25 @@ int ctr_model_categorical_f32(const float *pmf, int is_device, uint32_t n_models
 int ctr_model_categorical_f64(const double *pmf, int is_device, uint32_t n_models, uint32_t alphabet, void *stream,
                               ctr_model_t *out);
 
+/* Categorical with the reference's "perfect" quantisation: perfectly_quantized_probabilities
+ * (src/stream/model/categorical.rs:56-177) + from_floating_point_probabilities_perfect (categorical/contiguous.rs:301-312),
+ * what Python `Categorical(probs)` and `Bernoulli(p)` construct BY DEFAULT (pybindings/stream/model.rs:508-523,1010-1050).
+ * Computed in f64 whatever the input type; one device thread per model (the optimisation is sequential). */
+int ctr_model_categorical_perfect_f32(const float *pmf, int is_device, uint32_t n_models, uint32_t alphabet, void *stream,
+                                      ctr_model_t *out);
+int ctr_model_categorical_perfect_f64(const double *pmf, int is_device, uint32_t n_models, uint32_t alphabet, void *stream,
+                                      ctr_model_t *out);
+
+/* The leaky quantiser over other two-parameter distributions (pybindings/stream/model.rs:740-900): kind 0
+ * QuantizedGaussian(mean, std), 1 QuantizedLaplace(mean, scale), 2 QuantizedCauchy(location, scale); parameters are HOST
+ * arrays of length n_models.  And Binomial(n, p) over {0..n} (pybindings/stream/model.rs:925-960); rows are padded to the
+ * widest model.  The Laplace / Cauchy / Binomial CDFs live in the crate `probability`, which is not part of the
+ * reference tree, and the reference holds no golden vectors for them: they follow the textbook definitions and their
+ * bit-parity with a Rust build is UNPINNED (encoder and decoder of this library always agree with each other). */
+int ctr_model_quantized(int32_t kind, int32_t min_symbol, int32_t max_symbol, const double *p0_host, const double *p1_host,
+                        uint32_t n_models, void *stream, ctr_model_t *out);
+int ctr_model_binomial(const int32_t *n_host, const double *p_host, uint32_t n_models, void *stream, ctr_model_t *out);
+
 /* From ready-made fixed-point CDF rows u32[n_models][alphabet+1] (HOST or DEVICE memory; copied).
  * Reference: categorical/contiguous.rs:471-520 from_nonzero_fixed_point_probabilities /
  * from_fixed_point_cdf; lookup_contiguous.rs:297-333. */

@@ -72,6 +72,14 @@ def lib():
             getattr(L, f"orc_cat_cdf_{sfx}").argtypes = [fp, C.c_size_t, u32p]
             getattr(L, f"orc_cat_lazy_left_prob_{sfx}").argtypes = [fp, C.c_size_t, C.c_int32, u32p, u32p]
             getattr(L, f"orc_cat_lazy_quantile_{sfx}").argtypes = [fp, C.c_size_t, C.c_uint32, i32p, u32p, u32p]
+        L.orc_log1p.argtypes = [C.c_double]
+        L.orc_log1p.restype = C.c_double
+        L.orc_atan.argtypes = [C.c_double]
+        L.orc_atan.restype = C.c_double
+        L.orc_qdist_cdf.argtypes = [C.c_int, C.c_int32, C.c_int32, C.c_double, C.c_double, u32p]
+        L.orc_binomial_cdf.argtypes = [C.c_int32, C.c_double, u32p]
+        L.orc_cat_perfect_cdf_f32.argtypes = [f32p, C.c_size_t, u32p]
+        L.orc_cat_perfect_cdf_f64.argtypes = [f64p, C.c_size_t, u32p]
         L.orc_cdf_left_prob.argtypes = [u32p, C.c_size_t, C.c_int64, u32p, u32p]
         L.orc_cdf_quantile.argtypes = [u32p, C.c_size_t, C.c_uint32, C.POINTER(C.c_size_t), u32p, u32p]
         L.orc_cdf_quantile.restype = None
@@ -193,6 +201,55 @@ def cat_cdf(pmf: np.ndarray) -> np.ndarray:
     else:
         raise TypeError("pmf must be float32 or float64")
     return cdf
+
+
+def log1p(x: float) -> float:
+    return lib().orc_log1p(float(x))
+
+
+def atan(x: float) -> float:
+    return lib().orc_atan(float(x))
+
+
+def cat_perfect_cdf(pmf: np.ndarray) -> np.ndarray:
+    """categorical.rs:56-177 + contiguous.rs:301-312 (Categorical / Bernoulli with perfect=True)."""
+    pmf = np.ascontiguousarray(pmf)
+    cdf = np.empty(pmf.shape[0] + 1, dtype=np.uint32)
+    if pmf.dtype == np.float32:
+        _raise(lib().orc_cat_perfect_cdf_f32(_p(pmf, f32p), pmf.shape[0], _p(cdf, u32p)))
+    elif pmf.dtype == np.float64:
+        _raise(lib().orc_cat_perfect_cdf_f64(_p(pmf, f64p), pmf.shape[0], _p(cdf, u32p)))
+    else:
+        raise TypeError("pmf must be float32 or float64")
+    return cdf
+
+
+QDIST_KINDS = {"gaussian": 0, "laplace": 1, "cauchy": 2}
+
+
+def qdist_cdf(kind: str, min_sym: int, max_sym: int, p0: float, p1: float) -> np.ndarray:
+    cdf = np.empty(max_sym - min_sym + 2, dtype=np.uint32)
+    _raise(lib().orc_qdist_cdf(QDIST_KINDS[kind], min_sym, max_sym, float(p0), float(p1), _p(cdf, u32p)))
+    return cdf
+
+
+def binomial_cdf(n: int, p: float) -> np.ndarray:
+    cdf = np.empty(int(n) + 2, dtype=np.uint32)
+    _raise(lib().orc_binomial_cdf(int(n), float(p), _p(cdf, u32p)))
+    return cdf
+
+
+def custom_cdf(cdf_fn, lo: int, hi: int, args=()) -> np.ndarray:
+    """LeakyQuantizer over a Python CDF callback (internals.rs:255-420; quantize.rs:525-568)."""
+    n = hi - lo + 1
+    fw = float((1 << 24) - 1 - (hi - lo))
+    row = np.empty(n + 1, dtype=np.uint32)
+    row[0], row[n] = 0, 1 << 24
+    for i in range(1, n):
+        v = fw * float(cdf_fn(float(lo + i) - 0.5, *args))
+        q = 0 if not v > 0.0 else (0xFFFFFFFF if v >= 4294967295.0 else int(v))
+        row[i] = (q + i) & 0xFFFFFFFF
+    return row
 
 
 def ans_encode_iid(symbols: np.ndarray, cdf: np.ndarray, min_sym: int) -> np.ndarray:
@@ -450,6 +507,26 @@ class _TableCat(_Concrete):
         return int(i.value), l.value, p.value
 
 
+class _Table(_Concrete):
+    """Any model given as a CDF row over {lo .. lo + n - 1} (contiguous.rs:628-700)."""
+
+    def __init__(self, cdf, lo=0):
+        self.cdf = np.ascontiguousarray(cdf, dtype=np.uint32)
+        self.lo = int(lo)
+
+    def left_prob(self, symbol):
+        l, p = C.c_uint32(), C.c_uint32()
+        _raise(lib().orc_cdf_left_prob(_p(self.cdf, u32p), self.cdf.size - 1, int(symbol) - self.lo, C.byref(l), C.byref(p)))
+        if p.value == 0:
+            _raise(1)  # a padded / empty bin: ImpossibleSymbol
+        return l.value, p.value
+
+    def quantile(self, q):
+        i, l, p = C.c_size_t(), C.c_uint32(), C.c_uint32()
+        lib().orc_cdf_quantile(_p(self.cdf, u32p), self.cdf.size - 1, int(q), C.byref(i), C.byref(l), C.byref(p))
+        return self.lo + int(i.value), l.value, p.value
+
+
 class _Uniform(_Concrete):
     def __init__(self, size):
         self.size = int(size)
@@ -537,14 +614,16 @@ class Categorical(Model):
             raise ValueError("Both arguments `lazy` and `perfect` cannot be set to `True` at the same time.")
         else:
             lazy, perfect = bool(lazy), bool(perfect)
-        if perfect:
-            raise NotImplementedError("oracle: Categorical(perfect=True) is out of scope (SURVEY 8f rank 4)")
+        self._perfect = perfect
         self._lazy = lazy
         if probabilities is not None:
             probabilities = np.asarray(probabilities)
             if probabilities.ndim != 1:
                 raise TypeError("probabilities must be rank 1")
-            self._concrete = _LazyCat(probabilities) if lazy else _TableCat(probabilities)
+            if perfect:
+                self._concrete = _Table(cat_perfect_cdf(probabilities))
+            else:
+                self._concrete = _LazyCat(probabilities) if lazy else _TableCat(probabilities)
 
     def length(self, param0):
         if self._concrete is not None:
@@ -561,7 +640,109 @@ class Categorical(Model):
             raise TypeError("probabilities must be a rank-2 float32/float64 array")
         order = range(probs.shape[0] - 1, -1, -1) if reverse else range(probs.shape[0])
         for i in order:
-            yield _LazyCat(probs[i])  # internals.rs:449-458 always lazy unless perfect
+            # internals.rs:431-460: perfectly quantised table if `perfect`, else always lazy
+            yield _Table(cat_perfect_cdf(probs[i])) if self._perfect else _LazyCat(probs[i])
+
+
+class Bernoulli(Model):
+    """pybindings/stream/model.rs:985-1060"""
+
+    def __init__(self, p=None, perfect=None):
+        perfect = True if perfect is None else bool(perfect)
+        make = (lambda q: _Table(cat_perfect_cdf(np.array([1.0 - q, q])))) if perfect else \
+            (lambda q: _TableCat(np.array([1.0 - q, q])))
+        if p is not None:
+            self._concrete = make(float(p))
+        else:
+            self._nparams, self._build = 1, make
+
+
+class _TwoParam(Model):
+    _kind = None
+
+    def __init__(self, lo, hi, a=None, b=None):
+        lo, hi, kind = int(lo), int(hi), self._kind
+
+        def make(x, y):
+            if not y > 0.0:
+                raise ValueError("Invalid model parameter: `scale` must be positive.")
+            return _Table(qdist_cdf(kind, lo, hi, x, y), lo)
+
+        if a is not None and b is not None:
+            self._concrete = make(float(a), float(b))
+        elif a is None and b is None:
+            self._nparams, self._build = 2, make
+        elif a is None:
+            self._nparams, self._build = 1, lambda x: make(x, float(b))
+        else:
+            self._nparams, self._build = 1, lambda y: make(float(a), y)
+
+
+class QuantizedLaplace(_TwoParam):
+    _kind = "laplace"
+
+    def __init__(self, min_symbol_inclusive, max_symbol_inclusive, mean=None, scale=None):
+        super().__init__(min_symbol_inclusive, max_symbol_inclusive, mean, scale)
+
+
+class QuantizedCauchy(_TwoParam):
+    _kind = "cauchy"
+
+    def __init__(self, min_symbol_inclusive, max_symbol_inclusive, loc=None, scale=None):
+        super().__init__(min_symbol_inclusive, max_symbol_inclusive, loc, scale)
+
+
+class Binomial(Model):
+    def __init__(self, n=None, p=None):
+        make = lambda nn, pp: _Table(binomial_cdf(int(nn), float(pp)))  # noqa: E731
+        self._n, self._p = n, p
+        if n is not None and p is not None:
+            self._concrete = make(n, p)
+        elif n is None and p is None:
+            self._nparams, self._build = 2, make
+        elif n is None:
+            self._nparams, self._build = 1, lambda nn: make(nn, p)
+        else:
+            self._nparams, self._build = 1, lambda pp: make(n, pp)
+
+    def parameterize(self, params, reverse):
+        if self._concrete is not None:
+            raise ValueError("Model parameters were specified but the model is already fully parameterized.")
+        if len(params) != self._nparams:
+            raise ValueError(f"Wrong number of model parameters: expected {self._nparams}, got {len(params)}.")
+        cols = [np.asarray(p) for p in params]
+        n = len(cols[0])
+        if any(len(c) != n for c in cols):
+            raise ValueError("Model parameters have unequal shape")
+        order = range(n - 1, -1, -1) if reverse else range(n)
+        for i in order:
+            yield self._build(*[c[i] for c in cols])
+
+
+class CustomModel(Model):
+    def __init__(self, cdf, approximate_inverse_cdf, min_symbol_inclusive, max_symbol_inclusive):
+        self._cdf, self._lo, self._hi = cdf, int(min_symbol_inclusive), int(max_symbol_inclusive)
+        self._nparams = None
+
+    def as_parameterized(self):
+        return _Table(custom_cdf(self._cdf, self._lo, self._hi), self._lo)
+
+    def length(self, param0):
+        return len(param0)
+
+    def parameterize(self, params, reverse):
+        cols = [self._cast(p) for p in params]
+        n = len(cols[0])
+        if any(len(c) != n for c in cols):
+            raise ValueError("Model parameters have unequal lengths.")
+        order = range(n - 1, -1, -1) if reverse else range(n)
+        for i in order:
+            yield _Table(custom_cdf(self._cdf, self._lo, self._hi, tuple(float(c[i]) for c in cols)), self._lo)
+
+
+class ScipyModel(CustomModel):
+    def __init__(self, scipy_model, min_symbol_inclusive, max_symbol_inclusive):
+        super().__init__(scipy_model.cdf, scipy_model.ppf, min_symbol_inclusive, max_symbol_inclusive)
 
 
 # ---------------------------------------------------------------------------

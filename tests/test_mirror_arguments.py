@@ -12,12 +12,18 @@ def test_model_argument_errors():
         M.QuantizedGaussian(-5, 5, 0.0, -1.0)
     with pytest.raises(ValueError):
         M.Categorical(lazy=True, perfect=True)
-    with pytest.raises(NotImplementedError):
-        M.Categorical(np.array([0.5, 0.5]))            # default is perfect=True: outside the accelerated path
-    with pytest.raises(NotImplementedError):
-        M.Bernoulli(0.5)
-    with pytest.raises(NotImplementedError):
-        M.QuantizedLaplace(-5, 5, 0.0, 1.0)
+    with pytest.raises(ValueError):
+        M.QuantizedLaplace(-5, 5, 0.0, 0.0)           # scale must be positive
+    with pytest.raises(ValueError):
+        M.QuantizedCauchy(-5, 5, 0.0, -2.0)
+    with pytest.raises(ValueError):
+        M.CustomModel(lambda x: 0.5, lambda q: 0.0, 3, 3)
+    assert M.Categorical()._perfect and M.Bernoulli()._perfect   # the reference's defaults (model.rs:508-523,1010-1050)
+    assert not M.Categorical(lazy=True)._perfect and not M.Categorical(perfect=False)._perfect
+    b = M.Binomial()
+    with pytest.raises(TypeError):
+        b._family_len((np.array([3.0]), np.array([0.5])))       # n must be int32
+    assert b._family_len((np.array([3, 4], dtype=np.int32), np.array([0.5, 0.1]))) == 2
     fam = M.QuantizedGaussian(-5, 5)
     with pytest.raises(ValueError):
         fam._concrete_table()                          # "No model parameters specified."
