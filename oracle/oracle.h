@@ -177,6 +177,26 @@ int orc_multi_range_decode(const uint32_t *words, const uint64_t *offsets, uint6
                            size_t alphabet, int32_t *symbols_out, int threads);
 void orc_free(void *p);
 
+/* ---------- any preset (oracle_generic.c): Word bits W in {16, 32}, State = 2 W bits, PRECISION P <= W ----------
+ * The reference's coders and categorical models are generic over their integer types; these functions restate
+ * that generic code once.  (W, P) = (32, 24) is the Default preset and must equal the functions above (which the
+ * reference's golden vectors pin); (16, 12) is the Small preset (stack.rs:153, queue.rs:156,747), for which the
+ * reference holds no golden vectors.  Words travel as uint32_t array elements whatever W; `*words_out` is
+ * malloc'ed (orc_free).  `table` (2^P entries, orc_g_lookup_table) selects the lookup decoder model
+ * (lookup_contiguous.rs:297-333,564-607), NULL the binary search (contiguous.rs:628-665). */
+int orc_g_lookup_table(unsigned P, const uint32_t *cdf, size_t n, uint32_t *table);
+int orc_g_ans_encode_iid_reverse(unsigned W, unsigned P, const int32_t *symbols, size_t n, const uint32_t *cdf,
+                                 int32_t min_sym, size_t alphabet, uint32_t **words_out, size_t *n_words);
+int orc_g_ans_decode_iid(unsigned W, unsigned P, const uint32_t *words, size_t n_words, size_t n, const uint32_t *cdf,
+                         int32_t min_sym, size_t alphabet, const uint32_t *table, int32_t *symbols_out);
+int orc_g_range_encode_iid(unsigned W, unsigned P, const int32_t *symbols, size_t n, const uint32_t *cdf, int32_t min_sym,
+                           size_t alphabet, uint32_t **words_out, size_t *n_words);
+int orc_g_range_decode_iid(unsigned W, unsigned P, const uint32_t *words, size_t n_words, size_t n, const uint32_t *cdf,
+                           int32_t min_sym, size_t alphabet, const uint32_t *table, int32_t *symbols_out);
+int orc_g_cat_cdf_f32(unsigned P, unsigned prob_bits, const float *pmf, size_t n, uint32_t *cdf);
+int orc_g_cat_cdf_f64(unsigned P, unsigned prob_bits, const double *pmf, size_t n, uint32_t *cdf);
+int orc_g_cat_perfect_cdf_f64(unsigned P, unsigned prob_bits, const double *pmf, size_t n, uint32_t *cdf);
+
 #ifdef __cplusplus
 }
 #endif

@@ -144,6 +144,16 @@ def lib():
         L.orc_multi_range_encode.argtypes = menc
         L.orc_multi_ans_decode.argtypes = mdec
         L.orc_multi_range_decode.argtypes = mdec
+        gen_enc = [C.c_uint, C.c_uint, i32p, C.c_size_t, u32p, C.c_int32, C.c_size_t, C.POINTER(u32p), C.POINTER(C.c_size_t)]
+        gen_dec = [C.c_uint, C.c_uint, u32p, C.c_size_t, C.c_size_t, u32p, C.c_int32, C.c_size_t, u32p, i32p]
+        L.orc_g_ans_encode_iid_reverse.argtypes = gen_enc
+        L.orc_g_range_encode_iid.argtypes = gen_enc
+        L.orc_g_ans_decode_iid.argtypes = gen_dec
+        L.orc_g_range_decode_iid.argtypes = gen_dec
+        L.orc_g_lookup_table.argtypes = [C.c_uint, u32p, C.c_size_t, u32p]
+        L.orc_g_cat_cdf_f32.argtypes = [C.c_uint, C.c_uint, f32p, C.c_size_t, u32p]
+        L.orc_g_cat_cdf_f64.argtypes = [C.c_uint, C.c_uint, f64p, C.c_size_t, u32p]
+        L.orc_g_cat_perfect_cdf_f64.argtypes = [C.c_uint, C.c_uint, f64p, C.c_size_t, u32p]
         L.orc_free.argtypes = [C.c_void_p]
         L.orc_free.restype = None
         _LIB = L
@@ -432,6 +442,73 @@ def multi_range_encode(symbols, K, cdf, min_sym, sym_offsets=None, threads=1):
 
 def multi_range_decode(words, offsets, n_total, K, cdf, min_sym, sym_offsets=None, threads=1):
     return _multi_decode(lib().orc_multi_range_decode, words, offsets, n_total, K, cdf, min_sym, sym_offsets, threads)
+
+
+# ---------------------------------------------------------------------------
+# any preset (oracle_generic.c): PRESETS[name] = (word bits, precision, probability bits)
+# ---------------------------------------------------------------------------
+PRESETS = {"default": (32, 24, 32), "small": (16, 12, 16)}
+
+
+def g_cat_cdf(preset: str, pmf: np.ndarray, perfect: bool = False) -> np.ndarray:
+    """Contiguous categorical model of a preset: `from_floating_point_probabilities_fast` / `_perfect`."""
+    W, P, pb = PRESETS[preset]
+    pmf = np.ascontiguousarray(pmf)
+    cdf = np.empty(pmf.shape[0] + 1, dtype=np.uint32)
+    if perfect:
+        _raise(lib().orc_g_cat_perfect_cdf_f64(P, pb, _p(pmf.astype(np.float64), f64p), pmf.shape[0], _p(cdf, u32p)))
+    elif pmf.dtype == np.float32:
+        _raise(lib().orc_g_cat_cdf_f32(P, pb, _p(pmf, f32p), pmf.shape[0], _p(cdf, u32p)))
+    else:
+        _raise(lib().orc_g_cat_cdf_f64(P, pb, _p(pmf.astype(np.float64), f64p), pmf.shape[0], _p(cdf, u32p)))
+    return cdf
+
+
+def g_lookup_table(preset: str, cdf: np.ndarray) -> np.ndarray:
+    W, P, _ = PRESETS[preset]
+    cdf = np.ascontiguousarray(cdf, dtype=np.uint32)
+    table = np.empty(1 << P, dtype=np.uint32)
+    _raise(lib().orc_g_lookup_table(P, _p(cdf, u32p), cdf.size - 1, _p(table, u32p)))
+    return table
+
+
+def _g_encode(fn, preset, symbols, cdf, min_sym):
+    W, P, _ = PRESETS[preset]
+    symbols = np.ascontiguousarray(symbols, dtype=np.int32)
+    cdf = np.ascontiguousarray(cdf, dtype=np.uint32)
+    out, n = u32p(), C.c_size_t()
+    _raise(fn(W, P, _p(symbols, i32p), symbols.size, _p(cdf, u32p), min_sym, cdf.size - 1, C.byref(out), C.byref(n)))
+    words = np.ctypeslib.as_array(out, shape=(n.value,)).copy() if n.value else np.empty(0, dtype=np.uint32)
+    lib().orc_free(out)
+    return words
+
+
+def _g_decode(fn, preset, words, n, cdf, min_sym, table):
+    W, P, _ = PRESETS[preset]
+    words = np.ascontiguousarray(words, dtype=np.uint32)
+    cdf = np.ascontiguousarray(cdf, dtype=np.uint32)
+    out = np.empty(n, dtype=np.int32)
+    t = None if table is None else np.ascontiguousarray(table, dtype=np.uint32)
+    _raise(fn(W, P, _p(words, u32p), words.size, n, _p(cdf, u32p), min_sym, cdf.size - 1, None if t is None else _p(t, u32p),
+              _p(out, i32p)))
+    return out
+
+
+def g_ans_encode(preset, symbols, cdf, min_sym=0):
+    """One AnsCoder of the preset: encode_iid_symbols_reverse + into_compressed (words as uint32 values)."""
+    return _g_encode(lib().orc_g_ans_encode_iid_reverse, preset, symbols, cdf, min_sym)
+
+
+def g_range_encode(preset, symbols, cdf, min_sym=0):
+    return _g_encode(lib().orc_g_range_encode_iid, preset, symbols, cdf, min_sym)
+
+
+def g_ans_decode(preset, words, n, cdf, min_sym=0, table=None):
+    return _g_decode(lib().orc_g_ans_decode_iid, preset, words, n, cdf, min_sym, table)
+
+
+def g_range_decode(preset, words, n, cdf, min_sym=0, table=None):
+    return _g_decode(lib().orc_g_range_decode_iid, preset, words, n, cdf, min_sym, table)
 
 
 # ---------------------------------------------------------------------------
