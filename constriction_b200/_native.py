@@ -82,6 +82,17 @@ SIGNATURES = {
     "ctr_range_encode_gaussian": (C.c_int, [C.c_int32, C.c_int32, vp, vp, vp, C.POINTER(Layout), vp, vp, C.c_size_t,
                                             vp, C.c_uint64, vp, vp, vp, vp]),
     "ctr_range_decode_gaussian": (C.c_int, [C.c_int32, C.c_int32, vp, vp, vp, vp, C.POINTER(Layout), vp, vp, vp, vp, vp, vp]),
+    "ctr_small_model_from_cdf": (C.c_int, [vp, C.c_int, C.c_uint32, C.c_uint32, C.c_int32, vp, vp, C.POINTER(vp)]),
+    "ctr_small_model_categorical_f32": (C.c_int, [vp, C.c_int, C.c_uint32, C.c_uint32, C.c_int, vp, C.POINTER(vp)]),
+    "ctr_small_model_categorical_f64": (C.c_int, [vp, C.c_int, C.c_uint32, C.c_uint32, C.c_int, vp, C.POINTER(vp)]),
+    "ctr_small_model_destroy": (C.c_int, [vp]),
+    "ctr_small_model_copy_cdf_host": (C.c_int, [vp, vp, vp]),
+    "ctr_small_encode_workspace_bytes": (C.c_size_t, [C.POINTER(Layout)]),
+    "ctr_small_max_compressed_words": (C.c_uint64, [C.POINTER(Layout)]),
+    "ctr_small_ans_encode_reverse": (C.c_int, [vp, vp, C.POINTER(Layout), vp, C.c_size_t, vp, C.c_uint64, vp, vp, vp]),
+    "ctr_small_ans_decode": (C.c_int, [vp, vp, vp, C.POINTER(Layout), vp, vp, vp]),
+    "ctr_small_range_encode": (C.c_int, [vp, vp, C.POINTER(Layout), vp, C.c_size_t, vp, C.c_uint64, vp, vp, vp]),
+    "ctr_small_range_decode": (C.c_int, [vp, vp, vp, C.POINTER(Layout), vp, vp, vp]),
     "ctr_ans_encode_reverse_host": (C.c_int, [vp, vp, C.c_uint64, C.c_uint64, vp, vp, C.c_int32, vp, C.c_uint64, vp,
                                               C.POINTER(C.c_int), u64p]),
     "ctr_ans_decode_host": (C.c_int, [vp, vp, vp, C.c_uint64, C.c_uint64, vp, vp, C.c_int32, vp, C.POINTER(C.c_int), u64p]),

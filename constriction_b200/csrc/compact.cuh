@@ -28,7 +28,7 @@ constexpr uint64_t kTileValueMask = (1ull << 62) - 1;
 struct CompactParams {
     uint64_t *tile_status;    // u64[n_tiles], zeroed before the launch
     unsigned int *ticket;     // zeroed before the launch
-    uint32_t *words_out;      // dense container
+    uint32_t *words_out;      // dense container (u16 words for the Small preset: see compact_tail's W)
     uint64_t words_capacity;  // capacity of words_out in words
     uint64_t *offsets_out;    // u64[K+1]
 };
@@ -73,9 +73,10 @@ __device__ __forceinline__ uint64_t warp_sum_u64(uint64_t v, int lane) {
 // Called by every thread of the CTA once its stream is complete in scratch.
 //   tile    : this CTA's tile index (stream k = tile * blockDim.x + threadIdx.x)
 //   src/len : my stream's words in scratch (len = 0 for threads without a stream)
-template <int BLOCK>
+//   W       : word type of the container (uint32_t: Default preset, uint16_t: Small preset)
+template <int BLOCK, typename W = uint32_t>
 __device__ __forceinline__ void compact_tail(const CompactParams &c, uint32_t tile, uint64_t k, uint64_t K, bool valid,
-                                             const uint32_t *src, uint32_t len, uint32_t *status) {
+                                             const W *src, uint32_t len, uint32_t *status) {
     constexpr int kWarps = BLOCK / 32;
     __shared__ uint64_t s_warp_totals[kWarps];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -144,7 +145,7 @@ __device__ __forceinline__ void compact_tail(const CompactParams &c, uint32_t ti
 #ifdef CTR_DBG_NO_GATHER
     if (n_max != 0xffffffffu) return;
 #endif
-    uint32_t *dst = c.words_out + my_off;
+    W *dst = reinterpret_cast<W *>(c.words_out) + my_off;
     __syncwarp();
     // The copy is latency-bound (one L2 round trip per batch of loads), so the loads of kGroup streams are
     // put in flight together: lane l moves words l, l+32, ... of each stream; kSlots chunks per stream cover
@@ -155,24 +156,24 @@ __device__ __forceinline__ void compact_tail(const CompactParams &c, uint32_t ti
     constexpr int kGroup = CTR_GATHER_GROUP, kSlots = 4;
     for (int i0 = 0; i0 < 32; i0 += kGroup) {
         uint32_t ni[kGroup];
-        const uint32_t *si[kGroup];
-        uint32_t *di[kGroup];
+        const W *si[kGroup];
+        W *di[kGroup];
         uint32_t group_max = 0;
 #pragma unroll
         for (int g = 0; g < kGroup; ++g) {
             ni[g] = __shfl_sync(kFullMask, n, i0 + g);
-            si[g] = (const uint32_t *)shfl_u64((uint64_t)src, i0 + g);
-            di[g] = (uint32_t *)shfl_u64((uint64_t)dst, i0 + g);
+            si[g] = (const W *)shfl_u64((uint64_t)src, i0 + g);
+            di[g] = (W *)shfl_u64((uint64_t)dst, i0 + g);
             group_max = max(group_max, ni[g]);
         }
         for (uint32_t j0 = 0; j0 < group_max; j0 += 32 * kSlots) {
-            uint32_t v[kGroup][kSlots];
+            W v[kGroup][kSlots];
 #pragma unroll
             for (int g = 0; g < kGroup; ++g)
 #pragma unroll
                 for (int u = 0; u < kSlots; ++u) {
                     const uint32_t j = j0 + u * 32 + lane;
-                    if (j < ni[g]) v[g][u] = ld_cg_u32(si[g] + j);
+                    if (j < ni[g]) v[g][u] = __ldcg(si[g] + j);
                 }
 #pragma unroll
             for (int g = 0; g < kGroup; ++g)

@@ -262,6 +262,41 @@ int ctr_range_decode_gaussian(int32_t min_symbol, int32_t max_symbol, const doub
                               const uint64_t *states_in_dev, int32_t *symbols_out_dev, uint64_t *states_out_dev,
                               uint64_t *words_read_dev, uint32_t *status_dev, void *stream);
 
+/* ---- the "Small" preset with lookup decoder models ------------------------------------------
+ * Word = u16, State = u32, Probability = u16, PRECISION = 12: SmallAnsCoder (src/stream/stack.rs:153),
+ * SmallRangeEncoder / SmallRangeDecoder (src/stream/queue.rs:156,747), SmallContiguousCategoricalEntropyModel
+ * (categorical/contiguous.rs:30) for encoding and ContiguousLookupDecoderModel / NonContiguousLookupDecoderModel
+ * (categorical/lookup_contiguous.rs:169-333,564-607; lookup_noncontiguous.rs:167,602-645) for decoding: a table
+ * with one entry per 12-bit quantile, so a decoded symbol costs one shared-memory load instead of a search.
+ * A model set is M CDF rows u16[alphabet + 1] with cdf[0] = 0, cdf[alphabet] = 4096 (alphabet <= 4096).  Batches and
+ * containers are described as for the Default preset, with u16 words (offsets count u16 words).  Models are shared
+ * (CTR_INDEX_NONE) or per stream (CTR_INDEX_PER_STREAM); flags must be 0.  Stream k's words equal what
+ * SmallAnsCoder::into_compressed() / SmallRangeEncoder::into_compressed() return for that stream. */
+typedef struct ctr_small_model_s *ctr_small_model_t;
+/* from fixed-point CDF rows (from_nonzero_fixed_point_probabilities, lookup_contiguous.rs:405-442).  symbols_host, if not
+ * NULL, is i32[alphabet]: index i stands for the symbol symbols_host[i] (non-contiguous alphabet) */
+int ctr_small_model_from_cdf(const uint16_t *cdf, int is_device, uint32_t n_models, uint32_t alphabet, int32_t min_symbol,
+                             const int32_t *symbols_host, void *stream, ctr_small_model_t *out);
+/* from_floating_point_probabilities_fast (perfect = 0; categorical.rs:16-54) / _perfect (categorical.rs:56-177) */
+int ctr_small_model_categorical_f32(const float *pmf, int is_device, uint32_t n_models, uint32_t alphabet, int perfect,
+                                    void *stream, ctr_small_model_t *out);
+int ctr_small_model_categorical_f64(const double *pmf, int is_device, uint32_t n_models, uint32_t alphabet, int perfect,
+                                    void *stream, ctr_small_model_t *out);
+int ctr_small_model_destroy(ctr_small_model_t model);
+int ctr_small_model_copy_cdf_host(ctr_small_model_t model, uint16_t *cdf_host, void *stream);
+size_t ctr_small_encode_workspace_bytes(const ctr_layout *layout);
+uint64_t ctr_small_max_compressed_words(const ctr_layout *layout);
+int ctr_small_ans_encode_reverse(ctr_small_model_t model, const int32_t *symbols_dev, const ctr_layout *layout,
+                                 void *workspace_dev, size_t workspace_bytes, uint16_t *words_out_dev, uint64_t words_capacity,
+                                 uint64_t *offsets_out_dev, uint32_t *status_dev, void *stream);
+int ctr_small_ans_decode(ctr_small_model_t model, const uint16_t *words_dev, const uint64_t *offsets_dev, const ctr_layout *layout,
+                         int32_t *symbols_out_dev, uint32_t *status_dev, void *stream);
+int ctr_small_range_encode(ctr_small_model_t model, const int32_t *symbols_dev, const ctr_layout *layout, void *workspace_dev,
+                           size_t workspace_bytes, uint16_t *words_out_dev, uint64_t words_capacity, uint64_t *offsets_out_dev,
+                           uint32_t *status_dev, void *stream);
+int ctr_small_range_decode(ctr_small_model_t model, const uint16_t *words_dev, const uint64_t *offsets_dev, const ctr_layout *layout,
+                           int32_t *symbols_out_dev, uint32_t *status_dev, void *stream);
+
 /* ---- host-buffer entry points (the reference-facing call: host in, host out) ------------------
  * Same semantics with HOST buffers: what a pyo3 / Rust binding for `AnsCoder::encode_iid_symbols_reverse` /
  * `decode_iid_symbols` (stack.rs:835-849, stream/mod.rs:1016-1031) over many coders calls; bench.py's `e2e` number
