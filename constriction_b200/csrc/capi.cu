@@ -322,7 +322,7 @@ struct EncodeWorkspace {
 EncodeWorkspace encode_workspace(const ctr_layout *L) {
     EncodeWorkspace w;
     w.scratch_words = scratch_start(L->n_symbols, L->n_streams) + 32;
-    w.n_tiles = (L->n_streams + kSmallBlock - 1) / kSmallBlock;  // enough for either CTA size
+    w.n_tiles = (L->n_streams + 31) / 32;  // enough for every CTA size (the chain kernels code 32 streams per CTA)
     w.status_off = align_up((size_t)w.scratch_words * 4, 256);
     w.ticket_off = w.status_off + (size_t)w.n_tiles * 8;
     w.total = align_up(w.ticket_off + 8, 256);
@@ -700,6 +700,18 @@ bool use_shared_enc_table(const ctr_model_s *m, const ctr_layout *L) {
     return use_shared_tables(m, L) && m->alphabet <= kMaxSharedEncAlphabet;
 }
 
+// Few, long streams (contiguous layout, one model per stream): the chain kernels (chain_kernels.cuh).  CTR_CHAIN=0
+// forces the general kernels (tests compare the two).
+bool use_chain_kernels(const ctr_layout *L, bool raw_states, bool raw_ok = false) {
+    static const bool enabled = [] {
+        const char *e = getenv("CTR_CHAIN");
+        return !(e && strcmp(e, "0") == 0);
+    }();
+    if (!enabled || !L->sym_offsets_dev || L->model_index_mode == CTR_INDEX_PER_SYMBOL) return false;
+    if (!raw_ok && ((L->flags & CTR_FLAG_RAW) || raw_states)) return false;
+    return L->n_streams <= 32768 && L->n_symbols >= 64 * L->n_streams;
+}
+
 // CTA size: big CTAs amortise the table staging, but a batch with fewer streams than one big CTA per SM is
 // latency-bound and wants its warps spread over as many SMs as possible.
 constexpr uint64_t kStreamsForBigCtas = 148ull * kAnsBlock;
@@ -943,6 +955,20 @@ int encode_common(ctr_model_t model, const int32_t *symbols_dev, const ctr_layou
     cfg.contig = L->sym_offsets_dev != nullptr;
     cfg.persym = L->model_index_mode == CTR_INDEX_PER_SYMBOL;
     cfg.f64 = model->enc_f64;
+    cfg.stream = s;
+    if (use_chain_kernels(L, states_in != nullptr || states_out != nullptr)) {
+        // few long streams: one coder warp per 32 streams, helper warps do everything that is not the state update
+        constexpr bool kAns = EncLauncher::kSlot == 0;
+        cfg.block = kChainCtaThreads;
+        cfg.grid = grid_for(L->n_streams, 32);
+        cfg.smem = 32 * (kEncRingWords + 4) * 4 + (cfg.shared ? ((size_t)model->alphabet + 1) * 16 : 0) + 128 +
+                   (size_t)kChainRingSlots * 1024 * (kAns ? 16 : 8);
+        ProfileScope prof(EncLauncher::kSlot, s);
+        const cudaError_t e = launch_encode_chain(cfg, p, kAns);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        if (e != cudaSuccess) return cuda_fail(e, "encode_chain_kernel");
+        return CTR_OK;
+    }
     cfg.block = encode_block(L);
     cfg.grid = grid_for(L->n_streams, cfg.block);
     // rings + parking slots; replicated table (128 B per entry); two symbol tiles
@@ -1038,6 +1064,34 @@ int decode_common(ctr_model_t model, const uint32_t *words, const uint64_t *offs
         cfg.grid = grid_for(L->n_streams, cfg.block);
         cfg.smem = coder_smem_bytes(0, L, cfg.block / 32, 32 * kDecRingWords, 1);
         return run_coder_kernel<DecLauncher>(cfg, p);
+    }
+    if (use_chain_kernels(L, false, /*raw_ok=*/true) && !cfg.persym) {
+        // few long streams: one coder warp per 32 streams with a straight-line loop, a second warp writes the symbols
+        size_t table_bytes = 0;
+        bool pool = false;
+        if (cfg.shared) {
+            table_bytes = (size_t)kLutBytes + model->dec_cdf_bytes;
+        } else if (model->d_cidx) {
+            const size_t cdf_bytes = align_up((size_t)model->n_models * ((size_t)model->alphabet + 1) * 4, 16);
+            const size_t cidx_bytes = align_up((size_t)model->n_models * 257 * (model->alphabet > 256 ? 2 : 1), 16);
+            if (cdf_bytes + cidx_bytes + 32 * kDecRingWords * 4 + 4 * 4096 + 256 <= kPoolSmemBudget) {
+                pool = true;
+                table_bytes = cdf_bytes + cidx_bytes;
+                p.model.pool_cdf_bytes = (uint32_t)cdf_bytes;
+                p.model.pool_cidx_bytes = (uint32_t)cidx_bytes;
+            }
+        }
+        if (cfg.shared || pool) {
+            cfg.pool = pool;
+            cfg.block = 64;
+            cfg.grid = grid_for(L->n_streams, 32);
+            cfg.smem = 32 * kDecRingWords * 4 + table_bytes + 4 * 4096;
+            ProfileScope prof(DecLauncher::kSlot, s);
+            const cudaError_t e = launch_decode_chain(cfg, p, DecLauncher::kSlot == 3);
+            g_launches.fetch_add(1, std::memory_order_relaxed);
+            if (e != cudaSuccess) return cuda_fail(e, "decode_chain_kernel");
+            return CTR_OK;
+        }
     }
     // interleaved deal, one model per stream: decoded symbols leave as TMA boxes (kDecBoxSlots per warp)
     size_t box_bytes_per_warp = 0;

@@ -28,6 +28,12 @@ cudaError_t launch_ans_encode(const LaunchCfg &cfg, const AnsParams &p);
 cudaError_t launch_ans_decode(const LaunchCfg &cfg, const AnsParams &p);
 cudaError_t launch_range_encode(const LaunchCfg &cfg, const AnsParams &p);
 cudaError_t launch_range_decode(const LaunchCfg &cfg, const AnsParams &p);
+// few long streams (contiguous layout): one coder warp + producer warps per CTA (chain_kernels.cuh); cfg.grid = ceil(K / 32)
+cudaError_t launch_encode_chain(const LaunchCfg &cfg, const AnsParams &p, bool ans);
+// decoders: cfg.shared (one model, quantile index in shared memory) or cfg.pool (model set in shared memory); 64 threads
+cudaError_t launch_decode_chain(const LaunchCfg &cfg, const AnsParams &p, bool range);
+constexpr int kChainCtaThreads = 128;
+constexpr int kChainRingSlots = 4;
 
 // shared by the translation units: opt in to > 48 KB of dynamic shared memory, launch, report
 template <typename Kernel>

@@ -150,14 +150,28 @@ __global__ void __launch_bounds__(BLOCK, BLOCK >= 256 ? 4 : 8) range_encode_kern
     };
     // one reference encode_symbol (queue.rs:612-705) on a looked-up (left, prob).  An impossible symbol
     // (prob 0) collapses the range to zero: the words from there on are garbage and the stream is flagged.
+    // The most recent word is HELD in a register instead of being pushed right away: `lower` wraps for about one
+    // symbol in fifty (the interval is often a sizeable fraction of 2^64) and the carry then is one add on that
+    // register.  Only if there is no held word yet (a resumed coder before its first new word) or the held word itself
+    // overflows (it was 0xffffffff: probability 2^-32 per carry) the carry ripples into words that have already left
+    // for the ring or the scratch region -- the cold path.
+    uint32_t held = 0u;
+    bool has_held = false;
     auto encode_entry = [&](const uint2 &e) {
         min_prob = min(min_prob, e.y);
         const uint64_t scale = range >> kPrecision;
         const uint64_t nr = scale * (uint64_t)e.y;
         const uint64_t nl = lower + scale * (uint64_t)e.x;
-        if (nl < lower) propagate_carry();
+        const bool wrap = nl < lower;
+        held += (wrap && has_held) ? 1u : 0u;
+        if (wrap && (!has_held || held == 0u)) propagate_carry();
         const bool renorm = (uint32_t)(nr >> 32) == 0u;
-        if (renorm) push((uint32_t)(nl >> 32));
+        const bool spill = renorm && has_held;  // a new word arrives: the held one goes to the ring
+        if (spill) sts_u32(ring | (pushed & (kEncRingBytes - 1u)), held);
+        pushed += spill ? 4u : 0u;
+        pending += spill ? 4u : 0u;
+        held = renorm ? (uint32_t)(nl >> 32) : held;
+        has_held = has_held || renorm;
         lower = renorm ? nl << 32 : nl;
         range = renorm ? nr << 32 : nr;
     };
@@ -322,7 +336,7 @@ __global__ void __launch_bounds__(BLOCK, BLOCK >= 256 ? 4 : 8) range_encode_kern
             if (ckpt_every != 0u && c != 0u) {
                 if (to_ckpt == 0u) {
                     uint64_t *rec = p.ckpt_out + 4u * (ckpt_base + first / ckpt_every);
-                    rec[0] = pushed >> 2;
+                    rec[0] = (pushed >> 2) + (has_held ? 1u : 0u);
                     rec[1] = lower;
                     rec[2] = range;
                     rec[3] = 0;
@@ -367,6 +381,8 @@ __global__ void __launch_bounds__(BLOCK, BLOCK >= 256 ? 4 : 8) range_encode_kern
     }
 
     // ---- seal (queue.rs:349-355, 458-523), or hand the raw state back to the caller -----------------------
+    drain_ring();
+    if (has_held) push(held);
     drain_ring();
     const bool raw = (p.flags & 1u) != 0;
     const bool bad = min_prob == 0u;
