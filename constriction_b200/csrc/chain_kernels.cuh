@@ -388,6 +388,16 @@ __global__ void __launch_bounds__(kChainBlock) encode_chain_kernel(const __grid_
 //   TABLE : kTableLut (one shared model: quantile index + cdf in shared memory) or kTablePool (model set in shared
 //           memory, one model per stream)
 // =====================================================================================================================
+// u64 -> float within a few ulp and 1 / x to 22 bits: three and one instruction (the results only seed an estimate)
+__device__ __forceinline__ float u64_to_float_cheap(uint64_t v) {
+    return fmaf(__uint2float_rz((uint32_t)(v >> 32)), 4294967296.0f, __uint2float_rz((uint32_t)v));
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
 constexpr int kDecChainBlock = 64;
 constexpr int kDecChainTiles = 4;
 
@@ -567,24 +577,41 @@ __global__ void __launch_bounds__(kDecChainBlock) decode_chain_kernel(const __gr
     }
     top_up();
     uint32_t nxt = peek_word();
+    float rscale = rcp_approx(u64_to_float_cheap(st.range >> kPrecision));  // 1 / scale, single precision (RANGE)
 
     // one symbol; `act` = this lane still owns a symbol at this position
-    auto decode_one = [&](bool act) -> uint32_t {
+    auto decode_one = [&](bool act_in, auto all_tag) -> uint32_t {
+        const bool act = decltype(all_tag)::value ? true : act_in;  // ALL: every lane owns this position (full tile)
         uint32_t left, right, s;
         if (RANGE) {
-            uint32_t q = kQuantileMask;
-            const bool ok = range_peek_quantile(st, q);
-            invalid_data |= act && !ok;
-            s = lookup(q, q, left, right);
+            // queue.rs:989-993 needs q = (point - lower) / (range >> 24) only to find the symbol with left <= q < right,
+            // i.e. scale * left <= point - lower < scale * right.  So the division is ESTIMATED in single precision
+            // (reciprocal of the scale computed right after the previous update, off the critical path; error of a few
+            // quantiles), the symbol is looked up for the estimate, and the exact test is the decoder's own invariant
+            // after the update, (point - new_lower) < new_range.  Only if it fails (the estimate fell on the wrong side
+            // of a symbol boundary: ~1e-4 per symbol) the exact division runs.
             const uint64_t scale = st.range >> kPrecision;
-            const uint64_t nl = st.lower + scale * (uint64_t)left;
-            const uint64_t nr = scale * (uint64_t)(right - left);
+            const uint64_t diff = st.point - st.lower;
+            invalid_data |= act && diff >= (scale << kPrecision);
+            uint32_t q = __float2uint_rz(u64_to_float_cheap(diff) * rscale);
+            q = min(q, kQuantileMask);
+            s = lookup(q, q, left, right);
+            uint64_t nl = st.lower + scale * (uint64_t)left;
+            uint64_t nr = scale * (uint64_t)(right - left);
+            if (st.point - nl >= nr) {  // cold: exact quantile
+                q = kQuantileMask;
+                range_peek_quantile(st, q);
+                s = lookup(q, q, left, right);
+                nl = st.lower + scale * (uint64_t)left;
+                nr = scale * (uint64_t)(right - left);
+            }
             const bool renorm = (uint32_t)(nr >> 32) == 0u;  // queue.rs:1018-1032
             const bool pop = act && renorm && avail != 0u;
             const uint64_t np = renorm ? ((st.point << 32) | (pop ? nxt : 0u)) : st.point;
             st.lower = act ? (renorm ? nl << 32 : nl) : st.lower;
             st.range = act ? (renorm ? nr << 32 : nr) : st.range;
             st.point = act ? np : st.point;
+            rscale = rcp_approx(u64_to_float_cheap(st.range >> kPrecision));
             pop_off += pop ? 4u : 0u;
             avail -= pop ? 1u : 0u;
         } else {
@@ -610,15 +637,28 @@ __global__ void __launch_bounds__(kDecChainBlock) decode_chain_kernel(const __gr
         const uint64_t done = t * 32;
         const uint32_t c = n_k > done ? (uint32_t)min((uint64_t)32, n_k - done) : 0u;
         const uint32_t base = tiles_addr + slot * 4096u;
-        const uint32_t cmax = __reduce_max_sync(kFullMask, c);
-        for (uint32_t j = 0; j < cmax; j += 4) {
-            top_up();
-            nxt = peek_word();
+        const uint32_t cmax = __reduce_max_sync(kFullMask, c), cmin = __reduce_min_sync(kFullMask, c);
+        if (cmin == 32u) {  // the common case: nothing in the loop is predicated on the stream's length
+            for (uint32_t j = 0; j < 32u; j += 4) {
+                top_up();
+                nxt = peek_word();
 #pragma unroll
-            for (uint32_t u = 0; u < 4; ++u) {
-                const uint32_t jj = j + u;
-                const uint32_t sym = decode_one(jj < c);
-                sts_u32(base + (jj * 32u + ((uint32_t)lane ^ jj)) * 4u, sym);
+                for (uint32_t u = 0; u < 4; ++u) {
+                    const uint32_t jj = j + u;
+                    const uint32_t sym = decode_one(true, std::true_type{});
+                    sts_u32(base + (jj * 32u + ((uint32_t)lane ^ jj)) * 4u, sym);
+                }
+            }
+        } else {
+            for (uint32_t j = 0; j < cmax; j += 4) {
+                top_up();
+                nxt = peek_word();
+#pragma unroll
+                for (uint32_t u = 0; u < 4; ++u) {
+                    const uint32_t jj = j + u;
+                    const uint32_t sym = decode_one(jj < c, std::false_type{});
+                    sts_u32(base + (jj * 32u + ((uint32_t)lane ^ jj)) * 4u, sym);
+                }
             }
         }
         __syncwarp();
