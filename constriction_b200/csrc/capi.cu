@@ -709,7 +709,10 @@ bool use_chain_kernels(const ctr_layout *L, bool raw_states, bool raw_ok = false
     }();
     if (!enabled || !L->sym_offsets_dev || L->model_index_mode == CTR_INDEX_PER_SYMBOL) return false;
     if (!raw_ok && ((L->flags & CTR_FLAG_RAW) || raw_states)) return false;
-    return L->n_streams <= 32768 && L->n_symbols >= 64 * L->n_streams;
+    // long streams (the time is the dependent chain of one stream), or so few streams that the general kernels cannot
+    // fill the GPU anyway; many medium-length streams (e.g. 12,288 x 1024) stay with the general kernels
+    if (L->n_streams > 32768 || L->n_symbols < 64 * L->n_streams) return false;
+    return L->n_symbols >= 4096 * L->n_streams || L->n_streams <= 2048;
 }
 
 // CTA size: big CTAs amortise the table staging, but a batch with fewer streams than one big CTA per SM is
@@ -1074,7 +1077,7 @@ int decode_common(ctr_model_t model, const uint32_t *words, const uint64_t *offs
         } else if (model->d_cidx) {
             const size_t cdf_bytes = align_up((size_t)model->n_models * ((size_t)model->alphabet + 1) * 4, 16);
             const size_t cidx_bytes = align_up((size_t)model->n_models * 257 * (model->alphabet > 256 ? 2 : 1), 16);
-            if (cdf_bytes + cidx_bytes + 32 * kDecRingWords * 4 + 4 * 4096 + 256 <= kPoolSmemBudget) {
+            if (cdf_bytes + cidx_bytes <= 48 * 1024) {  // (every CTA stages the set: only worth it for small sets)
                 pool = true;
                 table_bytes = cdf_bytes + cidx_bytes;
                 p.model.pool_cdf_bytes = (uint32_t)cdf_bytes;
