@@ -47,6 +47,14 @@ class Layout(C.Structure):
     ]
 
 
+class ContainerView(C.Structure):
+    """ctr_container_view"""
+    _fields_ = [("coder", C.c_uint32), ("word_bits", C.c_uint32), ("precision", C.c_uint32), ("checkpoint_every", C.c_uint32),
+                ("flags", C.c_uint32), ("reserved", C.c_uint32), ("n_streams", C.c_uint64), ("n_symbols", C.c_uint64),
+                ("total_words", C.c_uint64), ("n_records", C.c_uint64), ("sym_offsets", vp), ("offsets", vp),
+                ("ckpt_offsets", vp), ("records", vp), ("words", vp)]
+
+
 # every symbol include/constriction_b200.h declares: name -> (restype, argtypes)
 SIGNATURES = {
     "ctr_abi_version": (C.c_int, []),
@@ -110,6 +118,9 @@ SIGNATURES = {
     "ctr_host_job_wait": (C.c_int, [vp]),
     "ctr_stream_write_value32": (C.c_int, [vp, C.c_uint32, vp]),
     "ctr_stream_wait_value32": (C.c_int, [vp, C.c_uint32, vp]),
+    "ctr_container_size": (C.c_size_t, [C.POINTER(ContainerView)]),
+    "ctr_container_pack": (C.c_int, [C.POINTER(ContainerView), vp, C.c_size_t]),
+    "ctr_container_unpack": (C.c_int, [vp, C.c_size_t, C.POINTER(ContainerView)]),
     "ctr_gather_create": (C.c_int, [C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint64, vp, vp, vp, C.POINTER(vp)]),
     "ctr_gather_destroy": (C.c_int, [vp]),
     "ctr_gather_begin_turn": (C.c_int, [vp, u32p, C.POINTER(vp), u64p, C.POINTER(vp)]),

@@ -26,7 +26,7 @@ NVCC_FLAGS = [
     "-Xptxas", "-v",
 ]
 # one translation unit per kernel family (they compile in parallel); capi.cu holds the C ABI
-UNITS = ["capi", "gather", "host_pipeline", "small_kernels", "chain_encode", "chain_decode", "ans_encode", "ans_decode", "range_encode", "range_decode"]
+UNITS = ["capi", "container", "gather", "host_pipeline", "small_kernels", "chain_encode", "chain_decode", "ans_encode", "ans_decode", "range_encode", "range_decode"]
 OBJ_DIR = os.path.join(HERE, "_obj")
 
 

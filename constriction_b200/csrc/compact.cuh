@@ -182,6 +182,21 @@ __device__ __forceinline__ void compact_tail(const CompactParams &c, uint32_t ti
                     const uint32_t j = j0 + u * 32 + lane;
                     if (j < ni[g]) di[g][j] = v[g][u];
                 }
+#ifndef CTR_NO_DISCARD
+            // The scratch words just read are dead.  Their cache lines are still dirty in L2 (this kernel wrote them
+            // moments ago): drop them instead of letting the L2 write them back to HBM later -- a round trip of the
+            // whole compressed size that nobody would ever read.  (Scratch regions start on 128-byte boundaries and
+            // belong to one stream each; a line is discarded only if every byte of it has been gathered.)
+            if (sizeof(W) == 4) {
+#pragma unroll
+                for (int g = 0; g < kGroup; ++g)
+#pragma unroll
+                    for (int u = 0; u < kSlots; ++u) {
+                        const uint32_t j = j0 + u * 32;  // words [j, j + 32) of stream g: one 128-byte line
+                        if (lane == 0 && j + 32 <= ni[g]) asm volatile("discard.global.L2 [%0], 128;" ::"l"(si[g] + j) : "memory");
+                    }
+            }
+#endif
         }
     }
 }

@@ -351,6 +351,33 @@ int ctr_range_decode_host_async(ctr_model_t model, const uint32_t *words_host, c
                                 int *data_status, uint64_t *failing_stream, ctr_host_job_t *job);
 int ctr_host_job_wait(ctr_host_job_t job);
 
+/* ---- wire / on-disk form of a batch container ----------------------------------------------------
+ * The reference stores raw native-endian words and leaves framing to the user (src/lib.rs:425-580 describes the
+ * (position, state) snapshots -- Pos::pos / Seek::seek -- that make random access possible).  A batch needs framing:
+ * little-endian header {magic "CTRB200", version, coder, word bits, precision, K, N, total words, checkpoint_every,
+ * flags, n_records}, then [sym_offsets u64[K+1]] offsets u64[K+1] [ckpt_offsets u64[K+1], records] words (csrc/container.cu
+ * has the byte layout).  words[offsets[k] .. offsets[k+1]) is one stock constriction stream; a record is what
+ * AnsCoder::pos() / RangeEncoder::pos() returned at a chunk boundary, so stock coders can seek() to it.
+ * Host memory only, no device work.  pack() copies the arrays of `view` into `out` (ctr_container_size bytes);
+ * unpack() validates a buffer (8-byte aligned) and fills `view` with pointers INTO it (no copy). */
+typedef struct {
+    uint32_t coder;            /* 0 = ANS (stack), 1 = range coder (queue)                               */
+    uint32_t word_bits;        /* 32 (Default preset) or 16 (Small preset)                               */
+    uint32_t precision;        /* 24 or 12                                                               */
+    uint32_t checkpoint_every; /* 0 = no records                                                         */
+    uint32_t flags;            /* bit 0: interleaved deal (stream k owns symbols k, k+K, ...; sym_offsets NULL) */
+    uint32_t reserved;
+    uint64_t n_streams, n_symbols, total_words, n_records;
+    const uint64_t *sym_offsets; /* u64[K+1] or NULL                                                     */
+    const uint64_t *offsets;     /* u64[K+1], in words                                                   */
+    const uint64_t *ckpt_offsets;/* u64[K+1] or NULL                                                     */
+    const uint64_t *records;     /* n_records x 2 (ANS) or x 4 (range) u64                               */
+    const void *words;           /* total_words words of word_bits bits                                  */
+} ctr_container_view;
+size_t ctr_container_size(const ctr_container_view *view);
+int ctr_container_pack(const ctr_container_view *view, void *out, size_t out_bytes);
+int ctr_container_unpack(const void *bytes, size_t n_bytes, ctr_container_view *view);
+
 /* ---- multi-GPU exchange of compressed containers (ctr_gather_compressed) ----------------------
  * Streams are independent coders, so encode and decode shard over the GPUs of a node with no communication; the one
  * exchange step is an all-gather of the per-rank containers (what a host does with the per-shard Vec<u32>s that

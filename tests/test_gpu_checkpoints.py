@@ -153,3 +153,31 @@ def test_chunked_decode_models_and_big_batch(env, coder):
     out = dec(comp, model)
     bc.check()
     assert torch.equal(out, big)
+
+
+@pytest.mark.parametrize("coder", ["ans", "range"])
+def test_wire_container_round_trip_through_the_device(env, coder):
+    """encode on the GPU with records -> bytes (ctr_container_pack) -> device again -> chunk-parallel decode; a stream
+    cut from the bytes decodes with the oracle's stock coder."""
+    from constriction_b200 import container as Cn
+    B, bc, O = env["B"], env["bc"], env["O"]
+    syms, off, d_syms, d_off = make_batch(env, 9, LENGTHS)
+    model = B.ModelTable.quantized_gaussian(LO, HI, [MEAN], [STD])
+    enc, dec = (bc.ans_encode, bc.ans_decode) if coder == "ans" else (bc.range_encode, bc.range_decode)
+    comp = enc(d_syms, model, sym_offsets=d_off, checkpoint_every=64)
+    bc.check()
+    data = Cn.pack(comp)
+    back = Cn.unpack(data)
+    assert back.coder == coder and back.checkpoint_every == 64
+    for use in (True, False):
+        out = dec(back, model, use_checkpoints=use)
+        bc.check()
+        assert np.array_equal(out.cpu().numpy(), syms)
+    h = Cn.unpack_host(data)
+    omodel = O.QuantizedGaussian(LO, HI, MEAN, STD)
+    k = 8
+    w = h["words"][int(h["offsets"][k]):int(h["offsets"][k + 1])]
+    stock = O.AnsCoder(w) if coder == "ans" else O.RangeDecoder(w)
+    assert np.array_equal(stock.decode(omodel, LENGTHS[k]), syms[off[k]:off[k + 1]])
+    plain = Cn.unpack(Cn.pack(enc(d_syms, model, n_streams=7)))  # interleaved deal, no records
+    assert np.array_equal(dec(plain, model).cpu().numpy(), syms)
