@@ -64,3 +64,13 @@ def test_reference_test_passes_on_the_oracle(oracle, fn, name, monkeypatch):
         if any(word in str(exc) for word in OUT_OF_SCOPE) or any(word in name for word in OUT_OF_SCOPE):
             pytest.xfail(f"out of scope component: {exc}")
         raise
+
+
+def test_recorded_trace_replays_on_the_oracle(oracle):
+    """The committed fixture (tests/golden/reference_trace.json.gz) is self-consistent: replayed on the oracle it
+    recorded from, every call returns what was written down.  (The GPU suite replays it on the CUDA path.)"""
+    import trace_replay as T
+    traces = T.load()
+    assert len(traces) >= 100
+    for trace in traces:
+        T.replay(oracle, trace)
