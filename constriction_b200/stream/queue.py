@@ -67,7 +67,22 @@ class RangeEncoder:
         return c
 
     def _encode(self, symbols, table, per_symbol):
-        words, st = self._run(symbols, table, per_symbol, raw=True)
+        try:
+            words, st = self._run(symbols, table, per_symbol, raw=True)
+        except KeyError:
+            # reference semantics (stream/mod.rs:592-607): the symbols before the impossible one stay encoded
+            from ._common import first_impossible
+            done = first_impossible(symbols, table, per_symbol, reverse=False)
+            if 0 < done < symbols.size:
+                from ..batch import GaussianParams as G, ModelTable
+                if per_symbol and isinstance(table, G):
+                    table = G(table.min_symbol, table.max_symbol, table.means[:done], table.stds[:done])
+                elif per_symbol:
+                    table = ModelTable.from_cdf(table.cdf()[:done], table.min_symbol)
+                words, st = self._run(symbols[:done], table, per_symbol, raw=True)
+                self._bulk = np.concatenate([self._bulk, words])
+                self._st = st
+            raise
         self._bulk = np.concatenate([self._bulk, words])
         self._st = st
 

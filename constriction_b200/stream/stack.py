@@ -8,7 +8,7 @@ import torch
 
 from .. import _native as N
 from ..batch import GaussianParams
-from ._common import coder, from_dev_u64, is_scalar, symbols_array, to_dev_i32, to_dev_u64
+from ._common import coder, first_impossible, from_dev_u64, is_scalar, symbols_array, to_dev_i32, to_dev_u64
 
 _MASK32 = 0xFFFFFFFF
 
@@ -90,6 +90,23 @@ class AnsCoder:
 
     # -- coding ------------------------------------------------------------------------------------
     def _encode(self, symbols: np.ndarray, table, per_symbol: bool):
+        try:
+            self._encode_all(symbols, table, per_symbol)
+        except KeyError:
+            # reference semantics: the symbols coded before the impossible one stay on the coder (it codes the LAST
+            # symbols first); the kernels rejected the whole call, so that part is encoded again
+            done = first_impossible(symbols, table, per_symbol, reverse=True)
+            if 0 < done < symbols.size:
+                keep = slice(symbols.size - done, symbols.size)
+                from ..batch import GaussianParams as G, ModelTable
+                if per_symbol and isinstance(table, G):
+                    table = G(table.min_symbol, table.max_symbol, table.means[keep], table.stds[keep])
+                elif per_symbol:
+                    table = ModelTable.from_cdf(table.cdf()[keep], table.min_symbol)
+                self._encode_all(symbols[keep], table, per_symbol)
+            raise
+
+    def _encode_all(self, symbols: np.ndarray, table, per_symbol: bool):
         bc = coder()
         n = symbols.size
         per_symbol = per_symbol and not isinstance(table, GaussianParams)  # table-free kernels need no index

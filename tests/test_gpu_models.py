@@ -136,3 +136,31 @@ def test_custom_and_scipy_models(env):
     both_ways(env, lambda api: api.CustomModel(lambda x, loc, scale: scipy_stats.norm.cdf(x, loc, scale),
                                                lambda q, loc, scale: scipy_stats.norm.ppf(q, loc, scale), -100, 100),
               syms, (locs, np.full(150, 4.9)))
+
+
+def test_impossible_symbol_keeps_the_symbols_coded_before_it(env):
+    """Reference semantics after KeyError (stream/mod.rs:592-607: symbol-by-symbol loops): the coder holds the symbols
+    that were coded before the impossible one -- the LAST ones for AnsCoder.encode_reverse, the FIRST ones for
+    RangeEncoder.encode.  Same state in the mirror and in the oracle's restatement."""
+    S, O = env["S"], env["O"]
+    good = np.array([3, -7, 12, 0, 5, -1], dtype=np.int32)
+    bad = good.copy()
+    bad[2] = 99
+    means = np.linspace(-3, 3, 6)
+    stds = np.linspace(2, 8, 6)
+    probs = np.array([0.25, 0.0, 0.5, 0.25])
+    cases = [(lambda api: api.QuantizedGaussian(-50, 50, 1.0, 6.0), bad, ()),
+             (lambda api: api.QuantizedGaussian(-50, 50), bad, (means, stds)),
+             (lambda api: api.Categorical(probs, perfect=False), np.array([0, 2, 3, 9, 2, 0], dtype=np.int32), ())]
+    for make, syms, params in cases:
+        states = []
+        for api in (S, O):
+            a, e = api.AnsCoder(), api.RangeEncoder()
+            with pytest.raises(KeyError):
+                a.encode_reverse(syms, make(api), *params)
+            with pytest.raises(KeyError):
+                e.encode(syms, make(api), *params)
+            states.append((a.get_compressed(), e.get_compressed(), a.pos(), e.pos()))
+        assert np.array_equal(states[0][0], states[1][0]) and np.array_equal(states[0][1], states[1][1])
+        assert states[0][2] == states[1][2] and states[0][3] == states[1][3]
+        assert states[0][0].size > 0  # something was kept
