@@ -38,6 +38,21 @@
 namespace ctr {
 
 constexpr int kAnsBlock = 256;  // threads per CTA (8 warps)
+#ifndef CTR_ENC_SELP
+#define CTR_ENC_SELP 1
+#endif
+#ifndef CTR_DEC_SPEC_POP
+#define CTR_DEC_SPEC_POP 0
+#endif
+#ifndef CTR_ENC_FMA_PIPE
+#define CTR_ENC_FMA_PIPE 0
+#endif
+#ifndef CTR_ENC_RING_T
+#define CTR_ENC_RING_T 0
+#endif
+#ifndef CTR_ENC_UNROLL_SLOTS
+#define CTR_ENC_UNROLL_SLOTS 1
+#endif
 // Interleaved deal with one model per stream: symbols move between HBM and shared memory as 2-D TMA boxes of
 // kBoxRows rows x 32 streams per warp (device_utils.cuh), kEncBoxSlots / kDecBoxSlots boxes in flight per warp.
 #ifndef CTR_ENC_BOX_SLOTS
@@ -59,6 +74,8 @@ struct ModelView {
     const uint8_t *cidx;   // [n_models][kCoarseSize + 1] u8 (alphabet <= 256) or u16: coarse quantile index for
                            // decoding with global tables; cidx[m][b] = symbol of model m containing quantile b << 16
     const uint32_t *dec;   // model 0 only: quantile index uint2[kLutSize] ++ cdf u32[alphabet + 2] (padded to 16 B)
+    const uint32_t *dec_big;  // the same with 2^kBigLutBits buckets (large-batch ANS decoder); nullptr until first used
+    uint32_t dec_big_bytes;   // its size (the split form of small alphabets differs: device_utils.cuh, CTR_DEC_SPLIT)
     uint32_t n_models;
     uint32_t alphabet;
     int32_t min_symbol;
@@ -105,6 +122,9 @@ struct AnsParams {
     double gauss_free_weight;
     // interleaved deal: the symbol array as a [full rows][K] int32 tensor (boxes of kBoxRows x 32), if use_tma
     uint32_t use_tma;
+    // 1, 2^8 and 2^24 as run-time values: multiplying by them keeps adds and shifts of the ANS encoder's update on the
+    // FMA pipe (IMAD) instead of the ALU pipe, which is the busier one (device_utils.cuh: imad_*)
+    uint32_t k_one, k_256, k_2p24;
     alignas(64) CUtensorMap tmap;
 };
 
@@ -183,10 +203,13 @@ static __device__ __noinline__ uint32_t lookup_far_cold(uint32_t cdf_addr, uint3
 }
 
 // `word` is any value whose low 24 bits are the quantile q; SMALL: alphabet <= 256 (s fits the top byte of x)
-template <bool SMALL>
+//   BITS    : log2 of the number of buckets of the index at lut_addr
+//   UNIFORM : the second probe sits behind a warp-uniform branch (fine indices: no lane needs it in most warp steps)
+template <bool SMALL, int BITS = kLutBits, bool UNIFORM = false>
 __device__ __forceinline__ uint32_t lookup_shared(uint32_t lut_addr, uint32_t cdf_addr, uint32_t alphabet, uint32_t word,
                                                   uint32_t q, uint32_t &left, uint32_t &right) {
-    const uint2 e = lds_table_v2(lut_addr + ((word >> (kLutShift - 3)) & ((kLutSize - 1) << 3)));
+    constexpr int kShift = kPrecision - BITS;
+    const uint2 e = lds_table_v2(lut_addr + ((word >> (kShift - 3)) & (((1u << BITS) - 1u) << 3)));
     uint32_t s = e.x >> 24;
     left = e.x & kQuantileMask;
     right = e.y;
@@ -195,16 +218,36 @@ __device__ __forceinline__ uint32_t lookup_shared(uint32_t lut_addr, uint32_t cd
         right = e.y & 0x1ffffffu;
     }
     const bool beyond = q >= right;  // the bucket straddles the boundary and q lies past it
-    uint32_t next = right;
-    if (beyond) next = lds_table_u32(cdf_addr + (s + 2) * 4u);
-    left = beyond ? right : left;
-    right = beyond ? next : right;
-    s += beyond ? 1u : 0u;
-    if (q >= right) {
-        s = lookup_far_cold(cdf_addr, alphabet, s, q);
-        left = lds_table_u32(cdf_addr + s * 4u);
-        right = lds_table_u32(cdf_addr + s * 4u + 4u);
+    if (!UNIFORM || __any_sync(kFullMask, beyond)) {
+        uint32_t next = right;
+        if (beyond) next = lds_table_u32(cdf_addr + (s + 2) * 4u);
+        left = beyond ? right : left;
+        right = beyond ? next : right;
+        s += beyond ? 1u : 0u;
+        if (q >= right) {
+            s = lookup_far_cold(cdf_addr, alphabet, s, q);
+            left = lds_table_u32(cdf_addr + s * 4u);
+            right = lds_table_u32(cdf_addr + s * 4u + 4u);
+        }
     }
+    return s;
+}
+
+// Split decoder table (alphabet <= 256, large-batch ANS decoder): a one-byte probe names the first symbol of q's
+// bucket, then its {left, right} pair is read from the lane's own copy (pairs_addr = pair table + (lane % 16) * 8).
+template <int BITS>
+__device__ __forceinline__ uint32_t lookup_split(uint32_t lut_addr, uint32_t pairs_addr, uint32_t q, uint32_t &left,
+                                                 uint32_t &right) {
+    uint32_t s = lds_table_u8(lut_addr + (q >> (kPrecision - BITS)));
+    uint2 pr = lds_table_v2(pairs_addr + s * (kPairCopies * 8u));
+    if (__any_sync(kFullMask, q >= pr.y)) {  // q lies beyond the bucket's first symbol: rare with a fine index
+        while (q >= pr.y) {                  // (the last symbol's right end is 2^24 > q)
+            s += 1u;
+            pr = lds_table_v2(pairs_addr + s * (kPairCopies * 8u));
+        }
+    }
+    left = pr.x;
+    right = pr.y;
     return s;
 }
 
@@ -324,14 +367,23 @@ __global__ void __launch_bounds__(BLOCK, BLOCK >= 256 ? CTR_ENC_MIN_CTAS : 8) an
     const int warp_in_cta = threadIdx.x >> 5;
     constexpr int kWarpsPerCta = BLOCK / 32;
 
-    // shared memory carve-up: [lane rings (32 B each) + per-thread parking slots (16 B each)][table][symbol
-    // tiles][index tiles].  The parking slot keeps values that are only needed again at the very end
-    // (scratch base, capacity) out of the hot loop's registers.
+    // shared memory carve-up: [lane rings (32 B each)][table][symbol tiles / TMA boxes][index tiles]
     const uint32_t alphabet = p.model.alphabet;
     const uint32_t table_words = SHARED ? (alphabet + 1) * 32 : 0;
-    constexpr uint32_t kRingsWords = BLOCK * (kEncRingWords + 4);
+    constexpr uint32_t kEncRingBytes = kAnsEncRingWords * 4u;  // (shadows the 8-word constant of the other encoders)
+    constexpr uint32_t kRingsWords = BLOCK * kAnsEncRingWords;
+    static_assert(!(CTR_ENC_D32 && CTR_ENC_RING_T), "32-byte drains are written for the lane-major ring");
+#if CTR_ENC_RING_T
+    // The rings of a warp are stored slot-major: slot j of lane l is word (j * 32 + l) of the warp's 1 KB block, i.e.
+    // lane l only ever touches bank l.  Pushes (predicated STS of a few lanes at uncorrelated slots) and the 16-byte
+    // drain reads are therefore free of bank conflicts -- the kernel is bound by the L1 data pipe, where the
+    // lane-major layout cost ~2.5 extra wavefronts per symbol (ncu: 26 % of the shared-memory wavefronts).
+    const uint32_t ring = smem_u32_pinned(smem) + (uint32_t)warp_in_cta * (32u * kEncRingBytes) + (uint32_t)lane * 4u;
+    auto ring_slot = [&](uint32_t byte_pos) -> uint32_t { return ring + ((byte_pos & (kEncRingBytes - 4u)) << 5); };
+#else
     const uint32_t ring = smem_u32_pinned(smem) + threadIdx.x * kEncRingBytes;  // 32-byte aligned
-    const uint32_t park = smem_u32(smem) + BLOCK * kEncRingBytes + threadIdx.x * 16u;
+    auto ring_slot = [&](uint32_t byte_pos) -> uint32_t { return ring | (byte_pos & (kEncRingBytes - 1u)); };
+#endif
     // lane l reads copy (l & 7) of an entry: the 8 lanes of a quarter-warp always hit 8 different 16-byte bank
     // groups, so the random-index LDS.128 is conflict free
     const uint32_t table_addr = smem_u32_pinned(smem + kRingsWords) + (uint32_t)(lane & 7) * 16u;
@@ -361,15 +413,14 @@ __global__ void __launch_bounds__(BLOCK, BLOCK >= 256 ? CTR_ENC_MIN_CTAS : 8) an
         n_k = interleaved_len(N, K, kc);
         o_k = interleaved_start(N, K, kc);
     }
-    char *gw;        // write cursor in my scratch region (128-byte aligned start)
-    uint32_t room;   // bytes of scratch capacity left
+    // my scratch region (128-byte aligned start) and its capacity in bytes; the write cursor is gbase + drained
+    char *gbase;
+    uint32_t cap;
     {
         uint32_t *const gbegin = p.scratch + scratch_start(o_k, k);
         const uint64_t r = valid ? scratch_start(o_k + n_k, k + 1) - scratch_start(o_k, k) : 0;
-        room = r > 0x3ffffff0u ? 0xffffffc0u : (uint32_t)r * 4u;
-        gw = reinterpret_cast<char *>(gbegin);
-        const uint64_t gb = (uint64_t)gbegin;
-        asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(park), "r"((uint32_t)gb), "r"((uint32_t)(gb >> 32)) : "memory");
+        cap = r > 0x1ffffff0u ? 0x7fffffc0u : (uint32_t)r * 4u;
+        gbase = reinterpret_cast<char *>(gbegin);
     }
 
     uint64_t state = (valid && p.states_in) ? p.states_in[k] : 0;
@@ -392,15 +443,59 @@ __global__ void __launch_bounds__(BLOCK, BLOCK >= 256 ? CTR_ENC_MIN_CTAS : 8) an
         return __ldg(p.model.enc + (uint64_t)m * (alphabet + 1) + idx);
     };
     auto encode_entry_nomin = [&](const uint4 &e) {
+#if CTR_ENC_FMA_PIPE
+        // One reference encode_symbol with the adds, shifts and selects that do not need the ALU pipe expressed as
+        // integer multiply-adds by run-time constants (p.k_*): ncu shows the ALU pipe as the busiest unit of this
+        // kernel (55 % vs 16 % for the FMA pipe), and both accept one warp instruction every other cycle.
+        const uint32_t prob = e.y;
+        const uint32_t prob_shl8 = imad_lo(prob, p.k_256, 0u);      // (state >> 40) >= prob  <=>  hi >= prob << 8
+        const uint32_t neg_prob = 0u - prob;
+        const uint32_t bump = imad_lo(neg_prob, p.k_one, kTotal);   // 2^24 - prob
         uint32_t lo = (uint32_t)state, hi = (uint32_t)(state >> 32);
-        if (shr_clamp(hi, push_shift) >= e.y) {  // stack.rs:1035-1040
-            sts_u32(ring | (pushed & (kEncRingBytes - 1u)), lo);
+        if (hi >= prob_shl8) {  // stack.rs:1035-1040 (lanes without a stream push into their own ring: harmless)
+            sts_u32(ring_slot(pushed), lo);
             pushed += 4u;
             lo = hi;
             hi = 0u;
         }
         const uint64_t n = ((uint64_t)hi << 32) | lo;
+        const uint64_t q = ans_quotient_estimate<F64DIV>(n, e.z, e.w);  // in {true quotient - 1, true quotient}
+        const uint32_t r = imad_lo((uint32_t)q, neg_prob, lo);      // n - q * prob, in [0, 2 prob)
+        uint32_t x = imad_lo(r, p.k_one, e.x);                      // left + r
+        x = imad_lo_if_ge(x, r, prob, bump, p.k_one);               // r >= prob: the quotient was one short
+        // state = (q << 24) + x; bits 40.. of q are not part of the quotient (see ans_quotient_estimate)
+        const uint64_t low = imad_wide((uint32_t)q, p.k_2p24, (uint64_t)x);
+        state = ((uint64_t)imad_lo((uint32_t)(q >> 32), p.k_2p24, (uint32_t)(low >> 32)) << 32) | (uint32_t)low;
+#elif CTR_ENC_SELP
+        // stack.rs:1035-1040 as one block of straight-line PTX: the push is predicated, and the renormalised state is
+        // selected straight into the register pair the conversion reads (the compiler's own code moves it around)
+        uint64_t n;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t.reg .b32 a, b, t;\n\t"
+            "shr.u32 t, %3, %5;\n\t"
+            "setp.ge.u32 p, t, %4;\n\t"
+            "@p st.shared.u32 [%6], %2;\n\t"
+            "@p add.u32 %1, %1, 4;\n\t"
+            "selp.b32 a, %3, %2, p;\n\t"
+            "selp.b32 b, 0, %3, p;\n\t"
+            "mov.b64 %0, {a, b};\n\t}"
+            : "=l"(n), "+r"(pushed)
+            : "r"((uint32_t)state), "r"((uint32_t)(state >> 32)), "r"(e.y), "r"(push_shift),
+              "r"(ring_slot(pushed))
+            : "memory");
+#else
+        uint32_t lo = (uint32_t)state, hi = (uint32_t)(state >> 32);
+        if (shr_clamp(hi, push_shift) >= e.y) {  // stack.rs:1035-1040
+            sts_u32(ring_slot(pushed), lo);
+            pushed += 4u;
+            lo = hi;
+            hi = 0u;
+        }
+        const uint64_t n = ((uint64_t)hi << 32) | lo;
+#endif
+#if !CTR_ENC_FMA_PIPE
         state = ans_encode_recombine(n, ans_quotient_estimate<F64DIV>(n, e.z, e.w), e.x, e.y);
+#endif
     };
     auto encode_entry = [&](const uint4 &e) {
         min_prob = min(min_prob, e.y);
@@ -422,33 +517,32 @@ __global__ void __launch_bounds__(BLOCK, BLOCK >= 256 ? CTR_ENC_MIN_CTAS : 8) an
     auto in_ring = [&]() -> uint32_t { return (pushed - drained) & 0x7fffffffu; };
     auto drain_store = [&](const uint4 &v) {
         if (in_ring() >= 16u) {
-            if (room >= 16u) {
-                st_stream_v4(gw, v);
-                gw += 16;
-                room -= 16u;
-            } else {
-                room = 0u;  // words dropped: the stream is flagged at the end
-                pushed |= 0x80000000u;
-            }
+            if (drained + 16u <= cap)
+                st_scratch_v4(gbase + drained, v);
+            else
+                pushed |= 0x80000000u;  // words dropped: the stream is flagged at the end
             drained += 16u;
         }
     };
     // the oldest (possibly incomplete) 16-byte group of my ring; harmless to read when it is not yet complete
-    auto drain_load = [&]() -> uint4 { return lds_v4(ring | (drained & (kEncRingBytes - 16u))); };
+    auto drain_load = [&]() -> uint4 {
+#if CTR_ENC_RING_T
+        const uint32_t g = ring + ((drained & (kEncRingBytes - 16u)) << 5);
+        return make_uint4(lds_u32(g), lds_u32(g + 128u), lds_u32(g + 256u), lds_u32(g + 384u));
+#else
+        return lds_v4(ring | (drained & (kEncRingBytes - 16u)));
+#endif
+    };
     auto drain_ring = [&]() { drain_store(drain_load()); };
     // split form: `full = in_ring() >= 16` and `oldest = drain_load()` are taken at the check, the store is issued
     // a couple of symbols later so that the shared-memory latency is covered by coding work (a group that
     // completes in between waits for the next check; the ring has room for that)
     auto drain_decided = [&](bool full, const uint4 &oldest) {
         if (full) {
-            if (room >= 16u) {
-                st_stream_v4(gw, oldest);
-                gw += 16;
-                room -= 16u;
-            } else {
-                room = 0u;
+            if (drained + 16u <= cap)
+                st_scratch_v4(gbase + drained, oldest);
+            else
                 pushed |= 0x80000000u;
-            }
             drained += 16u;
         }
     };
@@ -472,11 +566,13 @@ __global__ void __launch_bounds__(BLOCK, BLOCK >= 256 ? CTR_ENC_MIN_CTAS : 8) an
             {  // the rows above the highest box, one at a time
                 const int32_t *ps = p.symbols_in + (g.T - 2) * K + kc;
                 for (uint32_t j = 0; j < top_rows; ++j) {
-                    if ((j & (kCheckEvery - 1)) == 0) drain_ring();
+                    // (32-byte drains: nothing is drained before the boxes -- at most 8 words so far, and `drained`
+                    // must stay a multiple of 32 for the 256-bit stores)
+                    if (!CTR_ENC_D32 && (j & (kCheckEvery - 1)) == 0) drain_ring();
                     encode_one(ld_stream_s32(ps), stream_model);
                     ps -= K;
                 }
-                drain_ring();
+                if (!CTR_ENC_D32) drain_ring();
             }
             const uint32_t bars = smem_u32(&tma_bar[warp_in_cta][0]);
             const uint32_t boxes = smem_u32_pinned(smem + kRingsWords + table_words) + (uint32_t)warp_in_cta * (kEncBoxSlots * kBoxBytes);
@@ -499,9 +595,9 @@ __global__ void __launch_bounds__(BLOCK, BLOCK >= 256 ? CTR_ENC_MIN_CTAS : 8) an
             };
 #pragma unroll
             for (int sl = 0; sl < kEncBoxSlots; ++sl) request_box(sl);
-            uint32_t slot = 0, parity = 0;
             const uint32_t my_col = boxes + (uint32_t)lane * 4u;
-            for (; nbox > 0; --nbox) {
+            // one box: wait for it, code its rows top down, hand the slot back to the TMA engine
+            auto code_box = [&](uint32_t slot, uint32_t parity) {
                 mbar_wait_addr(bars + 8u * slot, parity);
                 const uint32_t box = my_col + slot * kBoxBytes;
 #pragma unroll
@@ -510,20 +606,63 @@ __global__ void __launch_bounds__(BLOCK, BLOCK >= 256 ? CTR_ENC_MIN_CTAS : 8) an
 #pragma unroll
                     for (int u = 0; u < kCheckEvery; ++u)
                         idx[u] = index_of((int32_t)lds_u32(box + (uint32_t)(half * kCheckEvery + (kCheckEvery - 1 - u)) * 128u));
+#if CTR_ENC_D32
+                    // one check per box: a full 32-byte sector of my scratch region per store (<= 15 words are in the
+                    // 16-word ring when a box starts, <= 7 after the drain, <= 8 more by the end of the box)
+                    static_assert(kBoxRows == 8, "one 32-byte drain per box keeps up with 8 rows");
+                    if (half == kBoxRows / kCheckEvery - 1) {
+                        const bool full = in_ring() >= 32u;
+                        const uint32_t at = ring | (drained & 32u);
+                        const uint4 a = lds_v4(at), b = lds_v4(at | 16u);
+                        encode_pair(idx[0], idx[1], stream_model);
+                        if (full) {
+                            if (drained + 32u <= cap)
+                                st_scratch_v8(gbase + drained, a, b);
+                            else
+                                pushed |= 0x80000000u;
+                            drained += 32u;
+                        }
+                        encode_pair(idx[2], idx[3], stream_model);
+                    } else {
+                        encode_pair(idx[0], idx[1], stream_model);
+                        encode_pair(idx[2], idx[3], stream_model);
+                    }
+#else
                     const bool full = in_ring() >= 16u;
                     const uint4 oldest = drain_load();
                     encode_pair(idx[0], idx[1], stream_model);
                     drain_decided(full, oldest);
                     encode_pair(idx[2], idx[3], stream_model);
+#endif
                 }
                 __syncwarp();  // every lane has read the box: its slot is requested again
                 request_box(slot);
+            };
+#if CTR_ENC_UNROLL_SLOTS
+            // the slots in turn with compile-time slot numbers (no slot / parity arithmetic in the loop)
+            static_assert(kEncBoxSlots == 2, "the unrolled loop is written for two slots");
+            uint32_t parity = 0;
+            for (; nbox >= 2u; nbox -= 2u) {
+                code_box(0u, parity);
+                code_box(1u, parity);
+                parity ^= 1u;
+            }
+            if (nbox != 0u) code_box(0u, parity);
+#else
+            uint32_t slot = 0, parity = 0;
+            for (; nbox > 0; --nbox) {
+                code_box(slot, parity);
                 if (++slot == kEncBoxSlots) {
                     slot = 0;
                     parity ^= 1u;
                 }
             }
+#endif
             drain_ring();
+            if (CTR_ENC_D32) {  // up to 15 words are left: 16 bytes at a time again
+                drain_ring();
+                drain_ring();
+            }
         } else
         if (g.T > 1) {
             const uint64_t rows_total = g.T - 1;  // full rows T-2 .. 0
@@ -696,23 +835,20 @@ __global__ void __launch_bounds__(BLOCK, BLOCK >= 256 ? CTR_ENC_MIN_CTAS : 8) an
     const bool raw = (p.flags & 1u) != 0;
     const uint32_t n_state = (valid && !raw) ? ans_state_words(state) : 0u;
     if (n_state >= 1) {
-        sts_u32(ring | (pushed & (kEncRingBytes - 1u)), (uint32_t)state);
+        sts_u32(ring_slot(pushed), (uint32_t)state);
         pushed += 4u;
     }
     if (n_state == 2) {
-        sts_u32(ring | (pushed & (kEncRingBytes - 1u)), (uint32_t)(state >> 32));
+        sts_u32(ring_slot(pushed), (uint32_t)(state >> 32));
         pushed += 4u;
     }
     drain_ring();
     bool overflow = (pushed & 0x80000000u) != 0u;
     while (in_ring() != 0u) {  // < 4 words, one at a time
-        if (room >= 4u) {
-            *reinterpret_cast<uint32_t *>(gw) = lds_u32(ring | (drained & (kEncRingBytes - 1u)));
-            gw += 4;
-            room -= 4u;
-        } else {
+        if (drained + 4u <= cap)
+            *reinterpret_cast<uint32_t *>(gbase + drained) = lds_u32(ring_slot(drained));
+        else
             overflow = true;
-        }
         drained += 4u;
     }
     if (valid) {
@@ -721,14 +857,12 @@ __global__ void __launch_bounds__(BLOCK, BLOCK >= 256 ? CTR_ENC_MIN_CTAS : 8) an
         if (overflow) report_error(p.status, kErrOutOfSpace, k);
     }
     // ---- K6: place my stream in the dense container ---------------------------------------------------
-    uint32_t gb_lo, gb_hi;
-    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(gb_lo), "=r"(gb_hi) : "r"(park) : "memory");
-    const uint32_t *gbegin = reinterpret_cast<const uint32_t *>(((uint64_t)gb_hi << 32) | gb_lo);
+    const uint32_t *gbegin = reinterpret_cast<const uint32_t *>(gbase);
 #ifdef CTR_DBG_NO_TAIL
     if (threadIdx.x == 0x7fffffff)
 #endif
     compact_tail<BLOCK>(p.compact, tile, k, K, valid, gbegin,
-                        (valid && !overflow) ? (uint32_t)((reinterpret_cast<const uint32_t *>(gw)) - gbegin) : 0u, p.status);
+                        (valid && !overflow) ? drained >> 2 : 0u, p.status);
 }
 
 // =====================================================================================================
@@ -747,6 +881,11 @@ __global__ void __launch_bounds__(BLOCK ? BLOCK : 1024, BLOCK == 0 || BLOCK >= 1
     __shared__ uint64_t bar;
 
     constexpr bool SHARED = TABLE == kTableLut, POOL = TABLE == kTablePool, GAUSS = TABLE == kTableGauss;
+    // one CTA per SM: room for the finer quantile index (p.model.dec_big)
+    constexpr bool BIG_LUT = SHARED && BLOCK == kDecBlockShared && kBigLutBits != kLutBits;
+    constexpr bool SPLIT = BIG_LUT && SMALL && CTR_DEC_SPLIT;  // u8 index + replicated {left, right} pairs
+    constexpr int kIndexBits = BIG_LUT ? kBigLutBits : kLutBits;
+    constexpr uint32_t kIndexBytes = SPLIT ? kSplitLutBytes : 8u << kIndexBits;
     const uint32_t kBlock = BLOCK ? (uint32_t)BLOCK : blockDim.x;
     const int lane = threadIdx.x & 31;
     const int warp_in_cta = threadIdx.x >> 5;
@@ -754,17 +893,20 @@ __global__ void __launch_bounds__(BLOCK ? BLOCK : 1024, BLOCK == 0 || BLOCK >= 1
 
     // shared memory carve-up: [lane rings (64 B each)][quantile index + cdf | model pool][symbol tiles][index tiles]
     const uint32_t alphabet = p.model.alphabet;
-    const uint32_t table_words = SHARED ? (kLutBytes + p.model.dec_cdf_bytes) / 4
+    const uint32_t dec_table_bytes = BIG_LUT ? p.model.dec_big_bytes : kIndexBytes + p.model.dec_cdf_bytes;
+    const uint32_t table_words = SHARED ? dec_table_bytes / 4
                                         : (POOL ? (p.model.pool_cdf_bytes + p.model.pool_cidx_bytes) / 4 : 0);
     const uint32_t kRingsWords = kBlock * kDecRingWords;
     const uint32_t ring = smem_u32_pinned(smem) + threadIdx.x * kDecRingBytes;  // 64-byte aligned
     const uint32_t lut_addr = smem_u32_pinned(smem + kRingsWords);
-    uint32_t cdf_addr = lut_addr + (POOL ? 0u : kLutBytes);  // POOL: [n_models][alphabet + 1] starts the table area
+    // POOL: [n_models][alphabet + 1] starts the table area; SPLIT: my copy of the pair table
+    uint32_t cdf_addr = lut_addr + (POOL ? 0u : kIndexBytes) + (SPLIT ? (uint32_t)(lane & (kPairCopies - 1)) * 8u : 0u);
     asm volatile("" : "+r"(cdf_addr));
     uint32_t *sym_tile = smem + kRingsWords + table_words + warp_in_cta * kTileWords;
     uint32_t *idx_tile = sym_tile + kWarpsPerCta * kTileWords;
 
-    if (SHARED) stage_table(smem + kRingsWords, p.model.dec, kLutBytes + p.model.dec_cdf_bytes, &bar);
+    // (the index is needed by the first decode_one only: the copy runs during the prologue)
+    if (SHARED) stage_table_begin(smem + kRingsWords, BIG_LUT ? p.model.dec_big : p.model.dec, dec_table_bytes, &bar);
     if (POOL)
         stage_tables(smem + kRingsWords, p.model.cdf, p.model.pool_cdf_bytes, smem + kRingsWords + p.model.pool_cdf_bytes / 4,
                      p.model.cidx, p.model.pool_cidx_bytes, &bar);
@@ -795,12 +937,15 @@ __global__ void __launch_bounds__(BLOCK ? BLOCK : 1024, BLOCK == 0 || BLOCK >= 1
     }
     // low 32 bits of the global byte address just past the next word to pop
     uint32_t pop_off = (uint32_t)(uintptr_t)(p.words + end);
-    uint32_t avail = 0;                     // words in my ring that have landed and are unread
+    // ... and of the lowest word of my stream that has landed in the ring: (pop_off - landed_off) / 4 words are unread
+    // (the per-symbol path then only moves pop_off)
+    uint32_t landed_off = pop_off;
     uint32_t pending = 0;                   // words of the 16-byte block that is in flight
     // (a stream of >= 2^32 words does not exist: the encoder's lengths are 32-bit)
     uint32_t unstaged = (uint32_t)(end - begin);  // words of my stream not yet requested
     const char *gblock = reinterpret_cast<const char *>(p.words) + ((end * 4u) & ~(uint64_t)15);  // block holding word end
     if ((end & 3u) == 0) gblock -= 16;      // ... or rather the block holding word end-1
+    auto avail_bytes = [&]() -> uint32_t { return pop_off - landed_off; };
 
     // request the next block below (asynchronously); the first block of a stream may be partial at the top,
     // the last one at the bottom
@@ -812,12 +957,12 @@ __global__ void __launch_bounds__(BLOCK ? BLOCK : 1024, BLOCK == 0 || BLOCK >= 1
         pending = n;
     };
     // every kCheckEvery symbols: the block requested at the previous check has landed; request the next
-    // one if there is room for it.  Invariant after the check: avail >= kCheckEvery or nothing is left.
+    // one if there is room for it.  Invariant after the check: >= kCheckEvery words unread or nothing is left.
     auto top_up = [&]() {
         cp_async_wait_all();
-        avail += pending;
+        landed_off -= pending * 4u;
         pending = 0;
-        if (avail <= (uint32_t)(kDecRingWords - 4) && unstaged != 0u) request_block(4u);
+        if (avail_bytes() <= (uint32_t)(kDecRingWords - 4) * 4u && unstaged != 0u) request_block(4u);
         cp_async_commit();
     };
     // start-up: stage at least 8 words (or the whole stream) synchronously
@@ -828,13 +973,12 @@ __global__ void __launch_bounds__(BLOCK ? BLOCK : 1024, BLOCK == 0 || BLOCK >= 1
 #pragma unroll 1
         for (int i = 0; i < 3; ++i) top_up();
         cp_async_wait_all();
-        avail += pending;
+        landed_off -= pending * 4u;
         pending = 0;
     }
 
     auto pop_word = [&]() -> uint32_t {
         pop_off -= 4u;
-        avail -= 1u;
         return lds_u32(ring | (pop_off & (kDecRingBytes - 1u)));
     };
 
@@ -848,16 +992,17 @@ __global__ void __launch_bounds__(BLOCK ? BLOCK : 1024, BLOCK == 0 || BLOCK >= 1
             hi = (uint32_t)(s >> 32);
         }
     } else {
-        if (avail != 0u) {
+        if (avail_bytes() != 0u) {
             lo = pop_word();
             trailing_zero = lo == 0u;
-            if (avail != 0u && lo != 0u) {
+            if (avail_bytes() != 0u && lo != 0u) {
                 hi = lo;
                 lo = pop_word();
             }
         }
     }
     top_up();
+    if (SHARED) stage_table_wait(&bar);
 
     const uint32_t n_models = p.model.n_models;
     uint32_t min_symbol = (uint32_t)p.model.min_symbol;
@@ -870,10 +1015,18 @@ __global__ void __launch_bounds__(BLOCK ? BLOCK : 1024, BLOCK == 0 || BLOCK >= 1
     bool bad_model = false;  // GAUSS: a std that is not > 0 (the symbols decoded with it are garbage)
     // one reference decode_symbol (stack.rs:1070-1100)
     auto decode_one = [&](uint32_t m) -> int32_t {
+#if CTR_DEC_SPEC_POP
+        // The word a refill would pop is read now, next to the table probe, instead of after the state update that
+        // decides whether it is needed: one shared-memory round trip less on the coder's dependent chain (the
+        // kernel is bound by that chain's latency).  Unused (and possibly stale) if nothing is popped.
+        const uint32_t next_word = lds_u32(ring | ((pop_off - 4u) & (kDecRingBytes - 1u)));
+#endif
         const uint32_t q = lo & kQuantileMask;
         uint32_t left, right, s;
-        if (SHARED) {
-            s = lookup_shared<SMALL>(lut_addr, cdf_addr, alphabet, lo, q, left, right);
+        if (SPLIT) {
+            s = lookup_split<kIndexBits>(lut_addr, cdf_addr, q, left, right);
+        } else if (SHARED) {
+            s = lookup_shared<SMALL, kIndexBits, BIG_LUT>(lut_addr, cdf_addr, alphabet, lo, q, left, right);
         } else if (GAUSS) {
             m = m < n_models ? m : n_models - 1;
             const double mean = __ldg(p.gauss_means + m), std = __ldg(p.gauss_stds + m);
@@ -894,10 +1047,17 @@ __global__ void __launch_bounds__(BLOCK ? BLOCK : 1024, BLOCK == 0 || BLOCK >= 1
         const uint64_t t = (uint64_t)__funnelshift_r(lo, hi, kPrecision) * prob + (uint64_t)(q - left);
         hi = (uint32_t)(t >> 32) + (hi >> kPrecision) * prob;
         lo = (uint32_t)t;
-        if (hi == 0u && avail != 0u) {  // stack.rs:1091-1097
+#if CTR_DEC_SPEC_POP
+        const bool refill = hi == 0u && pop_off != landed_off;  // stack.rs:1091-1097 (a word is left to pop)
+        hi = refill ? lo : hi;
+        lo = refill ? next_word : lo;
+        pop_off -= refill ? 4u : 0u;
+#else
+        if (hi == 0u && pop_off != landed_off) {  // stack.rs:1091-1097 (a word is left to pop)
             hi = lo;
             lo = pop_word();
         }
+#endif
         return (int32_t)(min_symbol + s);
     };
 
@@ -1031,7 +1191,7 @@ __global__ void __launch_bounds__(BLOCK ? BLOCK : 1024, BLOCK == 0 || BLOCK >= 1
     cp_async_wait_all();
     if (valid) {
         if (p.states_out) p.states_out[k] = ((uint64_t)hi << 32) | lo;
-        if (p.words_left) p.words_left[k] = (uint64_t)unstaged + pending + avail;
+        if (p.words_left) p.words_left[k] = (uint64_t)unstaged + pending + (avail_bytes() >> 2);
         if (trailing_zero) report_error(p.status, kErrTrailingZero, k);
         if (GAUSS && bad_model) report_error(p.status, kErrBadModel, k);
     }

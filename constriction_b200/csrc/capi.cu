@@ -135,6 +135,7 @@ struct ctr_model_s {
     uint4 *d_enc = nullptr;     // [n_models][alphabet + 1], built on first encode
     uint4 *d_enc_rep = nullptr; // model 0, every entry 8 times (small alphabets only)
     uint32_t *d_dec = nullptr;  // model 0: quantile index + cdf, for the shared-memory decoders
+    uint32_t *d_dec_big = nullptr;  // the same with 2^kBigLutBits buckets (large-batch ANS decoder), built on first use
     uint8_t *d_cidx = nullptr;  // coarse quantile index of every model, for the global-table decoders
     uint32_t dec_cdf_bytes = 0;  // (alphabet + 2) * 4 rounded up to 16: the cdf part of d_dec
     bool shared_ok = false;  // small enough for the shared-memory table kernels
@@ -146,7 +147,7 @@ struct ctr_model_s {
     // only after its build kernel is enqueued (under `lazy_mutex`) together with an event recorded behind it;
     // calls on other streams / host threads wait for that event before their kernel reads the table.
     std::mutex lazy_mutex;
-    LazyTable enc_ready, dec_ready, cidx_ready;
+    LazyTable enc_ready, dec_ready, dec_big_ready, cidx_ready;
 };
 
 namespace {
@@ -230,10 +231,36 @@ int ensure_dec_table(ctr_model_s *m, cudaStream_t s) {
     uint32_t *d_dec = nullptr;
     CUDA_TRY(cudaMalloc(&d_dec, kLutBytes + m->dec_cdf_bytes));
     const uint32_t threads = m->alphabet + 2 > (uint32_t)kLutSize ? m->alphabet + 2 : (uint32_t)kLutSize;
-    build_dec_table_kernel<<<grid_for(threads, 256), 256, 0, s>>>(m->d_cdf, m->alphabet, d_dec);
+    build_dec_table_kernel<<<grid_for(threads, 256), 256, 0, s>>>(m->d_cdf, m->alphabet, d_dec, kLutBits);
     LAUNCH_CHECK("build_dec_table_kernel");
     const int rc = publish_lazy_table(m->dec_ready, s);
     m->d_dec = d_dec;
+    return rc;
+}
+
+// the finer quantile index of the large-batch ANS decoder (ans_kernels.cuh: kDecBlockShared); split form for
+// alphabets of up to 256 symbols (device_utils.cuh: CTR_DEC_SPLIT)
+bool dec_big_is_split(const ctr_model_s *m) { return CTR_DEC_SPLIT && m->alphabet <= 256; }
+size_t dec_big_bytes(const ctr_model_s *m) {
+    return dec_big_is_split(m) ? (size_t)kSplitLutBytes + (size_t)m->alphabet * kPairCopies * 8 : (size_t)kBigLutBytes + m->dec_cdf_bytes;
+}
+int ensure_dec_big_table(ctr_model_s *m, cudaStream_t s) {
+    if (!m->shared_ok) return CTR_OK;
+    std::lock_guard<std::mutex> lock(m->lazy_mutex);
+    if (m->d_dec_big) return join_lazy_table(m->dec_big_ready, s);
+    uint32_t *d_dec = nullptr;
+    CUDA_TRY(cudaMalloc(&d_dec, dec_big_bytes(m)));
+    if (dec_big_is_split(m)) {
+        const uint32_t threads = std::max<uint32_t>(m->alphabet * kPairCopies, 1u << kBigLutBits);
+        build_dec_split_kernel<<<grid_for(threads, 256), 256, 0, s>>>(m->d_cdf, m->alphabet, reinterpret_cast<uint8_t *>(d_dec),
+                                                                      kBigLutBits);
+    } else {
+        const uint32_t threads = std::max<uint32_t>(m->alphabet + 2, 1u << kBigLutBits);
+        build_dec_table_kernel<<<grid_for(threads, 256), 256, 0, s>>>(m->d_cdf, m->alphabet, d_dec, kBigLutBits);
+    }
+    LAUNCH_CHECK("build_dec_table_kernel");
+    const int rc = publish_lazy_table(m->dec_big_ready, s);
+    m->d_dec_big = d_dec;
     return rc;
 }
 
@@ -290,6 +317,8 @@ ModelView model_view(const ctr_model_s *m) {
     v.enc_rep = m->d_enc_rep;
     v.cidx = m->d_cidx;
     v.dec = m->d_dec;
+    v.dec_big = m->d_dec_big;
+    v.dec_big_bytes = (uint32_t)dec_big_bytes(m);
     v.n_models = m->n_models;
     v.alphabet = m->alphabet;
     v.min_symbol = m->min_symbol;
@@ -651,7 +680,8 @@ extern "C" int ctr_model_destroy(ctr_model_t m) {
     if (m->d_enc_rep) cudaFree(m->d_enc_rep);
     if (m->d_cidx) cudaFree(m->d_cidx);
     if (m->d_dec) cudaFree(m->d_dec);
-    for (LazyTable *t : {&m->enc_ready, &m->dec_ready, &m->cidx_ready})
+    if (m->d_dec_big) cudaFree(m->d_dec_big);
+    for (LazyTable *t : {&m->enc_ready, &m->dec_ready, &m->dec_big_ready, &m->cidx_ready})
         if (t->built) cudaEventDestroy(t->built);
     delete m;
     return CTR_OK;
@@ -830,6 +860,9 @@ AnsParams base_params(const ctr_model_s *m, const ctr_layout *L) {
     p.model_index = L->model_index_dev;
     p.index_mode = L->model_index_mode;
     p.flags = L->flags;
+    p.k_one = 1u;
+    p.k_256 = 256u;
+    p.k_2p24 = 1u << 24;
     if (L->flags & CTR_FLAG_CHECKPOINTS) {
         p.ckpt_every = L->checkpoint_every;
         p.ckpt_off = L->ckpt_offsets_dev;
@@ -974,9 +1007,9 @@ int encode_common(ctr_model_t model, const int32_t *symbols_dev, const ctr_layou
     }
     cfg.block = encode_block(L);
     cfg.grid = grid_for(L->n_streams, cfg.block);
-    // rings + parking slots; replicated table (128 B per entry); two symbol tiles
+    // rings (the range encoder: + parking slots); replicated table (128 B per entry); two symbol tiles
     cfg.smem = coder_smem_bytes(cfg.shared ? ((size_t)model->alphabet + 1) * 128 : 0, L, cfg.block / 32,
-                                32 * (kEncRingWords + 4), 2);
+                                32 * (EncLauncher::kSlot == 0 ? kAnsEncRingWords : kEncRingWords + 4), 2);
     if (EncLauncher::kTma && !cfg.contig && !cfg.persym && make_symbol_tensor_map(&p.tmap, symbols_dev, L)) {
         p.use_tma = 1;
         cfg.smem += (size_t)(cfg.block / 32) * kEncBoxSlots * kBoxBytes;  // TMA boxes
@@ -998,8 +1031,13 @@ int decode_common(ctr_model_t model, const uint32_t *words, const uint64_t *offs
     cudaStream_t s = (cudaStream_t)stream;
     if (L->n_streams == 0) return CTR_OK;
     const bool lazy_gauss = model->lazy_means != nullptr;
+    // large-batch ANS decode (one 1024-thread CTA per SM): the finer quantile index (device_utils.cuh: kBigLutBits)
+    const bool big_lut = DecLauncher::kSlot == 1 && kBigLutBits != kLutBits && !lazy_gauss && use_shared_tables(model, L) &&
+                         !L->sym_offsets_dev && !(L->flags & CTR_FLAG_CHECKPOINTS) &&
+                         decode_block(L, true, false) == (unsigned)kDecBlockShared;
     if (!lazy_gauss) {
         if ((rc = ensure_dec_table(model, s))) return rc;
+        if (big_lut && (rc = ensure_dec_big_table(model, s))) return rc;
         if (!use_shared_tables(model, L) && (rc = ensure_coarse_index(model, s))) return rc;
     }
 
@@ -1098,7 +1136,7 @@ int decode_common(ctr_model_t model, const uint32_t *words, const uint64_t *offs
     }
     // interleaved deal, one model per stream: decoded symbols leave as TMA boxes (kDecBoxSlots per warp)
     size_t box_bytes_per_warp = 0;
-    if (DecLauncher::kTma && tma_decode_enabled() && !cfg.contig && !cfg.persym && make_symbol_tensor_map(&p.tmap, symbols_out, L)) {
+    if (DecLauncher::kTma && tma_decode_enabled() && !big_lut && !cfg.contig && !cfg.persym && make_symbol_tensor_map(&p.tmap, symbols_out, L)) {
         p.use_tma = 1;
         box_bytes_per_warp = (size_t)kDecBoxSlots * kBoxBytes;
     }
@@ -1124,7 +1162,9 @@ int decode_common(ctr_model_t model, const uint32_t *words, const uint64_t *offs
     }
     cfg.block = decode_block(L, cfg.shared, cfg.contig);
     cfg.grid = grid_for(L->n_streams, cfg.block);
-    cfg.smem = coder_smem_bytes(cfg.shared ? (size_t)kLutBytes + model->dec_cdf_bytes : 0, L, cfg.block / 32,
+    const size_t dec_table_bytes = big_lut && cfg.block == (unsigned)kDecBlockShared ? dec_big_bytes(model)
+                                                                                     : (size_t)kLutBytes + model->dec_cdf_bytes;
+    cfg.smem = coder_smem_bytes(cfg.shared ? dec_table_bytes : 0, L, cfg.block / 32,
                                 32 * kDecRingWords, 1) + (cfg.block / 32) * box_bytes_per_warp + (box_bytes_per_warp ? 128 : 0);
     return run_coder_kernel<DecLauncher>(cfg, p);
 }

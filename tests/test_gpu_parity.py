@@ -120,6 +120,29 @@ def test_interleaved_iid_matches_oracle(env, coder, n, k):
     assert np.array_equal(dec_o(want_words, want_off, n, k, cdf, -50, threads=8), syms)
 
 
+@pytest.mark.parametrize("lo,hi,mean,std", [(-500, 500, 20.5, 100.0), (-2000, 2000, -3.3, 3.0), (0, 255, 100.0, 30.0)])
+def test_large_batch_ans_decoder_quantile_index(env, lo, hi, mean, std):
+    """>= 148 * 1024 streams of one shared model: the one-CTA-per-SM ANS decoder with the fine quantile index
+    (device_utils.cuh: kBigLutBits), for alphabets above and below 256 symbols, with tail symbols that share an index
+    bucket with many others (second probe and cold search).  Words and symbols equal the oracle's."""
+    B, O, bc = env["B"], env["O"], env["bc"]
+    n, k = 700_000, 148 * 1024 + 40
+    rng = np.random.default_rng(hi * 7 + 1)
+    syms = gauss_symbols(rng, n, mean, std, lo, hi)
+    syms[::5] = rng.integers(lo, hi + 1, size=syms[::5].size)  # every symbol of the alphabet, however improbable
+    model = B.ModelTable.quantized_gaussian(lo, hi, [mean], [std])
+    cdf = model.cdf()[0]
+    want_words, want_off = O.multi_ans_encode(syms, k, cdf, lo, threads=8)
+    comp = bc.ans_encode(dev(env, syms), model, n_streams=k)
+    words, off = comp.to_host()
+    bc.check()
+    assert np.array_equal(off, want_off)
+    assert np.array_equal(words, want_words)
+    out = bc.ans_decode(comp, model)
+    bc.check()
+    assert np.array_equal(out.cpu().numpy(), syms)
+
+
 def test_interleaved_unaligned_symbol_buffer(env):
     """A symbol array that does not start on a 16-byte boundary cannot be a TMA tensor: per-row path, same words."""
     B, bc, torch = env["B"], env["bc"], env["torch"]

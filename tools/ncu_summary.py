@@ -12,7 +12,13 @@ WANT = ["Kernel Name", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__
         "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active", "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active",
         "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active",
         "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
-        "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "lts__t_sector_hit_rate.pct", "sm__cycles_elapsed.max",
+        "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared_op_ld.sum",
+        "l1tex__data_pipe_lsu_wavefronts_mem_shared_op_st.sum", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared_op_ld.sum",
+        "l1tex__data_bank_conflicts_pipe_lsu_mem_shared_op_st.sum", "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed",
+        "l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__lsuin_requests.avg.pct_of_peak_sustained_elapsed",
+        "l1tex__lsu_writeback_active.avg.pct_of_peak_sustained_elapsed", "sm__mio_inst_issued.avg.pct_of_peak_sustained_elapsed",
+        "lts__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__t_sectors_pipe_lsu_mem_global_op_st.sum",
+        "l1tex__t_requests_pipe_lsu_mem_global_op_st.sum", "lts__t_sector_hit_rate.pct", "sm__cycles_elapsed.max",
         "smsp__thread_inst_executed_per_inst_executed.ratio", "launch__shared_mem_per_block_dynamic", "launch__grid_size",
         "launch__block_size", "launch__waves_per_multiprocessor", "smsp__warps_eligible.avg.per_cycle_active"]
 rows = list(csv.reader(open(sys.argv[1])))

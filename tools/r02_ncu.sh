@@ -8,3 +8,6 @@ python tools/ncu_summary.py $out/raw.csv > $out/summary.txt; cat $out/summary.tx
 ncu -i $out/rep.ncu-rep --page source --csv --print-source cuda,sass > $out/src.csv 2>/dev/null
 python tools/ncu_source_hot.py $out/src.csv 22 > $out/hot.txt; cat $out/hot.txt
 rm -f $out/src.csv
+ncu -i $out/rep.ncu-rep --page source --csv --print-source sass > $out/sass.csv 2>/dev/null
+python tools/ncu_sass_hot.py $out/sass.csv ${TOP:-60} > $out/sass_hot.txt; head -8 $out/sass_hot.txt
+rm -f $out/sass.csv
