@@ -38,21 +38,6 @@
 namespace ctr {
 
 constexpr int kAnsBlock = 256;  // threads per CTA (8 warps)
-#ifndef CTR_ENC_SELP
-#define CTR_ENC_SELP 1
-#endif
-#ifndef CTR_DEC_SPEC_POP
-#define CTR_DEC_SPEC_POP 0
-#endif
-#ifndef CTR_ENC_FMA_PIPE
-#define CTR_ENC_FMA_PIPE 0
-#endif
-#ifndef CTR_ENC_RING_T
-#define CTR_ENC_RING_T 0
-#endif
-#ifndef CTR_ENC_UNROLL_SLOTS
-#define CTR_ENC_UNROLL_SLOTS 1
-#endif
 // Interleaved deal with one model per stream: symbols move between HBM and shared memory as 2-D TMA boxes of
 // kBoxRows rows x 32 streams per warp (device_utils.cuh), kEncBoxSlots / kDecBoxSlots boxes in flight per warp.
 #ifndef CTR_ENC_BOX_SLOTS
@@ -75,7 +60,6 @@ struct ModelView {
                            // decoding with global tables; cidx[m][b] = symbol of model m containing quantile b << 16
     const uint32_t *dec;   // model 0 only: quantile index uint2[kLutSize] ++ cdf u32[alphabet + 2] (padded to 16 B)
     const uint32_t *dec_big;  // the same with 2^kBigLutBits buckets (large-batch ANS decoder); nullptr until first used
-    uint32_t dec_big_bytes;   // its size (the split form of small alphabets differs: device_utils.cuh, CTR_DEC_SPLIT)
     uint32_t n_models;
     uint32_t alphabet;
     int32_t min_symbol;
@@ -122,9 +106,6 @@ struct AnsParams {
     double gauss_free_weight;
     // interleaved deal: the symbol array as a [full rows][K] int32 tensor (boxes of kBoxRows x 32), if use_tma
     uint32_t use_tma;
-    // 1, 2^8 and 2^24 as run-time values: multiplying by them keeps adds and shifts of the ANS encoder's update on the
-    // FMA pipe (IMAD) instead of the ALU pipe, which is the busier one (device_utils.cuh: imad_*)
-    uint32_t k_one, k_256, k_2p24;
     alignas(64) CUtensorMap tmap;
 };
 
@@ -230,24 +211,6 @@ __device__ __forceinline__ uint32_t lookup_shared(uint32_t lut_addr, uint32_t cd
             right = lds_table_u32(cdf_addr + s * 4u + 4u);
         }
     }
-    return s;
-}
-
-// Split decoder table (alphabet <= 256, large-batch ANS decoder): a one-byte probe names the first symbol of q's
-// bucket, then its {left, right} pair is read from the lane's own copy (pairs_addr = pair table + (lane % 16) * 8).
-template <int BITS>
-__device__ __forceinline__ uint32_t lookup_split(uint32_t lut_addr, uint32_t pairs_addr, uint32_t q, uint32_t &left,
-                                                 uint32_t &right) {
-    uint32_t s = lds_table_u8(lut_addr + (q >> (kPrecision - BITS)));
-    uint2 pr = lds_table_v2(pairs_addr + s * (kPairCopies * 8u));
-    if (__any_sync(kFullMask, q >= pr.y)) {  // q lies beyond the bucket's first symbol: rare with a fine index
-        while (q >= pr.y) {                  // (the last symbol's right end is 2^24 > q)
-            s += 1u;
-            pr = lds_table_v2(pairs_addr + s * (kPairCopies * 8u));
-        }
-    }
-    left = pr.x;
-    right = pr.y;
     return s;
 }
 
@@ -372,18 +335,8 @@ __global__ void __launch_bounds__(BLOCK, BLOCK >= 256 ? CTR_ENC_MIN_CTAS : 8) an
     const uint32_t table_words = SHARED ? (alphabet + 1) * 32 : 0;
     constexpr uint32_t kEncRingBytes = kAnsEncRingWords * 4u;  // (shadows the 8-word constant of the other encoders)
     constexpr uint32_t kRingsWords = BLOCK * kAnsEncRingWords;
-    static_assert(!(CTR_ENC_D32 && CTR_ENC_RING_T), "32-byte drains are written for the lane-major ring");
-#if CTR_ENC_RING_T
-    // The rings of a warp are stored slot-major: slot j of lane l is word (j * 32 + l) of the warp's 1 KB block, i.e.
-    // lane l only ever touches bank l.  Pushes (predicated STS of a few lanes at uncorrelated slots) and the 16-byte
-    // drain reads are therefore free of bank conflicts -- the kernel is bound by the L1 data pipe, where the
-    // lane-major layout cost ~2.5 extra wavefronts per symbol (ncu: 26 % of the shared-memory wavefronts).
-    const uint32_t ring = smem_u32_pinned(smem) + (uint32_t)warp_in_cta * (32u * kEncRingBytes) + (uint32_t)lane * 4u;
-    auto ring_slot = [&](uint32_t byte_pos) -> uint32_t { return ring + ((byte_pos & (kEncRingBytes - 4u)) << 5); };
-#else
     const uint32_t ring = smem_u32_pinned(smem) + threadIdx.x * kEncRingBytes;  // 32-byte aligned
     auto ring_slot = [&](uint32_t byte_pos) -> uint32_t { return ring | (byte_pos & (kEncRingBytes - 1u)); };
-#endif
     // lane l reads copy (l & 7) of an entry: the 8 lanes of a quarter-warp always hit 8 different 16-byte bank
     // groups, so the random-index LDS.128 is conflict free
     const uint32_t table_addr = smem_u32_pinned(smem + kRingsWords) + (uint32_t)(lane & 7) * 16u;
@@ -443,30 +396,6 @@ __global__ void __launch_bounds__(BLOCK, BLOCK >= 256 ? CTR_ENC_MIN_CTAS : 8) an
         return __ldg(p.model.enc + (uint64_t)m * (alphabet + 1) + idx);
     };
     auto encode_entry_nomin = [&](const uint4 &e) {
-#if CTR_ENC_FMA_PIPE
-        // One reference encode_symbol with the adds, shifts and selects that do not need the ALU pipe expressed as
-        // integer multiply-adds by run-time constants (p.k_*): ncu shows the ALU pipe as the busiest unit of this
-        // kernel (55 % vs 16 % for the FMA pipe), and both accept one warp instruction every other cycle.
-        const uint32_t prob = e.y;
-        const uint32_t prob_shl8 = imad_lo(prob, p.k_256, 0u);      // (state >> 40) >= prob  <=>  hi >= prob << 8
-        const uint32_t neg_prob = 0u - prob;
-        const uint32_t bump = imad_lo(neg_prob, p.k_one, kTotal);   // 2^24 - prob
-        uint32_t lo = (uint32_t)state, hi = (uint32_t)(state >> 32);
-        if (hi >= prob_shl8) {  // stack.rs:1035-1040 (lanes without a stream push into their own ring: harmless)
-            sts_u32(ring_slot(pushed), lo);
-            pushed += 4u;
-            lo = hi;
-            hi = 0u;
-        }
-        const uint64_t n = ((uint64_t)hi << 32) | lo;
-        const uint64_t q = ans_quotient_estimate<F64DIV>(n, e.z, e.w);  // in {true quotient - 1, true quotient}
-        const uint32_t r = imad_lo((uint32_t)q, neg_prob, lo);      // n - q * prob, in [0, 2 prob)
-        uint32_t x = imad_lo(r, p.k_one, e.x);                      // left + r
-        x = imad_lo_if_ge(x, r, prob, bump, p.k_one);               // r >= prob: the quotient was one short
-        // state = (q << 24) + x; bits 40.. of q are not part of the quotient (see ans_quotient_estimate)
-        const uint64_t low = imad_wide((uint32_t)q, p.k_2p24, (uint64_t)x);
-        state = ((uint64_t)imad_lo((uint32_t)(q >> 32), p.k_2p24, (uint32_t)(low >> 32)) << 32) | (uint32_t)low;
-#elif CTR_ENC_SELP
         // stack.rs:1035-1040 as one block of straight-line PTX: the push is predicated, and the renormalised state is
         // selected straight into the register pair the conversion reads (the compiler's own code moves it around)
         uint64_t n;
@@ -483,19 +412,7 @@ __global__ void __launch_bounds__(BLOCK, BLOCK >= 256 ? CTR_ENC_MIN_CTAS : 8) an
             : "r"((uint32_t)state), "r"((uint32_t)(state >> 32)), "r"(e.y), "r"(push_shift),
               "r"(ring_slot(pushed))
             : "memory");
-#else
-        uint32_t lo = (uint32_t)state, hi = (uint32_t)(state >> 32);
-        if (shr_clamp(hi, push_shift) >= e.y) {  // stack.rs:1035-1040
-            sts_u32(ring_slot(pushed), lo);
-            pushed += 4u;
-            lo = hi;
-            hi = 0u;
-        }
-        const uint64_t n = ((uint64_t)hi << 32) | lo;
-#endif
-#if !CTR_ENC_FMA_PIPE
         state = ans_encode_recombine(n, ans_quotient_estimate<F64DIV>(n, e.z, e.w), e.x, e.y);
-#endif
     };
     auto encode_entry = [&](const uint4 &e) {
         min_prob = min(min_prob, e.y);
@@ -518,7 +435,7 @@ __global__ void __launch_bounds__(BLOCK, BLOCK >= 256 ? CTR_ENC_MIN_CTAS : 8) an
     auto drain_store = [&](const uint4 &v) {
         if (in_ring() >= 16u) {
             if (drained + 16u <= cap)
-                st_scratch_v4(gbase + drained, v);
+                st_stream_v4(gbase + drained, v);
             else
                 pushed |= 0x80000000u;  // words dropped: the stream is flagged at the end
             drained += 16u;
@@ -526,12 +443,7 @@ __global__ void __launch_bounds__(BLOCK, BLOCK >= 256 ? CTR_ENC_MIN_CTAS : 8) an
     };
     // the oldest (possibly incomplete) 16-byte group of my ring; harmless to read when it is not yet complete
     auto drain_load = [&]() -> uint4 {
-#if CTR_ENC_RING_T
-        const uint32_t g = ring + ((drained & (kEncRingBytes - 16u)) << 5);
-        return make_uint4(lds_u32(g), lds_u32(g + 128u), lds_u32(g + 256u), lds_u32(g + 384u));
-#else
         return lds_v4(ring | (drained & (kEncRingBytes - 16u)));
-#endif
     };
     auto drain_ring = [&]() { drain_store(drain_load()); };
     // split form: `full = in_ring() >= 16` and `oldest = drain_load()` are taken at the check, the store is issued
@@ -540,7 +452,7 @@ __global__ void __launch_bounds__(BLOCK, BLOCK >= 256 ? CTR_ENC_MIN_CTAS : 8) an
     auto drain_decided = [&](bool full, const uint4 &oldest) {
         if (full) {
             if (drained + 16u <= cap)
-                st_scratch_v4(gbase + drained, oldest);
+                st_stream_v4(gbase + drained, oldest);
             else
                 pushed |= 0x80000000u;
             drained += 16u;
@@ -566,13 +478,11 @@ __global__ void __launch_bounds__(BLOCK, BLOCK >= 256 ? CTR_ENC_MIN_CTAS : 8) an
             {  // the rows above the highest box, one at a time
                 const int32_t *ps = p.symbols_in + (g.T - 2) * K + kc;
                 for (uint32_t j = 0; j < top_rows; ++j) {
-                    // (32-byte drains: nothing is drained before the boxes -- at most 8 words so far, and `drained`
-                    // must stay a multiple of 32 for the 256-bit stores)
-                    if (!CTR_ENC_D32 && (j & (kCheckEvery - 1)) == 0) drain_ring();
+                    if ((j & (kCheckEvery - 1)) == 0) drain_ring();
                     encode_one(ld_stream_s32(ps), stream_model);
                     ps -= K;
                 }
-                if (!CTR_ENC_D32) drain_ring();
+                drain_ring();
             }
             const uint32_t bars = smem_u32(&tma_bar[warp_in_cta][0]);
             const uint32_t boxes = smem_u32_pinned(smem + kRingsWords + table_words) + (uint32_t)warp_in_cta * (kEncBoxSlots * kBoxBytes);
@@ -606,39 +516,15 @@ __global__ void __launch_bounds__(BLOCK, BLOCK >= 256 ? CTR_ENC_MIN_CTAS : 8) an
 #pragma unroll
                     for (int u = 0; u < kCheckEvery; ++u)
                         idx[u] = index_of((int32_t)lds_u32(box + (uint32_t)(half * kCheckEvery + (kCheckEvery - 1 - u)) * 128u));
-#if CTR_ENC_D32
-                    // one check per box: a full 32-byte sector of my scratch region per store (<= 15 words are in the
-                    // 16-word ring when a box starts, <= 7 after the drain, <= 8 more by the end of the box)
-                    static_assert(kBoxRows == 8, "one 32-byte drain per box keeps up with 8 rows");
-                    if (half == kBoxRows / kCheckEvery - 1) {
-                        const bool full = in_ring() >= 32u;
-                        const uint32_t at = ring | (drained & 32u);
-                        const uint4 a = lds_v4(at), b = lds_v4(at | 16u);
-                        encode_pair(idx[0], idx[1], stream_model);
-                        if (full) {
-                            if (drained + 32u <= cap)
-                                st_scratch_v8(gbase + drained, a, b);
-                            else
-                                pushed |= 0x80000000u;
-                            drained += 32u;
-                        }
-                        encode_pair(idx[2], idx[3], stream_model);
-                    } else {
-                        encode_pair(idx[0], idx[1], stream_model);
-                        encode_pair(idx[2], idx[3], stream_model);
-                    }
-#else
                     const bool full = in_ring() >= 16u;
                     const uint4 oldest = drain_load();
                     encode_pair(idx[0], idx[1], stream_model);
                     drain_decided(full, oldest);
                     encode_pair(idx[2], idx[3], stream_model);
-#endif
                 }
                 __syncwarp();  // every lane has read the box: its slot is requested again
                 request_box(slot);
             };
-#if CTR_ENC_UNROLL_SLOTS
             // the slots in turn with compile-time slot numbers (no slot / parity arithmetic in the loop)
             static_assert(kEncBoxSlots == 2, "the unrolled loop is written for two slots");
             uint32_t parity = 0;
@@ -648,21 +534,7 @@ __global__ void __launch_bounds__(BLOCK, BLOCK >= 256 ? CTR_ENC_MIN_CTAS : 8) an
                 parity ^= 1u;
             }
             if (nbox != 0u) code_box(0u, parity);
-#else
-            uint32_t slot = 0, parity = 0;
-            for (; nbox > 0; --nbox) {
-                code_box(slot, parity);
-                if (++slot == kEncBoxSlots) {
-                    slot = 0;
-                    parity ^= 1u;
-                }
-            }
-#endif
             drain_ring();
-            if (CTR_ENC_D32) {  // up to 15 words are left: 16 bytes at a time again
-                drain_ring();
-                drain_ring();
-            }
         } else
         if (g.T > 1) {
             const uint64_t rows_total = g.T - 1;  // full rows T-2 .. 0
@@ -883,9 +755,8 @@ __global__ void __launch_bounds__(BLOCK ? BLOCK : 1024, BLOCK == 0 || BLOCK >= 1
     constexpr bool SHARED = TABLE == kTableLut, POOL = TABLE == kTablePool, GAUSS = TABLE == kTableGauss;
     // one CTA per SM: room for the finer quantile index (p.model.dec_big)
     constexpr bool BIG_LUT = SHARED && BLOCK == kDecBlockShared && kBigLutBits != kLutBits;
-    constexpr bool SPLIT = BIG_LUT && SMALL && CTR_DEC_SPLIT;  // u8 index + replicated {left, right} pairs
     constexpr int kIndexBits = BIG_LUT ? kBigLutBits : kLutBits;
-    constexpr uint32_t kIndexBytes = SPLIT ? kSplitLutBytes : 8u << kIndexBits;
+    constexpr uint32_t kIndexBytes = 8u << kIndexBits;
     const uint32_t kBlock = BLOCK ? (uint32_t)BLOCK : blockDim.x;
     const int lane = threadIdx.x & 31;
     const int warp_in_cta = threadIdx.x >> 5;
@@ -893,14 +764,13 @@ __global__ void __launch_bounds__(BLOCK ? BLOCK : 1024, BLOCK == 0 || BLOCK >= 1
 
     // shared memory carve-up: [lane rings (64 B each)][quantile index + cdf | model pool][symbol tiles][index tiles]
     const uint32_t alphabet = p.model.alphabet;
-    const uint32_t dec_table_bytes = BIG_LUT ? p.model.dec_big_bytes : kIndexBytes + p.model.dec_cdf_bytes;
+    const uint32_t dec_table_bytes = kIndexBytes + p.model.dec_cdf_bytes;
     const uint32_t table_words = SHARED ? dec_table_bytes / 4
                                         : (POOL ? (p.model.pool_cdf_bytes + p.model.pool_cidx_bytes) / 4 : 0);
     const uint32_t kRingsWords = kBlock * kDecRingWords;
     const uint32_t ring = smem_u32_pinned(smem) + threadIdx.x * kDecRingBytes;  // 64-byte aligned
     const uint32_t lut_addr = smem_u32_pinned(smem + kRingsWords);
-    // POOL: [n_models][alphabet + 1] starts the table area; SPLIT: my copy of the pair table
-    uint32_t cdf_addr = lut_addr + (POOL ? 0u : kIndexBytes) + (SPLIT ? (uint32_t)(lane & (kPairCopies - 1)) * 8u : 0u);
+    uint32_t cdf_addr = lut_addr + (POOL ? 0u : kIndexBytes);  // POOL: [n_models][alphabet + 1] starts the table area
     asm volatile("" : "+r"(cdf_addr));
     uint32_t *sym_tile = smem + kRingsWords + table_words + warp_in_cta * kTileWords;
     uint32_t *idx_tile = sym_tile + kWarpsPerCta * kTileWords;
@@ -1015,17 +885,9 @@ __global__ void __launch_bounds__(BLOCK ? BLOCK : 1024, BLOCK == 0 || BLOCK >= 1
     bool bad_model = false;  // GAUSS: a std that is not > 0 (the symbols decoded with it are garbage)
     // one reference decode_symbol (stack.rs:1070-1100)
     auto decode_one = [&](uint32_t m) -> int32_t {
-#if CTR_DEC_SPEC_POP
-        // The word a refill would pop is read now, next to the table probe, instead of after the state update that
-        // decides whether it is needed: one shared-memory round trip less on the coder's dependent chain (the
-        // kernel is bound by that chain's latency).  Unused (and possibly stale) if nothing is popped.
-        const uint32_t next_word = lds_u32(ring | ((pop_off - 4u) & (kDecRingBytes - 1u)));
-#endif
         const uint32_t q = lo & kQuantileMask;
         uint32_t left, right, s;
-        if (SPLIT) {
-            s = lookup_split<kIndexBits>(lut_addr, cdf_addr, q, left, right);
-        } else if (SHARED) {
+        if (SHARED) {
             s = lookup_shared<SMALL, kIndexBits, BIG_LUT>(lut_addr, cdf_addr, alphabet, lo, q, left, right);
         } else if (GAUSS) {
             m = m < n_models ? m : n_models - 1;
@@ -1047,17 +909,10 @@ __global__ void __launch_bounds__(BLOCK ? BLOCK : 1024, BLOCK == 0 || BLOCK >= 1
         const uint64_t t = (uint64_t)__funnelshift_r(lo, hi, kPrecision) * prob + (uint64_t)(q - left);
         hi = (uint32_t)(t >> 32) + (hi >> kPrecision) * prob;
         lo = (uint32_t)t;
-#if CTR_DEC_SPEC_POP
-        const bool refill = hi == 0u && pop_off != landed_off;  // stack.rs:1091-1097 (a word is left to pop)
-        hi = refill ? lo : hi;
-        lo = refill ? next_word : lo;
-        pop_off -= refill ? 4u : 0u;
-#else
         if (hi == 0u && pop_off != landed_off) {  // stack.rs:1091-1097 (a word is left to pop)
             hi = lo;
             lo = pop_word();
         }
-#endif
         return (int32_t)(min_symbol + s);
     };
 

@@ -238,26 +238,16 @@ int ensure_dec_table(ctr_model_s *m, cudaStream_t s) {
     return rc;
 }
 
-// the finer quantile index of the large-batch ANS decoder (ans_kernels.cuh: kDecBlockShared); split form for
-// alphabets of up to 256 symbols (device_utils.cuh: CTR_DEC_SPLIT)
-bool dec_big_is_split(const ctr_model_s *m) { return CTR_DEC_SPLIT && m->alphabet <= 256; }
-size_t dec_big_bytes(const ctr_model_s *m) {
-    return dec_big_is_split(m) ? (size_t)kSplitLutBytes + (size_t)m->alphabet * kPairCopies * 8 : (size_t)kBigLutBytes + m->dec_cdf_bytes;
-}
+// the finer quantile index of the large-batch ANS decoder (ans_kernels.cuh: kDecBlockShared)
+size_t dec_big_bytes(const ctr_model_s *m) { return (size_t)kBigLutBytes + m->dec_cdf_bytes; }
 int ensure_dec_big_table(ctr_model_s *m, cudaStream_t s) {
     if (!m->shared_ok) return CTR_OK;
     std::lock_guard<std::mutex> lock(m->lazy_mutex);
     if (m->d_dec_big) return join_lazy_table(m->dec_big_ready, s);
     uint32_t *d_dec = nullptr;
     CUDA_TRY(cudaMalloc(&d_dec, dec_big_bytes(m)));
-    if (dec_big_is_split(m)) {
-        const uint32_t threads = std::max<uint32_t>(m->alphabet * kPairCopies, 1u << kBigLutBits);
-        build_dec_split_kernel<<<grid_for(threads, 256), 256, 0, s>>>(m->d_cdf, m->alphabet, reinterpret_cast<uint8_t *>(d_dec),
-                                                                      kBigLutBits);
-    } else {
-        const uint32_t threads = std::max<uint32_t>(m->alphabet + 2, 1u << kBigLutBits);
-        build_dec_table_kernel<<<grid_for(threads, 256), 256, 0, s>>>(m->d_cdf, m->alphabet, d_dec, kBigLutBits);
-    }
+    const uint32_t threads = std::max<uint32_t>(m->alphabet + 2, 1u << kBigLutBits);
+    build_dec_table_kernel<<<grid_for(threads, 256), 256, 0, s>>>(m->d_cdf, m->alphabet, d_dec, kBigLutBits);
     LAUNCH_CHECK("build_dec_table_kernel");
     const int rc = publish_lazy_table(m->dec_big_ready, s);
     m->d_dec_big = d_dec;
@@ -318,7 +308,6 @@ ModelView model_view(const ctr_model_s *m) {
     v.cidx = m->d_cidx;
     v.dec = m->d_dec;
     v.dec_big = m->d_dec_big;
-    v.dec_big_bytes = (uint32_t)dec_big_bytes(m);
     v.n_models = m->n_models;
     v.alphabet = m->alphabet;
     v.min_symbol = m->min_symbol;
@@ -860,9 +849,6 @@ AnsParams base_params(const ctr_model_s *m, const ctr_layout *L) {
     p.model_index = L->model_index_dev;
     p.index_mode = L->model_index_mode;
     p.flags = L->flags;
-    p.k_one = 1u;
-    p.k_256 = 256u;
-    p.k_2p24 = 1u << 24;
     if (L->flags & CTR_FLAG_CHECKPOINTS) {
         p.ckpt_every = L->checkpoint_every;
         p.ckpt_off = L->ckpt_offsets_dev;

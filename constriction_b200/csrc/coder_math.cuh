@@ -97,27 +97,11 @@ CTR_HD uint64_t reciprocal_f64_bits(uint32_t d) {
     return b;
 }
 
-#ifndef CTR_ENC_CVT_MAGIC
-#define CTR_ENC_CVT_MAGIC 0
-#endif
 template <bool F64>
 CTR_HD uint64_t ans_quotient_estimate(uint64_t n, uint32_t rcp_lo, uint32_t rcp_hi) {
     if (F64) {
 #if defined(__CUDA_ARCH__)
-#if CTR_ENC_CVT_MAGIC
-        // The two 64-bit conversions without the XU pipe (quarter rate, long latency, and on the coder's dependent
-        // chain), with the same roundings: 2^84 + hi * 2^32 and 2^52 + lo are exact doubles with the integer in their
-        // mantissa; their sum minus the two offsets is n, rounded once (toward zero, like cvt.rz.f64.u64); and
-        // 2^52 + x rounded toward zero carries trunc(x) in its low mantissa bits (x < 2^40).  Bits 52.. of the
-        // result are not a quotient: ans_encode_recombine only uses bits 0..39.
-        const double hi_d = __hiloint2double(0x45300000, (int)(uint32_t)(n >> 32));
-        const double lo_d = __hiloint2double(0x43300000, (int)(uint32_t)n);
-        const double n_d = __dadd_rz(__dadd_rn(hi_d, -19342813118337666422669312.0), lo_d);  // -(2^84 + 2^52): exact
-        const double q_d = __dmul_rn(n_d, __hiloint2double((int)rcp_hi, (int)rcp_lo));
-        return (uint64_t)__double_as_longlong(__dadd_rz(q_d, 4503599627370496.0));
-#else
         return __double2ull_rz(__ull2double_rz(n) * __hiloint2double((int)rcp_hi, (int)rcp_lo));
-#endif
 #else
         double nd = (double)n;  // round to nearest; step down if that rounded up (round toward zero)
         if (nd >= 18446744073709551616.0 || (uint64_t)nd > n) nd = nextafter(nd, 0.0);

@@ -47,19 +47,6 @@ __device__ __forceinline__ uint32_t ld_cg_u32(const uint32_t *p) {
     return v;
 }
 
-// scratch words on their way to the container: dead after this read
-template <typename W>
-__device__ __forceinline__ W ld_scratch(const W *p) {
-#if CTR_L2_HINTS
-    if (sizeof(W) == 4) {
-        uint32_t v;
-        asm volatile("ld.global.L1::no_allocate.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(l2_policy_evict_first()));
-        return (W)v;
-    }
-#endif
-    return __ldcg(p);
-}
-
 // The tile this CTA works on (all threads get the same value).
 __device__ __forceinline__ uint32_t take_tile_ticket(unsigned int *ticket) {
     __shared__ uint32_t s_tile;
@@ -186,7 +173,7 @@ __device__ __forceinline__ void compact_tail(const CompactParams &c, uint32_t ti
 #pragma unroll
                 for (int u = 0; u < kSlots; ++u) {
                     const uint32_t j = j0 + u * 32 + lane;
-                    if (j < ni[g]) v[g][u] = ld_scratch(si[g] + j);
+                    if (j < ni[g]) v[g][u] = __ldcg(si[g] + j);
                 }
 #pragma unroll
             for (int g = 0; g < kGroup; ++g)

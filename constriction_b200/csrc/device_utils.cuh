@@ -30,10 +30,7 @@ constexpr int kDecRingWords = 16;   // decoder: <= 12 unread + 4 arriving words
 constexpr uint32_t kEncRingBytes = kEncRingWords * 4u;
 // the ANS encoder's TMA loop can drain its rings 32 bytes at a time (one 256-bit store per full sector, one check per
 // box of 8 rows): the ring then holds 16 words
-#ifndef CTR_ENC_D32
-#define CTR_ENC_D32 0
-#endif
-constexpr int kAnsEncRingWords = CTR_ENC_D32 ? 16 : 8;
+constexpr int kAnsEncRingWords = kEncRingWords;  // (the ANS encoder has no parking slots: see capi.cu)
 constexpr uint32_t kDecRingBytes = kDecRingWords * 4u;
 
 // ---- explicit shared-memory accesses by 32-bit shared address ------------------------------------------
@@ -51,22 +48,6 @@ __device__ __forceinline__ uint32_t shr_clamp(uint32_t v, uint32_t amount) {
     uint32_t r;
     asm("shr.u32 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(amount));
     return r;
-}
-// integer multiply-adds that stay multiply-adds (FMA pipe): `b` is a run-time value the compiler cannot fold
-__device__ __forceinline__ uint32_t imad_lo(uint32_t a, uint32_t b, uint32_t c) {
-    uint32_t d;
-    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
-    return d;
-}
-__device__ __forceinline__ uint64_t imad_wide(uint32_t a, uint32_t b, uint64_t c) {
-    uint64_t d;
-    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(d) : "r"(a), "r"(b), "l"(c));
-    return d;
-}
-// x + (u >= v ? w * one : 0) with the addition predicated (one compare on the ALU pipe, one IMAD)
-__device__ __forceinline__ uint32_t imad_lo_if_ge(uint32_t x, uint32_t u, uint32_t v, uint32_t w, uint32_t one) {
-    asm("{\n\t.reg .pred p;\n\tsetp.ge.u32 p, %1, %2;\n\t@p mad.lo.u32 %0, %3, %4, %0;\n\t}" : "+r"(x) : "r"(u), "r"(v), "r"(w), "r"(one));
-    return x;
 }
 // table reads: the tables are immutable once staged, so these may be scheduled freely
 __device__ __forceinline__ uint32_t lds_table_u32(uint32_t addr) {
@@ -91,36 +72,6 @@ __device__ __forceinline__ uint4 lds_v4(uint32_t addr) {
 }
 __device__ __forceinline__ void st_stream_v4(void *p, const uint4 &v) {
     asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
-                 : "memory");
-}
-// L2 eviction priorities (experiment switch, default off): the encoder's scratch words are read again by the compaction
-// tail, the symbols never are, so scratch lines are marked evict-last and the symbol stream evict-first.
-#ifndef CTR_L2_HINTS
-#define CTR_L2_HINTS 0
-#endif
-__device__ __forceinline__ uint64_t l2_policy_evict_last() {
-    uint64_t pol;
-    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
-    return pol;
-}
-__device__ __forceinline__ uint64_t l2_policy_evict_first() {
-    uint64_t pol;
-    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-    return pol;
-}
-// scratch words of the encoders (read back once, by the compaction tail)
-__device__ __forceinline__ void st_scratch_v4(void *p, const uint4 &v) {
-#if CTR_L2_HINTS
-    asm volatile("st.global.L1::no_allocate.L2::cache_hint.v4.u32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(p), "r"(v.x), "r"(v.y),
-                 "r"(v.z), "r"(v.w), "l"(l2_policy_evict_last())
-                 : "memory");
-#else
-    st_stream_v4(p, v);
-#endif
-}
-__device__ __forceinline__ void st_scratch_v8(void *p, const uint4 &a, const uint4 &b) {
-    asm volatile("st.global.L1::no_allocate.v8.u32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z),
-                 "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w)
                  : "memory");
 }
 // 16-byte asynchronous copy global -> shared (LDGSTS), tracked by cp.async groups
@@ -162,15 +113,6 @@ constexpr uint32_t kLutBytes = kLutSize * 8u;
 #endif
 constexpr int kBigLutBits = CTR_BIG_LUT_BITS;
 constexpr uint32_t kBigLutBytes = (1u << kBigLutBits) * 8u;
-// Alphabets of up to 256 symbols use a split form of it that costs fewer shared-memory wavefronts (the decoders are
-// bound by the L1 data pipe, and a random 8-byte probe of a 128 KB table is a 3-4-way bank conflict):
-//   u8 symbol_of_bucket[2^kBigLutBits], then {cdf[s], cdf[s+1]} pairs, every pair kPairCopies times (lane l reads
-//   copy l % 16, so the 8-byte probe is conflict free whatever the symbols are).
-#ifndef CTR_DEC_SPLIT
-#define CTR_DEC_SPLIT 0
-#endif
-constexpr uint32_t kPairCopies = 16;
-constexpr uint32_t kSplitLutBytes = 1u << kBigLutBits;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 // Same, but opaque to the optimiser: the value stays in a register instead of being rematerialised from the
@@ -244,15 +186,9 @@ __device__ __forceinline__ void mbar_wait_addr(uint32_t bar, uint32_t parity) {
 }
 // box at column x, row y of the tensor -> shared memory at `dst` (128-byte aligned); completes on `bar`
 __device__ __forceinline__ void tma_load_box(uint32_t dst, const void *tmap, int32_t x, int32_t y, uint32_t bar) {
-#if CTR_L2_HINTS
-    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3}], [%4], %5;" ::"r"(dst),
-                 "l"(tmap), "r"(x), "r"(y), "r"(bar), "l"(l2_policy_evict_first())
-                 : "memory");
-#else
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
                  "l"(tmap), "r"(x), "r"(y), "r"(bar)
                  : "memory");
-#endif
 }
 // shared memory at `src` -> box at column x, row y of the tensor (columns / rows outside the tensor are clipped)
 __device__ __forceinline__ void tma_store_box(const void *tmap, int32_t x, int32_t y, uint32_t src) {

@@ -348,24 +348,4 @@ __global__ void build_dec_table_kernel(const uint32_t *cdf, uint32_t alphabet, u
 }
 
 
-// split decoder table of model 0 (alphabet <= 256; see lookup_split in ans_kernels.cuh):
-// u8 symbol_of_bucket[2^lut_bits] ++ uint2 pairs[alphabet][kPairCopies] = {cdf[s], cdf[s + 1]}
-__global__ void build_dec_split_kernel(const uint32_t *cdf, uint32_t alphabet, uint8_t *dec, int lut_bits) {
-    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
-    uint2 *pairs = reinterpret_cast<uint2 *>(dec + (1u << lut_bits));
-    if (tid < alphabet * kPairCopies) pairs[tid] = make_uint2(cdf[tid / kPairCopies], cdf[tid / kPairCopies + 1]);
-    if (tid < (1u << lut_bits)) {
-        const uint32_t q = tid << (kPrecision - lut_bits);
-        uint32_t lo = 0, hi = alphabet - 1;  // last symbol whose left cumulative is <= q
-        while (lo < hi) {
-            const uint32_t mid = (lo + hi + 1) >> 1;
-            if (cdf[mid] <= q)
-                lo = mid;
-            else
-                hi = mid - 1;
-        }
-        dec[tid] = (uint8_t)lo;
-    }
-}
-
 }  // namespace ctr
