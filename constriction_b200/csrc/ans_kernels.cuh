@@ -754,7 +754,7 @@ __global__ void __launch_bounds__(BLOCK ? BLOCK : 1024, BLOCK == 0 || BLOCK >= 1
 
     constexpr bool SHARED = TABLE == kTableLut, POOL = TABLE == kTablePool, GAUSS = TABLE == kTableGauss;
     // one CTA per SM: room for the finer quantile index (p.model.dec_big)
-    constexpr bool BIG_LUT = SHARED && BLOCK == kDecBlockShared && kBigLutBits != kLutBits;
+    constexpr bool BIG_LUT = SHARED && BLOCK == kDecBlockShared;
     constexpr int kIndexBits = BIG_LUT ? kBigLutBits : kLutBits;
     constexpr uint32_t kIndexBytes = 8u << kIndexBits;
     const uint32_t kBlock = BLOCK ? (uint32_t)BLOCK : blockDim.x;
@@ -884,11 +884,14 @@ __global__ void __launch_bounds__(BLOCK ? BLOCK : 1024, BLOCK == 0 || BLOCK >= 1
 
     bool bad_model = false;  // GAUSS: a std that is not > 0 (the symbols decoded with it are garbage)
     // one reference decode_symbol (stack.rs:1070-1100)
-    auto decode_one = [&](uint32_t m) -> int32_t {
+    // `converged`: std::true_type where every lane of the warp makes this call together (the hot loops), so that the
+    // lookup may vote; std::false_type at the ragged ends, where only some lanes still own a symbol
+    auto decode_one = [&](uint32_t m, auto converged) -> int32_t {
+        constexpr bool kVote = BIG_LUT && decltype(converged)::value;
         const uint32_t q = lo & kQuantileMask;
         uint32_t left, right, s;
         if (SHARED) {
-            s = lookup_shared<SMALL, kIndexBits, BIG_LUT>(lut_addr, cdf_addr, alphabet, lo, q, left, right);
+            s = lookup_shared<SMALL, kIndexBits, kVote>(lut_addr, cdf_addr, alphabet, lo, q, left, right);
         } else if (GAUSS) {
             m = m < n_models ? m : n_models - 1;
             const double mean = __ldg(p.gauss_means + m), std = __ldg(p.gauss_stds + m);
@@ -936,7 +939,7 @@ __global__ void __launch_bounds__(BLOCK ? BLOCK : 1024, BLOCK == 0 || BLOCK >= 1
             for (int half = 0; half < kBoxRows / kCheckEvery; ++half) {
 #pragma unroll
                 for (int u = 0; u < kCheckEvery; ++u)
-                    sts_u32(box + (uint32_t)(half * kCheckEvery + u) * 128u, (uint32_t)decode_one(stream_model));
+                    sts_u32(box + (uint32_t)(half * kCheckEvery + u) * 128u, (uint32_t)decode_one(stream_model, std::true_type{}));
                 top_up();
             }
             fence_proxy_async_smem();
@@ -950,12 +953,12 @@ __global__ void __launch_bounds__(BLOCK ? BLOCK : 1024, BLOCK == 0 || BLOCK >= 1
         {  // the rows after the last box, then the ragged last row
             int32_t *po = p.symbols_out + (uint64_t)nbox * kBoxRows * K + kc;
             for (uint64_t r = (uint64_t)nbox * kBoxRows; r < rows_total; ++r) {
-                const int32_t sym = decode_one(stream_model);
+                const int32_t sym = decode_one(stream_model, std::true_type{});
                 if (valid) st_stream_s32(po, sym);
                 po += K;
                 top_up();
             }
-            if (valid && k < g.last) st_stream_s32(p.symbols_out + (g.T - 1) * K + k, decode_one(stream_model));
+            if (valid && k < g.last) st_stream_s32(p.symbols_out + (g.T - 1) * K + k, decode_one(stream_model, std::false_type{}));
         }
         if (lane == 0) tma_store_wait_all();
     } else if (!CONTIG) {
@@ -983,7 +986,7 @@ __global__ void __launch_bounds__(BLOCK ? BLOCK : 1024, BLOCK == 0 || BLOCK >= 1
                     }
 #pragma unroll
                     for (int u = 0; u < kCheckEvery; ++u) {
-                        const int32_t sym = decode_one(mbuf[u]);
+                        const int32_t sym = decode_one(mbuf[u], std::true_type{});
                         if (FULL || valid) st_stream_s32(reinterpret_cast<int32_t *>(po), sym);
                         po += row_bytes;
                     }
@@ -995,7 +998,7 @@ __global__ void __launch_bounds__(BLOCK ? BLOCK : 1024, BLOCK == 0 || BLOCK >= 1
                         m = ld_stream_u32(reinterpret_cast<const uint32_t *>(pm));
                         pm += row_bytes;
                     }
-                    const int32_t sym = decode_one(m);
+                    const int32_t sym = decode_one(m, std::true_type{});
                     if (FULL || valid) st_stream_s32(reinterpret_cast<int32_t *>(po), sym);
                     po += row_bytes;
                     rows_left -= 1;
@@ -1010,7 +1013,7 @@ __global__ void __launch_bounds__(BLOCK ? BLOCK : 1024, BLOCK == 0 || BLOCK >= 1
         if (g.T > 0) {  // ragged last row
             if (valid && k < g.last) {
                 const uint64_t i = (g.T - 1) * K + k;
-                const int32_t sym = decode_one(PERSYM ? ld_stream_u32(p.model_index + i) : stream_model);
+                const int32_t sym = decode_one(PERSYM ? ld_stream_u32(p.model_index + i) : stream_model, std::false_type{});
                 st_stream_s32(p.symbols_out + i, sym);
             }
         }
@@ -1031,12 +1034,12 @@ __global__ void __launch_bounds__(BLOCK ? BLOCK : 1024, BLOCK == 0 || BLOCK >= 1
 #pragma unroll
                 for (int u = 0; u < kCheckEvery; ++u) {
                     const uint32_t at = (s + (uint32_t)u) * 4u;
-                    sts_u32(row + at, (uint32_t)decode_one(PERSYM ? lds_u32(idx_row + at) : stream_model));
+                    sts_u32(row + at, (uint32_t)decode_one(PERSYM ? lds_u32(idx_row + at) : stream_model, std::true_type{}));
                 }
             }
             for (; s < cmax; ++s) {  // ragged end of the round
                 if ((s & (kCheckEvery - 1)) == 0) top_up();
-                if (s < c) sts_u32(row + s * 4u, (uint32_t)decode_one(PERSYM ? lds_u32(idx_row + s * 4u) : stream_model));
+                if (s < c) sts_u32(row + s * 4u, (uint32_t)decode_one(PERSYM ? lds_u32(idx_row + s * 4u) : stream_model, std::false_type{}));
             }
             warp_flush_rows(have, sym_tile, reinterpret_cast<uint32_t *>(p.symbols_out + o_k + done), c, lane);
             done += c;

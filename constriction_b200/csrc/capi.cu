@@ -1017,10 +1017,12 @@ int decode_common(ctr_model_t model, const uint32_t *words, const uint64_t *offs
     cudaStream_t s = (cudaStream_t)stream;
     if (L->n_streams == 0) return CTR_OK;
     const bool lazy_gauss = model->lazy_means != nullptr;
-    // large-batch ANS decode (one 1024-thread CTA per SM): the finer quantile index (device_utils.cuh: kBigLutBits)
-    const bool big_lut = DecLauncher::kSlot == 1 && kBigLutBits != kLutBits && !lazy_gauss && use_shared_tables(model, L) &&
-                         !L->sym_offsets_dev && !(L->flags & CTR_FLAG_CHECKPOINTS) &&
-                         decode_block(L, true, false) == (unsigned)kDecBlockShared;
+    // the finer quantile index (device_utils.cuh: kBigLutBits): large batches of one shared model in the interleaved
+    // layout (one 1024-thread CTA per SM), and the chain decoders
+    const bool big_lut = !lazy_gauss && use_shared_tables(model, L) &&
+                         !(L->flags & CTR_FLAG_CHECKPOINTS) &&
+                         (L->sym_offsets_dev ? use_chain_kernels(L, false, /*raw_ok=*/true) && L->model_index_mode != CTR_INDEX_PER_SYMBOL
+                                             : decode_block(L, true, false) == (unsigned)kDecBlockShared);
     if (!lazy_gauss) {
         if ((rc = ensure_dec_table(model, s))) return rc;
         if (big_lut && (rc = ensure_dec_big_table(model, s))) return rc;
@@ -1097,7 +1099,7 @@ int decode_common(ctr_model_t model, const uint32_t *words, const uint64_t *offs
         size_t table_bytes = 0;
         bool pool = false;
         if (cfg.shared) {
-            table_bytes = (size_t)kLutBytes + model->dec_cdf_bytes;
+            table_bytes = dec_big_bytes(model);
         } else if (model->d_cidx) {
             const size_t cdf_bytes = align_up((size_t)model->n_models * ((size_t)model->alphabet + 1) * 4, 16);
             const size_t cidx_bytes = align_up((size_t)model->n_models * 257 * (model->alphabet > 256 ? 2 : 1), 16);

@@ -412,14 +412,16 @@ __global__ void __launch_bounds__(kDecChainBlock) decode_chain_kernel(const __gr
     const uint32_t alphabet = p.model.alphabet;
     // shared memory: [32 lane rings (64 B each)][tables][kDecChainTiles symbol tiles of 32 x 32 words]
     constexpr uint32_t kRingsWords = 32 * kDecRingWords;
-    const uint32_t table_words = SHARED ? (kLutBytes + p.model.dec_cdf_bytes) / 4 : (p.model.pool_cdf_bytes + p.model.pool_cidx_bytes) / 4;
+    // SHARED: the finer quantile index (p.model.dec_big): its rarely taken second probe is off the coder's chain
+    constexpr uint32_t kIndexBytes = kBigLutBytes;
+    const uint32_t table_words = SHARED ? (kIndexBytes + p.model.dec_cdf_bytes) / 4 : (p.model.pool_cdf_bytes + p.model.pool_cidx_bytes) / 4;
     const uint32_t ring = smem_u32_pinned(smem) + (uint32_t)lane * kDecRingBytes;
     const uint32_t lut_addr = smem_u32_pinned(smem + kRingsWords);
-    uint32_t cdf_addr = lut_addr + (POOL ? 0u : kLutBytes);
+    uint32_t cdf_addr = lut_addr + (POOL ? 0u : kIndexBytes);
     asm volatile("" : "+r"(cdf_addr));
     const uint32_t tiles_addr = smem_u32(smem + kRingsWords + table_words);
 
-    if (SHARED) stage_table(smem + kRingsWords, p.model.dec, kLutBytes + p.model.dec_cdf_bytes, &bar);
+    if (SHARED) stage_table(smem + kRingsWords, p.model.dec_big, kIndexBytes + p.model.dec_cdf_bytes, &bar);
     if (POOL)
         stage_tables(smem + kRingsWords, p.model.cdf, p.model.pool_cdf_bytes, smem + kRingsWords + p.model.pool_cdf_bytes / 4,
                      p.model.cidx, p.model.pool_cidx_bytes, &bar);
@@ -527,8 +529,10 @@ __global__ void __launch_bounds__(kDecChainBlock) decode_chain_kernel(const __gr
     m = m < n_models ? m : n_models - 1;
     const uint32_t pool_row = cdf_addr + m * ((alphabet + 1) * 4u);
     const uint32_t pool_cidx = cdf_addr + p.model.pool_cdf_bytes + m * ((alphabet > 256 ? 2u : 1u) * (kCoarseSize + 1));
-    auto lookup = [&](uint32_t word, uint32_t q, uint32_t &left, uint32_t &right) -> uint32_t {
-        if (SHARED) return lookup_shared<SMALL>(lut_addr, cdf_addr, alphabet, word, q, left, right);
+    // `converged`: std::true_type where the whole coder warp makes the call together (the lookup may then vote)
+    auto lookup = [&](uint32_t word, uint32_t q, uint32_t &left, uint32_t &right, auto converged) -> uint32_t {
+        if (SHARED)
+            return lookup_shared<SMALL, kBigLutBits, decltype(converged)::value>(lut_addr, cdf_addr, alphabet, word, q, left, right);
         return lookup_pool(pool_row, pool_cidx, alphabet > 256, q, left, right);
     };
 
@@ -595,13 +599,13 @@ __global__ void __launch_bounds__(kDecChainBlock) decode_chain_kernel(const __gr
             invalid_data |= act && diff >= (scale << kPrecision);
             uint32_t q = __float2uint_rz(u64_to_float_cheap(diff) * rscale);
             q = min(q, kQuantileMask);
-            s = lookup(q, q, left, right);
+            s = lookup(q, q, left, right, std::true_type{});
             uint64_t nl = st.lower + scale * (uint64_t)left;
             uint64_t nr = scale * (uint64_t)(right - left);
             if (st.point - nl >= nr) {  // cold: exact quantile
                 q = kQuantileMask;
                 range_peek_quantile(st, q);
-                s = lookup(q, q, left, right);
+                s = lookup(q, q, left, right, std::false_type{});  // (only the lanes whose estimate missed are here)
                 nl = st.lower + scale * (uint64_t)left;
                 nr = scale * (uint64_t)(right - left);
             }
@@ -616,7 +620,7 @@ __global__ void __launch_bounds__(kDecChainBlock) decode_chain_kernel(const __gr
             avail -= pop ? 1u : 0u;
         } else {
             const uint32_t q = lo & kQuantileMask;
-            s = lookup(lo, q, left, right);
+            s = lookup(lo, q, left, right, std::true_type{});
             const uint32_t prob = right - left;
             const uint64_t t = (uint64_t)__funnelshift_r(lo, hi, kPrecision) * prob + (uint64_t)(q - left);
             const uint32_t nhi = (uint32_t)(t >> 32) + (hi >> kPrecision) * prob, nlo = (uint32_t)t;

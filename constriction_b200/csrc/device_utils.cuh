@@ -105,11 +105,13 @@ constexpr int kLutBits = 12;
 constexpr int kLutSize = 1 << kLutBits;
 constexpr int kLutShift = kPrecision - kLutBits;
 constexpr uint32_t kLutBytes = kLutSize * 8u;
-// The large-batch ANS decoder (one 1024-thread CTA per SM) has shared memory to spare and stages a finer index of the
-// same format: with 2^14 buckets a quantile falls beyond its bucket's first symbol in < 0.5 % of the lookups, so the
-// second probe becomes a rarely taken warp-uniform branch instead of predicated instructions in every symbol.
+// Decoders with shared memory to spare (the large-batch kernels: one 1024-thread CTA per SM; the chain kernels: one
+// coder warp per CTA) stage a finer index of the same format: with 2^13 buckets a quantile falls beyond its bucket's
+// first symbol in < 1 % of the lookups, so the second probe becomes a rarely taken warp-uniform branch instead of
+// predicated instructions (and a dependent shared-memory load) in every symbol.  (2^14 buckets: 1 % faster still in
+// the large-batch ANS decoder, but 128 KB per CTA would halve the chain decoders' CTAs per SM.)
 #ifndef CTR_BIG_LUT_BITS
-#define CTR_BIG_LUT_BITS 14
+#define CTR_BIG_LUT_BITS 13
 #endif
 constexpr int kBigLutBits = CTR_BIG_LUT_BITS;
 constexpr uint32_t kBigLutBytes = (1u << kBigLutBits) * 8u;

@@ -443,6 +443,10 @@ __global__ void __launch_bounds__(BLOCK ? BLOCK : 1024, BLOCK == 0 || BLOCK >= 1
     __shared__ uint64_t bar;
 
     constexpr bool SHARED = TABLE == kTableLut, POOL = TABLE == kTablePool, GAUSS = TABLE == kTableGauss;
+    // one CTA per SM: room for the finer quantile index (p.model.dec_big), as in ans_decode_kernel
+    constexpr bool BIG_LUT = SHARED && BLOCK == kDecBlockShared;
+    constexpr int kIndexBits = BIG_LUT ? kBigLutBits : kLutBits;
+    constexpr uint32_t kIndexBytes = 8u << kIndexBits;
     const uint32_t kBlock = BLOCK ? (uint32_t)BLOCK : blockDim.x;
     const int lane = threadIdx.x & 31;
     const int warp_in_cta = threadIdx.x >> 5;
@@ -450,17 +454,17 @@ __global__ void __launch_bounds__(BLOCK ? BLOCK : 1024, BLOCK == 0 || BLOCK >= 1
 
     // shared memory carve-up as in ans_decode_kernel
     const uint32_t alphabet = p.model.alphabet;
-    const uint32_t table_words = SHARED ? (kLutBytes + p.model.dec_cdf_bytes) / 4
+    const uint32_t table_words = SHARED ? (kIndexBytes + p.model.dec_cdf_bytes) / 4
                                         : (POOL ? (p.model.pool_cdf_bytes + p.model.pool_cidx_bytes) / 4 : 0);
     const uint32_t kRingsWords = kBlock * kDecRingWords;
     const uint32_t ring = smem_u32_pinned(smem) + threadIdx.x * kDecRingBytes;  // 64-byte aligned
     const uint32_t lut_addr = smem_u32_pinned(smem + kRingsWords);
-    uint32_t cdf_addr = lut_addr + (POOL ? 0u : kLutBytes);
+    uint32_t cdf_addr = lut_addr + (POOL ? 0u : kIndexBytes);
     asm volatile("" : "+r"(cdf_addr));
     uint32_t *sym_tile = smem + kRingsWords + table_words + warp_in_cta * kTileWords;
     uint32_t *idx_tile = sym_tile + kWarpsPerCta * kTileWords;
 
-    if (SHARED) stage_table(smem + kRingsWords, p.model.dec, kLutBytes + p.model.dec_cdf_bytes, &bar);
+    if (SHARED) stage_table(smem + kRingsWords, BIG_LUT ? p.model.dec_big : p.model.dec, kIndexBytes + p.model.dec_cdf_bytes, &bar);
     if (POOL)
         stage_tables(smem + kRingsWords, p.model.cdf, p.model.pool_cdf_bytes, smem + kRingsWords + p.model.pool_cdf_bytes / 4,
                      p.model.cidx, p.model.pool_cidx_bytes, &bar);
@@ -555,12 +559,14 @@ __global__ void __launch_bounds__(BLOCK ? BLOCK : 1024, BLOCK == 0 || BLOCK >= 1
     // one reference decode_symbol (queue.rs:968-1035); after invalid data the lane keeps running on a
     // clamped quantile (its symbols are garbage and the stream is flagged)
     bool bad_model = false;  // GAUSS: a std that is not > 0
-    auto decode_one = [&](uint32_t m) -> int32_t {
+    // `converged`: std::true_type where every lane of the warp makes this call together (see ans_decode_kernel)
+    auto decode_one = [&](uint32_t m, auto converged) -> int32_t {
+        constexpr bool kVote = BIG_LUT && decltype(converged)::value;
         uint32_t q = kQuantileMask;
         invalid_data |= !range_peek_quantile(st, q);
         uint32_t left, right, s;
         if (SHARED) {
-            s = lookup_shared<SMALL>(lut_addr, cdf_addr, alphabet, q, q, left, right);
+            s = lookup_shared<SMALL, kIndexBits, kVote>(lut_addr, cdf_addr, alphabet, q, q, left, right);
         } else if (GAUSS) {
             m = m < n_models ? m : n_models - 1;
             const double mean = __ldg(p.gauss_means + m), std = __ldg(p.gauss_stds + m);
@@ -606,7 +612,7 @@ __global__ void __launch_bounds__(BLOCK ? BLOCK : 1024, BLOCK == 0 || BLOCK >= 1
                     }
 #pragma unroll
                     for (int u = 0; u < kCheckEvery; ++u) {
-                        const int32_t sym = decode_one(mbuf[u]);
+                        const int32_t sym = decode_one(mbuf[u], std::true_type{});
                         if (FULL || valid) st_stream_s32(reinterpret_cast<int32_t *>(po), sym);
                         po += row_bytes;
                     }
@@ -618,7 +624,7 @@ __global__ void __launch_bounds__(BLOCK ? BLOCK : 1024, BLOCK == 0 || BLOCK >= 1
                         m = ld_stream_u32(reinterpret_cast<const uint32_t *>(pm));
                         pm += row_bytes;
                     }
-                    const int32_t sym = decode_one(m);
+                    const int32_t sym = decode_one(m, std::true_type{});
                     if (FULL || valid) st_stream_s32(reinterpret_cast<int32_t *>(po), sym);
                     po += row_bytes;
                     rows_left -= 1;
@@ -633,7 +639,7 @@ __global__ void __launch_bounds__(BLOCK ? BLOCK : 1024, BLOCK == 0 || BLOCK >= 1
         if (g.T > 0) {
             if (valid && k < g.last) {
                 const uint64_t i = (g.T - 1) * K + k;
-                const int32_t sym = decode_one(PERSYM ? ld_stream_u32(p.model_index + i) : stream_model);
+                const int32_t sym = decode_one(PERSYM ? ld_stream_u32(p.model_index + i) : stream_model, std::false_type{});
                 st_stream_s32(p.symbols_out + i, sym);
             }
         }
@@ -654,12 +660,12 @@ __global__ void __launch_bounds__(BLOCK ? BLOCK : 1024, BLOCK == 0 || BLOCK >= 1
 #pragma unroll
                 for (int u = 0; u < kCheckEvery; ++u) {
                     const uint32_t at = (s + (uint32_t)u) * 4u;
-                    sts_u32(row + at, (uint32_t)decode_one(PERSYM ? lds_u32(idx_row + at) : stream_model));
+                    sts_u32(row + at, (uint32_t)decode_one(PERSYM ? lds_u32(idx_row + at) : stream_model, std::true_type{}));
                 }
             }
             for (; s < cmax; ++s) {  // ragged end of the round
                 if ((s & (kCheckEvery - 1)) == 0) top_up();
-                if (s < c) sts_u32(row + s * 4u, (uint32_t)decode_one(PERSYM ? lds_u32(idx_row + s * 4u) : stream_model));
+                if (s < c) sts_u32(row + s * 4u, (uint32_t)decode_one(PERSYM ? lds_u32(idx_row + s * 4u) : stream_model, std::false_type{}));
             }
             warp_flush_rows(have, sym_tile, reinterpret_cast<uint32_t *>(p.symbols_out + o_k + done), c, lane);
             done += c;
