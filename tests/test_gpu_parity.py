@@ -143,6 +143,30 @@ def test_large_batch_ans_decoder_quantile_index(env, lo, hi, mean, std):
     assert np.array_equal(out.cpu().numpy(), syms)
 
 
+@pytest.mark.parametrize("coder", ["ans", "range"])
+@pytest.mark.parametrize("n", [0, 1, 148 * 1024 + 39, 148 * 1024 + 41, 3 * (148 * 1024 + 40) + 17])
+def test_large_batch_decoders_short_streams(env, coder, n):
+    """The one-CTA-per-SM decoders with (almost) nothing to decode: no symbols at all, fewer symbols than streams (empty
+    streams and one-symbol streams side by side), a ragged last row.  Words, offsets and symbols equal the oracle's."""
+    B, O, bc = env["B"], env["O"], env["bc"]
+    k = 148 * 1024 + 40
+    rng = np.random.default_rng(n + 5)
+    syms = gauss_symbols(rng, n)
+    model = B.ModelTable.quantized_gaussian(*BASE[:2], [BASE[2]], [BASE[3]])
+    cdf = model.cdf()[0]
+    enc_o = O.multi_ans_encode if coder == "ans" else O.multi_range_encode
+    want_words, want_off = enc_o(syms, k, cdf, -50, threads=8)
+    d_syms = dev(env, syms) if n else env["torch"].zeros(0, dtype=env["torch"].int32, device="cuda")
+    comp = (bc.ans_encode if coder == "ans" else bc.range_encode)(d_syms, model, n_streams=k)
+    words, off = comp.to_host()
+    bc.check()
+    assert np.array_equal(off, want_off)
+    assert np.array_equal(words, want_words)
+    out = (bc.ans_decode if coder == "ans" else bc.range_decode)(comp, model)
+    bc.check()
+    assert np.array_equal(out.cpu().numpy(), syms)
+
+
 def test_interleaved_unaligned_symbol_buffer(env):
     """A symbol array that does not start on a 16-byte boundary cannot be a TMA tensor: per-row path, same words."""
     B, bc, torch = env["B"], env["bc"], env["torch"]
