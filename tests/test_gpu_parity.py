@@ -453,3 +453,36 @@ def test_full_size_round_trip(env, coder):
         seg = syms[s::k].cpu().numpy()
         want = (O.ans_encode_iid if coder == "ans" else O.range_encode_iid)(seg, cdf, -50)
         assert np.array_equal(comp.stream_words(s), want), s
+
+
+def test_north_star_size_round_trip(env):
+    """BASELINE.json's target size: 1e9 i.i.d. symbols on one GPU (ANS).  Size-independent properties (decode(encode(x))
+    == x, monotone offsets, bits per symbol next to the model's entropy) plus streams cut out of the container and
+    compared with the oracle word for word."""
+    B, O, bc, torch = env["B"], env["O"], env["bc"], env["torch"]
+    n, k = 1_000_000_000, 148 * 1024
+    free, _ = torch.cuda.mem_get_info()
+    if free < 40 * (1 << 30):
+        pytest.skip("needs ~30 GB of device memory")
+    g = torch.Generator(device="cuda")
+    g.manual_seed(7)
+    syms = torch.empty(n, dtype=torch.int32, device="cuda")
+    for lo in range(0, n, 250_000_000):  # in pieces: the float temporaries of 1e9 elements would be 8 GB each
+        piece = torch.randn(250_000_000, device="cuda", generator=g)
+        syms[lo:lo + 250_000_000] = torch.clamp(torch.round(piece * 9.6 + 3.2), -50, 50).to(torch.int32)
+        del piece
+    model = B.ModelTable.quantized_gaussian(*BASE[:2], [BASE[2]], [BASE[3]])
+    comp = bc.ans_encode(syms, model, n_streams=k)
+    out = bc.ans_decode(comp, model)
+    bc.check()
+    assert torch.equal(out, syms)
+    del out
+    bits_per_symbol = 32.0 * comp.total_words() / n
+    assert 5.31 < bits_per_symbol < 5.31 * 1.01
+    off = comp.offsets.cpu().numpy()
+    assert np.all(np.diff(off) >= 0) and off[0] == 0
+    cdf = model.cdf()[0]
+    for s in [0, 31, 4097, k // 2 + 7, k - 1]:
+        want = O.ans_encode_iid(syms[s::k].cpu().numpy(), cdf, -50)
+        assert np.array_equal(comp.stream_words(s), want), s
+
