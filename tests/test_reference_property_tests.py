@@ -1,0 +1,178 @@
+"""Ports of the reference's Rust property tests for the hot path (the Python tests are replayed elsewhere):
+
+  * model/quantize.rs:879-904   `split_almost_delta_distribution`   (a known answer for Gaussian, Cauchy and Laplace)
+  * model/quantize.rs:906-995   `leakily_quantized_{normal,cauchy,laplace}` = `test_entropy_model` (model.rs:960-988)
+                                over the reference's grid of 6 scales x 9 locations on the support -127..=127
+  * stack.rs:1456-1548          `seek` of the ANS coder: 100 chunks x 100 symbols, a jump table of `pos()`, decoding back
+                                to front with equal positions, 100 random seeks
+  * queue.rs:1332-1396          `seek` of the range coder: the same with `RangeEncoder.pos()` / `RangeDecoder.seek()`
+
+Every test runs twice: against the oracle (`-m "not gpu"`) and against the CUDA path (`-m gpu`): the model tables come
+from the device kernels and `quantile_function` is the decode kernel itself, fed raw coder states whose low 24 bits are
+the quantile; the coders are the `constriction_b200.stream` mirror.  (The reference draws its symbols with Xoshiro256**;
+the properties do not depend on the generator, numpy's is used here.)"""
+import numpy as np
+import pytest
+
+SUPPORT = (-127, 127)
+SCALES = [1e-40, 0.0001, 0.1, 3.5, 123.45, 1234.56]
+LOCATIONS = [-300.6, -127.5, -100.2, -4.5, 0.0, 50.3, 127.5, 180.2, 2000.0]
+TOTAL = 1 << 24
+
+
+class OracleImpl:
+    name = "oracle"
+
+    def __init__(self, oracle):
+        self.O = oracle
+        self.AnsCoder, self.RangeEncoder, self.RangeDecoder = oracle.AnsCoder, oracle.RangeEncoder, oracle.RangeDecoder
+        self.QuantizedGaussian = oracle.QuantizedGaussian
+
+    def tables(self, kind, lo, hi, p0, p1):
+        return np.stack([self.O.qdist_cdf(kind, lo, hi, a, b) for a, b in zip(p0, p1)])
+
+    def quantiles(self, cdfs, lo, queries):
+        """symbol = quantile_function(q) for queries[m] (one row per model): the last s with cdf[s] <= q"""
+        return np.stack([lo + np.searchsorted(c[:-1], q, side="right") - 1 for c, q in zip(cdfs, queries)]).astype(np.int32)
+
+
+class CudaImpl:
+    name = "cuda"
+
+    def __init__(self):
+        import torch
+        assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+        import constriction_b200.stream as S
+        from constriction_b200 import batch as B
+        self.torch, self.B, self.bc = torch, B, B.BatchCoder()
+        self.AnsCoder, self.RangeEncoder, self.RangeDecoder = S.stack.AnsCoder, S.queue.RangeEncoder, S.queue.RangeDecoder
+        self.QuantizedGaussian = S.model.QuantizedGaussian
+
+    def tables(self, kind, lo, hi, p0, p1):
+        self._models = self.B.ModelTable.quantized(kind, lo, hi, p0, p1)
+        return self._models.cdf()
+
+    def quantiles(self, cdfs, lo, queries):
+        """The ANS decode kernel as `quantile_function`: one coder per query, started from the raw state 2^32 + q with no
+        words to read, decodes one symbol under model m (per-stream model index)."""
+        torch, B = self.torch, self.B
+        m, nq = queries.shape
+        k = m * nq
+        states = torch.from_numpy(((1 << 32) + queries.reshape(-1).astype(np.uint64)).astype(np.int64)).cuda()
+        index = torch.arange(m, dtype=torch.int32, device="cuda").repeat_interleave(nq)
+        empty = B.Compressed(torch.zeros(4, dtype=torch.int32, device="cuda"), torch.zeros(k + 1, dtype=torch.int64, device="cuda"),
+                             k, k, "ans")
+        from constriction_b200 import _native as N
+        out = self.bc.ans_decode(empty, self._models, n_symbols=k, model_index=index, index_mode=N.INDEX_PER_STREAM,
+                                 states_in=states, raw=True)
+        self.bc.check()
+        return out.cpu().numpy().reshape(m, nq)
+
+
+@pytest.fixture(scope="module", params=["oracle", pytest.param("cuda", marks=pytest.mark.gpu)])
+def impl(request, oracle):
+    return OracleImpl(oracle) if request.param == "oracle" else CudaImpl()
+
+
+@pytest.mark.parametrize("kind", ["gaussian", "cauchy", "laplace"])
+def test_split_almost_delta_distribution(impl, kind):
+    """quantize.rs:879-904: a peak of width 1e-40 at 2.5 is split evenly between the symbols 2 and 3, and the 19 other
+    symbols of -10..=10 keep one quantile each."""
+    cdf = impl.tables(kind, -10, 10, [2.5], [1e-40])[0].astype(np.int64)
+    left_cdf, left_prob = cdf[2 + 10], cdf[3 + 10] - cdf[2 + 10]
+    right_cdf, right_prob = cdf[3 + 10], cdf[4 + 10] - cdf[3 + 10]
+    assert left_prob == right_prob - 1, "peak not split evenly"
+    assert TOTAL - left_prob - right_prob == 19, "peak has the wrong probability mass"
+    assert left_cdf + left_prob == right_cdf
+
+
+@pytest.mark.parametrize("kind", ["gaussian", "cauchy", "laplace"])
+def test_leakily_quantized_models(impl, kind):
+    """quantize.rs:906-995 with model.rs:960-988 (`test_entropy_model`): for every model of the grid the left cumulatives
+    start at 0, add up through non-zero probabilities to exactly 2^24, and the quantile function maps the first, the
+    last and the middle quantile of every symbol back to that symbol."""
+    lo, hi = SUPPORT
+    p1, p0 = (a.reshape(-1) for a in np.meshgrid(np.array(SCALES), np.array(LOCATIONS), indexing="ij"))
+    cdfs = impl.tables(kind, lo, hi, p0, p1).astype(np.int64)
+    assert cdfs.shape == (len(SCALES) * len(LOCATIONS), hi - lo + 2)
+    assert np.all(cdfs[:, 0] == 0) and np.all(cdfs[:, -1] == TOTAL)
+    prob = np.diff(cdfs, axis=1)
+    assert np.all(prob > 0), "every symbol of the support keeps a non-zero probability (leaky quantisation)"
+    left, right = cdfs[:, :-1], cdfs[:, 1:]
+    queries = np.concatenate([left, right - 1, left + prob // 2], axis=1)
+    got = impl.quantiles(cdfs.astype(np.uint32), lo, queries.astype(np.uint32))
+    want = np.tile(np.arange(lo, hi + 1, dtype=np.int32), 3)
+    assert np.array_equal(got, np.broadcast_to(want, got.shape))
+
+
+def _chunks(oracle, rng, num_chunks, per_chunk):
+    """symbols = quantile_function(uniform 24-bit quantile) of QuantizedGaussian(-100, 100, 0, 10), as the reference draws them"""
+    cdf = oracle.qgauss_cdf(-100, 100, 0.0, 10.0)
+    q = rng.integers(0, TOTAL, size=(num_chunks, per_chunk), dtype=np.uint32)
+    return (-100 + np.searchsorted(cdf[:-1], q, side="right") - 1).astype(np.int32)
+
+
+def test_ans_seek_jump_table(impl, oracle):
+    """stack.rs:1456-1548 (the part that does not need the reversed-words backend)."""
+    num_chunks, per_chunk = 100, 100
+    rng = np.random.default_rng(123)
+    symbols = _chunks(oracle, rng, num_chunks, per_chunk)
+    model = impl.QuantizedGaussian(-100, 100, 0.0, 10.0)
+    encoder = impl.AnsCoder()
+    initial = encoder.pos()
+    jump_table = []
+    for chunk in symbols:
+        encoder.encode_reverse(chunk, model)
+        jump_table.append(encoder.pos())
+    # the oracle agrees on every position (for the CUDA path this pins the records; trivially true for the oracle)
+    ref = oracle.AnsCoder()
+    ref_model = oracle.QuantizedGaussian(-100, 100, 0.0, 10.0)
+    for chunk, want in zip(symbols, jump_table):
+        ref.encode_reverse(chunk, ref_model)
+        assert ref.pos() == want
+    assert np.array_equal(ref.get_compressed(), encoder.get_compressed())
+    # decoding from back to front passes through the same positions and states
+    decoder = encoder.clone()
+    for chunk, want in zip(symbols[::-1], jump_table[::-1]):
+        assert decoder.pos() == want
+        assert np.array_equal(decoder.decode(model, per_chunk), chunk)
+    assert decoder.pos() == initial
+    assert decoder.is_empty()
+    # random seeks (a Vec-backed AnsCoder truncates when it seeks, stack.rs:1117-1139: the reference's seekable decoder
+    # is a cursor over the same words, i.e. a fresh clone per jump)
+    for _ in range(100):
+        i = int(rng.integers(num_chunks))
+        decoder = encoder.clone()
+        decoder.seek(*jump_table[i])
+        assert np.array_equal(decoder.decode(model, per_chunk), symbols[i])
+
+
+def test_range_seek_jump_table(impl, oracle):
+    """queue.rs:1332-1396."""
+    num_chunks, per_chunk = 100, 100
+    rng = np.random.default_rng(123)
+    symbols = _chunks(oracle, rng, num_chunks, per_chunk)
+    model = impl.QuantizedGaussian(-100, 100, 0.0, 10.0)
+    encoder = impl.RangeEncoder()
+    ref, ref_model = oracle.RangeEncoder(), oracle.QuantizedGaussian(-100, 100, 0.0, 10.0)
+    jump_table = []
+    for chunk in symbols:
+        jump_table.append(encoder.pos())
+        assert ref.pos() == jump_table[-1]
+        encoder.encode(chunk, model)
+        ref.encode(chunk, ref_model)
+    final = encoder.pos()
+    assert ref.pos() == final
+    assert np.array_equal(ref.get_compressed(), encoder.get_compressed())
+    decoder = encoder.get_decoder()
+    for chunk in symbols:
+        assert np.array_equal(decoder.decode(model, per_chunk), chunk)
+    assert decoder.maybe_exhausted()
+    for i in range(100):
+        j = 0 if i == 3 else int(rng.integers(num_chunks))  # jump to the beginning at least once
+        decoder.seek(*jump_table[j])
+        assert np.array_equal(decoder.decode(model, per_chunk), symbols[j])
+    decoder.seek(*jump_table[0])
+    assert not decoder.maybe_exhausted()
+    decoder.seek(*final)
+    assert decoder.maybe_exhausted()
