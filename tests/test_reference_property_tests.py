@@ -3,6 +3,7 @@
   * model/quantize.rs:879-904   `split_almost_delta_distribution`   (a known answer for Gaussian, Cauchy and Laplace)
   * model/quantize.rs:906-995   `leakily_quantized_{normal,cauchy,laplace}` = `test_entropy_model` (model.rs:960-988)
                                 over the reference's grid of 6 scales x 9 locations on the support -127..=127
+  * model/quantize.rs:997-1023  `leakily_quantized_binomial`: the same invariants for Binomial(n, p), n up to 10,000
   * stack.rs:1456-1548          `seek` of the ANS coder: 100 chunks x 100 symbols, a jump table of `pos()`, decoding back
                                 to front with equal positions, 100 random seeks
   * queue.rs:1332-1396          `seek` of the range coder: the same with `RangeEncoder.pos()` / `RangeDecoder.seek()`
@@ -31,6 +32,9 @@ class OracleImpl:
     def tables(self, kind, lo, hi, p0, p1):
         return np.stack([self.O.qdist_cdf(kind, lo, hi, a, b) for a, b in zip(p0, p1)])
 
+    def binomial_tables(self, n, ps):
+        return np.stack([self.O.binomial_cdf(n, p) for p in ps])
+
     def quantiles(self, cdfs, lo, queries):
         """symbol = quantile_function(q) for queries[m] (one row per model): the last s with cdf[s] <= q"""
         return np.stack([lo + np.searchsorted(c[:-1], q, side="right") - 1 for c, q in zip(cdfs, queries)]).astype(np.int32)
@@ -50,6 +54,10 @@ class CudaImpl:
 
     def tables(self, kind, lo, hi, p0, p1):
         self._models = self.B.ModelTable.quantized(kind, lo, hi, p0, p1)
+        return self._models.cdf()
+
+    def binomial_tables(self, n, ps):
+        self._models = self.B.ModelTable.binomial([n] * len(ps), ps)
         return self._models.cdf()
 
     def quantiles(self, cdfs, lo, queries):
@@ -102,6 +110,22 @@ def test_leakily_quantized_models(impl, kind):
     queries = np.concatenate([left, right - 1, left + prob // 2], axis=1)
     got = impl.quantiles(cdfs.astype(np.uint32), lo, queries.astype(np.uint32))
     want = np.tile(np.arange(lo, hi + 1, dtype=np.int32), 3)
+    assert np.array_equal(got, np.broadcast_to(want, got.shape))
+
+
+@pytest.mark.parametrize("n", [1, 2, 10, 100, 1000, 10_000])
+def test_leakily_quantized_binomial(impl, n):
+    """quantize.rs:997-1023 (with the reference's own exclusion of large n with tiny p)."""
+    ps = [p for p in [1e-30, 1e-20, 1e-10, 0.1, 0.4, 0.9] if n < 1000 or p >= 0.1]
+    cdfs = impl.binomial_tables(n, ps).astype(np.int64)
+    assert cdfs.shape == (len(ps), n + 2)
+    assert np.all(cdfs[:, 0] == 0) and np.all(cdfs[:, -1] == TOTAL)
+    prob = np.diff(cdfs, axis=1)
+    assert np.all(prob > 0)
+    left, right = cdfs[:, :-1], cdfs[:, 1:]
+    queries = np.concatenate([left, right - 1, left + prob // 2], axis=1)
+    got = impl.quantiles(cdfs.astype(np.uint32), 0, queries.astype(np.uint32))
+    want = np.tile(np.arange(0, n + 1, dtype=np.int32), 3)
     assert np.array_equal(got, np.broadcast_to(want, got.shape))
 
 
