@@ -4,6 +4,9 @@
   * model/quantize.rs:906-995   `leakily_quantized_{normal,cauchy,laplace}` = `test_entropy_model` (model.rs:960-988)
                                 over the reference's grid of 6 scales x 9 locations on the support -127..=127
   * model/quantize.rs:997-1023  `leakily_quantized_binomial`: the same invariants for Binomial(n, p), n up to 10,000
+  * categorical/contiguous.rs:734-872  `nontrivial_optimal_weights_f64 / _f32` (Default-preset halves) and
+                                `perfect_converges`: the perfect quantiser beats the fast one in KL divergence, keeps the
+                                order of the weights, converges on the two inputs of constriction issue #20
   * stack.rs:1456-1548          `seek` of the ANS coder: 100 chunks x 100 symbols, a jump table of `pos()`, decoding back
                                 to front with equal positions, 100 random seeks
   * queue.rs:1332-1396          `seek` of the range coder: the same with `RangeEncoder.pos()` / `RangeDecoder.seek()`
@@ -35,6 +38,9 @@ class OracleImpl:
     def binomial_tables(self, n, ps):
         return np.stack([self.O.binomial_cdf(n, p) for p in ps])
 
+    def categorical(self, pmf, perfect):
+        return (self.O.cat_perfect_cdf if perfect else self.O.cat_cdf)(pmf)
+
     def quantiles(self, cdfs, lo, queries):
         """symbol = quantile_function(q) for queries[m] (one row per model): the last s with cdf[s] <= q"""
         return np.stack([lo + np.searchsorted(c[:-1], q, side="right") - 1 for c, q in zip(cdfs, queries)]).astype(np.int32)
@@ -59,6 +65,9 @@ class CudaImpl:
     def binomial_tables(self, n, ps):
         self._models = self.B.ModelTable.binomial([n] * len(ps), ps)
         return self._models.cdf()
+
+    def categorical(self, pmf, perfect):
+        return (self.B.ModelTable.categorical_perfect if perfect else self.B.ModelTable.categorical)(pmf).cdf()[0]
 
     def quantiles(self, cdfs, lo, queries):
         """The ANS decode kernel as `quantile_function`: one coder per query, started from the raw state 2^32 + q with no
@@ -127,6 +136,47 @@ def test_leakily_quantized_binomial(impl, n):
     got = impl.quantiles(cdfs.astype(np.uint32), 0, queries.astype(np.uint32))
     want = np.tile(np.arange(0, n + 1, dtype=np.int32), 3)
     assert np.array_equal(got, np.broadcast_to(want, got.shape))
+
+
+HIST = [1, 186545, 237403, 295700, 361445, 433686, 509456, 586943, 663946, 737772, 1657269, 896675, 922197, 930672, 916665,
+        0, 0, 0, 0, 0, 723031, 650522, 572300, 494702, 418703, 347600, 1, 283500, 226158, 178194, 136301, 103158, 76823,
+        55540, 39258, 27988, 54269]
+
+
+def _verify_iterable_entropy_model(cdf, hist, tol):
+    """model.rs:1016-1060: positive weights that add up to 2^24, sorted like the histogram, KL divergence below tol"""
+    weights = np.diff(cdf.astype(np.int64))
+    hist = np.asarray(hist, dtype=np.float64)
+    assert weights.size == hist.size and weights.sum() == TOTAL and np.all(weights > 0)
+    order = np.lexsort((hist, weights))  # by weight, ties by histogram value
+    assert np.all(np.diff(hist[order]) >= 0), "sorting by weight is not compatible with sorting by the histogram"
+    p = hist / hist.sum()
+    nz = p > 0
+    kl = float(np.sum(p[nz] * np.log2(p[nz] / (weights[nz] / TOTAL))))
+    assert kl < tol
+    return kl
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_nontrivial_optimal_weights(impl, dtype):
+    """categorical/contiguous.rs:734-833, the DefaultContiguousCategoricalEntropyModel halves."""
+    pmf = np.asarray(HIST, dtype=dtype)
+    kl_fast = _verify_iterable_entropy_model(impl.categorical(pmf, perfect=False), HIST, 1e-6)
+    kl_perfect = _verify_iterable_entropy_model(impl.categorical(pmf, perfect=True), HIST, 1e-6)
+    assert kl_perfect < kl_fast
+
+
+def test_perfect_converges(impl):
+    """categorical/contiguous.rs:835-872: two inputs on which constriction 0.2.6 looped forever (issue #20)."""
+    example1 = np.array([0.15, 0.69, 0.15])
+    example2 = np.array([1.34673042e-04, 6.52306480e-04, 3.14999325e-03, 1.49921896e-02, 6.67127371e-02, 2.26679876e-01,
+                         3.75356406e-01, 2.26679876e-01, 6.67127594e-02, 1.49922138e-02, 3.14990873e-03, 6.52299321e-04,
+                         1.34715927e-04])
+    cdf1 = impl.categorical(example1, perfect=True)
+    w = np.diff(cdf1.astype(np.int64))
+    assert -1 <= w[0] - w[2] <= 1
+    _verify_iterable_entropy_model(cdf1, example1, 1e-10)
+    _verify_iterable_entropy_model(impl.categorical(example2, perfect=True), example2, 1e-10)
 
 
 def _chunks(oracle, rng, num_chunks, per_chunk):
