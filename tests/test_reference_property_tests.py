@@ -7,6 +7,7 @@
   * categorical/contiguous.rs:734-872  `nontrivial_optimal_weights_f64 / _f32` (Default-preset halves) and
                                 `perfect_converges`: the perfect quantiser beats the fast one in KL divergence, keeps the
                                 order of the weights, converges on the two inputs of constriction issue #20
+  * model/uniform.rs:194-210    `uniform` (the 24-bit instances): `test_entropy_model` for 14 range sizes
   * stack.rs:1456-1548          `seek` of the ANS coder: 100 chunks x 100 symbols, a jump table of `pos()`, decoding back
                                 to front with equal positions, 100 random seeks
   * queue.rs:1332-1396          `seek` of the range coder: the same with `RangeEncoder.pos()` / `RangeDecoder.seek()`
@@ -41,6 +42,15 @@ class OracleImpl:
     def categorical(self, pmf, perfect):
         return (self.O.cat_perfect_cdf if perfect else self.O.cat_cdf)(pmf)
 
+    def uniform(self, size):
+        u = self.O._Uniform(size)
+        rows = [u.left_prob(s) for s in range(size)]
+        self._uniform = u
+        return np.array([l for l, _ in rows] + [rows[-1][0] + rows[-1][1]], dtype=np.uint32)
+
+    def uniform_quantiles(self, queries):
+        return np.array([self._uniform.quantile(int(q))[0] for q in queries], dtype=np.int32)
+
     def quantiles(self, cdfs, lo, queries):
         """symbol = quantile_function(q) for queries[m] (one row per model): the last s with cdf[s] <= q"""
         return np.stack([lo + np.searchsorted(c[:-1], q, side="right") - 1 for c, q in zip(cdfs, queries)]).astype(np.int32)
@@ -68,6 +78,13 @@ class CudaImpl:
 
     def categorical(self, pmf, perfect):
         return (self.B.ModelTable.categorical_perfect if perfect else self.B.ModelTable.categorical)(pmf).cdf()[0]
+
+    def uniform(self, size):
+        self._models = self.B.ModelTable.uniform(size)
+        return self._models.cdf()[0]
+
+    def uniform_quantiles(self, queries):
+        return self.quantiles(None, 0, np.asarray(queries, dtype=np.uint32)[None, :])[0]
 
     def quantiles(self, cdfs, lo, queries):
         """The ANS decode kernel as `quantile_function`: one coder per query, started from the raw state 2^32 + q with no
@@ -136,6 +153,18 @@ def test_leakily_quantized_binomial(impl, n):
     got = impl.quantiles(cdfs.astype(np.uint32), 0, queries.astype(np.uint32))
     want = np.tile(np.arange(0, n + 1, dtype=np.int32), 3)
     assert np.array_equal(got, np.broadcast_to(want, got.shape))
+
+
+@pytest.mark.parametrize("size", [2, 3, 4, 5, 6, 7, 8, 9, 62, 63, 64, 254, 255, 256])
+def test_uniform(impl, size):
+    """model/uniform.rs:194-210 for UniformModel<u32, 24>: floor(2^24 / size) quantiles per symbol, the last symbol
+    takes the remainder; the quantile function inverts it."""
+    cdf = impl.uniform(size).astype(np.int64)
+    assert cdf.size == size + 1 and cdf[0] == 0 and cdf[-1] == TOTAL
+    prob = np.diff(cdf)
+    assert np.all(prob[:-1] == TOTAL // size) and prob[-1] == TOTAL - (size - 1) * (TOTAL // size)
+    queries = np.concatenate([cdf[:-1], cdf[1:] - 1, cdf[:-1] + prob // 2])
+    assert np.array_equal(impl.uniform_quantiles(queries), np.tile(np.arange(size, dtype=np.int32), 3))
 
 
 HIST = [1, 186545, 237403, 295700, 361445, 433686, 509456, 586943, 663946, 737772, 1657269, 896675, 922197, 930672, 916665,
