@@ -826,14 +826,25 @@ __global__ void __launch_bounds__(BLOCK ? BLOCK : 1024, BLOCK == 0 || BLOCK >= 1
         unstaged -= n;
         pending = n;
     };
-    // every kCheckEvery symbols: the block requested at the previous check has landed; request the next
-    // one if there is room for it.  Invariant after the check: >= kCheckEvery words unread or nothing is left.
+    // every kCheckEvery symbols: the block requested TWO checks ago has landed (a request has two check intervals,
+    // ~3000 cycles, to arrive: with one interval 10 % of the kernel's stall samples were this wait); request the next
+    // one if the ring has room for it next to the block still in flight.  With S = unread + in-flight words, a
+    // request whenever S <= 12 keeps S >= 9 and therefore >= 5 unread words after every check while the stream has
+    // words left: the coder never finds its ring empty before the stream really is.
+    uint32_t pending_old = 0;  // words of the block requested at the previous check (in flight)
     auto top_up = [&]() {
-        cp_async_wait_all();
-        landed_off -= pending * 4u;
+        cp_async_wait_group<1>();
+        landed_off -= pending_old * 4u;
+        pending_old = pending;
         pending = 0;
-        if (avail_bytes() <= (uint32_t)(kDecRingWords - 4) * 4u && unstaged != 0u) request_block(4u);
+        if (avail_bytes() + pending_old * 4u <= (uint32_t)(kDecRingWords - 4) * 4u && unstaged != 0u) request_block(4u);
         cp_async_commit();
+    };
+    auto land_all = [&]() {
+        cp_async_wait_all();
+        landed_off -= (pending_old + pending) * 4u;
+        pending_old = 0;
+        pending = 0;
     };
     // start-up: stage at least 8 words (or the whole stream) synchronously
     {
@@ -842,9 +853,7 @@ __global__ void __launch_bounds__(BLOCK ? BLOCK : 1024, BLOCK == 0 || BLOCK >= 1
         cp_async_commit();
 #pragma unroll 1
         for (int i = 0; i < 3; ++i) top_up();
-        cp_async_wait_all();
-        landed_off -= pending * 4u;
-        pending = 0;
+        land_all();
     }
 
     auto pop_word = [&]() -> uint32_t {
@@ -1049,7 +1058,7 @@ __global__ void __launch_bounds__(BLOCK ? BLOCK : 1024, BLOCK == 0 || BLOCK >= 1
     cp_async_wait_all();
     if (valid) {
         if (p.states_out) p.states_out[k] = ((uint64_t)hi << 32) | lo;
-        if (p.words_left) p.words_left[k] = (uint64_t)unstaged + pending + (avail_bytes() >> 2);
+        if (p.words_left) p.words_left[k] = (uint64_t)unstaged + pending + pending_old + (avail_bytes() >> 2);
         if (trailing_zero) report_error(p.status, kErrTrailingZero, k);
         if (GAUSS && bad_model) report_error(p.status, kErrBadModel, k);
     }

@@ -502,11 +502,14 @@ __global__ void __launch_bounds__(kDecChainBlock) decode_chain_kernel(const __gr
         unstaged -= n;
         pending = n;
     };
+    // (two blocks in flight: a request has two check intervals to arrive; see ans_decode_kernel for the invariant)
+    uint32_t pending_old = 0;
     auto top_up = [&]() {
-        cp_async_wait_all();
-        avail += pending;
+        cp_async_wait_group<1>();
+        avail += pending_old;
+        pending_old = pending;
         pending = 0;
-        if (avail <= (uint32_t)(kDecRingWords - 4) && unstaged != 0u) request_block(4u);
+        if (avail + pending_old <= (uint32_t)(kDecRingWords - 4) && unstaged != 0u) request_block(4u);
         cp_async_commit();
     };
     {
@@ -516,8 +519,9 @@ __global__ void __launch_bounds__(kDecChainBlock) decode_chain_kernel(const __gr
 #pragma unroll 1
         for (int i = 0; i < 3; ++i) top_up();
         cp_async_wait_all();
-        avail += pending;
+        avail += pending + pending_old;
         pending = 0;
+        pending_old = 0;
     }
     // the word the next refill would take (valid only while avail != 0)
     auto peek_word = [&]() -> uint32_t { return lds_u32(ring | ((RANGE ? pop_off : pop_off - 4u) & (kDecRingBytes - 1u))); };
@@ -681,7 +685,7 @@ __global__ void __launch_bounds__(kDecChainBlock) decode_chain_kernel(const __gr
             }
         }
         if (p.words_left) {
-            const uint32_t left_n = unstaged + pending + avail;
+            const uint32_t left_n = unstaged + pending + pending_old + avail;
             p.words_left[k] = RANGE ? (uint64_t)((uint32_t)(end - begin) - left_n) : (uint64_t)left_n;
         }
         if (trailing_zero) report_error(p.status, kErrTrailingZero, k);

@@ -504,11 +504,14 @@ __global__ void __launch_bounds__(BLOCK ? BLOCK : 1024, BLOCK == 0 || BLOCK >= 1
         unstaged -= n;
         pending = n;
     };
+    // (two blocks in flight: a request has two check intervals to arrive; see ans_decode_kernel for the invariant)
+    uint32_t pending_old = 0;
     auto top_up = [&]() {
-        cp_async_wait_all();
-        avail += pending;
+        cp_async_wait_group<1>();
+        avail += pending_old;
+        pending_old = pending;
         pending = 0;
-        if (avail <= (uint32_t)(kDecRingWords - 4) && unstaged != 0u) request_block(4u);
+        if (avail + pending_old <= (uint32_t)(kDecRingWords - 4) && unstaged != 0u) request_block(4u);
         cp_async_commit();
     };
     {
@@ -518,8 +521,9 @@ __global__ void __launch_bounds__(BLOCK ? BLOCK : 1024, BLOCK == 0 || BLOCK >= 1
 #pragma unroll 1
         for (int i = 0; i < 3; ++i) top_up();
         cp_async_wait_all();
-        avail += pending;
+        avail += pending + pending_old;
         pending = 0;
+        pending_old = 0;
     }
     auto pop_word = [&]() -> uint32_t {
         const uint32_t w = lds_u32(ring | (pop_off & (kDecRingBytes - 1u)));
@@ -681,7 +685,7 @@ __global__ void __launch_bounds__(BLOCK ? BLOCK : 1024, BLOCK == 0 || BLOCK >= 1
             p.states_out[4 * k + 3] = 0;
         }
         // words consumed so far (Pos::pos().0, queue.rs:182-196)
-        if (p.words_left) p.words_left[k] = (uint64_t)(total_words - unstaged - pending - avail);
+        if (p.words_left) p.words_left[k] = (uint64_t)(total_words - unstaged - pending - pending_old - avail);
         if (invalid_data) report_error(p.status, kErrInvalidData, k);
         if (GAUSS && bad_model) report_error(p.status, kErrBadModel, k);
     }
