@@ -344,7 +344,8 @@ __global__ void __launch_bounds__(BLOCK, BLOCK >= 256 ? CTR_ENC_MIN_CTAS : 8) an
     uint32_t *sym_tile = smem + kRingsWords + table_words + warp_in_cta * (2 * kTileWords);
     uint32_t *idx_tile = smem + kRingsWords + table_words + kWarpsPerCta * (2 * kTileWords) + warp_in_cta * kTileWords;
 
-    if (SHARED) stage_table(smem + kRingsWords, p.model.enc_rep, (alphabet + 1) * 128u, &bar);
+    // (the copy runs during the prologue: it is waited for right before the first symbol is coded)
+    if (SHARED) stage_table_begin(smem + kRingsWords, p.model.enc_rep, (alphabet + 1) * 128u, &bar);
 
     const uint64_t K = p.K, N = p.N;
     const uint32_t tile = take_tile_ticket(p.compact.ticket);  // which BLOCK streams this CTA codes
@@ -462,49 +463,64 @@ __global__ void __launch_bounds__(BLOCK, BLOCK >= 256 ? CTR_ENC_MIN_CTAS : 8) an
     if (!CONTIG) {
         // ---- interleaved deal: row t holds symbols[t*K .. t*K+K); coded from the last row backwards ---
         const Interleave g = interleave_of(N, K);
-        if (g.T > 0) {  // ragged last row
-            if (valid && k < g.last) {
-                const uint64_t i = (g.T - 1) * K + k;
-                encode_one(ld_stream_s32(p.symbols_in + i), PERSYM ? ld_stream_u32(p.model_index + i) : stream_model);
-            }
-        }
-        if (!PERSYM && p.use_tma && g.T > 1) {
-            // ---- TMA path: the warp's column strip arrives as boxes of kBoxRows rows (one UTMALDG by lane 0 per
-            // box, completion on a per-slot mbarrier); lanes read their column with LDS.  kEncBoxSlots boxes
-            // are in flight per warp, which covers the HBM latency without holding any register.
-            const uint64_t rows_total = g.T - 1;  // full rows T-2 .. 0
-            uint32_t nbox = (uint32_t)(rows_total / kBoxRows);
-            const uint32_t top_rows = (uint32_t)(rows_total - (uint64_t)nbox * kBoxRows);
-            {  // the rows above the highest box, one at a time
-                const int32_t *ps = p.symbols_in + (g.T - 2) * K + kc;
-                for (uint32_t j = 0; j < top_rows; ++j) {
-                    if ((j & (kCheckEvery - 1)) == 0) drain_ring();
-                    encode_one(ld_stream_s32(ps), stream_model);
-                    ps -= K;
+        // TMA path (one model per stream): the warp's column strip arrives as boxes of kBoxRows rows (one UTMALDG by lane 0
+        // per box, completion on a per-slot mbarrier); lanes read their column with LDS.  kEncBoxSlots boxes are in
+        // flight per warp, which covers the HBM latency without holding any register.  The first boxes are requested
+        // before anything is coded, and the symbols that are not part of a box (the ragged last row, the rows above the
+        // highest box) are all loaded before the first of them is used: one HBM round trip instead of up to nine.
+        const bool use_boxes = !PERSYM && p.use_tma && g.T > 1;
+        const uint64_t rows_total = g.T > 1 ? g.T - 1 : 0;  // full rows T-2 .. 0
+        uint32_t nbox = use_boxes ? (uint32_t)(rows_total / kBoxRows) : 0u;
+        const uint32_t top_rows = use_boxes ? (uint32_t)(rows_total - (uint64_t)nbox * kBoxRows) : 0u;
+        const uint32_t bars = smem_u32(&tma_bar[warp_in_cta][0]);
+        const uint32_t boxes = smem_u32_pinned(smem + kRingsWords + table_words) + (uint32_t)warp_in_cta * (kEncBoxSlots * kBoxBytes);
+        const int32_t x0 = (int32_t)((uint32_t)tile * BLOCK + (uint32_t)warp_in_cta * 32u);  // my warp's first stream
+        uint32_t next = nbox;  // boxes [0, next) are not requested yet; they are taken from the top
+        auto request_box = [&](uint32_t slot) {
+            if (next != 0u) {
+                next -= 1u;
+                if (lane == 0) {
+                    mbar_expect_tx_addr(bars + 8u * slot, kBoxBytes);
+                    tma_load_box(boxes + slot * kBoxBytes, &p.tmap, x0, (int32_t)(next * kBoxRows), bars + 8u * slot);
                 }
-                drain_ring();
             }
-            const uint32_t bars = smem_u32(&tma_bar[warp_in_cta][0]);
-            const uint32_t boxes = smem_u32_pinned(smem + kRingsWords + table_words) + (uint32_t)warp_in_cta * (kEncBoxSlots * kBoxBytes);
-            const int32_t x0 = (int32_t)((uint32_t)tile * BLOCK + (uint32_t)warp_in_cta * 32u);  // my warp's first stream
+        };
+        if (use_boxes) {
             if (lane == 0) {
 #pragma unroll
                 for (int sl = 0; sl < kEncBoxSlots; ++sl) mbar_init_addr(bars + 8u * sl, 1);
                 fence_mbar_init();
             }
             __syncwarp();
-            uint32_t next = nbox;  // boxes [0, next) are not requested yet; they are taken from the top
-            auto request_box = [&](uint32_t slot) {
-                if (next != 0u) {
-                    next -= 1u;
-                    if (lane == 0) {
-                        mbar_expect_tx_addr(bars + 8u * slot, kBoxBytes);
-                        tma_load_box(boxes + slot * kBoxBytes, &p.tmap, x0, (int32_t)(next * kBoxRows), bars + 8u * slot);
-                    }
-                }
-            };
 #pragma unroll
             for (int sl = 0; sl < kEncBoxSlots; ++sl) request_box(sl);
+        }
+        const bool has_last = g.T > 0 && valid && k < g.last;
+        int32_t last_sym = 0, top_sym[kBoxRows - 1];
+        uint32_t last_model = stream_model;
+        if (has_last) {
+            const uint64_t i = (g.T - 1) * K + k;
+            last_sym = ld_stream_s32(p.symbols_in + i);
+            if (PERSYM) last_model = ld_stream_u32(p.model_index + i);
+        }
+        if (use_boxes) {
+            const int32_t *ps = p.symbols_in + (g.T - 2) * K + kc;
+#pragma unroll
+            for (int j = 0; j < kBoxRows - 1; ++j)
+                if (j < (int)top_rows) top_sym[j] = ld_stream_s32(ps - (uint64_t)j * K);
+        }
+        if (SHARED) stage_table_wait(&bar);
+        if (has_last) encode_one(last_sym, last_model);  // ragged last row
+        if (use_boxes) {
+            // the rows above the highest box
+#pragma unroll
+            for (int j = 0; j < kBoxRows - 1; ++j) {
+                if (j < (int)top_rows) {
+                    if ((j & (kCheckEvery - 1)) == 0) drain_ring();
+                    encode_one(top_sym[j], stream_model);
+                }
+            }
+            drain_ring();
             const uint32_t my_col = boxes + (uint32_t)lane * 4u;
             // one box: wait for it, code its rows top down, hand the slot back to the TMA engine
             auto code_box = [&](uint32_t slot, uint32_t parity) {
@@ -629,6 +645,7 @@ __global__ void __launch_bounds__(BLOCK, BLOCK >= 256 ? CTR_ENC_MIN_CTAS : 8) an
             }
         }
     } else {
+        if (SHARED) stage_table_wait(&bar);
         // ---- contiguous: 32x32 tiles, transposed through shared memory ---------------------------
         // The tile of the next round is filled asynchronously (LDGSTS) while this one is coded.  Within a
         // tile, groups of four symbols are looked up first (independent of the coder state) and then coded,
