@@ -4,8 +4,8 @@
 Workload (BASELINE.json configs[1]): 1e8 i.i.d. int32 symbols ~ QuantizedGaussian(-50,50,3.2,9.6),
 dealt round-robin to K lane-streams (one independent reference coder per GPU lane), CDF tables in
 shared memory.  A "step" is one pass of the hot path over the batch: ANS encode of all streams
-(coder kernel + compaction into the dense container), [N>1: NCCL all-gather of the compressed
-containers], ANS decode of all streams.  `value` is measured with inputs resident in HBM; `e2e` is
+(coder kernel + compaction into the dense container), [N>1: all-gather of the compressed containers
+through the C ABI's slotted copy-engine exchange, ctr_gather_*], ANS decode of all streams.  `value` is measured with inputs resident in HBM; `e2e` is
 the same step through the host-buffer C ABI (pinned host buffers, H2D/D2H copies inside the timed
 region).  Weak scaling: every GPU gets its own 1e8-symbol shard.  The line also carries `extra_configs`:
 BASELINE.json configs[3] (1e9 symbols in 8192 RangeEncoder streams, sharded over the N ranks, gathered),
